@@ -66,7 +66,7 @@ def test_qags_matches_quadpack_path(oracle_mod, kind, alphas, rng_):
             out = quad(_FS[kind], rng_[0], rng_[1], args=(al,), epsabs=ea, epsrel=er, limit=1000, full_output=1)
             assert ne == out[2]["neval"] and last == out[2]["last"]
             assert abs(r - out[0]) <= 1e-14 * max(1, abs(out[0]))
-            assert abs(e - out[1]) <= 1e-5 * abs(out[1]) + 1e-18  # error estimates are cancellation-prone
+            assert abs(e - out[1]) <= 1e-5 * abs(out[1]) + 1e-13 * max(1, abs(out[0]))  # estimates are cancellation-prone
 
 
 def test_survey_anchors_tables(get_oracle):
