@@ -1,0 +1,195 @@
+/*
+ * upcgpu.h -- C-ABI of the B200-native (sm_100a, FP64) two-photon-luminosity / sigma-table /
+ * event-sampling path.  This is the drop-in boundary: plain C, opaque handle, int status,
+ * caller-owned host buffers, no exceptions, no torch/CUDA types in any signature.
+ *
+ * The reference (nburmaso/upcgen) has no FFI; its boundary is the public C++ surface of
+ * UpcCrossSection / UpcSampler / UpcGenerator.  Each entry point below names
+ * the reference interface it replaces (paths relative to the reference root).  The C++ facade
+ * with the reference's own class/method names lives in upcgen_b200/host/ and calls only this
+ * header; INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns UPCGPU_OK (0) or a negative UPCGPU_E* code; the message of the
+ *     last failure on a context is available from upcgpu_last_error().
+ *   - one context = one CUDA device; a context is thread-compatible, not thread-safe.
+ *   - there is NO CPU fallback: without a usable CUDA device upcgpu_create fails.
+ *   - tables are FP64.  lumi tables are [nm][ny] (im-major, as TH2D hD2LDMDY x=M, y=Y);
+ *     sigma tables are [ny][nm] (transposed, as the reference's crossSectionYM).
+ */
+#ifndef UPCGPU_H
+#define UPCGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPCGPU_OK 0
+#define UPCGPU_EINVAL (-1)   /* bad argument / state */
+#define UPCGPU_ECUDA (-2)    /* CUDA runtime error (see upcgpu_last_error) */
+#define UPCGPU_ENODEV (-3)   /* no CUDA device */
+#define UPCGPU_EQAGS (-4)    /* device QAGS hit an error state the reference would abort on */
+#define UPCGPU_ERANGE (-5)   /* uniform outside the cumulative pdf (GSL: "cannot find r1") */
+
+typedef struct upcgpu_ctx upcgpu_ctx;
+
+/* Parameter block.  Mirrors the public data members of UpcCrossSection
+ * (include/UpcCrossSection.h:73-85 statics Z,A,R,a,sqrts,g1,g2; :114-164 instance fields) plus
+ * the UpcGenerator members used by the event stage (include/UpcGenerator.h:63-76).
+ * gtot is passed explicitly because the reference fixes it in the UpcCrossSection constructor
+ * from the default sqrts (src/UpcCrossSection.cpp:51-54). */
+typedef struct {
+  int Z, A;
+  double R, a;
+  double sqrts, g1, g2, gtot;
+  int is_point;        /* FLUX_POINT        -> UpcCrossSection::isPoint */
+  int breakup_mode;    /* BREAKUP_MODE      -> UpcCrossSection::breakupMode (1..4) */
+  int use_pol;         /* USE_POLARIZED_CS  -> UpcCrossSection::usePolarizedCS */
+  int nonzero_gam_pt;  /* NON_ZERO_GAM_PT   -> UpcCrossSection::useNonzeroGamPt */
+  int nm, ny, nz;
+  double mmin, mmax, ymin, ymax, zmin, zmax;
+  int nb1, nb2;        /* UpcCrossSection::nb1, nb2 (120) */
+  /* event stage */
+  int part_pdg;        /* UpcElemProcess::partPDG */
+  double m_part;       /* UpcElemProcess::mPart */
+  int is_charged;      /* UpcElemProcess::isCharged */
+  int is_pair;         /* UpcGenerator::isPairProduction */
+  int is_single;       /* UpcGenerator::isSingleProduction */
+  int ignore_csz;      /* UpcGenerator::ignoreCSZ */
+  int decay_uniform_pdg; /* !=0: twoPartDecayUniform of particle 1 into two of this pdg (ALP: 22) */
+  int do_pt_cut, do_eta_cut;
+  double pt_min, eta_min, eta_max;
+} upcgpu_params;
+
+enum { UPCGPU_TABLE_GAA = 0, UPCGPU_TABLE_TA = 1, UPCGPU_TABLE_FORMFAC = 2, UPCGPU_TABLE_BREAKUP = 3 };
+
+/* Scalars computed while preparing the tables. */
+typedef struct {
+  double rho0;       /* UpcCrossSection::calcWSRho     src/UpcCrossSection.cpp:152-163 */
+  double sigma_nn;   /* csNN in prepareGAA              src/UpcCrossSection.cpp:368-369 */
+  double factor;     /* UpcCrossSection::factor         src/UpcCrossSection.cpp:120 */
+  double breakup_p20;/* P(b=20): the clamp value of     src/UpcCrossSection.cpp:260 */
+  int n_breakup_energy_knots;
+} upcgpu_table_info;
+
+/* Work counters of the last lumi fill (for the roofline arithmetic; not needed by callers). */
+typedef struct {
+  long long qags_integrals;   /* number of form-factor flux integrals evaluated */
+  long long qags_evals;       /* integrand evaluations inside them (21 per GK21 call) */
+  long long qags_overflow;    /* integrals that needed the large-workspace pass */
+  long long qags_errors;      /* integrals ending in a GSL error state (reference: abort) */
+  long long flux_rows;        /* photon-energy rows tabulated */
+  long long band_pairs;       /* (b1,b2) pairs with some b < 20 fm that were evaluated */
+  double ms_tables, ms_flux, ms_cells, ms_total; /* device time of the stages, CUDA events */
+} upcgpu_fill_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* replaces: new UpcCrossSection() + parameter assignment (src/UpcGenerator.cpp:30-40,183-305) */
+int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out);
+void upcgpu_destroy(upcgpu_ctx* ctx);
+/* message of the last failure (ctx may be NULL for create failures) */
+const char* upcgpu_last_error(const upcgpu_ctx* ctx);
+/* library/ABI version, and the device the context runs on */
+int upcgpu_abi_version(void);
+int upcgpu_device_name(const upcgpu_ctx* ctx, char* buf, size_t cap);
+
+/* ---- tables T1-T4 -------------------------------------------------------------------- */
+/* replaces UpcCrossSection::init's calcWSRho/prepareGAA/prepareFormFac/prepareBreakupProb
+ * (src/UpcCrossSection.cpp:116-131, :152-163, :364-461).  All on the device. */
+int upcgpu_prepare_tables(upcgpu_ctx* ctx);
+int upcgpu_get_table_info(const upcgpu_ctx* ctx, upcgpu_table_info* info);
+/* copies knots i0..i0+n-1 of a spline table: x (knot), y (value), c (GSL c-coefficient);
+ * any of x,y,c may be NULL.  Replaces reading gslSplineGAA/FormFac/BreakP (:31-38). */
+int upcgpu_get_table(upcgpu_ctx* ctx, int which, size_t i0, size_t n, double* x, double* y, double* c);
+/* spline evaluation on the device, test hook for gsl_spline_eval call sites (:188,:260,:262) */
+int upcgpu_eval_table(upcgpu_ctx* ctx, int which, const double* x, size_t n, double* out);
+/* un-splined breakup probability, test hook for UpcCrossSection::calcBreakupProb(b, mode)
+ * (src/UpcCrossSection.cpp:752-1019); needs breakup_mode > 1 at create time */
+int upcgpu_breakup_raw(upcgpu_ctx* ctx, const double* b, int mode, size_t n, double* out);
+
+/* ---- fluxes F1-F3 -------------------------------------------------------------------- */
+/* replaces UpcCrossSection::fluxPoint / fluxForm (src/UpcCrossSection.cpp:166-218) on n
+ * (b,k) points; neval (may be NULL) receives the QAGS evaluation count (0 for point flux). */
+int upcgpu_flux_point(upcgpu_ctx* ctx, const double* b, const double* k, size_t n, double* out);
+int upcgpu_flux_form(upcgpu_ctx* ctx, const double* b, const double* k, size_t n, double* out, int* neval);
+
+/* ---- luminosity L1-L3 ---------------------------------------------------------------- */
+/* replaces UpcCrossSection::prepareTwoPhotonLumi (src/UpcCrossSection.cpp:463-592): fills the
+ * whole grid, values already multiplied by dm*dy (:546-550).  Unpolarised: lumi[nm*ny];
+ * polarised (use_pol): lumi_s, lumi_p.  Unused pointers may be NULL.  Host buffers. */
+int upcgpu_fill_lumi(upcgpu_ctx* ctx, double* lumi, double* lumi_s, double* lumi_p);
+/* Same, but computes only the m-rows im = shard, shard+nshards, ... (cyclic), keeps the result
+ * on the device (see upcgpu_lumi_device) and copies nothing.  One rank per GPU calls this with
+ * its rank; the exchange between ranks is the caller's (NCCL all-gather of the packed shard). */
+int upcgpu_fill_lumi_shard(upcgpu_ctx* ctx, int shard, int nshards);
+/* single cells, test hook for calcTwoPhotonLumi / calcTwoPhotonLumiPol (:221-335): n pairs
+ * (M,Y) -> out (unpol) or out_s/out_p, NOT multiplied by dm*dy */
+int upcgpu_lumi_cells(upcgpu_ctx* ctx, const double* M, const double* Y, size_t n, double* out,
+                      double* out_s, double* out_p);
+int upcgpu_get_fill_stats(const upcgpu_ctx* ctx, upcgpu_fill_stats* st);
+
+/* Device-resident buffers for the multi-GPU exchange (device pointers as integers so that no
+ * CUDA type appears here).  packed shard: [rows_per_shard][ny] per table, rows im=shard+i*nshards
+ * (rows_per_shard = ceil(nm/nshards), padding rows zero).  which: 0 unpol, 1 scalar, 2 pseudo. */
+int upcgpu_lumi_shard_buffer(upcgpu_ctx* ctx, int which, uint64_t* dev_ptr, size_t* n_doubles);
+/* gathered buffer [nshards][rows_per_shard][ny] to be filled by the caller's all-gather, then
+ * un-permuted into the full [nm][ny] device table by upcgpu_lumi_unpack */
+int upcgpu_lumi_gather_buffer(upcgpu_ctx* ctx, int which, int nshards, uint64_t* dev_ptr, size_t* n_doubles);
+int upcgpu_lumi_unpack(upcgpu_ctx* ctx, int nshards);
+/* copy the full device table to / from the host (which as above) */
+int upcgpu_lumi_download(upcgpu_ctx* ctx, int which, double* host);
+int upcgpu_lumi_upload(upcgpu_ctx* ctx, int which, const double* host);
+
+/* ---- sigma fold X1 ------------------------------------------------------------------- */
+/* replaces UpcCrossSection::calcNucCrossSectionYM (src/UpcCrossSection.cpp:594-698) on the
+ * device-resident lumi table.  sig_m[nm] = elemProcess->calcCrossSectionM(m_im) (unpol, nb) or
+ * sig_s/sig_p[nm] = calcCrossSectionMPolS/PS (pol, fm^2), evaluated by the caller's plug-in.
+ * cs[ny*nm] (nb), ratio[ny*nm] (pol only) and totcs_mb may be NULL (results stay on device). */
+int upcgpu_fold_sigma(upcgpu_ctx* ctx, const double* sig_m, const double* sig_s, const double* sig_p,
+                      double* cs, double* ratio, double* totcs_mb);
+
+/* ---- samplers S1-S3 ------------------------------------------------------------------ */
+/* replaces the UpcSampler2D / UpcSampler1D constructors (include/UpcSampler.h:40-59, :81-109,
+ * i.e. gsl_histogram[2d]_pdf_init) built in UpcGenerator::computeNuclXsection
+ * (src/UpcGenerator.cpp:684-700).  cs: [ny][nm] or NULL to use the folded table on the device;
+ * cszm [nm][nz] (unpol) or cszm_s/cszm_ps (pol); NULL when ignore_csz. */
+int upcgpu_sampler_build(upcgpu_ctx* ctx, const double* cs, const double* cszm, const double* cszm_s,
+                         const double* cszm_ps);
+/* copy the cumulative tables back (test hook: hpdf->sum of the reference's samplers) */
+int upcgpu_sampler_get_cdf(upcgpu_ctx* ctx, double* sum2d /*ny*nm+1*/, double* sumz /*nm*(nz+1)*/,
+                           double* sumz_ps);
+/* replaces UpcSampler2D::operator() + getBinX/getBinY (include/UpcSampler.h:118-133) with
+ * INJECTED uniforms u[2*i], u[2*i+1]: bit-exact flat bin k, bins and (y, m). */
+int upcgpu_sample_ym(upcgpu_ctx* ctx, const double* u, size_t n, long long* k, int* ybin, int* mbin,
+                     double* y, double* m);
+/* replaces UpcSampler1D::operator() (:68-71) for sampler index mbin[i] with injected u[i];
+ * ps selects the pseudoscalar set */
+int upcgpu_sample_z(upcgpu_ctx* ctx, const int* mbin, const double* u, size_t n, int ps, double* z);
+
+/* ---- events E1-E5 -------------------------------------------------------------------- */
+#define UPCGPU_MAX_PART 4
+/* replaces the body of UpcGenerator::generateEvent (src/UpcGenerator.cpp:715-832) incl.
+ * getPairMomentum/getPhotonPt (src/UpcCrossSection.cpp:1021-1074), pairProduction,
+ * singleProduction, twoPartDecayUniform and checkKinCuts, for candidates
+ * [first_candidate, first_candidate + n_candidates) of the Philox4x32-10 stream keyed by seed.
+ * Output (host, SoA, sized n_candidates): npart[i] (0 = rejected by the cuts),
+ * pdg/status/mother[i*4+j], p4[(i*4+j)*4 + {px,py,pz,E}].  aux (may be NULL) [i*5+..] =
+ * yPair, mPair, cos(theta), pT(gamma1), pT(gamma2). */
+int upcgpu_generate(upcgpu_ctx* ctx, uint64_t seed, uint64_t first_candidate, size_t n_candidates,
+                    int* npart, int* pdg, int* status, int* mother, double* p4, double* aux,
+                    uint64_t* n_accepted);
+/* device-only variant for throughput measurement: generates and keeps results on the device,
+ * returns the accepted count */
+int upcgpu_generate_device(upcgpu_ctx* ctx, uint64_t seed, uint64_t first_candidate, size_t n_candidates,
+                           uint64_t* n_accepted);
+/* photon-pT pdf of getPhotonPt for one photon energy: cdf[5001] (TH1 integral), test hook */
+int upcgpu_photon_pt_cdf(upcgpu_ctx* ctx, double e_phot, double* cdf);
+/* Philox4x32-10 uniforms, test hook: out[2*i], out[2*i+1] for counter ctr0+i, block */
+int upcgpu_philox(uint64_t seed, uint64_t ctr0, uint32_t block, size_t n, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

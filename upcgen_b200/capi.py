@@ -1,0 +1,338 @@
+"""ctypes binding of libupcgpu.so (include/upcgpu.h) used by the tests, bench.py and the
+torch.distributed launcher.  This is plumbing: every numeric result comes from the CUDA library;
+there is no Python/NumPy fallback, and loading fails loudly if the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .config import LEPTON_MASS, UpcParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libupcgpu.so")
+_LIB = None
+
+OK, EINVAL, ECUDA, ENODEV, EQAGS, ERANGE = 0, -1, -2, -3, -4, -5
+TABLE_GAA, TABLE_TA, TABLE_FORMFAC, TABLE_BREAKUP = 0, 1, 2, 3
+MAX_PART = 4
+
+
+class UpcGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"upcgpu error {code}: {msg}")
+        self.code = code
+
+
+class CParams(C.Structure):
+    _fields_ = [
+        ("Z", C.c_int), ("A", C.c_int), ("R", C.c_double), ("a", C.c_double),
+        ("sqrts", C.c_double), ("g1", C.c_double), ("g2", C.c_double), ("gtot", C.c_double),
+        ("is_point", C.c_int), ("breakup_mode", C.c_int), ("use_pol", C.c_int), ("nonzero_gam_pt", C.c_int),
+        ("nm", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+        ("mmin", C.c_double), ("mmax", C.c_double), ("ymin", C.c_double), ("ymax", C.c_double),
+        ("zmin", C.c_double), ("zmax", C.c_double),
+        ("nb1", C.c_int), ("nb2", C.c_int),
+        ("part_pdg", C.c_int), ("m_part", C.c_double), ("is_charged", C.c_int), ("is_pair", C.c_int),
+        ("is_single", C.c_int), ("ignore_csz", C.c_int), ("decay_uniform_pdg", C.c_int),
+        ("do_pt_cut", C.c_int), ("do_eta_cut", C.c_int),
+        ("pt_min", C.c_double), ("eta_min", C.c_double), ("eta_max", C.c_double),
+    ]
+
+
+class CTableInfo(C.Structure):
+    _fields_ = [("rho0", C.c_double), ("sigma_nn", C.c_double), ("factor", C.c_double),
+                ("breakup_p20", C.c_double), ("n_breakup_energy_knots", C.c_int)]
+
+
+class CFillStats(C.Structure):
+    _fields_ = [("qags_integrals", C.c_longlong), ("qags_evals", C.c_longlong), ("qags_overflow", C.c_longlong),
+                ("qags_errors", C.c_longlong), ("flux_rows", C.c_longlong), ("band_pairs", C.c_longlong),
+                ("ms_tables", C.c_double), ("ms_flux", C.c_double), ("ms_cells", C.c_double), ("ms_total", C.c_double)]
+
+
+# every symbol include/upcgpu.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "upcgpu_create", "upcgpu_destroy", "upcgpu_last_error", "upcgpu_abi_version", "upcgpu_device_name",
+    "upcgpu_prepare_tables", "upcgpu_get_table_info", "upcgpu_get_table", "upcgpu_eval_table", "upcgpu_breakup_raw",
+    "upcgpu_flux_point", "upcgpu_flux_form", "upcgpu_fill_lumi", "upcgpu_fill_lumi_shard", "upcgpu_lumi_cells",
+    "upcgpu_get_fill_stats", "upcgpu_lumi_shard_buffer", "upcgpu_lumi_gather_buffer", "upcgpu_lumi_unpack",
+    "upcgpu_lumi_download", "upcgpu_lumi_upload", "upcgpu_fold_sigma", "upcgpu_sampler_build",
+    "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_device",
+    "upcgpu_photon_pt_cdf", "upcgpu_philox",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(f"{SO_PATH} is missing: build it with `python -m upcgen_b200.build` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        p, i, d, sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+        L.upcgpu_create.argtypes = [C.POINTER(CParams), i, C.POINTER(p)]
+        L.upcgpu_destroy.argtypes = [p]
+        L.upcgpu_destroy.restype = None
+        L.upcgpu_last_error.argtypes = [p]
+        L.upcgpu_last_error.restype = C.c_char_p
+        L.upcgpu_device_name.argtypes = [p, C.c_char_p, sz]
+        L.upcgpu_prepare_tables.argtypes = [p]
+        L.upcgpu_get_table_info.argtypes = [p, C.POINTER(CTableInfo)]
+        L.upcgpu_get_table.argtypes = [p, i, sz, sz, p, p, p]
+        L.upcgpu_eval_table.argtypes = [p, i, p, sz, p]
+        L.upcgpu_breakup_raw.argtypes = [p, p, i, sz, p]
+        L.upcgpu_flux_point.argtypes = [p, p, p, sz, p]
+        L.upcgpu_flux_form.argtypes = [p, p, p, sz, p, p]
+        L.upcgpu_fill_lumi.argtypes = [p, p, p, p]
+        L.upcgpu_fill_lumi_shard.argtypes = [p, i, i]
+        L.upcgpu_lumi_cells.argtypes = [p, p, p, sz, p, p, p]
+        L.upcgpu_get_fill_stats.argtypes = [p, C.POINTER(CFillStats)]
+        L.upcgpu_lumi_shard_buffer.argtypes = [p, i, C.POINTER(C.c_uint64), C.POINTER(sz)]
+        L.upcgpu_lumi_gather_buffer.argtypes = [p, i, i, C.POINTER(C.c_uint64), C.POINTER(sz)]
+        L.upcgpu_lumi_unpack.argtypes = [p, i]
+        L.upcgpu_lumi_download.argtypes = [p, i, p]
+        L.upcgpu_lumi_upload.argtypes = [p, i, p]
+        L.upcgpu_fold_sigma.argtypes = [p, p, p, p, p, p, C.POINTER(d)]
+        L.upcgpu_sampler_build.argtypes = [p, p, p, p, p]
+        L.upcgpu_sampler_get_cdf.argtypes = [p, p, p, p]
+        L.upcgpu_sample_ym.argtypes = [p, p, sz, p, p, p, p, p]
+        L.upcgpu_sample_z.argtypes = [p, p, p, sz, i, p]
+        L.upcgpu_generate.argtypes = [p, C.c_uint64, C.c_uint64, sz, p, p, p, p, p, p, C.POINTER(C.c_uint64)]
+        L.upcgpu_generate_device.argtypes = [p, C.c_uint64, C.c_uint64, sz, C.POINTER(C.c_uint64)]
+        L.upcgpu_photon_pt_cdf.argtypes = [p, d, p]
+        L.upcgpu_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, sz, p]
+        _LIB = L
+    return _LIB
+
+
+def to_cparams(P: UpcParams) -> CParams:
+    """UpcParams -> upcgpu_params, incl. the elementary-process members set by
+    UpcCrossSection::setElemProcess / UpcGenerator::init (src/UpcGenerator.cpp:69-140)."""
+    c = CParams()
+    for name, ctype in CParams._fields_:
+        if hasattr(P, name):
+            v = getattr(P, name)
+            setattr(c, name, int(v) if ctype is C.c_int else float(v))
+    pid = P.proc_id
+    if pid in (11, 13, 15):
+        c.part_pdg, c.m_part, c.is_charged, c.is_pair, c.is_single = pid, LEPTON_MASS[pid], 1, 1, 0
+        c.ignore_csz, c.decay_uniform_pdg = 0, 0
+    elif pid == 51:
+        c.part_pdg, c.m_part, c.is_charged, c.is_pair, c.is_single = 51, P.alp_mass, 0, 0, 1
+        c.ignore_csz, c.decay_uniform_pdg = 1, 22
+    elif pid == 22:
+        c.part_pdg, c.m_part, c.is_charged, c.is_pair, c.is_single = 22, 0.0, 0, 1, 0
+        c.ignore_csz, c.decay_uniform_pdg = 0, 0
+    else:
+        raise ValueError(f"PROC_ID {pid} is outside the GPU path (SURVEY.md section 2)")
+    return c
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class UpcGpu:
+    """One context = one GPU.  Thin, typed wrapper; methods map 1:1 onto include/upcgpu.h."""
+
+    def __init__(self, P: UpcParams, device: int = 0):
+        self.L = lib()
+        self.P = P
+        self.cp = to_cparams(P)
+        h = C.c_void_p()
+        rc = self.L.upcgpu_create(C.byref(self.cp), device, C.byref(h))
+        if rc != OK:
+            raise UpcGpuError(rc, self.L.upcgpu_last_error(None).decode())
+        self.h = h
+        self.nm, self.ny, self.nz = P.nm, P.ny, P.nz
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.upcgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise UpcGpuError(rc, self.L.upcgpu_last_error(self.h).decode())
+
+    def device_name(self):
+        buf = C.create_string_buffer(256)
+        self._chk(self.L.upcgpu_device_name(self.h, buf, 256))
+        return buf.value.decode()
+
+    # tables ------------------------------------------------------------------------------
+    def prepare_tables(self):
+        self._chk(self.L.upcgpu_prepare_tables(self.h))
+        return self.table_info()
+
+    def table_info(self):
+        info = CTableInfo()
+        self._chk(self.L.upcgpu_get_table_info(self.h, C.byref(info)))
+        return info
+
+    def get_table(self, which, i0, n):
+        x, y, c = np.zeros(n), np.zeros(n), np.zeros(n)
+        self._chk(self.L.upcgpu_get_table(self.h, which, i0, n, _p(x), _p(y), _p(c)))
+        return x, y, c
+
+    def eval_table(self, which, x):
+        x = _f64(x).ravel()
+        out = np.zeros_like(x)
+        self._chk(self.L.upcgpu_eval_table(self.h, which, _p(x), x.size, _p(out)))
+        return out
+
+    def breakup_raw(self, b, mode):
+        b = _f64(b).ravel()
+        out = np.zeros_like(b)
+        self._chk(self.L.upcgpu_breakup_raw(self.h, _p(b), mode, b.size, _p(out)))
+        return out
+
+    # fluxes ------------------------------------------------------------------------------
+    def flux_point(self, b, k):
+        b, k = np.broadcast_arrays(_f64(b), _f64(k))
+        bb, kk = _f64(b.ravel()), _f64(k.ravel())
+        out = np.zeros(bb.size)
+        self._chk(self.L.upcgpu_flux_point(self.h, _p(bb), _p(kk), bb.size, _p(out)))
+        return out.reshape(b.shape)
+
+    def flux_form(self, b, k, with_neval=False):
+        b, k = np.broadcast_arrays(_f64(b), _f64(k))
+        bb, kk = _f64(b.ravel()), _f64(k.ravel())
+        out = np.zeros(bb.size)
+        ne = np.zeros(bb.size, dtype=np.int32)
+        self._chk(self.L.upcgpu_flux_form(self.h, _p(bb), _p(kk), bb.size, _p(out), _p(ne)))
+        if with_neval:
+            return out.reshape(b.shape), ne.reshape(b.shape)
+        return out.reshape(b.shape)
+
+    # lumi --------------------------------------------------------------------------------
+    def fill_lumi(self):
+        """Whole grid through the host-buffer entry point (tables are prepared if needed)."""
+        if self.P.use_pol:
+            s, p = np.zeros((self.nm, self.ny)), np.zeros((self.nm, self.ny))
+            self._chk(self.L.upcgpu_fill_lumi(self.h, None, _p(s), _p(p)))
+            return s, p
+        out = np.zeros((self.nm, self.ny))
+        self._chk(self.L.upcgpu_fill_lumi(self.h, _p(out), None, None))
+        return out
+
+    def fill_lumi_shard(self, shard=0, nshards=1):
+        self._chk(self.L.upcgpu_fill_lumi_shard(self.h, shard, nshards))
+
+    def lumi_cells(self, M, Y):
+        M, Y = np.broadcast_arrays(_f64(M), _f64(Y))
+        mm, yy = _f64(M.ravel()), _f64(Y.ravel())
+        if self.P.use_pol:
+            s, p = np.zeros(mm.size), np.zeros(mm.size)
+            self._chk(self.L.upcgpu_lumi_cells(self.h, _p(mm), _p(yy), mm.size, None, _p(s), _p(p)))
+            return s.reshape(M.shape), p.reshape(M.shape)
+        out = np.zeros(mm.size)
+        self._chk(self.L.upcgpu_lumi_cells(self.h, _p(mm), _p(yy), mm.size, _p(out), None, None))
+        return out.reshape(M.shape)
+
+    def fill_stats(self):
+        st = CFillStats()
+        self._chk(self.L.upcgpu_get_fill_stats(self.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in CFillStats._fields_}
+
+    def lumi_shard_buffer(self, which):
+        ptr, n = C.c_uint64(), C.c_size_t()
+        self._chk(self.L.upcgpu_lumi_shard_buffer(self.h, which, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def lumi_gather_buffer(self, which, nshards):
+        ptr, n = C.c_uint64(), C.c_size_t()
+        self._chk(self.L.upcgpu_lumi_gather_buffer(self.h, which, nshards, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def lumi_unpack(self, nshards):
+        self._chk(self.L.upcgpu_lumi_unpack(self.h, nshards))
+
+    def lumi_download(self, which=0):
+        out = np.zeros((self.nm, self.ny))
+        self._chk(self.L.upcgpu_lumi_download(self.h, which, _p(out)))
+        return out
+
+    def lumi_upload(self, which, table):
+        t = _f64(table)
+        assert t.shape == (self.nm, self.ny)
+        self._chk(self.L.upcgpu_lumi_upload(self.h, which, _p(t)))
+
+    # fold / samplers ---------------------------------------------------------------------
+    def fold_sigma(self, sig_m=None, sig_s=None, sig_p=None, download=True):
+        sig_m = None if sig_m is None else _f64(sig_m)
+        sig_s = None if sig_s is None else _f64(sig_s)
+        sig_p = None if sig_p is None else _f64(sig_p)
+        cs = np.zeros((self.ny, self.nm)) if download else None
+        ratio = np.zeros((self.ny, self.nm)) if (download and self.P.use_pol) else None
+        tot = C.c_double()
+        self._chk(self.L.upcgpu_fold_sigma(self.h, _p(sig_m), _p(sig_s), _p(sig_p), _p(cs), _p(ratio), C.byref(tot)))
+        return cs, ratio, tot.value
+
+    def sampler_build(self, cs=None, cszm=None, cszm_s=None, cszm_ps=None):
+        arrs = [None if a is None else _f64(a) for a in (cs, cszm, cszm_s, cszm_ps)]
+        self._chk(self.L.upcgpu_sampler_build(self.h, *[_p(a) for a in arrs]))
+
+    def sampler_cdf(self):
+        n = self.nm * self.ny
+        s2 = np.zeros(n + 1)
+        have_z = not self.cp.ignore_csz
+        sz = np.zeros((self.nm, self.nz + 1)) if have_z else None
+        sps = np.zeros((self.nm, self.nz + 1)) if (have_z and self.P.use_pol) else None
+        self._chk(self.L.upcgpu_sampler_get_cdf(self.h, _p(s2), _p(sz), _p(sps)))
+        return s2, sz, sps
+
+    def sample_ym(self, u):
+        u = _f64(u).reshape(-1, 2)
+        n = u.shape[0]
+        k = np.zeros(n, np.int64); yb = np.zeros(n, np.int32); mb = np.zeros(n, np.int32)
+        y = np.zeros(n); m = np.zeros(n)
+        self._chk(self.L.upcgpu_sample_ym(self.h, _p(u), n, _p(k), _p(yb), _p(mb), _p(y), _p(m)))
+        return k, yb, mb, y, m
+
+    def sample_z(self, mbin, u, ps=0):
+        mbin = np.ascontiguousarray(mbin, np.int32); u = _f64(u).ravel()
+        z = np.zeros(u.size)
+        self._chk(self.L.upcgpu_sample_z(self.h, _p(mbin), _p(u), u.size, ps, _p(z)))
+        return z
+
+    # events ------------------------------------------------------------------------------
+    def generate(self, seed, first, n, with_aux=True):
+        npart = np.zeros(n, np.int32)
+        pdg = np.zeros((n, MAX_PART), np.int32); st = np.zeros((n, MAX_PART), np.int32); mo = np.zeros((n, MAX_PART), np.int32)
+        p4 = np.zeros((n, MAX_PART, 4)); aux = np.zeros((n, 5)) if with_aux else None
+        nacc = C.c_uint64()
+        self._chk(self.L.upcgpu_generate(self.h, seed, first, n, _p(npart), _p(pdg), _p(st), _p(mo), _p(p4), _p(aux),
+                                         C.byref(nacc)))
+        return dict(npart=npart, pdg=pdg, status=st, mother=mo, p4=p4, aux=aux, n_accepted=nacc.value)
+
+    def generate_device(self, seed, first, n):
+        nacc = C.c_uint64()
+        self._chk(self.L.upcgpu_generate_device(self.h, seed, first, n, C.byref(nacc)))
+        return nacc.value
+
+    def photon_pt_cdf(self, e):
+        cdf = np.zeros(5001)
+        self._chk(self.L.upcgpu_photon_pt_cdf(self.h, float(e), _p(cdf)))
+        return cdf
+
+
+def philox(seed, ctr0, block, n):
+    out = np.zeros((n, 2))
+    rc = lib().upcgpu_philox(seed, ctr0, block, n, _p(out))
+    if rc != OK:
+        raise UpcGpuError(rc, "philox")
+    return out

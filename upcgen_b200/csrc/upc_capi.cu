@@ -1,0 +1,315 @@
+// upc_capi.cu -- the extern "C" boundary declared in include/upcgpu.h.
+#include <cstring>
+#include <new>
+
+#include "upc_ctx.h"
+#include "upc_internal.h"
+
+using namespace upc;
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+int upcgpu_abi_version(void) { return 1; }
+
+const char* upcgpu_last_error(const upcgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out)
+{
+  if (!params || !out) { g_create_err = "upcgpu_create: null argument"; return UPCGPU_EINVAL; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("upcgpu_create: no CUDA device (") + cudaGetErrorString(e) +
+                   "); this library has no CPU fallback";
+    return UPCGPU_ENODEV;
+  }
+  if (device < 0 || device >= ndev) { g_create_err = "upcgpu_create: bad device index"; return UPCGPU_EINVAL; }
+  const upcgpu_params& p = *params;
+  if (p.nm < 1 || p.ny < 1 || p.nz < 1 || p.nb1 < 2 || p.nb2 < 2 || p.A < 1 || p.Z < 1 || !(p.R > 0) || !(p.a > 0) ||
+      !(p.g1 > 1) || !(p.g2 > 1) || p.breakup_mode < 1 || p.breakup_mode > 4 || !(p.mmax > p.mmin) ||
+      !(p.ymax > p.ymin) || !(p.mmin > 0)) {
+    g_create_err = "upcgpu_create: parameter block out of range";
+    return UPCGPU_EINVAL;
+  }
+  upcgpu_ctx* c = new (std::nothrow) upcgpu_ctx();
+  if (!c) { g_create_err = "upcgpu_create: out of memory"; return UPCGPU_EINVAL; }
+  c->p = p;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    g_create_err = std::string("upcgpu_create: ") + cudaGetErrorString(cudaGetLastError());
+    delete c;
+    return UPCGPU_ECUDA;
+  }
+  *out = c;
+  return UPCGPU_OK;
+}
+
+void upcgpu_destroy(upcgpu_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->gaa_x); cudaFree(c->gaa_y); cudaFree(c->gaa_c); cudaFree(c->ta_y); cudaFree(c->ta_c);
+  cudaFree(c->ff_y); cudaFree(c->ff_c); cudaFree(c->bk_y); cudaFree(c->bk_c);
+  cudaFree(c->gaa_seg); cudaFree(c->ff_seg); cudaFree(c->bk_seg); cudaFree(c->d_scal);
+  for (int w = 0; w < 3; w++) { cudaFree(c->lumi[w]); cudaFree(c->shard[w]); cudaFree(c->gather[w]); }
+  cudaFree(c->cs); cudaFree(c->ratio); cudaFree(c->sum2d); cudaFree(c->sumz); cudaFree(c->sumz_ps);
+  cudaFree(c->edges_y); cudaFree(c->edges_m); cudaFree(c->edges_z);
+  free_event_scratch(c);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int upcgpu_device_name(const upcgpu_ctx* c, char* buf, size_t cap)
+{
+  if (!c || !buf || cap == 0) return UPCGPU_EINVAL;
+  std::snprintf(buf, cap, "%s (sm_%d%d, %d SMs)", c->prop.name, c->prop.major, c->prop.minor, c->prop.multiProcessorCount);
+  return UPCGPU_OK;
+}
+
+#define CHECK_CTX(c)                 \
+  if (!(c)) return UPCGPU_EINVAL;    \
+  cudaSetDevice((c)->device);
+
+int upcgpu_prepare_tables(upcgpu_ctx* c)
+{
+  CHECK_CTX(c);
+  if (c->tables_ready) return UPCGPU_OK;
+  return prepare_tables(c);
+}
+
+int upcgpu_get_table_info(const upcgpu_ctx* c, upcgpu_table_info* info)
+{
+  if (!c || !info || !c->tables_ready) return UPCGPU_EINVAL;
+  *info = c->info;
+  return UPCGPU_OK;
+}
+
+int upcgpu_get_table(upcgpu_ctx* c, int which, size_t i0, size_t n, double* x, double* y, double* cc)
+{
+  CHECK_CTX(c);
+  if (!c->tables_ready) { c->err = "get_table: tables not prepared"; return UPCGPU_EINVAL; }
+  const double *dy = nullptr, *dc = nullptr;
+  size_t size = 0;
+  double x0 = 0, dx = 0;
+  switch (which) {
+    case UPCGPU_TABLE_GAA: dy = c->gaa_y; dc = c->gaa_c; size = kNB; break;
+    case UPCGPU_TABLE_TA: dy = c->ta_y; dc = c->ta_c; size = kNB; break;
+    case UPCGPU_TABLE_FORMFAC: dy = c->ff_y; dc = c->ff_c; size = kNQ2; x0 = kQ2min; dx = kDQ2; break;
+    case UPCGPU_TABLE_BREAKUP: dy = c->bk_y; dc = c->bk_c; size = c->bk_nknots; x0 = kBkBmin; dx = kBkDb; break;
+    default: c->err = "get_table: unknown table"; return UPCGPU_EINVAL;
+  }
+  if (!dy || i0 + n > size) { c->err = "get_table: range/table unavailable"; return UPCGPU_EINVAL; }
+  if (y) UPC_CUDA(c, cudaMemcpy(y, dy + i0, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cc) UPC_CUDA(c, cudaMemcpy(cc, dc + i0, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (x) {
+    if (which == UPCGPU_TABLE_GAA || which == UPCGPU_TABLE_TA) {
+      UPC_CUDA(c, cudaMemcpy(x, c->gaa_x + i0, n * sizeof(double), cudaMemcpyDeviceToHost));
+    } else {
+      for (size_t i = 0; i < n; i++) {
+        volatile double prod = (double)(i0 + i) * dx;  // two roundings, as the reference's knots
+        x[i] = x0 + prod;
+      }
+    }
+  }
+  return UPCGPU_OK;
+}
+
+int upcgpu_eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, double* out)
+{
+  CHECK_CTX(c);
+  if (!c->tables_ready || !x || !out) { c->err = "eval_table: bad state/argument"; return UPCGPU_EINVAL; }
+  if (n == 0) return UPCGPU_OK;
+  return eval_table(c, which, x, n, out);
+}
+
+int upcgpu_breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out)
+{
+  CHECK_CTX(c);
+  if (!c->tables_ready || !c->bk_seg) { c->err = "breakup_raw: breakup table not prepared (BREAKUP_MODE 1?)"; return UPCGPU_EINVAL; }
+  if (n == 0) return UPCGPU_OK;
+  return breakup_raw(c, b, mode, n, out);
+}
+
+int upcgpu_flux_point(upcgpu_ctx* c, const double* b, const double* k, size_t n, double* out)
+{
+  CHECK_CTX(c);
+  if (!b || !k || !out) return UPCGPU_EINVAL;
+  if (n == 0) return UPCGPU_OK;
+  return flux_points(c, b, k, n, 1, out, nullptr);
+}
+
+int upcgpu_flux_form(upcgpu_ctx* c, const double* b, const double* k, size_t n, double* out, int* neval)
+{
+  CHECK_CTX(c);
+  if (!b || !k || !out) return UPCGPU_EINVAL;
+  if (n == 0) return UPCGPU_OK;
+  return flux_points(c, b, k, n, 0, out, neval);
+}
+
+int upcgpu_fill_lumi_shard(upcgpu_ctx* c, int shard, int nshards)
+{
+  CHECK_CTX(c);
+  return fill_lumi_rows(c, shard, nshards);
+}
+
+int upcgpu_lumi_download(upcgpu_ctx* c, int which, double* host)
+{
+  CHECK_CTX(c);
+  if (which < 0 || which > 2 || !host || !c->lumi[which]) { c->err = "lumi_download: table not available"; return UPCGPU_EINVAL; }
+  UPC_CUDA(c, cudaMemcpy(host, c->lumi[which], (size_t)c->p.nm * c->p.ny * sizeof(double), cudaMemcpyDeviceToHost));
+  return UPCGPU_OK;
+}
+
+int upcgpu_lumi_upload(upcgpu_ctx* c, int which, const double* host)
+{
+  CHECK_CTX(c);
+  if (which < 0 || which > 2 || !host) return UPCGPU_EINVAL;
+  if ((which == 0) == (c->p.use_pol != 0)) { c->err = "lumi_upload: table kind does not match use_pol"; return UPCGPU_EINVAL; }
+  int rc = ensure_lumi_buffers(c, 0);
+  if (rc) return rc;
+  UPC_CUDA(c, cudaMemcpy(c->lumi[which], host, (size_t)c->p.nm * c->p.ny * sizeof(double), cudaMemcpyHostToDevice));
+  c->lumi_ready = true;
+  return UPCGPU_OK;
+}
+
+int upcgpu_fill_lumi(upcgpu_ctx* c, double* lumi, double* lumi_s, double* lumi_p)
+{
+  CHECK_CTX(c);
+  int rc = upcgpu_prepare_tables(c);
+  if (rc) return rc;
+  rc = fill_lumi_rows(c, 0, 1);
+  if (rc) return rc;
+  if (!c->p.use_pol) {
+    if (lumi) rc = upcgpu_lumi_download(c, 0, lumi);
+  } else {
+    if (lumi_s) rc = upcgpu_lumi_download(c, 1, lumi_s);
+    if (!rc && lumi_p) rc = upcgpu_lumi_download(c, 2, lumi_p);
+  }
+  return rc;
+}
+
+int upcgpu_lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* out, double* out_s, double* out_p)
+{
+  CHECK_CTX(c);
+  if (!M || !Y) return UPCGPU_EINVAL;
+  if (n == 0) return UPCGPU_OK;
+  return lumi_cells(c, M, Y, n, out, out_s, out_p);
+}
+
+int upcgpu_get_fill_stats(const upcgpu_ctx* c, upcgpu_fill_stats* st)
+{
+  if (!c || !st) return UPCGPU_EINVAL;
+  *st = c->stats;
+  return UPCGPU_OK;
+}
+
+int upcgpu_lumi_shard_buffer(upcgpu_ctx* c, int which, uint64_t* dev_ptr, size_t* n_doubles)
+{
+  CHECK_CTX(c);
+  if (which < 0 || which > 2 || !c->shard[which]) { c->err = "lumi_shard_buffer: no shard computed"; return UPCGPU_EINVAL; }
+  if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)c->shard[which];
+  if (n_doubles) *n_doubles = c->shard_rows * c->p.ny;
+  return UPCGPU_OK;
+}
+
+int upcgpu_lumi_gather_buffer(upcgpu_ctx* c, int which, int nshards, uint64_t* dev_ptr, size_t* n_doubles)
+{
+  CHECK_CTX(c);
+  if (which < 0 || which > 2 || nshards < 1 || c->shard_n != nshards) {
+    c->err = "lumi_gather_buffer: call fill_lumi_shard with the same nshards first";
+    return UPCGPU_EINVAL;
+  }
+  size_t n = c->shard_rows * c->p.ny * nshards;
+  if (c->gather_n != nshards) {
+    for (int w = 0; w < 3; w++) { cudaFree(c->gather[w]); c->gather[w] = nullptr; }
+    const int w0 = c->p.use_pol ? 1 : 0, w1 = c->p.use_pol ? 2 : 0;
+    for (int w = w0; w <= w1; w++) UPC_CUDA(c, cudaMalloc(&c->gather[w], n * sizeof(double)));
+    c->gather_n = nshards;
+  }
+  if (!c->gather[which]) { c->err = "lumi_gather_buffer: table kind does not match use_pol"; return UPCGPU_EINVAL; }
+  if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)c->gather[which];
+  if (n_doubles) *n_doubles = n;
+  return UPCGPU_OK;
+}
+
+int upcgpu_lumi_unpack(upcgpu_ctx* c, int nshards)
+{
+  CHECK_CTX(c);
+  return lumi_unpack(c, nshards);
+}
+
+int upcgpu_fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const double* sig_p, double* cs,
+                      double* ratio, double* totcs_mb)
+{
+  CHECK_CTX(c);
+  return fold_sigma(c, sig_m, sig_s, sig_p, cs, ratio, totcs_mb);
+}
+
+int upcgpu_sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps)
+{
+  CHECK_CTX(c);
+  return sampler_build(c, cs, cszm, cszm_s, cszm_ps);
+}
+
+int upcgpu_sampler_get_cdf(upcgpu_ctx* c, double* sum2d, double* sumz, double* sumz_ps)
+{
+  CHECK_CTX(c);
+  if (!c->sampler_ready) { c->err = "sampler_get_cdf: samplers not built"; return UPCGPU_EINVAL; }
+  const size_t n = (size_t)c->p.nm * c->p.ny, nsz = (size_t)c->p.nm * (c->p.nz + 1);
+  if (sum2d) UPC_CUDA(c, cudaMemcpy(sum2d, c->sum2d, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sumz && c->sumz) UPC_CUDA(c, cudaMemcpy(sumz, c->sumz, nsz * sizeof(double), cudaMemcpyDeviceToHost));
+  if (sumz_ps && c->sumz_ps) UPC_CUDA(c, cudaMemcpy(sumz_ps, c->sumz_ps, nsz * sizeof(double), cudaMemcpyDeviceToHost));
+  return UPCGPU_OK;
+}
+
+int upcgpu_sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int* ybin, int* mbin, double* y, double* m)
+{
+  CHECK_CTX(c);
+  if (!u) return UPCGPU_EINVAL;
+  if (n == 0) return UPCGPU_OK;
+  return sample_ym(c, u, n, k, ybin, mbin, y, m);
+}
+
+int upcgpu_sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, double* z)
+{
+  CHECK_CTX(c);
+  if (!u || !mbin || !z) return UPCGPU_EINVAL;
+  if (n == 0) return UPCGPU_OK;
+  return sample_z(c, mbin, u, n, ps, z);
+}
+
+int upcgpu_generate(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, int* npart, int* pdg,
+                    int* status, int* mother, double* p4, double* aux, uint64_t* n_accepted)
+{
+  CHECK_CTX(c);
+  if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
+  return generate(c, seed, first_candidate, n_candidates, npart, pdg, status, mother, p4, aux, n_accepted, false);
+}
+
+int upcgpu_generate_device(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, uint64_t* n_accepted)
+{
+  CHECK_CTX(c);
+  if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
+  return generate(c, seed, first_candidate, n_candidates, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_accepted,
+                  true);
+}
+
+int upcgpu_photon_pt_cdf(upcgpu_ctx* c, double e_phot, double* cdf)
+{
+  CHECK_CTX(c);
+  if (!cdf) return UPCGPU_EINVAL;
+  return photon_pt_cdf(c, e_phot, cdf);
+}
+
+int upcgpu_philox(uint64_t seed, uint64_t ctr0, uint32_t block, size_t n, double* out)
+{
+  if (!out) return UPCGPU_EINVAL;
+  for (size_t i = 0; i < n; i++) philox4x32_10(seed, ctr0 + i, block, out[2 * i], out[2 * i + 1]);
+  return UPCGPU_OK;
+}
+
+}  // extern "C"

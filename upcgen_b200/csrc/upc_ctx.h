@@ -1,0 +1,68 @@
+// upc_ctx.h -- host-side context behind the C-ABI handle (include/upcgpu.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/upcgpu.h"
+#include "upc_math.cuh"
+
+namespace upc {
+
+// device-resident lookup tables handed to the kernels by value
+struct DevTables {
+  // G_AA: 200 knots on [0,20]; seg[i], i<199, plus seg[199] = {1,0,0,0} for b >= 20
+  const SplineSeg* gaa_seg;
+  double gaa_inv_db;  // 199/20
+  double gaa_db;
+  // breakup: knots b_i = 1e-6 + db*i, i < nbk (covers [0, 20.2]); seg[nbk-1] = {P20,0,0,0}
+  const SplineSeg* bk_seg;
+  int bk_n;      // number of real segments (index clamp = bk_n)
+  double p20;
+  int use_breakup;
+  // form factor: 1e6 knots on [1e-9, 2)
+  const SplineSeg* ff_seg;
+  double ff_last;  // spline value at Q2max - dQ2 (the clamp of fluxFormIntegrand)
+};
+
+struct upcgpu_ctx_impl {
+  upcgpu_params p;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  cudaDeviceProp prop;
+  bool tables_ready = false;
+  upcgpu_table_info info{};
+  upcgpu_fill_stats stats{};
+
+  // raw spline tables (x, y, c) kept for the get_table test hooks
+  double *gaa_x = nullptr, *gaa_y = nullptr, *gaa_c = nullptr, *ta_y = nullptr, *ta_c = nullptr;
+  double *ff_y = nullptr, *ff_c = nullptr;
+  double *bk_y = nullptr, *bk_c = nullptr;
+  int bk_nknots = 0;
+  SplineSeg *gaa_seg = nullptr, *ff_seg = nullptr, *bk_seg = nullptr;
+  double* d_scal = nullptr;  // small device scratch for scalars
+  DevTables tab{};
+
+  // luminosity tables, full [nm][ny], index 0 unpol, 1 scalar, 2 pseudoscalar
+  double* lumi[3] = {nullptr, nullptr, nullptr};
+  double* shard[3] = {nullptr, nullptr, nullptr};
+  double* gather[3] = {nullptr, nullptr, nullptr};
+  size_t shard_rows = 0;
+  int shard_n = 0, gather_n = 0;
+  bool lumi_ready = false;
+
+  // fold / samplers
+  double *cs = nullptr, *ratio = nullptr;
+  double *sum2d = nullptr, *sumz = nullptr, *sumz_ps = nullptr;
+  double *edges_y = nullptr, *edges_m = nullptr, *edges_z = nullptr;
+  bool fold_ready = false, sampler_ready = false;
+
+  // event stage scratch (grown on demand)
+  void* ev = nullptr;
+};
+
+}  // namespace upc
+
+struct upcgpu_ctx : upc::upcgpu_ctx_impl {};

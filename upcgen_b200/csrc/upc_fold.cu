@@ -1,0 +1,302 @@
+// upc_fold.cu -- sigma fold (X1) and the inverse-CDF samplers (S1-S3).
+// Reference: src/UpcCrossSection.cpp:594-698 (calcNucCrossSectionYM) and include/UpcSampler.h
+// (GSL gsl_histogram[2d]_pdf_init / _pdf_sample, getBinX/getBinY).
+//
+// Everything that decides an integer bin is evaluated with explicit non-fused FP64 operations
+// (__dadd_rn/__dmul_rn/__ddiv_rn) in the reference's operation order, so that the cumulative
+// tables and the selected bins are bit-identical to a generic x86-64 build of the reference.
+#include <cstdio>
+
+#include "upc_ctx.h"
+#include "upc_internal.h"
+#include "upc_sampler.cuh"
+
+namespace upc {
+
+// cs[iy][im] = sigma(m_im) * lumi[im][iy]  (transposed), :643-659
+__global__ void k_fold(int nm, int ny, int pol, const double* __restrict__ lumi, const double* __restrict__ lumi_s,
+                       const double* __restrict__ lumi_p, const double* __restrict__ sig_m,
+                       const double* __restrict__ sig_s, const double* __restrict__ sig_p, double* __restrict__ cs,
+                       double* __restrict__ ratio)
+{
+  // 32x32 tile transpose through shared memory: coalesced reads along iy, writes along im
+  __shared__ double tile[32][33];
+  __shared__ double tile2[32][33];
+  const int im0 = blockIdx.x * 32, iy0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int im = im0 + r, iy = iy0 + threadIdx.x;
+    if (im < nm && iy < ny) {
+      const size_t src = (size_t)im * ny + iy;
+      if (!pol) {
+        tile[r][threadIdx.x] = __dmul_rn(sig_m[im], lumi[src]);  // :648
+      } else {
+        const double nuccs_s = __dmul_rn(lumi_s[src], sig_s[im]);  // :654
+        const double nuccs_p = __dmul_rn(lumi_p[src], sig_p[im]);  // :655
+        tile[r][threadIdx.x] = __dmul_rn(__dadd_rn(nuccs_s, nuccs_p), 1e7);  // :656-657
+        tile2[r][threadIdx.x] = __ddiv_rn(nuccs_s, nuccs_p);                 // :658
+      }
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int iy = iy0 + r, im = im0 + threadIdx.x;
+    if (im < nm && iy < ny) {
+      const size_t dst = (size_t)iy * nm + im;
+      cs[dst] = tile[threadIdx.x][r];
+      if (pol) ratio[dst] = tile2[threadIdx.x][r];
+    }
+  }
+}
+
+// totCS: fixed-shape pairwise tree, independent of grid/launch geometry and of the number of
+// GPUs (the reference's own sum order depends on OpenMP scheduling).
+__global__ void k_sum_blocks(const double* __restrict__ x, size_t n, double* __restrict__ partial)
+{
+  __shared__ double sm[256];
+  const size_t base = (size_t)blockIdx.x * 4096;
+  double acc = 0;
+  // each thread sums 16 strided elements in a fixed order
+  for (int r = 0; r < 16; r++) {
+    size_t i = base + (size_t)r * 256 + threadIdx.x;
+    if (i < n) acc += x[i];
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const double* sig_p, double* cs, double* ratio,
+               double* totcs_mb)
+{
+  const upcgpu_params& p = c->p;
+  const size_t n = (size_t)p.nm * p.ny;
+  if (!c->lumi_ready) { c->err = "fold_sigma: lumi table not filled (or not gathered)"; return UPCGPU_EINVAL; }
+  if (p.use_pol ? (!sig_s || !sig_p) : !sig_m) { c->err = "fold_sigma: missing sigma array"; return UPCGPU_EINVAL; }
+  cudaStream_t st = c->stream;
+  if (!c->cs) UPC_CUDA(c, cudaMalloc(&c->cs, n * sizeof(double)));
+  if (p.use_pol && !c->ratio) UPC_CUDA(c, cudaMalloc(&c->ratio, n * sizeof(double)));
+  double* dsig = nullptr;
+  UPC_CUDA(c, cudaMalloc(&dsig, 3 * (size_t)p.nm * sizeof(double)));
+  if (sig_m) UPC_CUDA(c, cudaMemcpyAsync(dsig, sig_m, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (sig_s) UPC_CUDA(c, cudaMemcpyAsync(dsig + p.nm, sig_s, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (sig_p) UPC_CUDA(c, cudaMemcpyAsync(dsig + 2 * p.nm, sig_p, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
+  dim3 grid((p.nm + 31) / 32, (p.ny + 31) / 32), block(32, 8);
+  k_fold<<<grid, block, 0, st>>>(p.nm, p.ny, p.use_pol, c->lumi[0], c->lumi[1], c->lumi[2], dsig, dsig + p.nm,
+                                 dsig + 2 * p.nm, c->cs, c->ratio);
+  // totCS
+  double total = 0;
+  {
+    size_t cur = n;
+    double *a = c->cs, *b0 = nullptr, *b1 = nullptr;
+    size_t nb0 = (n + 4095) / 4096;
+    UPC_CUDA(c, cudaMalloc(&b0, nb0 * sizeof(double)));
+    UPC_CUDA(c, cudaMalloc(&b1, ((nb0 + 4095) / 4096) * sizeof(double)));
+    double* outb = b0;
+    while (true) {
+      size_t nblk = (cur + 4095) / 4096;
+      k_sum_blocks<<<(unsigned)nblk, 256, 0, st>>>(a, cur, outb);
+      if (nblk == 1) break;
+      a = outb;
+      outb = (outb == b0) ? b1 : b0;
+      cur = nblk;
+    }
+    UPC_CUDA(c, cudaMemcpyAsync(&total, outb, sizeof(double), cudaMemcpyDeviceToHost, st));
+    UPC_CUDA(c, cudaStreamSynchronize(st));
+    cudaFree(b0);
+    cudaFree(b1);
+  }
+  UPC_CUDA(c, cudaGetLastError());
+  if (totcs_mb) *totcs_mb = total * 1e-6;  // :696
+  if (cs) UPC_CUDA(c, cudaMemcpy(cs, c->cs, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (ratio && p.use_pol) UPC_CUDA(c, cudaMemcpy(ratio, c->ratio, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dsig);
+  c->fold_ready = true;
+  return UPCGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// S1: gsl_histogram2d_pdf_init.  The running mean and the cumulative sum are sequential
+// recurrences whose rounding the bin selection depends on: one thread walks them in the
+// reference's order.  (The per-bin divisions bin/mean/n have no dependency and run in parallel.)
+__global__ void k_running_mean(const double* __restrict__ bin, size_t n, double* __restrict__ mean_out)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mean = 0;
+  for (size_t i = 0; i < n; i++) mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn(bin[i], mean), (double)(i + 1)));
+  mean_out[0] = mean;
+}
+
+__global__ void k_pdf_terms(const double* __restrict__ bin, size_t n, const double* __restrict__ mean,
+                            double* __restrict__ term)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) term[i] = __ddiv_rn(__ddiv_rn(bin[i], mean[0]), (double)n);  // (bin/mean)/n
+}
+
+__global__ void k_seq_cumsum(const double* __restrict__ term, size_t n, double* __restrict__ sum)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0;
+  sum[0] = 0;
+  for (size_t i = 0; i < n; i++) {
+    s = __dadd_rn(s, term[i]);
+    sum[i + 1] = s;
+  }
+}
+
+// gsl_histogram_pdf_init for the nm z-samplers: one thread per sampler
+__global__ void k_pdf_init_rows(const double* __restrict__ bin, int nrows, int n, double* __restrict__ sum)
+{
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const double* b = bin + (size_t)r * n;
+  double* s = sum + (size_t)r * (n + 1);
+  double mean = 0;
+  for (int i = 0; i < n; i++) mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn(b[i], mean), (double)(i + 1)));
+  double acc = 0;
+  s[0] = 0;
+  for (int i = 0; i < n; i++) {
+    acc = __dadd_rn(acc, __ddiv_rn(__ddiv_rn(b[i], mean), (double)n));
+    s[i + 1] = acc;
+  }
+}
+
+__global__ void k_edges(double lo, double d, int n, double* e)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) e[i] = __dadd_rn(lo, __dmul_rn(d, (double)i));  // mmin + dm * i, UpcGenerator.cpp:675-682
+}
+
+int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps)
+{
+  const upcgpu_params& p = c->p;
+  const size_t n = (size_t)p.nm * p.ny;
+  cudaStream_t st = c->stream;
+  if (cs) {
+    if (!c->cs) UPC_CUDA(c, cudaMalloc(&c->cs, n * sizeof(double)));
+    UPC_CUDA(c, cudaMemcpyAsync(c->cs, cs, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else if (!c->fold_ready) {
+    c->err = "sampler_build: no cross-section table (call fold_sigma or pass cs)";
+    return UPCGPU_EINVAL;
+  }
+  if (!c->sum2d) UPC_CUDA(c, cudaMalloc(&c->sum2d, (n + 1) * sizeof(double)));
+  if (!c->edges_y) {
+    UPC_CUDA(c, cudaMalloc(&c->edges_y, (p.ny + 1) * sizeof(double)));
+    UPC_CUDA(c, cudaMalloc(&c->edges_m, (p.nm + 1) * sizeof(double)));
+    UPC_CUDA(c, cudaMalloc(&c->edges_z, (p.nz + 1) * sizeof(double)));
+  }
+  const double dm = (p.mmax - p.mmin) / p.nm, dy = (p.ymax - p.ymin) / p.ny, dz = (p.zmax - p.zmin) / p.nz;
+  k_edges<<<(p.ny + 128) / 128, 128, 0, st>>>(p.ymin, dy, p.ny, c->edges_y);
+  k_edges<<<(p.nm + 128) / 128, 128, 0, st>>>(p.mmin, dm, p.nm, c->edges_m);
+  k_edges<<<(p.nz + 128) / 128, 128, 0, st>>>(p.zmin, dz, p.nz, c->edges_z);
+  double *term = nullptr, *mean = nullptr;
+  UPC_CUDA(c, cudaMalloc(&term, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&mean, sizeof(double)));
+  k_running_mean<<<1, 1, 0, st>>>(c->cs, n, mean);
+  k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->cs, n, mean, term);
+  k_seq_cumsum<<<1, 1, 0, st>>>(term, n, c->sum2d);
+  // z samplers
+  const size_t nzm = (size_t)p.nm * p.nz, nsz = (size_t)p.nm * (p.nz + 1);
+  double* dz_in = nullptr;
+  const double* first = p.use_pol ? cszm_s : cszm;
+  if (!p.ignore_csz) {
+    if (!first || (p.use_pol && !cszm_ps)) {
+      cudaFree(term); cudaFree(mean);
+      c->err = "sampler_build: missing z cross-section table";
+      return UPCGPU_EINVAL;
+    }
+    UPC_CUDA(c, cudaMalloc(&dz_in, nzm * sizeof(double)));
+    if (!c->sumz) UPC_CUDA(c, cudaMalloc(&c->sumz, nsz * sizeof(double)));
+    UPC_CUDA(c, cudaMemcpyAsync(dz_in, first, nzm * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_pdf_init_rows<<<(p.nm + 63) / 64, 64, 0, st>>>(dz_in, p.nm, p.nz, c->sumz);
+    if (p.use_pol) {
+      if (!c->sumz_ps) UPC_CUDA(c, cudaMalloc(&c->sumz_ps, nsz * sizeof(double)));
+      UPC_CUDA(c, cudaStreamSynchronize(st));
+      UPC_CUDA(c, cudaMemcpyAsync(dz_in, cszm_ps, nzm * sizeof(double), cudaMemcpyHostToDevice, st));
+      k_pdf_init_rows<<<(p.nm + 63) / 64, 64, 0, st>>>(dz_in, p.nm, p.nz, c->sumz_ps);
+    }
+  }
+  UPC_CUDA(c, cudaStreamSynchronize(st));
+  UPC_CUDA(c, cudaGetLastError());
+  cudaFree(term); cudaFree(mean); cudaFree(dz_in);
+  c->sampler_ready = true;
+  return UPCGPU_OK;
+}
+
+__global__ void k_sample_ym(const double* __restrict__ u, size_t n, const double* __restrict__ sum, int ny, int nm,
+                            const double* __restrict__ ye, const double* __restrict__ me, long long* __restrict__ k,
+                            int* __restrict__ ybin, int* __restrict__ mbin, double* __restrict__ y,
+                            double* __restrict__ m)
+{
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  long long kk; double yy, mm;
+  sample_ym_dev(sum, ny, nm, ye, me, u[2 * t], u[2 * t + 1], kk, yy, mm);
+  k[t] = kk; y[t] = yy; m[t] = mm;
+  if (kk >= 0) {
+    ybin[t] = get_bin(ny, yy, ye[0], ye[ny]);
+    mbin[t] = get_bin(nm, mm, me[0], me[nm]);
+  } else {
+    ybin[t] = -1; mbin[t] = -1;
+  }
+}
+
+__global__ void k_sample_z(const int* __restrict__ mbin, const double* __restrict__ u, size_t n,
+                           const double* __restrict__ sumz, int nm, int nz, const double* __restrict__ ze,
+                           double* __restrict__ z)
+{
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int mb = mbin[t];
+  z[t] = (mb >= 0 && mb < nm) ? sample_1d_dev(sumz + (size_t)mb * (nz + 1), nz, ze, u[t]) : nan("");
+}
+
+int sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int* ybin, int* mbin, double* y, double* m)
+{
+  const upcgpu_params& p = c->p;
+  if (!c->sampler_ready) { c->err = "sample_ym: samplers not built"; return UPCGPU_EINVAL; }
+  double *du, *dy, *dm; long long* dk; int *dyb, *dmb;
+  UPC_CUDA(c, cudaMalloc(&du, 2 * n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dy, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dm, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dk, n * sizeof(long long)));
+  UPC_CUDA(c, cudaMalloc(&dyb, n * sizeof(int)));
+  UPC_CUDA(c, cudaMalloc(&dmb, n * sizeof(int)));
+  UPC_CUDA(c, cudaMemcpy(du, u, 2 * n * sizeof(double), cudaMemcpyHostToDevice));
+  k_sample_ym<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(du, n, c->sum2d, p.ny, p.nm, c->edges_y, c->edges_m, dk,
+                                                                 dyb, dmb, dy, dm);
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaGetLastError());
+  if (k) UPC_CUDA(c, cudaMemcpy(k, dk, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (ybin) UPC_CUDA(c, cudaMemcpy(ybin, dyb, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (mbin) UPC_CUDA(c, cudaMemcpy(mbin, dmb, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (y) UPC_CUDA(c, cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (m) UPC_CUDA(c, cudaMemcpy(m, dm, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(du); cudaFree(dy); cudaFree(dm); cudaFree(dk); cudaFree(dyb); cudaFree(dmb);
+  return UPCGPU_OK;
+}
+
+int sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, double* z)
+{
+  const upcgpu_params& p = c->p;
+  const double* tabz = ps ? c->sumz_ps : c->sumz;
+  if (!c->sampler_ready || !tabz) { c->err = "sample_z: z samplers not built"; return UPCGPU_EINVAL; }
+  double *du, *dz; int* dmb;
+  UPC_CUDA(c, cudaMalloc(&du, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dz, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dmb, n * sizeof(int)));
+  UPC_CUDA(c, cudaMemcpy(du, u, n * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_CUDA(c, cudaMemcpy(dmb, mbin, n * sizeof(int), cudaMemcpyHostToDevice));
+  k_sample_z<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(dmb, du, n, tabz, p.nm, p.nz, c->edges_z, dz);
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaGetLastError());
+  UPC_CUDA(c, cudaMemcpy(z, dz, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(du); cudaFree(dz); cudaFree(dmb);
+  return UPCGPU_OK;
+}
+
+}  // namespace upc

@@ -1,0 +1,46 @@
+// upc_internal.h -- declarations shared between the translation units of libupcgpu.so
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "upc_ctx.h"
+
+#define UPC_CUDA(ctx, call)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (call);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +      \
+                   std::to_string(__LINE__) + ")";                                               \
+      return UPCGPU_ECUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+namespace upc {
+
+// upc_tables.cu
+int prepare_tables(upcgpu_ctx* c);
+int eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, double* out);
+int breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out);
+
+// upc_lumi.cu
+int flux_points(upcgpu_ctx* c, const double* b, const double* k, size_t n, int force_point, double* out, int* neval);
+int fill_lumi_rows(upcgpu_ctx* c, int shard, int nshards);
+int lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* out, double* out_s, double* out_p);
+int lumi_unpack(upcgpu_ctx* c, int nshards);
+int ensure_lumi_buffers(upcgpu_ctx* c, int nshards);
+
+// upc_fold.cu
+int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const double* sig_p, double* cs, double* ratio,
+               double* totcs_mb);
+int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps);
+int sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int* ybin, int* mbin, double* y, double* m);
+int sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, double* z);
+
+// upc_events.cu
+int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart, int* pdg, int* status, int* mother,
+             double* p4, double* aux, uint64_t* n_acc, bool device_only);
+int photon_pt_cdf(upcgpu_ctx* c, double e, double* cdf);
+void free_event_scratch(upcgpu_ctx* c);
+
+}  // namespace upc

@@ -1,0 +1,528 @@
+// upc_tables.cu -- device construction of the lookup tables T1-T4:
+//   rho0 (calcWSRho), T_A and G_AA (prepareGAA), the 1e6-knot form-factor spline
+//   (prepareFormFac) and the breakup-probability spline (prepareBreakupProb/calcBreakupProb),
+// reference src/UpcCrossSection.cpp:152-163, :364-461, :752-1019.
+// All of it runs once per context in ~1 ms; nothing here is on the CPU.
+#include <cstdio>
+
+#include "upc_ctx.h"
+#include "upc_internal.h"
+
+namespace upc {
+
+// GL10 positive abscissas / weights, include/UpcCrossSection.h:90-111.  cos(pi x_k) is computed
+// on the host with the platform libm (as the reference does) and passed in.
+struct Gl5 {
+  double w[5], c[5], s[5];
+};
+
+// ---------------------------------------------------------------------------------------------
+// src/UpcCrossSection.cpp:139-150, literal (n = 200: index 199 is an end point, 198 gets weight 2)
+__device__ inline double simpson_seq(int n, const double* v, double h)
+{
+  double sum = v[0] + v[n - 1];
+  for (int i = 1; i < n - 1; i += 2) sum += 4. * v[i];
+  for (int i = 2; i < n - 1; i += 2) sum += 2. * v[i];
+  return sum * h / 3.;
+}
+
+// T1: calcWSRho, src/UpcCrossSection.cpp:152-163
+__global__ void k_rho0(double R, double a, int A, double* out)
+{
+  __shared__ double v[kNB];
+  const double bmax = 20.;
+  const double db = bmax / (kNB - 1.);
+  for (int ib = threadIdx.x; ib < kNB; ib += blockDim.x) {
+    double r = ib * db;
+    v[ib] = r * r / (1. + exp((r - R) / a));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = A / simpson_seq(kNB, v, db) / 4. / kPi;
+}
+
+// T2a: T_A(b) = 2 int rho dz, src/UpcCrossSection.cpp:374-383.  One block per b.
+__global__ void k_ta(double R, double a, const double* rho0p, double* xb, double* ta)
+{
+  __shared__ double v[kNB];
+  const double bmax = 20.;
+  const double db = bmax / (kNB - 1);
+  const double rho0 = rho0p[0];
+  const int ib = blockIdx.x;
+  const double b = ib * db;
+  for (int iz = threadIdx.x; iz < kNB; iz += blockDim.x) {
+    double z = iz * db;
+    double r = sqrt(b * b + z * z);
+    v[iz] = rho0 / (1 + exp((r - R) / a));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ta[ib] = 2. * simpson_seq(kNB, v, db);
+    xb[ib] = b;
+  }
+}
+
+// GSL cspline_init for a small table, one thread (gsl_linalg_solve_symm_tridiag, LDL^T)
+__global__ void k_spline_small(const double* xa, const double* ya, int size, double* c)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int max_index = size - 1;
+  const int N = max_index - 1;
+  double gamma[kNB], z[kNB], alpha[kNB];
+  c[0] = 0.;
+  c[max_index] = 0.;
+  auto diag = [&](int i) { return 2.0 * ((xa[i + 2] - xa[i + 1]) + (xa[i + 1] - xa[i])); };
+  auto off = [&](int i) { return xa[i + 2] - xa[i + 1]; };
+  auto rhs = [&](int i) {
+    double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
+    double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    return 3.0 * ((ya[i + 2] - ya[i + 1]) * g_ip1 - (ya[i + 1] - ya[i]) * g_i);
+  };
+  alpha[0] = diag(0);
+  gamma[0] = off(0) / alpha[0];
+  for (int i = 1; i < N - 1; i++) {
+    alpha[i] = diag(i) - off(i - 1) * gamma[i - 1];
+    gamma[i] = off(i) / alpha[i];
+  }
+  if (N > 1) alpha[N - 1] = diag(N - 1) - off(N - 2) * gamma[N - 2];
+  z[0] = rhs(0);
+  for (int i = 1; i < N; i++) z[i] = rhs(i) - gamma[i - 1] * z[i - 1];
+  double* x = c + 1;
+  x[N - 1] = z[N - 1] / alpha[N - 1];
+  for (int i = N - 2; i >= 0; i--) x[i] = z[i] / alpha[i] - gamma[i] * x[i + 1];
+}
+
+// T2b: G_AA(b) = exp(-sigma_NN T_AA(b)), src/UpcCrossSection.cpp:389-406.  One block per b,
+// one thread per s.
+__global__ void k_gaa(const double* xb, const double* ta, const double* ta_c, double csNN, Gl5 gl, double* gaa)
+{
+  __shared__ double vs[kNB];
+  const double bmax = 20.;
+  const double db = bmax / (kNB - 1);
+  const double inv_db = (kNB - 1) / bmax;
+  const int ib = blockIdx.x;
+  const double b = ib * db;
+  for (int is = threadIdx.x; is < kNB; is += blockDim.x) {
+    double s = is * db;
+    double sum_phi = 0;
+    for (int k = 0; k < 5; k++) {
+      double r = sqrt(b * b + s * s + 2. * b * s * gl.c[k]);
+      sum_phi += 2. * kPi * gl.w[k] * spline_eval_raw(xb, ta, ta_c, kNB, 0., inv_db, r < bmax ? r : bmax);
+    }
+    vs[is] = 2. * s * spline_eval_raw(xb, ta, ta_c, kNB, 0., inv_db, s < bmax ? s : bmax) * sum_phi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) gaa[ib] = exp(-csNN * simpson_seq(kNB, vs, db));
+}
+
+// evaluation-form segments for a table given by arrays
+__global__ void k_segs_from_arrays(const double* xa, const double* ya, const double* ca, int n, SplineSeg* seg,
+                                   double tail_value)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n - 1) seg[i] = make_seg(xa[i], xa[i + 1], ya[i], ya[i + 1], ca[i], ca[i + 1]);
+  if (i == n - 1) seg[i] = SplineSeg{tail_value, 0., 0., 0.};
+}
+
+// knot of a uniform table exactly as the reference forms it: x0 + i*dx (two roundings)
+__device__ __forceinline__ double knot(double x0, double dx, int i) { return __dadd_rn(x0, __dmul_rn((double)i, dx)); }
+// ... except the breakup table, which is written `bmin + db * i` (same thing)
+
+__global__ void k_segs_uniform(double x0, double dx, const double* ya, const double* ca, int n, SplineSeg* seg,
+                               int n_seg_out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n - 1 && i < n_seg_out)
+    seg[i] = make_seg(knot(x0, dx, i), knot(x0, dx, i + 1), ya[i], ya[i + 1], ca[i], ca[i + 1]);
+}
+
+// T3: calcFormFac on the 1e6 knots, src/UpcCrossSection.cpp:436-456
+__device__ inline double calc_formfac(double Q2, double R, double a, double rho0)
+{
+  double Q = sqrt(Q2) / kHc;
+  double coshVal = cosh(kPi * Q * a);
+  double sinhVal = sinh(kPi * Q * a);
+  double ff = 4 * kPi * kPi * rho0 * a * a * a / (Q * a * Q * a * sinhVal * sinhVal) *
+              (kPi * Q * a * coshVal * sin(Q * R) - Q * R * cos(Q * R) * sinhVal);
+  ff += 8 * kPi * rho0 * a * a * a * exp(-R / a) / (1 + Q * Q * a * a) / (1 + Q * Q * a * a);
+  return ff;
+}
+
+__global__ void k_ff_y(double R, double a, const double* rho0p, double* y)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kNQ2) y[i] = calc_formfac(knot(kQ2min, kDQ2, i), R, a, rho0p[0]);
+}
+
+// natural cubic spline c-coefficients of a long uniform table.  The (1,4,1)-type system is
+// strictly diagonally dominant, so the influence of a far knot decays as (2-sqrt 3)^distance
+// (1e-37 after 64 knots): each thread solves the system on its chunk plus a 64-knot halo with
+// the same LDL^T recurrences GSL uses and keeps the chunk.
+constexpr int kSpChunk = 192;
+constexpr int kSpHalo = 64;
+__global__ void k_spline_windowed(double x0, double dx, const double* ya, int size, double* c)
+{
+  const int N = size - 2;  // unknowns u = 0..N-1  <->  c[u+1]
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = t * kSpChunk;
+  if (t == 0) {
+    c[0] = 0.;
+    c[size - 1] = 0.;
+  }
+  if (s >= N) return;
+  const int e = min(N, s + kSpChunk);
+  const int ws = max(0, s - kSpHalo), we = min(N, e + kSpHalo);
+  const int W = we - ws;
+  double gamma[kSpChunk + 2 * kSpHalo], z[kSpChunk + 2 * kSpHalo];
+  auto h = [&](int i) { return __dsub_rn(knot(x0, dx, i + 1), knot(x0, dx, i)); };
+  auto rhs = [&](int i) {
+    double h_i = h(i), h_ip1 = h(i + 1);
+    double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    return 3.0 * ((ya[i + 2] - ya[i + 1]) * g_ip1 - (ya[i + 1] - ya[i]) * g_i);
+  };
+  // forward: alpha_i = diag_i - off_{i-1} gamma_{i-1}; gamma_i = off_i/alpha_i; z_i = b_i - gamma_{i-1} z_{i-1}
+  double alpha_prev = 0, gamma_prev = 0, z_prev = 0;
+  for (int j = 0; j < W; j++) {
+    const int i = ws + j;
+    double diag = 2.0 * (h(i + 1) + h(i));
+    double off = h(i + 1);
+    double alpha = (j == 0) ? diag : diag - h(i) * gamma_prev;  // off_{i-1} = h(i)
+    double g = off / alpha;
+    double zz = (j == 0) ? rhs(i) : rhs(i) - gamma_prev * z_prev;
+    gamma[j] = g;
+    z[j] = zz / alpha;  // store c_i = z_i/alpha_i
+    alpha_prev = alpha; gamma_prev = g; z_prev = zz;
+  }
+  (void)alpha_prev;
+  // back substitution x_i = c_i - gamma_i x_{i+1}
+  double xn = z[W - 1];
+  if (we - 1 >= s && we - 1 < e) c[we - 1 + 1] = xn;
+  for (int j = W - 2; j >= 0; j--) {
+    xn = z[j] - gamma[j] * xn;
+    const int i = ws + j;
+    if (i >= s && i < e) c[i + 1] = xn;
+  }
+}
+
+// T4: photo-nuclear table of calcBreakupProb, src/UpcCrossSection.cpp:853-969 (one thread)
+__device__ double g_bk_ee[700], g_bk_se[700];
+__device__ int g_bk_n;
+struct BkConst {
+  double zcon, o0, gammatarg, omaxx;
+};
+__device__ BkConst g_bk;
+
+__device__ const double bk_e1[23] = {0., 103., 106., 112., 119., 127., 132., 145., 171., 199., 230., 235.,
+                                     254., 280., 300., 320., 330., 333., 373., 390., 420., 426., 440.};
+__device__ const double bk_s1[23] = {0., 12.0, 11.5, 12.0, 12.0, 12.0, 15.0, 17.0, 28.0, 33.0, 52.0, 60.0,
+                                     70.0, 76.0, 85.0, 86.0, 89.0, 89.0, 75.0, 76.0, 69.0, 59.0, 61.0};
+__device__ const double bk_e2[12] = {0., 2000., 3270., 4100., 4810., 6210., 6600., 7790., 8400., 9510., 13600., 16400.};
+__device__ const double bk_s2[12] = {0., .1266, .1080, .0805, .1017, .0942, .0844, .0841, .0755, .0827, .0626, .0740};
+__device__ const double bk_e3[29] = {0., 26., 28., 30., 32., 34., 36., 38., 40., 44., 46., 48., 50., 52., 55.,
+                                     57., 62., 64., 66., 69., 72., 74., 76., 79., 82., 86., 92., 98., 103.};
+__device__ const double bk_s3[29] = {0., 30., 21.5, 22.5, 18.5, 17.5, 15., 14.5, 19., 17.5, 16., 14., 20., 16.5, 17.5,
+                                     17., 15.5, 18., 15.5, 15.5, 15., 13.5, 18., 14.5, 15.5, 12.5, 13., 13., 12.};
+// Armstrong et al. gamma-p / gamma-n totals, entries 0..70 (the loop at :932 reads 9..70)
+__device__ const double bk_sigt[71] = {
+  0., .4245, .4870, .5269, .4778, .4066, .3341, .2444, .2245, .2005, .1783, .1769, .1869, .1940, .2117, .2226,
+  .2327, .2395, .2646, .2790, .2756, .2607, .2447, .2211, .2063, .2137, .2088, .2017, .2050, .2015, .2121, .2175,
+  .2152, .1917, .1911, .1747, .1650, .1587, .1622, .1496, .1486, .1438, .1556, .1468, .1536, .1544, .1536, .1468,
+  .1535, .1442, .1515, .1559, .1541, .1461, .1388, .1565, .1502, .1503, .1454, .1389, .1445, .1425, .1415, .1424,
+  .1432, .1486, .1539, .1354, .1480, .1443, .1435};
+__device__ const double bk_sigtn[71] = {
+  0., .3125, .3930, .4401, .4582, .3774, .3329, .2996, .2715, .2165, .2297, .1861, .1551, .2020, .2073, .2064,
+  .2193, .2275, .2384, .2150, .2494, .2133, .2023, .1969, .1797, .1693, .1642, .1463, .1280, .1555, .1489, .1435,
+  .1398, .1573, .1479, .1493, .1417, .1403, .1258, .1354, .1394, .1420, .1364, .1325, .1455, .1326, .1397, .1286,
+  .1260, .1314, .1378, .1353, .1264, .1471, .1650, .1311, .1261, .1348, .1277, .1518, .1297, .1452, .1453, .1598,
+  .1323, .1234, .1212, .1333, .1434, .1380, .1330};
+
+__global__ void k_bk_init(double beam_gamma)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* ee = g_bk_ee;
+  double* se = g_bk_se;
+  int zp = 82, ap = 208;  // Q2: the reference hard-codes lead (:758-759, :882-883)
+  const double hbarcmev = 197.3269718;
+  const double pi = 3.14159;  // :767
+  double gammatarg = 2. * beam_gamma * beam_gamma - 1.;
+  double si1 = 640., g1 = 4.05, o1 = 13.42, o0 = 7.4;
+  double delo = .05;
+  double scon = .1 * g1 * g1 * si1;
+  double zcon = zp / (gammatarg * (pi) * (hbarcmev)) * zp / (gammatarg * (pi) * (hbarcmev)) / 137.04;
+  int ne = int((25. - o0) / delo) + 1;
+  for (int i = 1; i <= ne; i++) {
+    ee[i] = o0 + (i - 1) * delo;
+    se[i] = scon * ee[i] * ee[i] / (((o1 * o1 - ee[i] * ee[i]) * (o1 * o1 - ee[i] * ee[i])) + ee[i] * ee[i] * g1 * g1);
+  }
+  int ij = ne;
+  for (int j = 1; j <= 27; j++) { ij++; ee[ij] = bk_e3[j]; se[ij] = .1 * ap * bk_s3[j] / 208.; }
+  for (int j = 1; j <= 22; j++) { ij++; ee[ij] = bk_e1[j]; se[ij] = .1 * ap * bk_s1[j] / 208.; }
+  for (int j = 9; j <= 70; j++) {
+    ij++;
+    ee[ij] = ee[ij - 1] + 25.;
+    se[ij] = .1 * (zp * bk_sigt[j] + (ap - zp) * bk_sigtn[j]);
+  }
+  for (int j = 1; j <= 11; j++) { ij++; ee[ij] = bk_e2[j]; se[ij] = .1 * ap * bk_s2[j]; }
+  double x = .0677, y = .129, eps = .0808, eta = .4525, em = .94;
+  double exx = pow(10., .05);
+  double s = .002 * em * ee[ij];
+  int ictr = 100;
+  if (gammatarg > (2. * 150. * 150.)) ictr = 150;
+  for (int j = 1; j <= ictr; j++) {
+    ij++;
+    s = s * exx;
+    ee[ij] = 1000. * .5 * (s - em * em) / em;
+    double pom = x * pow(s, eps);
+    double vec = y * pow(s, (-eta));
+    se[ij] = .1 * .65 * ap * (pom + vec);
+  }
+  ee[ij + 1] = 99999999999.;
+  g_bk_n = ij;
+  g_bk.zcon = zcon;
+  g_bk.o0 = o0;
+  g_bk.gammatarg = gammatarg;
+  g_bk.omaxx = beam_gamma > 500. ? 1.E10 : 1.E7;
+}
+
+// calcBreakupProb for one b, src/UpcCrossSection.cpp:972-1018 (the unused one-neutron sum omitted)
+__device__ inline double calc_breakup(double b, int mode)
+{
+  const double hbarcmev = 197.3269718;
+  const double* ee = g_bk_ee;
+  const double* se = g_bk_se;
+  const double gammatarg = g_bk.gammatarg, zcon = g_bk.zcon;
+  double prob = 0.;
+  double pxn = 0.;
+  double omax = fmin(g_bk.omaxx, 4. * gammatarg * (hbarcmev) / b);
+  if (omax < g_bk.o0) return prob;
+  double gk1m = tmath_bessel_k1(ee[1] * b / ((hbarcmev)*gammatarg));
+  int k = 2;
+  while (ee[k] < omax) {
+    double gk1 = tmath_bessel_k1(ee[k] * b / ((hbarcmev)*gammatarg));
+    // explicit non-fused arithmetic in the reference's order
+    double t1 = __dmul_rn(__dmul_rn(__dmul_rn(se[k - 1], ee[k - 1]), gk1m), gk1m);
+    double t2 = __dmul_rn(__dmul_rn(__dmul_rn(se[k], ee[k]), gk1), gk1);
+    double term = __dmul_rn(__dmul_rn(__dmul_rn(zcon, __dsub_rn(ee[k], ee[k - 1])), .5), __dadd_rn(t1, t2));
+    pxn = __dadd_rn(pxn, term);
+    k = k + 1;
+    gk1m = gk1;
+  }
+  if (mode == 1) prob = 1.;
+  if (mode == 2) prob = (1 - exp(-1 * pxn)) * (1 - exp(-1 * pxn));
+  if (mode == 3) prob = exp(-2 * pxn);
+  if (mode == 4) prob = 2. * exp(-pxn) * (1. - exp(-pxn));
+  return prob;
+}
+
+__global__ void k_bk_prob(int mode, int n, double* y)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = calc_breakup(knot(kBkBmin, kBkDb, i), mode);
+}
+
+__global__ void k_bk_raw(const double* b, int mode, size_t n, double* out)
+{
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = calc_breakup(b[i], mode);
+}
+
+// scalar look-ups finishing the tables: ff_last = F(Q2max - dQ2), P20 = P(20)
+__global__ void k_table_scalars(const SplineSeg* ff_seg, const SplineSeg* bk_seg, int use_breakup, double* out)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  {
+    // src/UpcCrossSection.cpp:188: gsl_spline_eval(.., Q2max - dQ2): the last knot exactly
+    double x = kQ2max - kDQ2;
+    int i = kNQ2 - 2;
+    out[0] = seg_eval(ff_seg[i], x - knot(kQ2min, kDQ2, i));
+  }
+  if (use_breakup) {
+    double x = 20.;
+    int i = (int)((x - kBkBmin) / kBkDb);
+    while (knot(kBkBmin, kBkDb, i) > x) --i;
+    while (knot(kBkBmin, kBkDb, i + 1) <= x) ++i;
+    out[1] = seg_eval(bk_seg[i], x - knot(kBkBmin, kBkDb, i));
+  } else {
+    out[1] = 1.;
+  }
+}
+
+// generic spline evaluation hook (GSL bsearch semantics), which: see upcgpu.h
+__global__ void k_eval_uniform(const SplineSeg* seg, int nseg, double x0, double dx, const double* x, size_t n,
+                               double* out)
+{
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  double xv = x[t];
+  int i = (int)((xv - x0) / dx);
+  i = max(0, min(i, nseg - 1));
+  while (i > 0 && knot(x0, dx, i) > xv) --i;
+  while (i < nseg - 1 && knot(x0, dx, i + 1) <= xv) ++i;
+  out[t] = seg_eval(seg[i], xv - knot(x0, dx, i));
+}
+
+__global__ void k_eval_arrays(const double* xa, const SplineSeg* seg, int n, double inv_dx, const double* x, size_t cnt,
+                              double* out)
+{
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  double xv = x[t];
+  int i = (int)((xv - xa[0]) * inv_dx);
+  i = max(0, min(i, n - 2));
+  while (i > 0 && xa[i] > xv) --i;
+  while (i < n - 2 && xa[i + 1] <= xv) ++i;
+  out[t] = seg_eval(seg[i], xv - xa[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+static Gl5 make_gl5(bool pol_sign)
+{
+  // include/UpcCrossSection.h:90-111, positive half; cos/sin by the host libm as the reference
+  static const double w[5] = {0.2955242247147529, 0.2692667193099963, 0.2190863625159820, 0.1494513491505806,
+                              0.0666713443086881};
+  static const double x[5] = {0.1488743389816312, 0.4333953941292472, 0.6794095682990244, 0.8650633666889845,
+                              0.9739065285171717};
+  Gl5 g;
+  for (int k = 0; k < 5; k++) {
+    g.w[k] = w[k];
+    g.c[k] = cos(M_PI * x[k]);
+    g.s[k] = sin(M_PI * x[k]);
+  }
+  (void)pol_sign;
+  return g;
+}
+
+int prepare_tables(upcgpu_ctx* c)
+{
+  const upcgpu_params& p = c->p;
+  cudaStream_t st = c->stream;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+
+  UPC_CUDA(c, cudaMalloc(&c->d_scal, 64 * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->gaa_x, kNB * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->gaa_y, kNB * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->gaa_c, kNB * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->ta_y, kNB * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->ta_c, kNB * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->gaa_seg, (kNB + 1) * sizeof(SplineSeg)));
+  UPC_CUDA(c, cudaMalloc(&c->ff_y, kNQ2 * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->ff_c, kNQ2 * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&c->ff_seg, (size_t)kNQ2 * sizeof(SplineSeg)));
+
+  // sigma_NN, PDG 2016 fit, src/UpcCrossSection.cpp:368-369 (scalar, host libm like the reference)
+  double ssm = pow(p.sqrts, 2) / pow(2 * kMProt + 2.1206, 2);
+  double csNN = 0.1 * (34.41 + 0.2720 * pow(log(ssm), 2) + 13.07 * pow(ssm, -0.4473) - 7.394 * pow(ssm, -0.5486));
+  c->info.sigma_nn = csNN;
+  c->info.factor = p.Z * p.Z * kAlpha / M_PI / M_PI / kHc / kHc;  // :120
+
+  Gl5 gl = make_gl5(false);
+  k_rho0<<<1, 256, 0, st>>>(p.R, p.a, p.A, c->d_scal);
+  k_ta<<<kNB, 256, 0, st>>>(p.R, p.a, c->d_scal, c->gaa_x, c->ta_y);
+  k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->ta_y, kNB, c->ta_c);
+  k_gaa<<<kNB, 256, 0, st>>>(c->gaa_x, c->ta_y, c->ta_c, csNN, gl, c->gaa_y);
+  k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->gaa_y, kNB, c->gaa_c);
+  k_segs_from_arrays<<<1, 256, 0, st>>>(c->gaa_x, c->gaa_y, c->gaa_c, kNB, c->gaa_seg, 1.0);
+
+  k_ff_y<<<(kNQ2 + 255) / 256, 256, 0, st>>>(p.R, p.a, c->d_scal, c->ff_y);
+  {
+    int nthr = (kNQ2 - 2 + kSpChunk - 1) / kSpChunk;
+    k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kQ2min, kDQ2, c->ff_y, kNQ2, c->ff_c);
+  }
+  k_segs_uniform<<<(kNQ2 + 255) / 256, 256, 0, st>>>(kQ2min, kDQ2, c->ff_y, c->ff_c, kNQ2, c->ff_seg, kNQ2 - 1);
+
+  int use_bk = p.breakup_mode > 1;
+  if (use_bk) {
+    // knots up to b = 20.2 fm: 20 001 are reachable, 200 more isolate the artificial right end
+    c->bk_nknots = 20200;
+    UPC_CUDA(c, cudaMalloc(&c->bk_y, c->bk_nknots * sizeof(double)));
+    UPC_CUDA(c, cudaMalloc(&c->bk_c, c->bk_nknots * sizeof(double)));
+    UPC_CUDA(c, cudaMalloc(&c->bk_seg, (size_t)(c->bk_nknots + 1) * sizeof(SplineSeg)));
+    k_bk_init<<<1, 1, 0, st>>>(p.g1);
+    k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st>>>(p.breakup_mode, c->bk_nknots, c->bk_y);
+    int nthr = (c->bk_nknots - 2 + kSpChunk - 1) / kSpChunk;
+    k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
+    k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
+                                                              c->bk_seg, c->bk_nknots - 1);
+  }
+  k_table_scalars<<<1, 1, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, c->d_scal + 1);
+  cudaEventRecord(e1, st);
+  UPC_CUDA(c, cudaStreamSynchronize(st));
+  UPC_CUDA(c, cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  c->stats.ms_tables = ms;
+
+  double h[3];
+  UPC_CUDA(c, cudaMemcpy(h, c->d_scal, sizeof(h), cudaMemcpyDeviceToHost));
+  c->info.rho0 = h[0];
+  c->info.breakup_p20 = h[2];
+  if (use_bk) {
+    int nk = 0;
+    UPC_CUDA(c, cudaMemcpyFromSymbol(&nk, g_bk_n, sizeof(int)));
+    c->info.n_breakup_energy_knots = nk;
+    // the clamp segment used for b >= 20 (index bk_n): value P(20)
+    // number of real segments kept for lookups: those covering b < 20 -> index of b = 20
+    int i20 = (int)((20. - kBkBmin) / kBkDb) + 1;  // segments 0..i20-1 cover [bmin, >20)
+    SplineSeg tail{h[2], 0., 0., 0.};
+    UPC_CUDA(c, cudaMemcpy(c->bk_seg + i20, &tail, sizeof(tail), cudaMemcpyHostToDevice));
+    c->tab.bk_n = i20;
+  } else {
+    c->info.n_breakup_energy_knots = 0;
+    c->tab.bk_n = 0;
+  }
+  c->tab.gaa_seg = c->gaa_seg;
+  c->tab.gaa_db = 20. / (kNB - 1);
+  c->tab.gaa_inv_db = (kNB - 1) / 20.;
+  c->tab.bk_seg = c->bk_seg;
+  c->tab.p20 = h[2];
+  c->tab.use_breakup = use_bk;
+  c->tab.ff_seg = c->ff_seg;
+  c->tab.ff_last = h[1];
+  c->tables_ready = true;
+  return UPCGPU_OK;
+}
+
+int eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, double* out)
+{
+  double *dx = nullptr, *dout = nullptr;
+  UPC_CUDA(c, cudaMalloc(&dx, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dout, n * sizeof(double)));
+  UPC_CUDA(c, cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
+  unsigned g = (unsigned)((n + 127) / 128);
+  if (which == UPCGPU_TABLE_GAA) {
+    k_eval_arrays<<<g, 128, 0, c->stream>>>(c->gaa_x, c->gaa_seg, kNB, (kNB - 1) / 20., dx, n, dout);
+  } else if (which == UPCGPU_TABLE_FORMFAC) {
+    k_eval_uniform<<<g, 128, 0, c->stream>>>(c->ff_seg, kNQ2 - 1, kQ2min, kDQ2, dx, n, dout);
+  } else if (which == UPCGPU_TABLE_BREAKUP && c->bk_seg) {
+    k_eval_uniform<<<g, 128, 0, c->stream>>>(c->bk_seg, c->tab.bk_n, kBkBmin, kBkDb, dx, n, dout);
+  } else {
+    cudaFree(dx); cudaFree(dout);
+    c->err = "eval_table: table not available";
+    return UPCGPU_EINVAL;
+  }
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(dx);
+  cudaFree(dout);
+  return UPCGPU_OK;
+}
+
+int breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out)
+{
+  double *db = nullptr, *dout = nullptr;
+  UPC_CUDA(c, cudaMalloc(&db, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dout, n * sizeof(double)));
+  UPC_CUDA(c, cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
+  k_bk_raw<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(db, mode, n, dout);
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(db);
+  cudaFree(dout);
+  return UPCGPU_OK;
+}
+
+}  // namespace upc
