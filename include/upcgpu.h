@@ -83,6 +83,7 @@ typedef struct {
   long long flux_rows;        /* photon-energy rows tabulated */
   long long band_pairs;       /* (b1,b2) pairs with some b < 20 fm that were evaluated */
   double ms_tables, ms_flux, ms_cells, ms_total; /* device time of the stages, CUDA events */
+  double ms_qags;             /* of ms_flux: the persistent QAGS kernel alone */
 } upcgpu_fill_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------ */
@@ -100,6 +101,9 @@ int upcgpu_device_name(const upcgpu_ctx* ctx, char* buf, size_t cap);
  * (src/UpcCrossSection.cpp:116-131, :152-163, :364-461).  All on the device. */
 int upcgpu_prepare_tables(upcgpu_ctx* ctx);
 int upcgpu_get_table_info(const upcgpu_ctx* ctx, upcgpu_table_info* info);
+/* marks the tables stale so that the next upcgpu_prepare_tables recomputes them (bench: the
+ * table stage is part of every timed step) */
+int upcgpu_invalidate_tables(upcgpu_ctx* ctx);
 /* copies knots i0..i0+n-1 of a spline table: x (knot), y (value), c (GSL c-coefficient);
  * any of x,y,c may be NULL.  Replaces reading gslSplineGAA/FormFac/BreakP (:31-38). */
 int upcgpu_get_table(upcgpu_ctx* ctx, int which, size_t i0, size_t n, double* x, double* y, double* c);
@@ -186,6 +190,10 @@ int upcgpu_generate_device(upcgpu_ctx* ctx, uint64_t seed, uint64_t first_candid
                            uint64_t* n_accepted);
 /* photon-pT pdf of getPhotonPt for one photon energy: cdf[5001] (TH1 integral), test hook */
 int upcgpu_photon_pt_cdf(upcgpu_ctx* ctx, double e_phot, double* cdf);
+/* measurement aid: dependent-free DFMA loop on every SM; returns the FP64 FMA rate in TFLOP/s
+ * (2 flop per DFMA) and the kernel time.  Used as the roofline denominator (MEASURED_PEAKS.json
+ * carries no FP64 figure). */
+int upcgpu_fp64_peak(upcgpu_ctx* ctx, int iters, double* tflops, double* ms);
 /* Philox4x32-10 uniforms, test hook: out[2*i], out[2*i+1] for counter ctr0+i, block */
 int upcgpu_philox(uint64_t seed, uint64_t ctr0, uint32_t block, size_t n, double* out);
 

@@ -50,7 +50,8 @@ class CTableInfo(C.Structure):
 class CFillStats(C.Structure):
     _fields_ = [("qags_integrals", C.c_longlong), ("qags_evals", C.c_longlong), ("qags_overflow", C.c_longlong),
                 ("qags_errors", C.c_longlong), ("flux_rows", C.c_longlong), ("band_pairs", C.c_longlong),
-                ("ms_tables", C.c_double), ("ms_flux", C.c_double), ("ms_cells", C.c_double), ("ms_total", C.c_double)]
+                ("ms_tables", C.c_double), ("ms_flux", C.c_double), ("ms_cells", C.c_double), ("ms_total", C.c_double),
+                ("ms_qags", C.c_double)]
 
 
 # every symbol include/upcgpu.h declares (tests check that the library exports all of them)
@@ -61,7 +62,7 @@ SYMBOLS = [
     "upcgpu_get_fill_stats", "upcgpu_lumi_shard_buffer", "upcgpu_lumi_gather_buffer", "upcgpu_lumi_unpack",
     "upcgpu_lumi_download", "upcgpu_lumi_upload", "upcgpu_fold_sigma", "upcgpu_sampler_build",
     "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_device",
-    "upcgpu_photon_pt_cdf", "upcgpu_philox",
+    "upcgpu_photon_pt_cdf", "upcgpu_philox", "upcgpu_invalidate_tables", "upcgpu_fp64_peak",
 ]
 
 
@@ -104,6 +105,8 @@ def lib():
         L.upcgpu_generate_device.argtypes = [p, C.c_uint64, C.c_uint64, sz, C.POINTER(C.c_uint64)]
         L.upcgpu_photon_pt_cdf.argtypes = [p, d, p]
         L.upcgpu_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, sz, p]
+        L.upcgpu_invalidate_tables.argtypes = [p]
+        L.upcgpu_fp64_peak.argtypes = [p, i, C.POINTER(d), C.POINTER(d)]
         _LIB = L
     return _LIB
 
@@ -177,6 +180,14 @@ class UpcGpu:
     def prepare_tables(self):
         self._chk(self.L.upcgpu_prepare_tables(self.h))
         return self.table_info()
+
+    def invalidate_tables(self):
+        self._chk(self.L.upcgpu_invalidate_tables(self.h))
+
+    def fp64_peak(self, iters=200000):
+        tf, ms = C.c_double(), C.c_double()
+        self._chk(self.L.upcgpu_fp64_peak(self.h, iters, C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value
 
     def table_info(self):
         info = CTableInfo()

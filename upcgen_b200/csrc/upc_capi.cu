@@ -9,6 +9,10 @@ using namespace upc;
 
 static thread_local std::string g_create_err;
 
+#define CHECK_CTX(c)                 \
+  if (!(c)) return UPCGPU_EINVAL;    \
+  cudaSetDevice((c)->device);
+
 extern "C" {
 
 int upcgpu_abi_version(void) { return 1; }
@@ -54,11 +58,12 @@ void upcgpu_destroy(upcgpu_ctx* c)
   cudaSetDevice(c->device);
   cudaFree(c->gaa_x); cudaFree(c->gaa_y); cudaFree(c->gaa_c); cudaFree(c->ta_y); cudaFree(c->ta_c);
   cudaFree(c->ff_y); cudaFree(c->ff_c); cudaFree(c->bk_y); cudaFree(c->bk_c);
-  cudaFree(c->gaa_seg); cudaFree(c->ff_seg); cudaFree(c->bk_seg); cudaFree(c->d_scal);
+  cudaFree(c->gaa_seg); cudaFree(c->ff_seg); cudaFree(c->bk_seg); cudaFree(c->d_scal); cudaFree(c->bk_table);
   for (int w = 0; w < 3; w++) { cudaFree(c->lumi[w]); cudaFree(c->shard[w]); cudaFree(c->gather[w]); }
   cudaFree(c->cs); cudaFree(c->ratio); cudaFree(c->sum2d); cudaFree(c->sumz); cudaFree(c->sumz_ps);
   cudaFree(c->edges_y); cudaFree(c->edges_m); cudaFree(c->edges_z);
   free_event_scratch(c);
+  free_lumi_scratch(c);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -70,15 +75,25 @@ int upcgpu_device_name(const upcgpu_ctx* c, char* buf, size_t cap)
   return UPCGPU_OK;
 }
 
-#define CHECK_CTX(c)                 \
-  if (!(c)) return UPCGPU_EINVAL;    \
-  cudaSetDevice((c)->device);
 
 int upcgpu_prepare_tables(upcgpu_ctx* c)
 {
   CHECK_CTX(c);
   if (c->tables_ready) return UPCGPU_OK;
   return prepare_tables(c);
+}
+
+int upcgpu_invalidate_tables(upcgpu_ctx* c)
+{
+  if (!c) return UPCGPU_EINVAL;
+  c->tables_ready = false;
+  return UPCGPU_OK;
+}
+
+int upcgpu_fp64_peak(upcgpu_ctx* c, int iters, double* tflops, double* ms)
+{
+  CHECK_CTX(c);
+  return fp64_peak(c, iters, tflops, ms);
 }
 
 int upcgpu_get_table_info(const upcgpu_ctx* c, upcgpu_table_info* info)

@@ -41,6 +41,7 @@ struct upcgpu_ctx_impl {
   double *ff_y = nullptr, *ff_c = nullptr;
   double *bk_y = nullptr, *bk_c = nullptr;
   int bk_nknots = 0;
+  void* bk_table = nullptr;  // photo-nuclear energy table of calcBreakupProb (device)
   SplineSeg *gaa_seg = nullptr, *ff_seg = nullptr, *bk_seg = nullptr;
   double* d_scal = nullptr;  // small device scratch for scalars
   DevTables tab{};
@@ -61,6 +62,9 @@ struct upcgpu_ctx_impl {
 
   // event stage scratch (grown on demand)
   void* ev = nullptr;
+  // flux-row scratch of the lumi fill (allocated once, reused by every fill)
+  void* slab = nullptr;
+  int slab_max_m = 0;
 };
 
 }  // namespace upc

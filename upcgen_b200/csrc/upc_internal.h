@@ -29,6 +29,8 @@ int fill_lumi_rows(upcgpu_ctx* c, int shard, int nshards);
 int lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* out, double* out_s, double* out_p);
 int lumi_unpack(upcgpu_ctx* c, int nshards);
 int ensure_lumi_buffers(upcgpu_ctx* c, int nshards);
+void free_lumi_scratch(upcgpu_ctx* c);
+int fp64_peak(upcgpu_ctx* c, int iters, double* tflops, double* ms);
 
 // upc_fold.cu
 int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const double* sig_p, double* cs, double* ratio,

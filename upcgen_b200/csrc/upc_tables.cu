@@ -3,6 +3,7 @@
 //   (prepareFormFac) and the breakup-probability spline (prepareBreakupProb/calcBreakupProb),
 // reference src/UpcCrossSection.cpp:152-163, :364-461, :752-1019.
 // All of it runs once per context in ~1 ms; nothing here is on the CPU.
+#include <cstddef>
 #include <cstdio>
 
 #include "upc_ctx.h"
@@ -204,12 +205,12 @@ __global__ void k_spline_windowed(double x0, double dx, const double* ya, int si
 }
 
 // T4: photo-nuclear table of calcBreakupProb, src/UpcCrossSection.cpp:853-969 (one thread)
-__device__ double g_bk_ee[700], g_bk_se[700];
-__device__ int g_bk_n;
-struct BkConst {
+// per-context (the reference keeps these in function-local statics: one generator per process)
+struct BkTable {
+  double ee[700], se[700];
   double zcon, o0, gammatarg, omaxx;
+  int n;
 };
-__device__ BkConst g_bk;
 
 __device__ const double bk_e1[23] = {0., 103., 106., 112., 119., 127., 132., 145., 171., 199., 230., 235.,
                                      254., 280., 300., 320., 330., 333., 373., 390., 420., 426., 440.};
@@ -235,11 +236,11 @@ __device__ const double bk_sigtn[71] = {
   .1260, .1314, .1378, .1353, .1264, .1471, .1650, .1311, .1261, .1348, .1277, .1518, .1297, .1452, .1453, .1598,
   .1323, .1234, .1212, .1333, .1434, .1380, .1330};
 
-__global__ void k_bk_init(double beam_gamma)
+__global__ void k_bk_init(double beam_gamma, BkTable* T)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double* ee = g_bk_ee;
-  double* se = g_bk_se;
+  double* ee = T->ee;
+  double* se = T->se;
   int zp = 82, ap = 208;  // Q2: the reference hard-codes lead (:758-759, :882-883)
   const double hbarcmev = 197.3269718;
   const double pi = 3.14159;  // :767
@@ -276,24 +277,24 @@ __global__ void k_bk_init(double beam_gamma)
     se[ij] = .1 * .65 * ap * (pom + vec);
   }
   ee[ij + 1] = 99999999999.;
-  g_bk_n = ij;
-  g_bk.zcon = zcon;
-  g_bk.o0 = o0;
-  g_bk.gammatarg = gammatarg;
-  g_bk.omaxx = beam_gamma > 500. ? 1.E10 : 1.E7;
+  T->n = ij;
+  T->zcon = zcon;
+  T->o0 = o0;
+  T->gammatarg = gammatarg;
+  T->omaxx = beam_gamma > 500. ? 1.E10 : 1.E7;
 }
 
 // calcBreakupProb for one b, src/UpcCrossSection.cpp:972-1018 (the unused one-neutron sum omitted)
-__device__ inline double calc_breakup(double b, int mode)
+__device__ inline double calc_breakup(const BkTable* __restrict__ T, double b, int mode)
 {
   const double hbarcmev = 197.3269718;
-  const double* ee = g_bk_ee;
-  const double* se = g_bk_se;
-  const double gammatarg = g_bk.gammatarg, zcon = g_bk.zcon;
+  const double* ee = T->ee;
+  const double* se = T->se;
+  const double gammatarg = T->gammatarg, zcon = T->zcon;
   double prob = 0.;
   double pxn = 0.;
-  double omax = fmin(g_bk.omaxx, 4. * gammatarg * (hbarcmev) / b);
-  if (omax < g_bk.o0) return prob;
+  double omax = fmin(T->omaxx, 4. * gammatarg * (hbarcmev) / b);
+  if (omax < T->o0) return prob;
   double gk1m = tmath_bessel_k1(ee[1] * b / ((hbarcmev)*gammatarg));
   int k = 2;
   while (ee[k] < omax) {
@@ -313,16 +314,16 @@ __device__ inline double calc_breakup(double b, int mode)
   return prob;
 }
 
-__global__ void k_bk_prob(int mode, int n, double* y)
+__global__ void k_bk_prob(const BkTable* T, int mode, int n, double* y)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = calc_breakup(knot(kBkBmin, kBkDb, i), mode);
+  if (i < n) y[i] = calc_breakup(T, knot(kBkBmin, kBkDb, i), mode);
 }
 
-__global__ void k_bk_raw(const double* b, int mode, size_t n, double* out)
+__global__ void k_bk_raw(const BkTable* T, const double* b, int mode, size_t n, double* out)
 {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) out[i] = calc_breakup(b[i], mode);
+  if (i < n) out[i] = calc_breakup(T, b[i], mode);
 }
 
 // scalar look-ups finishing the tables: ff_last = F(Q2max - dQ2), P20 = P(20)
@@ -400,6 +401,7 @@ int prepare_tables(upcgpu_ctx* c)
   cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
 
+  if (!c->d_scal) {
   UPC_CUDA(c, cudaMalloc(&c->d_scal, 64 * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&c->gaa_x, kNB * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&c->gaa_y, kNB * sizeof(double)));
@@ -410,6 +412,7 @@ int prepare_tables(upcgpu_ctx* c)
   UPC_CUDA(c, cudaMalloc(&c->ff_y, kNQ2 * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&c->ff_c, kNQ2 * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&c->ff_seg, (size_t)kNQ2 * sizeof(SplineSeg)));
+  }
 
   // sigma_NN, PDG 2016 fit, src/UpcCrossSection.cpp:368-369 (scalar, host libm like the reference)
   double ssm = pow(p.sqrts, 2) / pow(2 * kMProt + 2.1206, 2);
@@ -436,11 +439,15 @@ int prepare_tables(upcgpu_ctx* c)
   if (use_bk) {
     // knots up to b = 20.2 fm: 20 001 are reachable, 200 more isolate the artificial right end
     c->bk_nknots = 20200;
+    if (!c->bk_y) {
     UPC_CUDA(c, cudaMalloc(&c->bk_y, c->bk_nknots * sizeof(double)));
     UPC_CUDA(c, cudaMalloc(&c->bk_c, c->bk_nknots * sizeof(double)));
     UPC_CUDA(c, cudaMalloc(&c->bk_seg, (size_t)(c->bk_nknots + 1) * sizeof(SplineSeg)));
-    k_bk_init<<<1, 1, 0, st>>>(p.g1);
-    k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st>>>(p.breakup_mode, c->bk_nknots, c->bk_y);
+    UPC_CUDA(c, cudaMalloc(&c->bk_table, sizeof(BkTable)));
+    }
+    k_bk_init<<<1, 1, 0, st>>>(p.g1, (BkTable*)c->bk_table);
+    k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
+                                                          c->bk_y);
     int nthr = (c->bk_nknots - 2 + kSpChunk - 1) / kSpChunk;
     k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
     k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
@@ -462,7 +469,7 @@ int prepare_tables(upcgpu_ctx* c)
   c->info.breakup_p20 = h[2];
   if (use_bk) {
     int nk = 0;
-    UPC_CUDA(c, cudaMemcpyFromSymbol(&nk, g_bk_n, sizeof(int)));
+    UPC_CUDA(c, cudaMemcpy(&nk, (const char*)c->bk_table + offsetof(BkTable, n), sizeof(int), cudaMemcpyDeviceToHost));
     c->info.n_breakup_energy_knots = nk;
     // the clamp segment used for b >= 20 (index bk_n): value P(20)
     // number of real segments kept for lookups: those covering b < 20 -> index of b = 20
@@ -517,7 +524,7 @@ int breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out)
   UPC_CUDA(c, cudaMalloc(&db, n * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&dout, n * sizeof(double)));
   UPC_CUDA(c, cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
-  k_bk_raw<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(db, mode, n, dout);
+  k_bk_raw<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const BkTable*)c->bk_table, db, mode, n, dout);
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   UPC_CUDA(c, cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(db);
