@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of upcgen on B200: luminosity/sigma table fill (cells/s) + events/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2]
+
+One STEP = one pass of the table path over the whole (y, m) grid of the workload:
+    prepare the lookup tables (T1-T4)  ->  fill the two-photon luminosity table (F1-F3, L1-L3)
+    [-> NCCL all-gather of the m-row shards when N > 1]  ->  fold with sigma(m) (X1).
+`value` is cells/s with everything resident in HBM, timed with CUDA events on the library's
+stream (max over ranks); `e2e` is the same step through the host-buffer C-ABI calls
+(upcgpu_fill_lumi / upcgpu_fold_sigma) with pinned host buffers and the copies inside the timed
+region.  The event stage (S1-S3, E1-E5) is timed separately and reported under "events".
+
+--impl reference times the CPU path (oracle/libupcoracle.so: our OpenMP restatement of the
+reference's algorithm -- the reference binary itself cannot be built here, it needs ROOT + GSL)
+on all host threads, on a bounded sample of the same grid.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD_TEXT = {
+    "cfg1": "cfg1: Pb-Pb 5.02 TeV ditau PROC_ID 15, point flux, no breakup, 1001x121 grid",
+    "cfg2": "cfg2: Pb-Pb 5.02 TeV dimuon PROC_ID 13, FLUX_POINT 0 (Woods-Saxon form-factor flux, QAGS), "
+            "BREAKUP_MODE 2 XNXN, 1001x121 (m,y) grid, 1e6 events",
+    "cfg3": "cfg3: Pb-Pb light-by-light grid, USE_POLARIZED_CS 1, BREAKUP_MODE 4, 1000x121 grid (lumi tables only)",
+    "cfg4": "cfg4: Pb-Pb dielectron PROC_ID 11, MMIN 1 MMAX 100, 10001x1201 grid, form-factor flux",
+    "cfg5": "cfg5: Xe-Xe 5.44 TeV ALP PROC_ID 51, NON_ZERO_GAM_PT 1, 0N0N, 1001x121 grid, 1e7 events",
+}
+
+# algorithmic work per unit
+FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegrand
+FLOP_CELL = {(0, 0): 1.19e6, (0, 1): 1.91e6, (1, 0): 1.30e6, (1, 1): 2.05e6}  # (pol, breakup) per cell
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args):
+    """CPU arm: the oracle (kind 'port') on all host threads, bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import pyoracle
+    from upcgen_b200.config import named_config
+    P = named_config(args.workload)
+    cores = os.cpu_count() or 1
+    o = pyoracle.Oracle(P, threads=cores)
+    # bounded sample: every im_step-th m row x every iy_step-th y column of the same grid
+    im_step = max(1, P.nm // 64)
+    iy_step = max(1, P.ny // 11)
+    n_cells = len(range(0, P.nm, im_step)) * len(range(0, P.ny, iy_step))
+
+    def step():
+        o.fill_lumi(im_step=im_step, iy_step=iy_step)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = n_cells / dt
+    sample = (f"{n_cells} cells per step = every {im_step}th m row x every {iy_step}th y column of the "
+              f"{P.nm}x{P.ny} grid; lumi fill only (table set-up excluded)")
+    line = {
+        "impl": "reference", "metric": "lumi_cells_per_s", "value": val, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "cells": P.nm * P.ny},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference algorithm (oracle/upc_oracle.c, OpenMP static m-slabs); "
+                "the reference binary needs ROOT+GSL and cannot be built in this image",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOAD_TEXT))
+    ap.add_argument("--events", type=int, default=None, help="events per rank for the event-stage timing")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    from upcgen_b200 import capi, dist as udist
+    from upcgen_b200.config import named_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    rank, local, world = udist.init_from_env("nccl")
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+
+    P = named_config(args.workload)
+    gpu = capi.UpcGpu(P, local)
+    ext_stream = torch.cuda.ExternalStream(gpu.stream_handle(), device=dev)
+    n_cells = P.nm * P.ny
+    pol, bk = int(P.use_pol), int(P.breakup_mode > 1)
+
+    # host plug-in values (elementary sigma(m)), computed once: they are inputs of the step
+    if pol:
+        sig = dict(sig_s=capi.elem_sigma_m(P, 1), sig_p=capi.elem_sigma_m(P, 2))
+    else:
+        sig = dict(sig_m=capi.elem_sigma_m(P, 0))
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        gpu.invalidate_tables()
+        gpu.prepare_tables()
+        udist.fill_lumi_distributed(gpu, rank, world, dev)
+        gpu.fold_sigma(download=False, **sig)
+
+    # ---- device-resident timing ---------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    peak_tf, _ = gpu.fp64_peak(400000)
+    clocks = ClockSampler(local)
+    stage = {"ms_tables": 0.0, "ms_flux": 0.0, "ms_qags": 0.0, "ms_cells": 0.0}
+    ms_steps = []
+    launches0 = gpu.launch_count()
+    barrier()
+    clocks.start()
+    for _ in range(args.steps):
+        l2_flush.fill_(1)                 # flush L2 between timed iterations (126 MB L2 < 256 MiB)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(ext_stream)
+        step_device()
+        e1.record(ext_stream)
+        barrier()
+        ms_steps.append(e0.elapsed_time(e1))
+        st = gpu.fill_stats()
+        for k in stage:
+            stage[k] += st[k] / args.steps
+    clk = clocks.stop()
+    launches = gpu.launch_count() - launches0
+    ms = float(np.mean(ms_steps))
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    st = gpu.fill_stats()
+
+    # ---- end-to-end through the host-buffer C-ABI (N = 1 only: the call fills the whole grid) ----
+    e2e = None
+    if world == 1:
+        n_tab = 2 if pol else 1
+        host_lumi = [torch.empty((P.nm, P.ny), dtype=torch.float64).pin_memory() for _ in range(n_tab)]
+        host_cs = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory()
+        host_ratio = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory() if pol else None
+        host_sig = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in sig.items()}
+        import ctypes as C
+        tot = C.c_double()
+
+        def vp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+
+        def step_e2e():
+            gpu.invalidate_tables()
+            if pol:
+                gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
+                gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, None, vp(host_sig["sig_s"]), vp(host_sig["sig_p"]),
+                                                 vp(host_cs), vp(host_ratio), C.byref(tot)))
+            else:
+                gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, vp(host_lumi[0]), None, None))
+                gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, vp(host_sig["sig_m"]), None, None, vp(host_cs), None,
+                                                 C.byref(tot)))
+            return tot.value
+
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            l2_flush.fill_(1)
+            torch.cuda.synchronize(dev)
+            step_e2e()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": n_cells / dt, "unit": "cells/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in host_sig.values())),
+               "d2h_bytes_per_step": int(n_tab * n_cells * 8 + n_cells * 8 * (2 if pol else 1) + 8),
+               "api": "upcgpu_fill_lumi + upcgpu_fold_sigma (include/upcgpu.h), pinned host buffers",
+               "total_cross_section_mb": tot.value}
+
+    # ---- event stage ----------------------------------------------------------------------
+    events = None
+    if args.workload in ("cfg1", "cfg2", "cfg5"):
+        if not P.ignore_csz:
+            gpu.sampler_build(cszm=capi.elem_cs_zm(P, 0))
+        else:
+            gpu.sampler_build()
+        n_ev = args.events or min(P.n_events, 1 << 20) // world
+        n_ev = max(n_ev, 1 << 14)
+        first = rank * n_ev
+        gpu.generate_device(12345, first, min(n_ev, 1 << 16))  # warm-up
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(ext_stream)
+        acc = gpu.generate_device(12345, first, n_ev)
+        e1.record(ext_stream)
+        barrier()
+        ms_ev = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_ev], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ev = float(t.item())
+        events = {"events_per_s": world * n_ev / (ms_ev * 1e-3), "candidates": world * n_ev, "accepted_rank0": int(acc),
+                  "ms": ms_ev, "sharding": "Philox counter ranges, no collective"}
+        if world == 1:
+            n_small = min(n_ev, 1 << 18)
+            t0 = time.perf_counter()
+            out = gpu.generate(12345, 0, n_small, with_aux=False)
+            dt = time.perf_counter() - t0
+            events["e2e_events_per_s"] = n_small / dt
+            events["e2e_d2h_bytes"] = int(out["p4"].nbytes + out["pdg"].nbytes * 3 + out["npart"].nbytes)
+
+    # ---- CPU baseline beside it (rank 0, N = 1, bounded sample) --------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyoracle
+        cores = os.cpu_count() or 1
+        o = pyoracle.Oracle(P, threads=cores)
+        im_step = max(1, P.nm // 64); iy_step = max(1, P.ny // 11)
+        nc = len(range(0, P.nm, im_step)) * len(range(0, P.ny, iy_step))
+        o.fill_lumi(im_step=im_step * 4, iy_step=iy_step)  # warm caches/threads
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 10.0 and reps < 50:
+            o.fill_lumi(im_step=im_step, iy_step=iy_step)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        cpu = {"value": nc / dt, "unit": "cells/s", "cores": cores, "kind": "port",
+               "sample": f"{nc} cells (every {im_step}th m row x every {iy_step}th y column of the grid), "
+                         f"{reps} repetitions, lumi fill only; oracle/upc_oracle.c with OpenMP static m-slabs"}
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------
+    if st["qags_evals"] > 0 and stage["ms_qags"] >= stage["ms_cells"]:
+        work = FLOP_PER_QAGS_EVAL * st["qags_evals"]
+        t_k = stage["ms_qags"] * 1e-3
+        kern = "k_flux_qags_rows"
+        units = f"{st['qags_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
+    else:
+        cells_rank = len(udist.cyclic_rows(P.nm, rank, world)) * P.ny
+        work = FLOP_CELL[(pol, bk)] * cells_rank
+        t_k = stage["ms_cells"] * 1e-3
+        kern = "k_cells"
+        units = f"{cells_rank} cells x {FLOP_CELL[(pol, bk)]:.3g} flop"
+    achieved = work / t_k / 1e12 if t_k > 0 else 0.0
+    roofline = {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                "peak_source": "measured live: upcgpu_fp64_peak DFMA loop (MEASURED_PEAKS.json has no FP64 figure; "
+                               "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
+                "algorithmic_work": units, "kernel_ms": t_k * 1e3}
+
+    if rank == 0:
+        line = {
+            "metric": "lumi_cells_per_s", "value": n_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.workload], "cells": n_cells, "grid": [P.nm, P.ny],
+                       "l2": "flushed between timed steps (256 MiB device write)",
+                       "parallelism": f"m rows cyclic over {world} GPU(s); NCCL all-gather of the table" if world > 1
+                       else "single GPU"},
+            "sigma_table_ms": ms,
+            "stage_ms": stage, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "events": events,
+            "work": {"qags_integrals": st["qags_integrals"], "qags_evals": st["qags_evals"],
+                     "band_pairs": st["band_pairs"], "flux_rows": st["flux_rows"]},
+            "device": gpu.device_name(),
+        }
+        print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

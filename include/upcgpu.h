@@ -95,6 +95,11 @@ const char* upcgpu_last_error(const upcgpu_ctx* ctx);
 /* library/ABI version, and the device the context runs on */
 int upcgpu_abi_version(void);
 int upcgpu_device_name(const upcgpu_ctx* ctx, char* buf, size_t cap);
+/* the CUDA stream all work of this context is issued on, as an integer (cudaStream_t), so that a
+ * caller can record its own timing events on it; and the number of kernels of this library
+ * launched on it so far */
+int upcgpu_stream_handle(const upcgpu_ctx* ctx, uint64_t* stream);
+long long upcgpu_launch_count(const upcgpu_ctx* ctx);
 
 /* ---- tables T1-T4 -------------------------------------------------------------------- */
 /* replaces UpcCrossSection::init's calcWSRho/prepareGAA/prepareFormFac/prepareBreakupProb
@@ -153,6 +158,17 @@ int upcgpu_lumi_upload(upcgpu_ctx* ctx, int which, const double* host);
  * cs[ny*nm] (nb), ratio[ny*nm] (pol only) and totcs_mb may be NULL (results stay on device). */
 int upcgpu_fold_sigma(upcgpu_ctx* ctx, const double* sig_m, const double* sig_s, const double* sig_p,
                       double* cs, double* ratio, double* totcs_mb);
+
+/* ---- elementary-process plug-ins P1 (host code) -------------------------------------- */
+/* C access to the built-in plug-ins UpcTwoPhotonDilep (proc_id 11/13/15) and UpcTwoPhotonALP (51)
+ * (reference src/UpcTwoPhotonDilep.cpp:46-134, src/UpcTwoPhotonALP.cpp:28-33), for callers that
+ * cannot instantiate the C++ classes.  which: 0 calcCrossSectionM, 1 ...MPolS, 2 ...MPolPS. */
+int upcgpu_elem_sigma_m(int proc_id, double a_lep, double alp_mass, double alp_width, int which, const double* m,
+                        size_t n, double* out);
+/* UpcCrossSection::fillCrossSectionZM (src/UpcCrossSection.cpp:337-362): out[nm][nz] =
+ * dsigma/dz(z_iz, m_im) * (hc)^2 * 1e7 / dm; flag 0 unpolarised, 1 scalar, 2 pseudoscalar. */
+int upcgpu_elem_fill_cs_zm(int proc_id, double a_lep, double alp_mass, double alp_width, int flag, double zmin,
+                           double zmax, int nz, double mmin, double mmax, int nm, double* out);
 
 /* ---- samplers S1-S3 ------------------------------------------------------------------ */
 /* replaces the UpcSampler2D / UpcSampler1D constructors (include/UpcSampler.h:40-59, :81-109,

@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libupcgpu.so")
-SOURCES = ["upc_capi.cu", "upc_tables.cu", "upc_lumi.cu", "upc_fold.cu", "upc_events.cu"]
+SOURCES = ["upc_capi.cu", "upc_tables.cu", "upc_lumi.cu", "upc_fold.cu", "upc_events.cu", "upc_elem_capi.cpp",
+           "../host/UpcTwoPhotonDilep.cpp", "../host/UpcTwoPhotonALP.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v", "-ccbin", "/usr/bin/g++"]
@@ -20,7 +21,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 def _newest_src():
     t = 0.0
-    for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+    for root in (CSRC, os.path.join(HERE, "host"), os.path.join(os.path.dirname(HERE), "include")):
         for f in os.listdir(root):
             t = max(t, os.path.getmtime(os.path.join(root, f)))
     return t
@@ -33,9 +34,9 @@ def build(force=False, verbose=False):
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(HERE, "build", os.path.basename(s).rsplit(".", 1)[0] + ".o")
         objs.append(o)
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [NVCC, *FLAGS, "-Xcompiler", "-ffp-contract=off", "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     failed = False

@@ -63,6 +63,7 @@ SYMBOLS = [
     "upcgpu_lumi_download", "upcgpu_lumi_upload", "upcgpu_fold_sigma", "upcgpu_sampler_build",
     "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_device",
     "upcgpu_photon_pt_cdf", "upcgpu_philox", "upcgpu_invalidate_tables", "upcgpu_fp64_peak",
+    "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
 ]
 
 
@@ -106,6 +107,11 @@ def lib():
         L.upcgpu_photon_pt_cdf.argtypes = [p, d, p]
         L.upcgpu_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, sz, p]
         L.upcgpu_invalidate_tables.argtypes = [p]
+        L.upcgpu_elem_sigma_m.argtypes = [i, d, d, d, i, p, sz, p]
+        L.upcgpu_elem_fill_cs_zm.argtypes = [i, d, d, d, i, d, d, i, d, d, i, p]
+        L.upcgpu_stream_handle.argtypes = [p, C.POINTER(C.c_uint64)]
+        L.upcgpu_launch_count.argtypes = [p]
+        L.upcgpu_launch_count.restype = C.c_longlong
         L.upcgpu_fp64_peak.argtypes = [p, i, C.POINTER(d), C.POINTER(d)]
         _LIB = L
     return _LIB
@@ -180,6 +186,14 @@ class UpcGpu:
     def prepare_tables(self):
         self._chk(self.L.upcgpu_prepare_tables(self.h))
         return self.table_info()
+
+    def stream_handle(self):
+        v = C.c_uint64()
+        self._chk(self.L.upcgpu_stream_handle(self.h, C.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        return self.L.upcgpu_launch_count(self.h)
 
     def invalidate_tables(self):
         self._chk(self.L.upcgpu_invalidate_tables(self.h))
@@ -339,6 +353,28 @@ class UpcGpu:
         cdf = np.zeros(5001)
         self._chk(self.L.upcgpu_photon_pt_cdf(self.h, float(e), _p(cdf)))
         return cdf
+
+
+def elem_sigma_m(P: UpcParams, which=0, m=None):
+    """sigma(m) of the built-in elementary process of P on the grid's lower mass edges (host plug-in)."""
+    if m is None:
+        m = P.mmin + P.dm * np.arange(P.nm)
+    m = _f64(m)
+    out = np.zeros_like(m)
+    rc = lib().upcgpu_elem_sigma_m(P.proc_id, P.a_lep, P.alp_mass, P.alp_width, which, _p(m), m.size, _p(out))
+    if rc != OK:
+        raise UpcGpuError(rc, "elem_sigma_m: process not built in")
+    return out
+
+
+def elem_cs_zm(P: UpcParams, flag=0):
+    """fillCrossSectionZM for the built-in process of P: [nm][nz]."""
+    out = np.zeros((P.nm, P.nz))
+    rc = lib().upcgpu_elem_fill_cs_zm(P.proc_id, P.a_lep, P.alp_mass, P.alp_width, flag, P.zmin, P.zmax, P.nz,
+                                      P.mmin, P.mmax, P.nm, _p(out))
+    if rc != OK:
+        raise UpcGpuError(rc, "elem_cs_zm: process not built in")
+    return out
 
 
 def philox(seed, ctr0, block, n):

@@ -83,6 +83,15 @@ int upcgpu_prepare_tables(upcgpu_ctx* c)
   return prepare_tables(c);
 }
 
+int upcgpu_stream_handle(const upcgpu_ctx* c, uint64_t* stream)
+{
+  if (!c || !stream) return UPCGPU_EINVAL;
+  *stream = (uint64_t)(uintptr_t)c->stream;
+  return UPCGPU_OK;
+}
+
+long long upcgpu_launch_count(const upcgpu_ctx* c) { return c ? c->launches : -1; }
+
 int upcgpu_invalidate_tables(upcgpu_ctx* c)
 {
   if (!c) return UPCGPU_EINVAL;

@@ -35,6 +35,7 @@ struct upcgpu_ctx_impl {
   bool tables_ready = false;
   upcgpu_table_info info{};
   upcgpu_fill_stats stats{};
+  long long launches = 0;  // kernels of this library launched so far (UPC_K)
 
   // raw spline tables (x, y, c) kept for the get_table test hooks
   double *gaa_x = nullptr, *gaa_y = nullptr, *gaa_c = nullptr, *ta_y = nullptr, *ta_c = nullptr;

@@ -1,0 +1,59 @@
+// upc_elem_capi.cpp -- C entry points over the host-side elementary-process plug-ins
+// (upcgen_b200/host/UpcTwoPhoton*.cpp), for callers that cannot instantiate the C++ classes
+// (the Python tests/bench).  The C++ facade calls the classes directly.
+#include <memory>
+
+#include "../../include/upcgpu.h"
+#include "../host/UpcPhysConstants.h"
+#include "../host/UpcTwoPhotonALP.h"
+#include "../host/UpcTwoPhotonDilep.h"
+
+static std::unique_ptr<UpcElemProcess> make_process(int proc_id, double a_lep, double alp_mass, double alp_width)
+{
+  // UpcCrossSection::setElemProcess, reference src/UpcCrossSection.cpp:67-114
+  switch (proc_id) {
+    case 11:
+    case 13:
+    case 15: {
+      auto p = std::make_unique<UpcTwoPhotonDilep>(proc_id);
+      p->aLep = a_lep;
+      return p;
+    }
+    case 51: return std::make_unique<UpcTwoPhotonALP>(alp_mass, alp_width);
+    default: return nullptr;
+  }
+}
+
+extern "C" {
+
+int upcgpu_elem_sigma_m(int proc_id, double a_lep, double alp_mass, double alp_width, int which, const double* m,
+                        size_t n, double* out)
+{
+  auto p = make_process(proc_id, a_lep, alp_mass, alp_width);
+  if (!p || !m || !out || which < 0 || which > 2) return UPCGPU_EINVAL;
+  for (size_t i = 0; i < n; i++)
+    out[i] = which == 0 ? p->calcCrossSectionM(m[i]) : which == 1 ? p->calcCrossSectionMPolS(m[i]) : p->calcCrossSectionMPolPS(m[i]);
+  return UPCGPU_OK;
+}
+
+// UpcCrossSection::fillCrossSectionZM, reference src/UpcCrossSection.cpp:337-362
+int upcgpu_elem_fill_cs_zm(int proc_id, double a_lep, double alp_mass, double alp_width, int flag, double zmin,
+                           double zmax, int nz, double mmin, double mmax, int nm, double* out)
+{
+  auto p = make_process(proc_id, a_lep, alp_mass, alp_width);
+  if (!p || !out || flag < 0 || flag > 2 || nz < 1 || nm < 1) return UPCGPU_EINVAL;
+  constexpr double scalingFactor = phys_consts::hc * phys_consts::hc * 1e7; // to [nb]
+  const double dm = (mmax - mmin) / nm;
+  const double dz = (zmax - zmin) / nz;
+  for (int im = 0; im < nm; ++im) {
+    const double m = mmin + dm * im;
+    for (int iz = 0; iz < nz; ++iz) {
+      const double z = zmin + dz * iz;
+      const double cs = flag == 0 ? p->calcCrossSectionZM(z, m) : flag == 1 ? p->calcCrossSectionZMPolS(z, m) : p->calcCrossSectionZMPolPS(z, m);
+      out[(size_t)im * nz + iz] = cs * scalingFactor / dm;
+    }
+  }
+  return UPCGPU_OK;
+}
+
+} // extern "C"

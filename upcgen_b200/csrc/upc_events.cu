@@ -418,7 +418,7 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
     UPC_CUDA(c, cudaMemsetAsync(s->n_acc, 0, sizeof(unsigned long long), st));
     UPC_CUDA(c, cudaMemsetAsync(s->err, 0, sizeof(int), st));
     const unsigned g = (unsigned)((cn + 127) / 128);
-    k_ev_sample<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, P.nonzero_gam_pt ? s->keys : nullptr,
+    UPC_K(c), k_ev_sample<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, P.nonzero_gam_pt ? s->keys : nullptr,
                                    s->err);
     int n_uniq = 0;
     if (P.nonzero_gam_pt) {
@@ -431,9 +431,9 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
       rc = ensure_scratch(c, 0, (size_t)n_uniq);
       if (rc) return rc;
       s = (EvScratch*)c->ev;
-      k_pt_tables<<<n_uniq, 256, 0, st>>>(n_uniq, s->uniq, nullptr, c->ff_seg, c->p.gtot, c->p.R, s->cdf);
+      UPC_K(c), k_pt_tables<<<n_uniq, 256, 0, st>>>(n_uniq, s->uniq, nullptr, c->ff_seg, c->p.gtot, c->p.R, s->cdf);
     }
-    k_ev_kin<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, s->uniq, n_uniq, s->cdf, s->npart, s->pdg,
+    UPC_K(c), k_ev_kin<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, s->uniq, n_uniq, s->cdf, s->npart, s->pdg,
                                 s->status, s->mother, s->p4, s->aux, s->n_acc);
     unsigned long long acc = 0;
     int herr = 0;
@@ -467,7 +467,7 @@ int photon_pt_cdf(upcgpu_ctx* c, double e, double* cdf)
   UPC_CUDA(c, cudaMalloc(&de, sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&dc, (kPtBins + 1) * sizeof(double)));
   UPC_CUDA(c, cudaMemcpy(de, &e, sizeof(double), cudaMemcpyHostToDevice));
-  k_pt_tables<<<1, 256, 0, c->stream>>>(1, nullptr, de, c->ff_seg, c->p.gtot, c->p.R, dc);
+  UPC_K(c), k_pt_tables<<<1, 256, 0, c->stream>>>(1, nullptr, de, c->ff_seg, c->p.gtot, c->p.R, dc);
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   UPC_CUDA(c, cudaGetLastError());
   UPC_CUDA(c, cudaMemcpy(cdf, dc, (kPtBins + 1) * sizeof(double), cudaMemcpyDeviceToHost));

@@ -85,7 +85,7 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
   if (sig_s) UPC_CUDA(c, cudaMemcpyAsync(dsig + p.nm, sig_s, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
   if (sig_p) UPC_CUDA(c, cudaMemcpyAsync(dsig + 2 * p.nm, sig_p, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
   dim3 grid((p.nm + 31) / 32, (p.ny + 31) / 32), block(32, 8);
-  k_fold<<<grid, block, 0, st>>>(p.nm, p.ny, p.use_pol, c->lumi[0], c->lumi[1], c->lumi[2], dsig, dsig + p.nm,
+  UPC_K(c), k_fold<<<grid, block, 0, st>>>(p.nm, p.ny, p.use_pol, c->lumi[0], c->lumi[1], c->lumi[2], dsig, dsig + p.nm,
                                  dsig + 2 * p.nm, c->cs, c->ratio);
   // totCS
   double total = 0;
@@ -98,7 +98,7 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
     double* outb = b0;
     while (true) {
       size_t nblk = (cur + 4095) / 4096;
-      k_sum_blocks<<<(unsigned)nblk, 256, 0, st>>>(a, cur, outb);
+      UPC_K(c), k_sum_blocks<<<(unsigned)nblk, 256, 0, st>>>(a, cur, outb);
       if (nblk == 1) break;
       a = outb;
       outb = (outb == b0) ? b1 : b0;
@@ -190,15 +190,15 @@ int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const dou
     UPC_CUDA(c, cudaMalloc(&c->edges_z, (p.nz + 1) * sizeof(double)));
   }
   const double dm = (p.mmax - p.mmin) / p.nm, dy = (p.ymax - p.ymin) / p.ny, dz = (p.zmax - p.zmin) / p.nz;
-  k_edges<<<(p.ny + 128) / 128, 128, 0, st>>>(p.ymin, dy, p.ny, c->edges_y);
-  k_edges<<<(p.nm + 128) / 128, 128, 0, st>>>(p.mmin, dm, p.nm, c->edges_m);
-  k_edges<<<(p.nz + 128) / 128, 128, 0, st>>>(p.zmin, dz, p.nz, c->edges_z);
+  UPC_K(c), k_edges<<<(p.ny + 128) / 128, 128, 0, st>>>(p.ymin, dy, p.ny, c->edges_y);
+  UPC_K(c), k_edges<<<(p.nm + 128) / 128, 128, 0, st>>>(p.mmin, dm, p.nm, c->edges_m);
+  UPC_K(c), k_edges<<<(p.nz + 128) / 128, 128, 0, st>>>(p.zmin, dz, p.nz, c->edges_z);
   double *term = nullptr, *mean = nullptr;
   UPC_CUDA(c, cudaMalloc(&term, n * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&mean, sizeof(double)));
-  k_running_mean<<<1, 1, 0, st>>>(c->cs, n, mean);
-  k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->cs, n, mean, term);
-  k_seq_cumsum<<<1, 1, 0, st>>>(term, n, c->sum2d);
+  UPC_K(c), k_running_mean<<<1, 1, 0, st>>>(c->cs, n, mean);
+  UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->cs, n, mean, term);
+  UPC_K(c), k_seq_cumsum<<<1, 1, 0, st>>>(term, n, c->sum2d);
   // z samplers
   const size_t nzm = (size_t)p.nm * p.nz, nsz = (size_t)p.nm * (p.nz + 1);
   double* dz_in = nullptr;
@@ -212,12 +212,12 @@ int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const dou
     UPC_CUDA(c, cudaMalloc(&dz_in, nzm * sizeof(double)));
     if (!c->sumz) UPC_CUDA(c, cudaMalloc(&c->sumz, nsz * sizeof(double)));
     UPC_CUDA(c, cudaMemcpyAsync(dz_in, first, nzm * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_pdf_init_rows<<<(p.nm + 63) / 64, 64, 0, st>>>(dz_in, p.nm, p.nz, c->sumz);
+    UPC_K(c), k_pdf_init_rows<<<(p.nm + 63) / 64, 64, 0, st>>>(dz_in, p.nm, p.nz, c->sumz);
     if (p.use_pol) {
       if (!c->sumz_ps) UPC_CUDA(c, cudaMalloc(&c->sumz_ps, nsz * sizeof(double)));
       UPC_CUDA(c, cudaStreamSynchronize(st));
       UPC_CUDA(c, cudaMemcpyAsync(dz_in, cszm_ps, nzm * sizeof(double), cudaMemcpyHostToDevice, st));
-      k_pdf_init_rows<<<(p.nm + 63) / 64, 64, 0, st>>>(dz_in, p.nm, p.nz, c->sumz_ps);
+      UPC_K(c), k_pdf_init_rows<<<(p.nm + 63) / 64, 64, 0, st>>>(dz_in, p.nm, p.nz, c->sumz_ps);
     }
   }
   UPC_CUDA(c, cudaStreamSynchronize(st));
@@ -267,7 +267,7 @@ int sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int* ybin,
   UPC_CUDA(c, cudaMalloc(&dyb, n * sizeof(int)));
   UPC_CUDA(c, cudaMalloc(&dmb, n * sizeof(int)));
   UPC_CUDA(c, cudaMemcpy(du, u, 2 * n * sizeof(double), cudaMemcpyHostToDevice));
-  k_sample_ym<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(du, n, c->sum2d, p.ny, p.nm, c->edges_y, c->edges_m, dk,
+  UPC_K(c), k_sample_ym<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(du, n, c->sum2d, p.ny, p.nm, c->edges_y, c->edges_m, dk,
                                                                  dyb, dmb, dy, dm);
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   UPC_CUDA(c, cudaGetLastError());
@@ -291,7 +291,7 @@ int sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, 
   UPC_CUDA(c, cudaMalloc(&dmb, n * sizeof(int)));
   UPC_CUDA(c, cudaMemcpy(du, u, n * sizeof(double), cudaMemcpyHostToDevice));
   UPC_CUDA(c, cudaMemcpy(dmb, mbin, n * sizeof(int), cudaMemcpyHostToDevice));
-  k_sample_z<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(dmb, du, n, tabz, p.nm, p.nz, c->edges_z, dz);
+  UPC_K(c), k_sample_z<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(dmb, du, n, tabz, p.nm, p.nz, c->edges_z, dz);
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   UPC_CUDA(c, cudaGetLastError());
   UPC_CUDA(c, cudaMemcpy(z, dz, n * sizeof(double), cudaMemcpyDeviceToHost));

@@ -421,19 +421,19 @@ int prepare_tables(upcgpu_ctx* c)
   c->info.factor = p.Z * p.Z * kAlpha / M_PI / M_PI / kHc / kHc;  // :120
 
   Gl5 gl = make_gl5(false);
-  k_rho0<<<1, 256, 0, st>>>(p.R, p.a, p.A, c->d_scal);
-  k_ta<<<kNB, 256, 0, st>>>(p.R, p.a, c->d_scal, c->gaa_x, c->ta_y);
-  k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->ta_y, kNB, c->ta_c);
-  k_gaa<<<kNB, 256, 0, st>>>(c->gaa_x, c->ta_y, c->ta_c, csNN, gl, c->gaa_y);
-  k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->gaa_y, kNB, c->gaa_c);
-  k_segs_from_arrays<<<1, 256, 0, st>>>(c->gaa_x, c->gaa_y, c->gaa_c, kNB, c->gaa_seg, 1.0);
+  UPC_K(c), k_rho0<<<1, 256, 0, st>>>(p.R, p.a, p.A, c->d_scal);
+  UPC_K(c), k_ta<<<kNB, 256, 0, st>>>(p.R, p.a, c->d_scal, c->gaa_x, c->ta_y);
+  UPC_K(c), k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->ta_y, kNB, c->ta_c);
+  UPC_K(c), k_gaa<<<kNB, 256, 0, st>>>(c->gaa_x, c->ta_y, c->ta_c, csNN, gl, c->gaa_y);
+  UPC_K(c), k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->gaa_y, kNB, c->gaa_c);
+  UPC_K(c), k_segs_from_arrays<<<1, 256, 0, st>>>(c->gaa_x, c->gaa_y, c->gaa_c, kNB, c->gaa_seg, 1.0);
 
-  k_ff_y<<<(kNQ2 + 255) / 256, 256, 0, st>>>(p.R, p.a, c->d_scal, c->ff_y);
+  UPC_K(c), k_ff_y<<<(kNQ2 + 255) / 256, 256, 0, st>>>(p.R, p.a, c->d_scal, c->ff_y);
   {
     int nthr = (kNQ2 - 2 + kSpChunk - 1) / kSpChunk;
-    k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kQ2min, kDQ2, c->ff_y, kNQ2, c->ff_c);
+    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kQ2min, kDQ2, c->ff_y, kNQ2, c->ff_c);
   }
-  k_segs_uniform<<<(kNQ2 + 255) / 256, 256, 0, st>>>(kQ2min, kDQ2, c->ff_y, c->ff_c, kNQ2, c->ff_seg, kNQ2 - 1);
+  UPC_K(c), k_segs_uniform<<<(kNQ2 + 255) / 256, 256, 0, st>>>(kQ2min, kDQ2, c->ff_y, c->ff_c, kNQ2, c->ff_seg, kNQ2 - 1);
 
   int use_bk = p.breakup_mode > 1;
   if (use_bk) {
@@ -445,15 +445,15 @@ int prepare_tables(upcgpu_ctx* c)
     UPC_CUDA(c, cudaMalloc(&c->bk_seg, (size_t)(c->bk_nknots + 1) * sizeof(SplineSeg)));
     UPC_CUDA(c, cudaMalloc(&c->bk_table, sizeof(BkTable)));
     }
-    k_bk_init<<<1, 1, 0, st>>>(p.g1, (BkTable*)c->bk_table);
-    k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
+    UPC_K(c), k_bk_init<<<1, 1, 0, st>>>(p.g1, (BkTable*)c->bk_table);
+    UPC_K(c), k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
                                                           c->bk_y);
     int nthr = (c->bk_nknots - 2 + kSpChunk - 1) / kSpChunk;
-    k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
-    k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
+    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
+    UPC_K(c), k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
                                                               c->bk_seg, c->bk_nknots - 1);
   }
-  k_table_scalars<<<1, 1, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, c->d_scal + 1);
+  UPC_K(c), k_table_scalars<<<1, 1, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, c->d_scal + 1);
   cudaEventRecord(e1, st);
   UPC_CUDA(c, cudaStreamSynchronize(st));
   UPC_CUDA(c, cudaGetLastError());
@@ -501,11 +501,11 @@ int eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, double* out)
   UPC_CUDA(c, cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice));
   unsigned g = (unsigned)((n + 127) / 128);
   if (which == UPCGPU_TABLE_GAA) {
-    k_eval_arrays<<<g, 128, 0, c->stream>>>(c->gaa_x, c->gaa_seg, kNB, (kNB - 1) / 20., dx, n, dout);
+    UPC_K(c), k_eval_arrays<<<g, 128, 0, c->stream>>>(c->gaa_x, c->gaa_seg, kNB, (kNB - 1) / 20., dx, n, dout);
   } else if (which == UPCGPU_TABLE_FORMFAC) {
-    k_eval_uniform<<<g, 128, 0, c->stream>>>(c->ff_seg, kNQ2 - 1, kQ2min, kDQ2, dx, n, dout);
+    UPC_K(c), k_eval_uniform<<<g, 128, 0, c->stream>>>(c->ff_seg, kNQ2 - 1, kQ2min, kDQ2, dx, n, dout);
   } else if (which == UPCGPU_TABLE_BREAKUP && c->bk_seg) {
-    k_eval_uniform<<<g, 128, 0, c->stream>>>(c->bk_seg, c->tab.bk_n, kBkBmin, kBkDb, dx, n, dout);
+    UPC_K(c), k_eval_uniform<<<g, 128, 0, c->stream>>>(c->bk_seg, c->tab.bk_n, kBkBmin, kBkDb, dx, n, dout);
   } else {
     cudaFree(dx); cudaFree(dout);
     c->err = "eval_table: table not available";
@@ -524,7 +524,7 @@ int breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out)
   UPC_CUDA(c, cudaMalloc(&db, n * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&dout, n * sizeof(double)));
   UPC_CUDA(c, cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
-  k_bk_raw<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const BkTable*)c->bk_table, db, mode, n, dout);
+  UPC_K(c), k_bk_raw<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const BkTable*)c->bk_table, db, mode, n, dout);
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   UPC_CUDA(c, cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost));
   cudaFree(db);
