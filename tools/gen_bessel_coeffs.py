@@ -75,6 +75,7 @@ def fit(f, tol, nmax=40):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
+    ap.add_argument("--device", action="store_true", help="emit the CUDA copy (__constant__ arrays)")
     args = ap.parse_args()
     tol = mp.mpf("2e-18")
 
@@ -167,16 +168,24 @@ def main():
         " * src/UpcCrossSection.cpp:171-172,189), which are not available in this image. */",
         "#pragma once",
         "#ifndef UPC_BESSEL_CONST",
-        "#define UPC_BESSEL_CONST static const double",
+        "#define UPC_BESSEL_CONST " + ("static __constant__ double" if args.device else "static const double"),
         "#endif",
     ]
     for name, f in tables:
         co = fit(f, tol)
         lines.append(f"#define UPC_{name}_N {len(co)}")
-        lines.append(f"UPC_BESSEL_CONST UPC_{name}[{len(co)}] = {{")
-        for c in co:
-            lines.append("  " + mp.nstr(c, 20, min_fixed=0, max_fixed=0) + ",")
-        lines.append("};")
+        if args.device:
+            # value list as a macro too, so that several tables can be concatenated into the one
+            # __constant__ block the QAGS kernel streams with LDCU (upc_hot.cuh)
+            lines.append(f"#define UPC_{name}_VALUES \\")
+            for i, c in enumerate(co):
+                lines.append("  " + mp.nstr(c, 20, min_fixed=0, max_fixed=0) + ("" if i == len(co) - 1 else ", \\"))
+            lines.append(f"UPC_BESSEL_CONST UPC_{name}[{len(co)}] = {{UPC_{name}_VALUES}};")
+        else:
+            lines.append(f"UPC_BESSEL_CONST UPC_{name}[{len(co)}] = {{")
+            for c in co:
+                lines.append("  " + mp.nstr(c, 20, min_fixed=0, max_fixed=0) + ",")
+            lines.append("};")
         print(name, len(co))
     with open(args.out, "w") as fh:
         fh.write("\n".join(lines) + "\n")

@@ -16,70 +16,153 @@ namespace upc {
 
 // GK21 nodes/weights (QUADPACK dqk21).  Stored pair-wise in the order GSL's qk() visits them:
 // first the 5 Gauss nodes (xgk[1],xgk[3],..,xgk[9]) then the 5 Kronrod-only nodes
-// (xgk[0],xgk[2],..,xgk[8]), so that the partial sums are formed in the same order.
-__device__ const double kGkX[10] = {
+// (xgk[0],xgk[2],..,xgk[8]), so that the partial sums are formed in the same order; entry 10 is
+// the centre (abscissa 0).  Gauss weights are 0 for the Kronrod-only nodes.
+__constant__ double kGkX[11] = {
   0.973906528517171720077964012084452, 0.865063366688984510732096688423493,
   0.679409568299024406234327365114874, 0.433395394129247190799265943165784,
   0.148874338981631210884826001129720,
   0.995657163025808080735527280689003, 0.930157491355708226001207180059508,
   0.780817726586416897063717578345042, 0.562757134668604683339000099272694,
-  0.294392862701460198131126603103866};
-__device__ const double kGkWk[10] = {
+  0.294392862701460198131126603103866, 0.0};
+__constant__ double kGkWk[11] = {
   0.032558162307964727478818972459390, 0.075039674810919952767043140916190,
   0.109387158802297641899210590325805, 0.134709217311473325928054001771707,
   0.147739104901338491374841515972068,
   0.011694638867371874278064396062192, 0.054755896574351996031381300244580,
   0.093125454583697605535065465083366, 0.123491976262065851077958109585166,
-  0.142775938577060080797094273138717};
-__device__ const double kGkWg[5] = {
+  0.142775938577060080797094273138717, 0.149445554002916905664936468389821};
+__constant__ double kGkWg[10] = {
   0.066671344308688137593568809893332, 0.149451349150580593145776339657697,
   0.219086362515982043995534934228163, 0.269266719309996355091226921569469,
-  0.295524224714752870173815619188769};
+  0.295524224714752870173815619188769, 0., 0., 0., 0., 0.};
 constexpr double kGkWkC = 0.149445554002916905664936468389821;
-// position of (pair p) in GSL's fv1/fv2 index j (result_asc is summed over j = 0..9)
-__device__ const int kGkJ[10] = {1, 3, 5, 7, 9, 0, 2, 4, 6, 8};
 
 struct GkOut {
   double result, abserr, resabs, resasc;
 };
 
 // gsl_integration_qk (integration/qk.c) specialised to the 21-point rule.
+//   F provides  void pair(double x1, double x2, double& f1, double& f2)  -- two integrand
+//   evaluations through ONE inlined call site (two interleaved instruction streams for ILP, and
+//   a kernel whose hot loop stays small enough for the instruction cache).
+//   fv: per-thread scratch of 20 doubles at fv[j * fv_stride] (shared memory, lane-interleaved).
+// Summation order: the centre term first, then the pairs in GSL's order; result_asc in GSL's
+// index order.  The centre is evaluated by the same pair() site (its second slot re-evaluates
+// the centre: one redundant evaluation in 22).
 template <class F>
-__device__ __forceinline__ GkOut gk21(const F& f, double a, double b)
+__device__ __forceinline__ GkOut gk21(const F& f, double a, double b, double* fv, int fv_stride)
 {
-  double fv1[10], fv2[10];
   const double center = 0.5 * (a + b);
   const double half_length = 0.5 * (b - a);
   const double abs_half_length = fabs(half_length);
-  const double f_center = f(center);
-  double result_gauss = 0;
-  double result_kronrod = f_center * kGkWkC;
-  double result_abs = fabs(result_kronrod);
+  double f_center = 0, result_gauss = 0, result_kronrod = 0, result_abs = 0;
 #pragma unroll 1
-  for (int p = 0; p < 10; ++p) {
+  for (int it = 0; it < 11; ++it) {
+    const int p = it == 0 ? 10 : it - 1;  // visiting order: centre (10), then pairs 0..9
     const double abscissa = half_length * kGkX[p];
-    const double fval1 = f(center - abscissa);
-    const double fval2 = f(center + abscissa);
-    const double fsum = fval1 + fval2;
-    fv1[kGkJ[p]] = fval1;
-    fv2[kGkJ[p]] = fval2;
-    if (p < 5) result_gauss += kGkWg[p] * fsum;
-    result_kronrod += kGkWk[p] * fsum;
-    result_abs += kGkWk[p] * (fabs(fval1) + fabs(fval2));
+    double fval1, fval2;
+    f.pair(center - abscissa, center + abscissa, fval1, fval2);
+    if (p == 10) {
+      f_center = fval1;
+      result_kronrod = f_center * kGkWkC;
+      result_abs = fabs(result_kronrod);
+    } else {
+      const double fsum = fval1 + fval2;
+      fv[(2 * p) * fv_stride] = fval1;
+      fv[(2 * p + 1) * fv_stride] = fval2;
+      result_gauss += kGkWg[p] * fsum;
+      result_kronrod += kGkWk[p] * fsum;
+      result_abs += kGkWk[p] * (fabs(fval1) + fabs(fval2));
+    }
   }
   const double mean = result_kronrod * 0.5;
   double result_asc = kGkWkC * fabs(f_center - mean);
-  // GSL sums j = 0..9 in index order with wgk[j]; wgk[j] belongs to pair p with kGkJ[p] == j
-#pragma unroll
+  // GSL sums j = 0..9 in xgk index order: j even -> pair 5 + j/2, j odd -> pair (j-1)/2
+#pragma unroll 1
   for (int j = 0; j < 10; ++j) {
     const int p = (j & 1) ? (j >> 1) : (5 + (j >> 1));
-    result_asc += kGkWk[p] * (fabs(fv1[j] - mean) + fabs(fv2[j] - mean));
+    result_asc += kGkWk[p] * (fabs(fv[(2 * p) * fv_stride] - mean) + fabs(fv[(2 * p + 1) * fv_stride] - mean));
   }
   double err = (result_kronrod - result_gauss) * half_length;
   result_kronrod *= half_length;
   result_abs *= abs_half_length;
   result_asc *= abs_half_length;
   // rescale_error
+  err = fabs(err);
+  if (result_asc != 0 && err != 0) {
+    double s = 200 * err / result_asc;
+    double scale = s * sqrt(s);  // pow(s, 1.5)
+    err = scale < 1 ? result_asc * scale : result_asc;
+  }
+  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
+    double min_err = 50 * DBL_EPSILON * result_abs;
+    if (min_err > err) err = min_err;
+  }
+  GkOut o;
+  o.result = result_kronrod;
+  o.abserr = err;
+  o.resabs = result_abs;
+  o.resasc = result_asc;
+  return o;
+}
+
+// signed abscissas of the 21 nodes in storage order: node 2p = -x_p, node 2p+1 = +x_p (pairs p in
+// the order of kGkX), node 20 = centre
+__constant__ double kGkNode[21] = {
+  -0.973906528517171720077964012084452, 0.973906528517171720077964012084452,
+  -0.865063366688984510732096688423493, 0.865063366688984510732096688423493,
+  -0.679409568299024406234327365114874, 0.679409568299024406234327365114874,
+  -0.433395394129247190799265943165784, 0.433395394129247190799265943165784,
+  -0.148874338981631210884826001129720, 0.148874338981631210884826001129720,
+  -0.995657163025808080735527280689003, 0.995657163025808080735527280689003,
+  -0.930157491355708226001207180059508, 0.930157491355708226001207180059508,
+  -0.780817726586416897063717578345042, 0.780817726586416897063717578345042,
+  -0.562757134668604683339000099272694, 0.562757134668604683339000099272694,
+  -0.294392862701460198131126603103866, 0.294392862701460198131126603103866, 0.0};
+
+// The same 21-point rule with the integrand evaluated three nodes at a time (F::tri) -- 7 trips,
+// no redundant evaluation -- into fv[0..20] (node order of kGkNode), followed by the weighted
+// sums in GSL's order.  fv: per-thread scratch of 21 doubles at fv[n * fv_stride].
+template <class F>
+__device__ __forceinline__ GkOut gk21_tri(const F& f, double a, double b, double* fv, int fv_stride)
+{
+  const double center = 0.5 * (a + b);
+  const double half_length = 0.5 * (b - a);
+  const double abs_half_length = fabs(half_length);
+#pragma unroll 1
+  for (int it = 0; it < 7; ++it) {
+    const int n = 3 * it;
+    double f0, f1, f2;
+    f.tri(fma(half_length, kGkNode[n], center), fma(half_length, kGkNode[n + 1], center),
+          fma(half_length, kGkNode[n + 2], center), f0, f1, f2);
+    fv[n * fv_stride] = f0;
+    fv[(n + 1) * fv_stride] = f1;
+    fv[(n + 2) * fv_stride] = f2;
+  }
+  const double f_center = fv[20 * fv_stride];
+  double result_gauss = 0;
+  double result_kronrod = f_center * kGkWkC;
+  double result_abs = fabs(result_kronrod);
+#pragma unroll 1
+  for (int p = 0; p < 10; ++p) {
+    const double fval1 = fv[(2 * p) * fv_stride], fval2 = fv[(2 * p + 1) * fv_stride];
+    const double fsum = fval1 + fval2;
+    result_gauss += kGkWg[p] * fsum;
+    result_kronrod += kGkWk[p] * fsum;
+    result_abs += kGkWk[p] * (fabs(fval1) + fabs(fval2));
+  }
+  const double mean = result_kronrod * 0.5;
+  double result_asc = kGkWkC * fabs(f_center - mean);
+#pragma unroll 1
+  for (int j = 0; j < 10; ++j) {
+    const int p = (j & 1) ? (j >> 1) : (5 + (j >> 1));
+    result_asc += kGkWk[p] * (fabs(fv[(2 * p) * fv_stride] - mean) + fabs(fv[(2 * p + 1) * fv_stride] - mean));
+  }
+  double err = (result_kronrod - result_gauss) * half_length;
+  result_kronrod *= half_length;
+  result_abs *= abs_half_length;
+  result_asc *= abs_half_length;
   err = fabs(err);
   if (result_asc != 0 && err != 0) {
     double s = 200 * err / result_asc;
@@ -106,7 +189,7 @@ struct EpsTable {
   double res3la[3];
 };
 
-__device__ inline void qelg(EpsTable& table, double& result, double& abserr)
+__device__ __noinline__ void qelg(EpsTable& table, double& result, double& abserr)
 {
   double* epstab = table.rlist2;
   double* res3la = table.res3la;
@@ -201,13 +284,25 @@ __device__ inline void qelg(EpsTable& table, double& result, double& abserr)
 // (1000) in all the places where the algorithm's decisions depend on it (qpsrt's `top`,
 // increase_nrmax's `jupbnd`, the iteration cap); running out of CAP sets `overflow` and the
 // integral is redone by a second pass with cap = 1000.
-struct Qags {
-  static constexpr int kLimit = 1000;
-  // interval list (gsl_integration_workspace), storage provided by the caller: local arrays of
-  // `cap` entries in the main pass, a global-memory workspace of 1000 in the overflow pass
+// interval-list storage: in-thread arrays (main pass) ...
+template <int CAP>
+struct QagsLocalStore {
+  double alist[CAP], blist[CAP], rlist[CAP], elist[CAP];
+  short order[CAP], level[CAP];
+  static constexpr int cap = CAP;
+};
+// ... or a caller-provided global-memory workspace of the reference's full size (overflow pass)
+struct QagsGlobalStore {
   double *alist, *blist, *rlist, *elist;
   short *order, *level;
-  int cap;
+  static constexpr int cap = 1000;
+};
+
+template <class Store>
+struct Qags : Store {
+  static constexpr int kLimit = 1000;
+  using Store::alist; using Store::blist; using Store::rlist; using Store::elist;
+  using Store::order; using Store::level; using Store::cap;
   int size, nrmax, i, maximum_level;
   // driver state (integration/qags.c)
   double a0, b0, epsabs, epsrel;
@@ -410,7 +505,7 @@ struct Qags {
   }
 
   // tail of qags(): choice between the extrapolated value and the plain sum
-  __device__ bool finish(bool direct_sum)
+  __device__ __noinline__ bool finish(bool direct_sum)
   {
     bool compute = direct_sum;
     bool ret_err = false;
