@@ -382,3 +382,86 @@ def test_events_distributions_independent_of_batching(get_gpu, get_oracle):
     p = a["p4"][:, 0] + a["p4"][:, 1]
     minv = np.sqrt(p[:, 3] ** 2 - p[:, 0] ** 2 - p[:, 1] ** 2 - p[:, 2] ** 2)
     assert np.max(np.abs(minv - a["aux"][:, 1]) / a["aux"][:, 1]) < 1e-9
+
+
+# ---- committed golden fixtures (tests/golden, generated by tools/gen_golden.py) -----------------
+import json as _json
+import os as _os
+
+_GOLD = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("cfg,tol", [("cfg1", RTOL_POINT), ("cfg2", RTOL_FF), ("cfg3", RTOL_POINT), ("cfg4", RTOL_FF),
+                                     ("cfg5", RTOL_POINT)])
+def test_golden_subgrids(get_gpu, capi, cfg, tol):
+    """Every BASELINE config on a sub-grid that includes the corner cells, against the fixtures."""
+    P, g = get_gpu(cfg)
+    gold = np.load(_os.path.join(_GOLD, f"{cfg}_subgrid.npz"))
+    M, Y = np.meshgrid(gold["M"], gold["Y"], indexing="ij")
+    if P.use_pol:
+        s, p = g.lumi_cells(M, Y)
+        es, ep = relerr(s, gold["lumi_s"]), relerr(p, gold["lumi_p"])
+        print(cfg, "golden pol max rel", es, ep)
+        assert es < tol and ep < tol
+    else:
+        got = g.lumi_cells(M, Y)
+        ref = gold["lumi"]
+        nz = ref > 1e-280          # Q7: cells beyond the Bessel underflow are 0 on both sides
+        e = relerr(got[nz], ref[nz])
+        print(cfg, "golden max rel", e, "cells", ref.size, "zero cells", int((~nz).sum()))
+        assert e < tol and np.all(got[~nz] < 1e-270)
+    info = g.table_info()
+    assert info.rho0 == pytest.approx(float(gold["rho0"]), rel=1e-13)
+    _, gy, _ = g.get_table(capi.TABLE_GAA, 0, 200)
+    assert np.max(np.abs(gy - gold["gaa_y"])) < 1e-12
+    if "bk_spline" in gold:
+        assert np.max(np.abs(g.eval_table(capi.TABLE_BREAKUP, gold["bk_b"]) - gold["bk_spline"])) < 1e-12
+    if "ff_flux" in gold:
+        fl, ne = g.flux_form(gold["ff_b"][:, None], gold["ff_k"][None, :], with_neval=True)
+        assert np.array_equal(ne, gold["ff_neval"])
+        big = gold["ff_flux"] > 1e-12 * gold["ff_flux"].max()
+        assert relerr(fl[big], gold["ff_flux"][big]) < tol
+    assert relerr(g.flux_point(gold["pt_b"][:, None], gold["pt_k"][None, :])[gold["pt_flux"] > 1e-280],
+                  gold["pt_flux"][gold["pt_flux"] > 1e-280]) < 1e-12
+    if "sigma_m" in gold:
+        assert np.array_equal(capi.elem_sigma_m(P, 0, gold["M"]), gold["sigma_m"])
+
+
+def test_qags_follows_the_oracle_on_the_whole_grid(get_gpu):
+    """Size-independent property at BASELINE's full size: over all 8.46 M form-factor flux integrals
+    of the cfg2 grid the device QAGS performs exactly as many integrand evaluations as the oracle's
+    (tests/golden/cfg2_qags_counts.json), i.e. it takes the same bisection/extrapolation decisions."""
+    P, g = get_gpu("cfg2")
+    g.fill_lumi_shard(0, 1)
+    st = g.fill_stats()
+    fx = _json.load(open(_os.path.join(_GOLD, "cfg2_qags_counts.json")))
+    assert st["qags_integrals"] == fx["qags_integrals"]
+    assert st["qags_evals"] == fx["qags_evals"]
+    assert st["qags_errors"] == 0 and st["qags_overflow"] == 0
+
+
+def test_sharded_fill_equals_monolithic_form_factor(get_gpu):
+    """Shards (cyclic m rows) assembled through the gather/unpack path reproduce the single-shot
+    table bit for bit (form-factor + breakup, 3 shards, one device)."""
+    import ctypes as C
+    from upcgen_b200.config import named_config
+    extra = "BINS_M 23\nBINS_Y 10\n"
+    P, g = get_gpu("cfg2", extra)
+    full = g.fill_lumi()
+    cudart = C.CDLL("libcudart.so.12")
+    world = 3
+    parts = []
+    for r in range(world):
+        g.fill_lumi_shard(r, world)
+        ptr, n = g.lumi_shard_buffer(0)
+        host = np.zeros(n)
+        assert cudart.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(n * 8), 2) == 0
+        parts.append(host)
+    gptr, gn = g.lumi_gather_buffer(0, world)
+    allp = np.concatenate(parts)
+    assert allp.size == gn
+    assert cudart.cudaMemcpy(C.c_void_p(gptr), C.c_void_p(allp.ctypes.data), C.c_size_t(gn * 8), 1) == 0
+    g.lumi_unpack(world)
+    assert np.array_equal(g.lumi_download(0), full)
+    from upcgen_b200 import dist as udist
+    assert np.array_equal(udist.unpack_host(allp, P.nm, P.ny, world), full)
