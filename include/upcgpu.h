@@ -188,6 +188,15 @@ int upcgpu_sample_ym(upcgpu_ctx* ctx, const double* u, size_t n, long long* k, i
  * ps selects the pseudoscalar set */
 int upcgpu_sample_z(upcgpu_ctx* ctx, const int* mbin, const double* u, size_t n, int ps, double* z);
 
+/* Generic forms of S1/S2 for the UpcSampler1D / UpcSampler2D classes (include/UpcSampler.h),
+ * which take an arbitrary histogram: gsl_histogram[2d]_pdf_init on bins[n] -> sum[n+1], and
+ * gsl_histogram2d_pdf_sample / gsl_histogram_pdf_sample with injected uniforms (host buffers). */
+int upcgpu_hist_pdf_init(upcgpu_ctx* ctx, const double* bins, size_t n, double* sum);
+int upcgpu_hist_sample2d(upcgpu_ctx* ctx, const double* sum, int nx, int ny, const double* xedges,
+                         const double* yedges, const double* u, size_t n, long long* k, double* x, double* y);
+int upcgpu_hist_sample1d(upcgpu_ctx* ctx, const double* sum, int n, const double* edges, const double* u,
+                         size_t nsamp, double* x);
+
 /* ---- events E1-E5 -------------------------------------------------------------------- */
 #define UPCGPU_MAX_PART 4
 /* replaces the body of UpcGenerator::generateEvent (src/UpcGenerator.cpp:715-832) incl.

@@ -1,0 +1,98 @@
+"""The C++ host facade (upcgen_b200/host: UpcCrossSection / UpcSampler / UpcGenerator with the
+reference's names) and the upcgen command line, on the GPU, against the oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "upcgen_b200", "host")
+
+
+def _build():
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    exe = os.path.join(ROOT, "tests", "cpp", "facade_check")
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-ffp-contract=off", "-I", HOST, "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "facade_check.cpp"), "-L", HOST, "-lupcgen_host",
+                           "-L", os.path.join(ROOT, "upcgen_b200"), "-lupcgpu", f"-Wl,-rpath,{HOST}",
+                           f"-Wl,-rpath,{os.path.join(ROOT, 'upcgen_b200')}"])
+    return exe
+
+
+def test_facade_classes_match_oracle(tmp_path, oracle_mod):
+    from upcgen_b200.config import named_config
+    exe = _build()
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    P = named_config("cfg2", "BINS_M 24\nBINS_Y 10\n")
+    o = oracle_mod.Oracle(P)
+    assert d["rho0"] == pytest.approx(o.rho0(), rel=1e-13)
+    assert d["fluxPoint"] == pytest.approx(o.flux_point(10.0, 1.0), rel=1e-12)
+    assert d["fluxForm"] == pytest.approx(o.flux_form(5.0, 1.0), rel=1e-9)
+    assert d["breakup"] == pytest.approx(o.breakup_raw([15.0], 2)[0], abs=1e-13)
+    assert d["lumi"] == pytest.approx(o.lumi(10.0, 0.5), rel=1e-9)
+    lumi = o.fill_lumi()
+    cs, _, tot = o.fold(lumi)
+    assert d["totCS"] == pytest.approx(tot, rel=1e-9)
+    assert d["cs00"] == pytest.approx(cs[0, 0], rel=1e-9) and d["cs_last"] == pytest.approx(cs[-1, -1], rel=1e-9)
+    assert abs(d["sum_last"] - 1) < 1e-12
+    ye = P.ymin + P.dy * np.arange(P.ny + 1)
+    me = P.mmin + P.dm * np.arange(P.nm + 1)
+    for y, m, yb, mb in d["samples"]:
+        assert ye[0] <= y < ye[-1] and me[0] <= m < me[-1]
+        assert yb == oracle_mod.get_bin(P.ny, y, ye[0], ye[-1]) and mb == oracle_mod.get_bin(P.nm, m, me[0], me[-1])
+    # 1-D sampler: the CDF is GSL's sequential one; draws avoid the empty bin [2,3)
+    assert d["s1sum"] == list(oracle_mod.pdf_init(np.array([1., 2., 0., 4., 3.])))
+    assert all(0 <= v < 5 and not (2 <= v < 3) for v in d["s1"])
+    # the cache file written by prepareTwoPhotonLumi is picked up by a second run
+    assert os.path.exists(tmp_path / "twoPhotonLumi.bin")
+    out2 = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert "Found pre-calculated" in out2.stderr
+    assert json.loads(out2.stdout.strip().splitlines()[-1])["totCS"] == d["totCS"]
+
+
+def test_upcgen_cli_writes_hepmc(tmp_path):
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    par = """NUCLEUS_Z 82
+NUCLEUS_A 208
+SQRTS 5020
+PROC_ID 13
+NEVENTS 3000
+DO_PT_CUT 1
+PT_MIN 0.5
+MMIN 4
+MMAX 30
+BINS_M 30
+BINS_Y 14
+BINS_Z 50
+FLUX_POINT 1
+BREAKUP_MODE 1
+NON_ZERO_GAM_PT 1
+SEED 4242
+USE_ROOT_OUTPUT 0
+USE_HEPMC_OUTPUT 1
+"""
+    (tmp_path / "my.in").write_text(par)
+    r = subprocess.run([os.path.join(HOST, "upcgen"), "-parfile", "my.in", "-nthreads", "4"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Number of rejected events" in r.stderr
+    lines = (tmp_path / "events.hepmc").read_text().splitlines()
+    assert lines[0] == "HepMC::Version 3.02.04" and lines[1] == "HepMC::Asciiv3-START_EVENT_LISTING"
+    assert lines[-1] == "HepMC::Asciiv3-END_EVENT_LISTING"
+    ev = [l for l in lines if l.startswith("E ")]
+    assert len(ev) == 3000 and ev[0] == "E 0 0 2" and ev[-1].startswith("E 2999 ")
+    parts = [l.split() for l in lines if l.startswith("P ")]
+    assert len(parts) == 6000
+    p = np.array([[float(x) for x in q[4:9]] for q in parts])
+    pdg = np.array([int(q[3]) for q in parts])
+    assert set(np.abs(pdg)) == {13} and pdg[0::2].tolist() == (-pdg[1::2]).tolist()
+    assert np.all(np.hypot(p[:, 0], p[:, 1]) >= 0.5)                       # PT_MIN cut
+    assert np.allclose(p[:, 4], 0.1056583745, atol=2e-6)                   # printed mass
+    pair = p[0::2, :4] + p[1::2, :4]
+    minv = np.sqrt(pair[:, 3] ** 2 - pair[:, 0] ** 2 - pair[:, 1] ** 2 - pair[:, 2] ** 2)
+    assert minv.min() >= 4 - 1e-6 and minv.max() <= 30 + 1e-6

@@ -64,6 +64,7 @@ SYMBOLS = [
     "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_device",
     "upcgpu_photon_pt_cdf", "upcgpu_philox", "upcgpu_invalidate_tables", "upcgpu_fp64_peak",
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
+    "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d",
 ]
 
 
@@ -107,6 +108,9 @@ def lib():
         L.upcgpu_photon_pt_cdf.argtypes = [p, d, p]
         L.upcgpu_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, sz, p]
         L.upcgpu_invalidate_tables.argtypes = [p]
+        L.upcgpu_hist_pdf_init.argtypes = [p, p, sz, p]
+        L.upcgpu_hist_sample2d.argtypes = [p, p, i, i, p, p, p, sz, p, p, p]
+        L.upcgpu_hist_sample1d.argtypes = [p, p, i, p, p, sz, p]
         L.upcgpu_elem_sigma_m.argtypes = [i, d, d, d, i, p, sz, p]
         L.upcgpu_elem_fill_cs_zm.argtypes = [i, d, d, d, i, d, d, i, d, d, i, p]
         L.upcgpu_stream_handle.argtypes = [p, C.POINTER(C.c_uint64)]
@@ -333,6 +337,28 @@ class UpcGpu:
         z = np.zeros(u.size)
         self._chk(self.L.upcgpu_sample_z(self.h, _p(mbin), _p(u), u.size, ps, _p(z)))
         return z
+
+    # generic histogram samplers (UpcSampler1D/2D semantics) ----------------------------------
+    def hist_pdf_init(self, bins):
+        b = _f64(bins).ravel()
+        s = np.zeros(b.size + 1)
+        self._chk(self.L.upcgpu_hist_pdf_init(self.h, _p(b), b.size, _p(s)))
+        return s
+
+    def hist_sample2d(self, s, xe, ye, u):
+        s, xe, ye = _f64(s), _f64(xe), _f64(ye)
+        u = _f64(u).reshape(-1, 2)
+        n = u.shape[0]
+        k = np.zeros(n, np.int64); x = np.zeros(n); y = np.zeros(n)
+        self._chk(self.L.upcgpu_hist_sample2d(self.h, _p(s), xe.size - 1, ye.size - 1, _p(xe), _p(ye), _p(u), n,
+                                              _p(k), _p(x), _p(y)))
+        return k, x, y
+
+    def hist_sample1d(self, s, edges, u):
+        s, edges, u = _f64(s), _f64(edges), _f64(u).ravel()
+        x = np.zeros(u.size)
+        self._chk(self.L.upcgpu_hist_sample1d(self.h, _p(s), edges.size - 1, _p(edges), _p(u), u.size, _p(x)))
+        return x
 
     # events ------------------------------------------------------------------------------
     def generate(self, seed, first, n, with_aux=True):

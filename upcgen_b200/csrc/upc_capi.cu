@@ -306,6 +306,31 @@ int upcgpu_sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, i
   return sample_z(c, mbin, u, n, ps, z);
 }
 
+int upcgpu_hist_pdf_init(upcgpu_ctx* c, const double* bins, size_t n, double* sum)
+{
+  CHECK_CTX(c);
+  if (!bins || !sum || n == 0) return UPCGPU_EINVAL;
+  return hist_pdf_init(c, bins, n, sum);
+}
+
+int upcgpu_hist_sample2d(upcgpu_ctx* c, const double* sum, int nx, int ny, const double* xe, const double* ye,
+                         const double* u, size_t n, long long* k, double* x, double* y)
+{
+  CHECK_CTX(c);
+  if (!sum || !xe || !ye || !u || !x || !y || nx < 1 || ny < 1) return UPCGPU_EINVAL;
+  if (n == 0) return UPCGPU_OK;
+  return hist_sample2d(c, sum, nx, ny, xe, ye, u, n, k, x, y);
+}
+
+int upcgpu_hist_sample1d(upcgpu_ctx* c, const double* sum, int n, const double* edges, const double* u, size_t nsamp,
+                         double* x)
+{
+  CHECK_CTX(c);
+  if (!sum || !edges || !u || !x || n < 1) return UPCGPU_EINVAL;
+  if (nsamp == 0) return UPCGPU_OK;
+  return hist_sample1d(c, sum, n, edges, u, nsamp, x);
+}
+
 int upcgpu_generate(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, int* npart, int* pdg,
                     int* status, int* mother, double* p4, double* aux, uint64_t* n_accepted)
 {

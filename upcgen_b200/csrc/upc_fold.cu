@@ -299,4 +299,87 @@ int sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, 
   return UPCGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// generic histogram samplers (UpcSampler1D/2D facade)
+int hist_pdf_init(upcgpu_ctx* c, const double* bins, size_t n, double* sum)
+{
+  double *db, *dt, *dm, *ds;
+  UPC_CUDA(c, cudaMalloc(&db, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dt, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dm, sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&ds, (n + 1) * sizeof(double)));
+  UPC_CUDA(c, cudaMemcpyAsync(db, bins, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  UPC_K(c), k_running_mean<<<1, 1, 0, c->stream>>>(db, n, dm);
+  UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(db, n, dm, dt);
+  UPC_K(c), k_seq_cumsum<<<1, 1, 0, c->stream>>>(dt, n, ds);
+  UPC_CUDA(c, cudaMemcpyAsync(sum, ds, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaGetLastError());
+  cudaFree(db); cudaFree(dt); cudaFree(dm); cudaFree(ds);
+  return UPCGPU_OK;
+}
+
+__global__ void k_hist_sample2d(const double* __restrict__ u, size_t n, const double* __restrict__ sum, int nx, int ny,
+                                const double* __restrict__ xe, const double* __restrict__ ye, long long* __restrict__ k,
+                                double* __restrict__ x, double* __restrict__ y)
+{
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  long long kk; double xx, yy;
+  sample_ym_dev(sum, nx, ny, xe, ye, u[2 * t], u[2 * t + 1], kk, xx, yy);
+  if (k) k[t] = kk;
+  x[t] = xx; y[t] = yy;
+}
+
+__global__ void k_hist_sample1d(const double* __restrict__ u, size_t n, const double* __restrict__ sum, int nb,
+                                const double* __restrict__ e, double* __restrict__ x)
+{
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t < n) x[t] = sample_1d_dev(sum, nb, e, u[t]);
+}
+
+int hist_sample2d(upcgpu_ctx* c, const double* sum, int nx, int ny, const double* xe, const double* ye, const double* u,
+                  size_t n, long long* k, double* x, double* y)
+{
+  const size_t nb = (size_t)nx * ny;
+  double *ds, *dxe, *dye, *du, *dx, *dy; long long* dk;
+  UPC_CUDA(c, cudaMalloc(&ds, (nb + 1) * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dxe, (nx + 1) * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dye, (ny + 1) * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&du, 2 * n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dx, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dy, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dk, n * sizeof(long long)));
+  UPC_CUDA(c, cudaMemcpy(ds, sum, (nb + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_CUDA(c, cudaMemcpy(dxe, xe, (nx + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_CUDA(c, cudaMemcpy(dye, ye, (ny + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_CUDA(c, cudaMemcpy(du, u, 2 * n * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_K(c), k_hist_sample2d<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(du, n, ds, nx, ny, dxe, dye, dk, dx, dy);
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaGetLastError());
+  if (k) UPC_CUDA(c, cudaMemcpy(k, dk, n * sizeof(long long), cudaMemcpyDeviceToHost));
+  UPC_CUDA(c, cudaMemcpy(x, dx, n * sizeof(double), cudaMemcpyDeviceToHost));
+  UPC_CUDA(c, cudaMemcpy(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(ds); cudaFree(dxe); cudaFree(dye); cudaFree(du); cudaFree(dx); cudaFree(dy); cudaFree(dk);
+  return UPCGPU_OK;
+}
+
+int hist_sample1d(upcgpu_ctx* c, const double* sum, int nb, const double* edges, const double* u, size_t n, double* x)
+{
+  double *ds, *de, *du, *dx;
+  UPC_CUDA(c, cudaMalloc(&ds, (nb + 1) * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&de, (nb + 1) * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&du, n * sizeof(double)));
+  UPC_CUDA(c, cudaMalloc(&dx, n * sizeof(double)));
+  UPC_CUDA(c, cudaMemcpy(ds, sum, (nb + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_CUDA(c, cudaMemcpy(de, edges, (nb + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_CUDA(c, cudaMemcpy(du, u, n * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_K(c), k_hist_sample1d<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(du, n, ds, nb, de, dx);
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaGetLastError());
+  UPC_CUDA(c, cudaMemcpy(x, dx, n * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(ds); cudaFree(de); cudaFree(du); cudaFree(dx);
+  return UPCGPU_OK;
+}
+
 }  // namespace upc

@@ -42,6 +42,10 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
 int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps);
 int sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int* ybin, int* mbin, double* y, double* m);
 int sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, double* z);
+int hist_pdf_init(upcgpu_ctx* c, const double* bins, size_t n, double* sum);
+int hist_sample2d(upcgpu_ctx* c, const double* sum, int nx, int ny, const double* xe, const double* ye, const double* u,
+                  size_t n, long long* k, double* x, double* y);
+int hist_sample1d(upcgpu_ctx* c, const double* sum, int nb, const double* edges, const double* u, size_t n, double* x);
 
 // upc_events.cu
 int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart, int* pdg, int* status, int* mother,

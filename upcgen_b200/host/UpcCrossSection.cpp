@@ -1,0 +1,369 @@
+// UpcCrossSection over the CUDA C-ABI.  Method-by-method counterpart of the reference's
+// src/UpcCrossSection.cpp; every numeric kernel of that file runs on the GPU here.
+#include "UpcCrossSection.h"
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <random>
+
+namespace
+{
+std::mt19937_64& hostRng()
+{
+  static std::mt19937_64 rng(0x5eedULL); // stands in for gRandom (TRandomMT64 is std::mt19937_64)
+  return rng;
+}
+double uniform(double a, double b) { return a + (b - a) * std::generate_canonical<double, 53>(hostRng()); }
+
+struct LumiCacheHeader {
+  char magic[8];
+  int32_t nm, ny, pol, isPoint, breakupMode, Z, A, pad;
+  double R, a, sqrts, mmin, mmax, ymin, ymax;
+};
+} // namespace
+
+UpcCrossSection::UpcCrossSection()
+{
+  // the reference fixes gtot here, before parameters.in is read (src/UpcCrossSection.cpp:51-54)
+  gtot = std::cosh((std::acosh(g1) + std::acosh(g2)) / 2.);
+}
+
+UpcCrossSection::~UpcCrossSection()
+{
+  delete elemProcess;
+  if (ctx) upcgpu_destroy(ctx);
+}
+
+void UpcCrossSection::fail(const char* what, int rc)
+{
+  // error convention of the reference: log and std::_Exit(-1) (src/UpcCrossSection.cpp:110-111)
+  PLOG_FATAL << what << " failed (" << rc << "): " << upcgpu_last_error(ctx);
+  std::_Exit(-1);
+}
+
+void UpcCrossSection::setElemProcess(int procID)
+{
+  switch (procID) {
+    case 11:
+    case 13:
+    case 15:
+      elemProcess = new UpcTwoPhotonDilep(procID);
+      break;
+    case 51:
+      elemProcess = new UpcTwoPhotonALP(alpMass, alpWidth);
+      break;
+    case 22:
+    case 111:
+    case 443:
+    case 100443:
+    case 553:
+      PLOG_FATAL << "Process " << procID << " needs ROOT input files / the vector-meson path, which are outside the "
+                 << "GPU build (see DESIGN.md, out of scope). Exiting...";
+      std::_Exit(-1);
+    default:
+      PLOG_FATAL << "Unknown process ID! Check manual and enter a correct ID! Exiting...";
+      std::_Exit(-1);
+  }
+}
+
+upcgpu_params UpcCrossSection::makeParams() const
+{
+  upcgpu_params p{};
+  p.Z = Z; p.A = A; p.R = R; p.a = a; p.sqrts = sqrts; p.g1 = g1; p.g2 = g2; p.gtot = gtot;
+  p.is_point = isPoint; p.breakup_mode = breakupMode; p.use_pol = usePolarizedCS; p.nonzero_gam_pt = useNonzeroGamPt;
+  p.nm = nm; p.ny = ny; p.nz = nz;
+  p.mmin = mmin; p.mmax = mmax; p.ymin = ymin; p.ymax = ymax; p.zmin = zmin; p.zmax = zmax;
+  p.nb1 = nb1; p.nb2 = nb2;
+  if (elemProcess) {
+    p.part_pdg = elemProcess->partPDG; p.m_part = elemProcess->mPart; p.is_charged = elemProcess->isCharged;
+  }
+  p.is_pair = evIsPair; p.is_single = evIsSingle; p.ignore_csz = evIgnoreCSZ; p.decay_uniform_pdg = evDecayUniformPDG;
+  p.do_pt_cut = evDoPtCut; p.do_eta_cut = evDoEtaCut; p.pt_min = evMinPt; p.eta_min = evMinEta; p.eta_max = evMaxEta;
+  return p;
+}
+
+void UpcCrossSection::ensureContext()
+{
+  if (ctx) return;
+  upcgpu_params p = makeParams();
+  int rc = upcgpu_create(&p, device, &ctx);
+  if (rc != UPCGPU_OK) {
+    PLOG_FATAL << "upcgpu_create failed (" << rc << "): " << upcgpu_last_error(nullptr);
+    std::_Exit(-1);
+  }
+}
+
+void UpcCrossSection::ensureTables()
+{
+  ensureContext();
+  if (tablesReady) return;
+  int rc = upcgpu_prepare_tables(ctx);
+  if (rc) fail("upcgpu_prepare_tables", rc);
+  upcgpu_table_info info;
+  upcgpu_get_table_info(ctx, &info);
+  rho0 = info.rho0;
+  tablesReady = true;
+}
+
+void UpcCrossSection::init()
+{
+  PLOG_INFO << "Initializing caches ...";
+  factor = Z * Z * phys_consts::alpha / M_PI / M_PI / phys_consts::hc / phys_consts::hc;
+  mNucl = (Z * phys_consts::mProt + (A - Z) * phys_consts::mNeut) / A;
+  rho0 = calcWSRho();
+  prepareGAA();
+  prepareFormFac();
+  if (breakupMode > 1) prepareBreakupProb();
+  prepareTwoPhotonLumi();
+}
+
+template <typename ArrayType>
+double UpcCrossSection::simpson(int n, ArrayType* v, double h)
+{
+  double sum = v[0] + v[n - 1];
+  for (int i = 1; i < n - 1; i += 2) sum += 4. * v[i];
+  for (int i = 2; i < n - 1; i += 2) sum += 2. * v[i];
+  return sum * h / 3.;
+}
+template double UpcCrossSection::simpson<double>(int, double*, double);
+
+// rho0, G_AA, the form-factor spline and the breakup spline are built together on the device
+double UpcCrossSection::calcWSRho() { ensureTables(); return rho0; }
+void UpcCrossSection::prepareGAA() { ensureTables(); }
+void UpcCrossSection::prepareFormFac() { ensureTables(); }
+void UpcCrossSection::prepareBreakupProb() { ensureTables(); }
+
+double UpcCrossSection::fluxPoint(const double b, const double k)
+{
+  ensureTables();
+  double out = 0;
+  int rc = upcgpu_flux_point(ctx, &b, &k, 1, &out);
+  if (rc) fail("upcgpu_flux_point", rc);
+  return out;
+}
+
+double UpcCrossSection::fluxForm(const double b, const double k)
+{
+  ensureTables();
+  double out = 0;
+  int rc = upcgpu_flux_form(ctx, &b, &k, 1, &out, nullptr);
+  if (rc) fail("upcgpu_flux_form", rc);
+  return out;
+}
+
+// analytic Woods-Saxon form factor; static in the reference (it is only called directly by the
+// vector-meson path), so it is a plain host function here as well
+double UpcCrossSection::calcFormFac(double Q2)
+{
+  double Q = std::sqrt(Q2) / phys_consts::hc;
+  double coshVal = std::cosh(M_PI * Q * a);
+  double sinhVal = std::sinh(M_PI * Q * a);
+  double ff = 4 * M_PI * M_PI * rho0 * a * a * a / (Q * a * Q * a * sinhVal * sinhVal) *
+              (M_PI * Q * a * coshVal * std::sin(Q * R) - Q * R * std::cos(Q * R) * sinhVal);
+  ff += 8 * M_PI * rho0 * a * a * a * std::exp(-R / a) / (1 + Q * Q * a * a) / (1 + Q * Q * a * a);
+  return ff;
+}
+
+double UpcCrossSection::calcTwoPhotonLumi(double M, double Y)
+{
+  ensureTables();
+  double out = 0;
+  int rc = upcgpu_lumi_cells(ctx, &M, &Y, 1, &out, nullptr, nullptr);
+  if (rc) fail("upcgpu_lumi_cells", rc);
+  return out;
+}
+
+void UpcCrossSection::calcTwoPhotonLumiPol(double& ns, double& np, double M, double Y)
+{
+  ensureTables();
+  int rc = upcgpu_lumi_cells(ctx, &M, &Y, 1, nullptr, &ns, &np);
+  if (rc) fail("upcgpu_lumi_cells", rc);
+}
+
+void UpcCrossSection::fillCrossSectionZM(std::vector<std::vector<double>>& crossSectionZM, double zmin, double zmax,
+                                         int nz, double mmin, double mmax, int nm, int flag)
+{
+  constexpr double scalingFactor = phys_consts::hc * phys_consts::hc * 1e7; // to [nb]
+  double dm = (mmax - mmin) / nm;
+  double dz = (zmax - zmin) / nz;
+  double cs = 0;
+  for (int im = 0; im < nm; ++im) {
+    double m = mmin + dm * im;
+    for (int iz = 0; iz < nz; ++iz) {
+      double z = zmin + dz * iz;
+      if (flag == 0) cs = elemProcess->calcCrossSectionZM(z, m);
+      if (flag == 1) cs = elemProcess->calcCrossSectionZMPolS(z, m);
+      if (flag == 2) cs = elemProcess->calcCrossSectionZMPolPS(z, m);
+      crossSectionZM[im][iz] = cs * scalingFactor / dm;
+    }
+  }
+}
+
+void UpcCrossSection::prepareTwoPhotonLumi()
+{
+  ensureTables();
+  const size_t n = (size_t)nm * ny;
+  // cache file: the reference keeps twoPhotonLumi[Pol].root and reuses it whenever it exists; here a
+  // raw binary with a parameter header, reused only when the header matches
+  std::string fname = std::string(lumiFileDirectory) + "/twoPhotonLumi" + (usePolarizedCS ? "Pol.bin" : ".bin");
+  LumiCacheHeader want{};
+  std::memcpy(want.magic, "UPCLUMI1", 8);
+  want.nm = nm; want.ny = ny; want.pol = usePolarizedCS; want.isPoint = isPoint; want.breakupMode = breakupMode;
+  want.Z = Z; want.A = A; want.R = R; want.a = a; want.sqrts = sqrts;
+  want.mmin = mmin; want.mmax = mmax; want.ymin = ymin; want.ymax = ymax;
+  {
+    std::ifstream in(fname, std::ios::binary);
+    LumiCacheHeader got{};
+    if (in && in.read(reinterpret_cast<char*>(&got), sizeof(got)) && std::memcmp(&got, &want, sizeof(got)) == 0) {
+      std::vector<double>& t0 = usePolarizedCS ? lumiS : lumi;
+      t0.resize(n);
+      in.read(reinterpret_cast<char*>(t0.data()), n * sizeof(double));
+      if (usePolarizedCS) {
+        lumiPs.resize(n);
+        in.read(reinterpret_cast<char*>(lumiPs.data()), n * sizeof(double));
+      }
+      if (in) {
+        PLOG_INFO << "Found pre-calculated " << (usePolarizedCS ? "polarized" : "unpolarized") << " 2D luminosity";
+        int rc = usePolarizedCS ? upcgpu_lumi_upload(ctx, 1, lumiS.data()) : upcgpu_lumi_upload(ctx, 0, lumi.data());
+        if (!rc && usePolarizedCS) rc = upcgpu_lumi_upload(ctx, 2, lumiPs.data());
+        if (rc) fail("upcgpu_lumi_upload", rc);
+        return;
+      }
+    }
+  }
+  PLOG_INFO << "Precalculated 2D luminosity is not found. Starting all over...";
+  int rc;
+  if (usePolarizedCS) {
+    lumiS.assign(n, 0.); lumiPs.assign(n, 0.);
+    rc = upcgpu_fill_lumi(ctx, nullptr, lumiS.data(), lumiPs.data());
+  } else {
+    lumi.assign(n, 0.);
+    rc = upcgpu_fill_lumi(ctx, lumi.data(), nullptr, nullptr);
+  }
+  if (rc) fail("upcgpu_fill_lumi", rc);
+  upcgpu_fill_stats st;
+  upcgpu_get_fill_stats(ctx, &st);
+  PLOG_INFO << "Two-photon luminosity: " << n << " cells in " << st.ms_total << " ms on the GPU";
+  std::ofstream out(fname, std::ios::binary);
+  if (out) {
+    out.write(reinterpret_cast<const char*>(&want), sizeof(want));
+    const std::vector<double>& t0 = usePolarizedCS ? lumiS : lumi;
+    out.write(reinterpret_cast<const char*>(t0.data()), n * sizeof(double));
+    if (usePolarizedCS) out.write(reinterpret_cast<const char*>(lumiPs.data()), n * sizeof(double));
+    PLOG_INFO << "Two-photon luminosity was written to " << fname;
+  }
+}
+
+void UpcCrossSection::calcNucCrossSectionYM(std::vector<std::vector<double>>& crossSectionYM,
+                                            std::vector<std::vector<double>>& polCSRatio, double& totCS)
+{
+  PLOG_INFO << "Calculating nuclear cross section...";
+  ensureTables();
+  const double dm = (mmax - mmin) / nm;
+  std::vector<double> sig0(nm), sig1(nm), cs((size_t)nm * ny), ratio;
+  for (int im = 0; im < nm; ++im) {
+    double m = mmin + dm * im;
+    if (!usePolarizedCS) {
+      sig0[im] = elemProcess->calcCrossSectionM(m);
+    } else {
+      sig0[im] = elemProcess->calcCrossSectionMPolS(m);
+      sig1[im] = elemProcess->calcCrossSectionMPolPS(m);
+    }
+  }
+  double tot = 0;
+  int rc;
+  if (usePolarizedCS) {
+    ratio.resize((size_t)nm * ny);
+    rc = upcgpu_fold_sigma(ctx, nullptr, sig0.data(), sig1.data(), cs.data(), ratio.data(), &tot);
+  } else {
+    rc = upcgpu_fold_sigma(ctx, sig0.data(), nullptr, nullptr, cs.data(), nullptr, &tot);
+  }
+  if (rc) fail("upcgpu_fold_sigma", rc);
+  for (int iy = 0; iy < ny; ++iy)
+    for (int im = 0; im < nm; ++im) {
+      crossSectionYM[iy][im] = cs[(size_t)iy * nm + im];
+      if (usePolarizedCS && (int)polCSRatio.size() > iy && (int)polCSRatio[iy].size() > im)
+        polCSRatio[iy][im] = ratio[(size_t)iy * nm + im];
+    }
+  totCS = totCS * 1e-6 + tot; // [mb]; the reference sums into the caller's variable, then scales it by 1e-6
+  PLOG_INFO << "Calculating nuclear cross section...Done!";
+  PLOG_INFO << "Total nuclear cross section = " << std::fixed << totCS << " mb";
+}
+
+double UpcCrossSection::calcBreakupProb(const double impactparameter, const int mode)
+{
+  ensureTables();
+  double out = 0;
+  int rc = upcgpu_breakup_raw(ctx, &impactparameter, mode, 1, &out);
+  if (rc) fail("upcgpu_breakup_raw", rc);
+  return out;
+}
+
+// per-call accessor kept for interface compatibility (the event loop of UpcGenerator uses the
+// batched upcgpu_generate instead): pdf tabulated on the GPU, cached per integer-MeV key as the
+// reference's photPtDistrMap, inverted with one uniform like TH1::GetRandom
+double UpcCrossSection::getPhotonPt(double ePhot)
+{
+  ensureTables();
+  int key = ePhot * 1e3;
+  auto it = photPtCdf.find(key);
+  if (it == photPtCdf.end()) {
+    std::vector<double> cdf(5001);
+    int rc = upcgpu_photon_pt_cdf(ctx, ePhot, cdf.data());
+    if (rc) fail("upcgpu_photon_pt_cdf", rc);
+    it = photPtCdf.emplace(key, std::move(cdf)).first;
+  }
+  const std::vector<double>& cdf = it->second;
+  if (cdf[5000] == 0) return 0;
+  double r1 = uniform(0., 1.);
+  int lo = 0, hi = 5000;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) / 2;
+    if (cdf[mid] <= r1) lo = mid; else hi = mid;
+  }
+  double bw = 6. * phys_consts::hc / R / 5000;
+  double x = lo * bw;
+  if (r1 > cdf[lo]) x += bw * (r1 - cdf[lo]) / (cdf[lo + 1] - cdf[lo]);
+  if (photPtCdf.size() > 30000) photPtCdf.clear();
+  return x;
+}
+
+void UpcCrossSection::getPairMomentum(double mPair, double yPair, TLorentzVector& pPair)
+{
+  if (!useNonzeroGamPt) {
+    double mtPair = mPair;
+    pPair.SetPxPyPzE(0., 0., mtPair * std::sinh(yPair), mtPair * std::cosh(yPair));
+    return;
+  }
+  double k1 = mPair / 2 * std::exp(yPair);
+  double k2 = mPair / 2 * std::exp(-yPair);
+  double angle1 = uniform(0, 2 * M_PI);
+  double angle2 = uniform(0, 2 * M_PI);
+  double pt1 = getPhotonPt(k1);
+  double pt2 = getPhotonPt(k2);
+  double px = pt1 * std::cos(angle1) + pt2 * std::cos(angle2);
+  double py = pt1 * std::sin(angle1) + pt2 * std::sin(angle2);
+  double pt = std::sqrt(px * px + py * py);
+  double mtPair = std::sqrt(mPair * mPair + pt * pt);
+  pPair.SetPxPyPzE(px, py, mtPair * std::sinh(yPair), mtPair * std::cosh(yPair));
+}
+
+// ---- vector-meson photoproduction path: out of scope of the GPU build ----
+double UpcCrossSection::calcPhotonFlux(double, double)
+{
+  PLOG_FATAL << "calcPhotonFlux: the 1-D vector-meson path is not part of the GPU build";
+  std::_Exit(-1);
+}
+void UpcCrossSection::calcNucCrossSectionY(std::vector<std::vector<double>>&, std::vector<std::vector<double>>&, double&)
+{
+  PLOG_FATAL << "calcNucCrossSectionY: the 1-D vector-meson path is not part of the GPU build";
+  std::_Exit(-1);
+}
+void UpcCrossSection::getMomentumVM(double, double, int, TLorentzVector&)
+{
+  PLOG_FATAL << "getMomentumVM: the 1-D vector-meson path is not part of the GPU build";
+  std::_Exit(-1);
+}

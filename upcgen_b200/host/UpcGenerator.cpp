@@ -1,0 +1,341 @@
+// UpcGenerator over the GPU path.  Counterpart of the reference's src/UpcGenerator.cpp for the
+// two-photon processes with closed-form elementary cross sections (dileptons, ALP).
+#include "UpcGenerator.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <ctime>
+#include <sstream>
+
+int UpcGenerator::debug = 0;
+
+namespace upc_host
+{
+static upcgpu_ctx* g_samplerCtx = nullptr;
+static upcgpu_ctx* g_ownCtx = nullptr;
+void registerSamplerContext(upcgpu_ctx* ctx) { g_samplerCtx = ctx; }
+upcgpu_ctx* samplerContext()
+{
+  if (g_samplerCtx) return g_samplerCtx;
+  if (!g_ownCtx) {
+    UpcCrossSection defaults;
+    defaults.setElemProcess(11);
+    upcgpu_params p = defaults.makeParams();
+    if (upcgpu_create(&p, 0, &g_ownCtx) != UPCGPU_OK) {
+      PLOG_FATAL << "UpcSampler: " << upcgpu_last_error(nullptr);
+      std::_Exit(-1);
+    }
+  }
+  return g_ownCtx;
+}
+} // namespace upc_host
+
+UpcGenerator::UpcGenerator()
+{
+  nucProcessCS = new UpcCrossSection();
+  totCS = 0.0;
+  fidCS = 0.0;
+  setCollisionSystem(5020., 82, 208);
+}
+
+UpcGenerator::~UpcGenerator()
+{
+  upc_host::registerSamplerContext(nullptr);
+  delete nucProcessCS; // (the reference leaks it)
+}
+
+void UpcGenerator::setCollisionSystem(float sqrts, int nucl_z, int nucl_a)
+{
+  UpcCrossSection::sqrts = sqrts;
+  UpcCrossSection::g1 = UpcCrossSection::sqrts / (2. * phys_consts::mProt);
+  UpcCrossSection::g2 = UpcCrossSection::sqrts / (2. * phys_consts::mProt);
+  UpcCrossSection::Z = nucl_z;
+  UpcCrossSection::A = nucl_a;
+  UpcCrossSection::mNucl = (nucl_z * phys_consts::mProt + (nucl_a - nucl_z) * phys_consts::mNeut) / nucl_a;
+}
+
+// KEY value pairs of parameters.in; unknown keys are ignored (src/UpcGenerator.cpp:183-305)
+void UpcGenerator::setParameterValue(const std::string& parameter, const std::string& parValue)
+{
+  using std::stod;
+  using std::stoi;
+  using std::stol;
+  auto* cs = nucProcessCS;
+  if (parameter == "NEVENTS") nEvents = stol(parValue);
+  if (parameter == "SQRTS") {
+    UpcCrossSection::sqrts = stod(parValue);
+    UpcCrossSection::g1 = UpcCrossSection::sqrts / (2. * phys_consts::mProt);
+    UpcCrossSection::g2 = UpcCrossSection::sqrts / (2. * phys_consts::mProt);
+  }
+  if (parameter == "PROC_ID") procID = stoi(parValue);
+  if (parameter == "LEP_A") aLep = stod(parValue);
+  if (parameter == "ALP_MASS") cs->alpMass = stod(parValue);
+  if (parameter == "ALP_WIDTH") cs->alpWidth = stod(parValue);
+  if (parameter == "DO_PT_CUT") doPtCut = stoi(parValue);
+  if (parameter == "PT_MIN") minPt = stod(parValue);
+  if (parameter == "DO_ETA_CUT") doEtaCut = stoi(parValue);
+  if (parameter == "ETA_MIN") minEta = stod(parValue);
+  if (parameter == "ETA_MAX") maxEta = stod(parValue);
+  if (parameter == "ZMIN") cs->zmin = stod(parValue);
+  if (parameter == "ZMAX") cs->zmax = stod(parValue);
+  if (parameter == "MMIN") cs->mmin = stod(parValue);
+  if (parameter == "MMAX") cs->mmax = stod(parValue);
+  if (parameter == "YMIN") cs->ymin = stod(parValue);
+  if (parameter == "YMAX") cs->ymax = stod(parValue);
+  if (parameter == "BINS_Z") cs->nz = stoi(parValue);
+  if (parameter == "BINS_M") cs->nm = stoi(parValue);
+  if (parameter == "BINS_Y") cs->ny = stoi(parValue);
+  if (parameter == "WS_R") UpcCrossSection::R = stod(parValue);
+  if (parameter == "WS_A") UpcCrossSection::a = stod(parValue);
+  if (parameter == "NUCLEUS_Z") UpcCrossSection::Z = stoi(parValue);
+  if (parameter == "NUCLEUS_A") UpcCrossSection::A = stoi(parValue);
+  if (parameter == "FLUX_POINT") cs->isPoint = stoi(parValue);
+  if (parameter == "BREAKUP_MODE") cs->breakupMode = stoi(parValue);
+  if (parameter == "PYTHIA_VERSION") pythiaVersion = stoi(parValue);
+  if (parameter == "PYTHIA8_FSR") doFSR = stoi(parValue);
+  if (parameter == "PYTHIA8_DECAYS") doDecays = stoi(parValue);
+  if (parameter == "NON_ZERO_GAM_PT") cs->useNonzeroGamPt = stoi(parValue);
+  if (parameter == "USE_POLARIZED_CS") {
+    cs->usePolarizedCS = stoi(parValue);
+    usePolarizedCS = stoi(parValue);
+  }
+  if (parameter == "SEED") seed = stol(parValue);
+  if (parameter == "USE_ROOT_OUTPUT") useROOTOut = stoi(parValue);
+  if (parameter == "USE_HEPMC_OUTPUT") useHepMCOut = stoi(parValue);
+  if (parameter == "DO_M_CUT") cs->doMassCut = stoi(parValue);
+  if (parameter == "LOW_M_CUT") cs->lowMCut = stod(parValue);
+  if (parameter == "HIGH_M_CUT") cs->hiMCut = stod(parValue);
+  if (parameter == "SHADOWING") cs->shadowingOption = stoi(parValue);
+  if (parameter == "DECAY_PDG") cs->dghtPDG = stoi(parValue);
+}
+
+void UpcGenerator::configGeneratorFromFile()
+{
+  std::ifstream fInputs(parFileName);
+  if (fInputs) {
+    PLOG_INFO << "Reading parameters from " << parFileName << " ...";
+    std::string line, parameter, parValue;
+    while (getline(fInputs, line)) {
+      std::istringstream iss(line);
+      if (line[0] == '#') continue;
+      iss >> parameter >> parValue; // not reset between lines, as the reference (a blank line re-applies the last pair)
+      setParameterValue(parameter, parValue);
+    }
+    if (!useROOTOut && !useHepMCOut)
+      PLOG_WARNING << "Output format not set! Choose ROOT or/and HepMC via flags USE_ROOT_OUTPUT and USE_HEPMC_OUTPUT!";
+  } else {
+    PLOG_WARNING << "Input file not found! Using default parameters...";
+  }
+}
+
+void UpcGenerator::printParameters()
+{
+  auto* cs = nucProcessCS;
+  PLOG_INFO << "OMP_NTHREADS " << numThreads << " (unused: GPU build)";
+  PLOG_INFO << "NUCLEUS_Z " << UpcCrossSection::Z;
+  PLOG_INFO << "NUCLEUS_A " << UpcCrossSection::A;
+  PLOG_INFO << "WS_R " << UpcCrossSection::R;
+  PLOG_INFO << "WS_A " << UpcCrossSection::a;
+  PLOG_INFO << "SQRTS " << UpcCrossSection::sqrts;
+  PLOG_INFO << "PROC_ID " << procID;
+  PLOG_INFO << "LEP_A " << aLep;
+  PLOG_INFO << "NEVENTS " << nEvents;
+  PLOG_INFO << "DO_PT_CUT " << doPtCut << " PT_MIN " << minPt << " DO_ETA_CUT " << doEtaCut << " ETA_MIN " << minEta
+            << " ETA_MAX " << maxEta;
+  PLOG_INFO << "ZMIN " << cs->zmin << " ZMAX " << cs->zmax << " MMIN " << cs->mmin << " MMAX " << cs->mmax << " YMIN "
+            << cs->ymin << " YMAX " << cs->ymax;
+  PLOG_INFO << "BINS_Z " << cs->nz << " BINS_M " << cs->nm << " BINS_Y " << cs->ny;
+  PLOG_INFO << "FLUX_POINT " << cs->isPoint << " BREAKUP_MODE " << cs->breakupMode << " NON_ZERO_GAM_PT "
+            << cs->useNonzeroGamPt << " USE_POLARIZED_CS " << usePolarizedCS;
+  PLOG_INFO << "SEED " << seed;
+}
+
+void UpcGenerator::init()
+{
+  if (nucProcessCS == nullptr) {
+    PLOG_FATAL << "UpcCrossSection was not initialized! Exiting...";
+    std::_Exit(-1);
+  }
+  ignoreCSZ = false;
+  auto* cs = nucProcessCS;
+  // process-specific set-up, src/UpcGenerator.cpp:69-140
+  if (procID == 51) {
+    ignoreCSZ = true; // cos(theta) uniform for the ALP
+    isSingleProduction = true;
+    cs->mmin = cs->alpMass - 4. * cs->alpWidth;
+    cs->mmax = cs->alpMass + 4. * cs->alpWidth;
+    PLOG_WARNING << "For ALP production angular distribution is ignored!";
+  }
+  cs->setElemProcess(procID);
+  if (procID >= 11 && procID <= 15) {
+    isPairProduction = true;
+    auto* proc = (UpcTwoPhotonDilep*)cs->elemProcess;
+    proc->aLep = aLep;
+    if (cs->mmin < proc->mPart * 2.) {
+      PLOG_WARNING << "MMIN is lower than 2 lepton masses! Setting MMIN to 2 lepton masses...";
+      cs->mmin = proc->mPart * 2.;
+    }
+  }
+  cs->numThreads = numThreads;
+  cs->evIsPair = isPairProduction;
+  cs->evIsSingle = isSingleProduction;
+  cs->evIgnoreCSZ = ignoreCSZ;
+  cs->evDecayUniformPDG = procID == 51 ? 22 : 0;
+  cs->evDoPtCut = doPtCut; cs->evMinPt = minPt;
+  cs->evDoEtaCut = doEtaCut; cs->evMinEta = minEta; cs->evMaxEta = maxEta;
+
+  PLOG_WARNING << "Check inputs:";
+  printParameters();
+  cs->init(); // tables + two-photon luminosity on the GPU
+  upc_host::registerSamplerContext(cs->gpu());
+  if (seed == 0) seed = time(nullptr); // the reference seeds gRandom with the wall clock for SEED 0
+  if ((doFSR || doDecays) && pythiaVersion > 0)
+    PLOG_WARNING << "Decays with Pythia are not used! (Pythia is not part of the GPU build)";
+  computeNuclXsection();
+}
+
+void UpcGenerator::computeNuclXsection()
+{
+  auto* cs = nucProcessCS;
+  const int nm = cs->nm, nz = cs->nz, ny = cs->ny;
+  const double dm = (cs->mmax - cs->mmin) / nm, dz = (cs->zmax - cs->zmin) / nz, dy = (cs->ymax - cs->ymin) / ny;
+  std::vector<std::vector<double>> csZM, csZMS, csZMPS;
+  if (usePolarizedCS) {
+    csZMS.resize(nm, std::vector<double>(nz, 0.));
+    csZMPS.resize(nm, std::vector<double>(nz, 0.));
+    cs->fillCrossSectionZM(csZMS, cs->zmin, cs->zmax, nz, cs->mmin, cs->mmax, nm, 1);
+    cs->fillCrossSectionZM(csZMPS, cs->zmin, cs->zmax, nz, cs->mmin, cs->mmax, nm, 2);
+  } else {
+    csZM.resize(nm, std::vector<double>(nz, 0.));
+    cs->fillCrossSectionZM(csZM, cs->zmin, cs->zmax, nz, cs->mmin, cs->mmax, nm, 0);
+  }
+  nucCSYM.assign(ny, std::vector<double>(nm, 0.));
+  if (usePolarizedCS) polCSRatio.assign(ny, std::vector<double>(nm));
+  totCS = 0;
+  cs->calcNucCrossSectionYM(nucCSYM, polCSRatio, totCS);
+
+  binEdgesM.resize(nm + 1);
+  binEdgesZ.resize(nz + 1);
+  binEdgesY.resize(ny + 1);
+  for (int i = 0; i < nm + 1; ++i) binEdgesM[i] = cs->mmin + dm * i;
+  for (int i = 0; i < nz + 1; ++i) binEdgesZ[i] = cs->zmin + dz * i;
+  for (int i = 0; i < ny + 1; ++i) binEdgesY[i] = cs->ymin + dy * i;
+
+  // samplers: the 2-D (y, m) CDF from the folded table already on the device, the nm z-CDFs from the
+  // plug-in's d sigma/dz table (src/UpcGenerator.cpp:684-700)
+  auto flat = [&](const std::vector<std::vector<double>>& t) {
+    std::vector<double> f((size_t)nm * nz);
+    for (int i = 0; i < nm; ++i) std::copy(t[i].begin(), t[i].end(), f.begin() + (size_t)i * nz);
+    return f;
+  };
+  int rc;
+  if (ignoreCSZ) {
+    rc = upcgpu_sampler_build(cs->gpu(), nullptr, nullptr, nullptr, nullptr);
+  } else if (usePolarizedCS) {
+    auto fs = flat(csZMS), fp = flat(csZMPS);
+    rc = upcgpu_sampler_build(cs->gpu(), nullptr, nullptr, fs.data(), fp.data());
+  } else {
+    auto f0 = flat(csZM);
+    rc = upcgpu_sampler_build(cs->gpu(), nullptr, f0.data(), nullptr, nullptr);
+  }
+  if (rc) {
+    PLOG_FATAL << "upcgpu_sampler_build failed: " << upcgpu_last_error(cs->gpu());
+    std::_Exit(-1);
+  }
+}
+
+void UpcGenerator::refillBlock()
+{
+  const size_t n = 1 << 16;
+  block.npart.resize(n);
+  block.pdg.resize(n * UPCGPU_MAX_PART);
+  block.status.resize(n * UPCGPU_MAX_PART);
+  block.mother.resize(n * UPCGPU_MAX_PART);
+  block.p4.resize(n * UPCGPU_MAX_PART * 4);
+  uint64_t nacc = 0;
+  int rc = upcgpu_generate(nucProcessCS->gpu(), (uint64_t)seed, nextCandidate, n, block.npart.data(), block.pdg.data(),
+                           block.status.data(), block.mother.data(), block.p4.data(), nullptr, &nacc);
+  if (rc) {
+    PLOG_FATAL << "upcgpu_generate failed: " << upcgpu_last_error(nucProcessCS->gpu());
+    std::_Exit(-1);
+  }
+  nextCandidate += n;
+  block.pos = 0;
+  block.n = n;
+}
+
+// one candidate per call; returns 1 when it passes the kinematic cuts, else 0 with empty vectors
+long int UpcGenerator::generateEvent(std::vector<int>& pdgs, std::vector<int>& statuses, std::vector<int>& mothers,
+                                     std::vector<TLorentzVector>& particles)
+{
+  pdgs.clear();
+  statuses.clear();
+  mothers.clear();
+  particles.clear();
+  if (block.pos == block.n) refillBlock();
+  const size_t i = block.pos++;
+  const int np = block.npart[i];
+  if (np == 0) return 0;
+  genParticles.clear();
+  for (int j = 0; j < np; ++j) {
+    const size_t o = i * UPCGPU_MAX_PART + j;
+    pdgs.emplace_back(block.pdg[o]);
+    statuses.emplace_back(block.status[o]);
+    mothers.emplace_back(block.mother[o]);
+    particles.emplace_back(block.p4[o * 4 + 0], block.p4[o * 4 + 1], block.p4[o * 4 + 2], block.p4[o * 4 + 3]);
+    genParticles.emplace_back(block.pdg[o], block.status[o], block.mother[o], block.mother[o], -1, -1,
+                              block.p4[o * 4 + 0], block.p4[o * 4 + 1], block.p4[o * 4 + 2], block.p4[o * 4 + 3], 0.0,
+                              0.0, 0.0, 0.0);
+  }
+  return 1;
+}
+
+void UpcGenerator::writeEvent(long int evt, const std::vector<int>& pdgs, const std::vector<int>& statuses,
+                              const std::vector<int>& mothers, const std::vector<TLorentzVector>& particles)
+{
+  if (!writerHepMC) return;
+  int nVertices = -1;
+  int lastMotherId = -1;
+  for (auto mother : mothers) {
+    if (mother != lastMotherId) {
+      nVertices++;
+      lastMotherId = mother;
+    }
+  }
+  writerHepMC->writeEventInfo(evt, static_cast<int>(particles.size()), nVertices);
+  for (size_t i = 0; i < particles.size(); ++i)
+    writerHepMC->writeParticleInfo((int)i + 1, mothers[i], pdgs[i], particles[i].Px(), particles[i].Py(),
+                                   particles[i].Pz(), particles[i].E(), particles[i].M(), statuses[i]);
+}
+
+void UpcGenerator::generateEvents()
+{
+  std::vector<int> pdgs, statuses, mothers;
+  std::vector<TLorentzVector> particles;
+  if (useROOTOut && !useHepMCOut) {
+    PLOG_WARNING << "events.root needs ROOT, which is not part of this build: writing events.hepmc instead";
+    useHepMCOut = true;
+  }
+  if (useHepMCOut) writerHepMC = new WriterHepMC("events.hepmc");
+  PLOG_INFO << "Generating " << nEvents << " events...";
+  long int rejected = 0;
+  long int evt = 0;
+  while (evt < nEvents) {
+    if (debug <= 1 && ((evt + 1) % 100000 == 0)) PLOG_INFO << "Event number: " << evt + 1;
+    if (generateEvent(pdgs, statuses, mothers, particles) == 1) {
+      writeEvent(evt, pdgs, statuses, mothers, particles);
+      evt++;
+    } else {
+      rejected++;
+    }
+  }
+  fidCS = totCS * (double)nEvents / (double)(nEvents + rejected);
+  PLOG_INFO << "Event generation is finished!";
+  if ((doPtCut || doEtaCut) && nEvents > 0) {
+    PLOG_INFO << "Kinematic cuts were used";
+    PLOG_INFO << "Number of rejected events = " << rejected;
+    PLOG_INFO << std::fixed << std::setprecision(6) << "Cross section with cuts = " << fidCS << " mb";
+  }
+  delete writerHepMC;
+  writerHepMC = nullptr;
+}

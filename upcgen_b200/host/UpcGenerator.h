@@ -1,0 +1,121 @@
+// UpcGenerator -- orchestration class with the reference's public interface
+// (include/UpcGenerator.h:58-128): parameters.in parsing, init(), computeNuclXsection(),
+// generateEvent()/generateEvents(), HepMC3-ASCII output.  The tables come from UpcCrossSection
+// (GPU); events are produced on the GPU in blocks of candidates (upcgpu_generate) and handed out
+// one at a time through generateEvent().
+#pragma once
+
+#include <cstdint>
+#include <fstream>
+#include <iomanip>
+#include <string>
+#include <vector>
+
+#include "UpcCompat.h"
+#include "UpcCrossSection.h"
+#include "UpcSampler.h"
+
+class UpcGenerator
+{
+ public:
+  UpcGenerator();
+  ~UpcGenerator();
+
+  // process-specific parameters
+  int procID{0};
+  double aLep{0};
+
+  // simulation parameters
+  bool doPtCut{false};
+  double minPt{0};
+  bool doEtaCut{false};
+  double minEta{0};
+  double maxEta{0};
+  bool usePolarizedCS{false};
+  long int seed{0};
+  long int nEvents{1000};
+
+  void setParameterValue(const std::string& parameter, const std::string& parValue);
+  static int debug;
+  void configGeneratorFromFile();
+  void init();
+  void setLumiFileDirectory(std::string directory) { nucProcessCS->setLumiFileDirectory(directory); };
+  void setDebugLevel(int level) { debug = level; }
+  void setNumThreads(int n) { numThreads = n; }
+  void setParFile(std::string parfilename) { parFileName = parfilename; }
+  void setCollisionSystem(float sqrts, int nucl_z, int nucl_a);
+  void setSeed(int seedIn) { seed = seedIn; PLOG_INFO << "<seed> = " << seed; }
+  void printParameters();
+  void computeNuclXsection();
+  double totNuclX() { return totCS; }
+  double fidNuclX() { return fidCS; }
+  long int generateEvent(std::vector<int>& pdgs, std::vector<int>& statuses, std::vector<int>& mothers,
+                         std::vector<TLorentzVector>& particles);
+  const std::vector<TParticle>& getParticles() const { return genParticles; };
+  void generateEvents();
+
+  // additions of the GPU build
+  void setDevice(int dev) { nucProcessCS->device = dev; }
+  UpcCrossSection* crossSection() { return nucProcessCS; }
+
+ private:
+  UpcCrossSection* nucProcessCS{nullptr};
+  std::string parFileName{"parameters.in"};
+  bool useROOTOut{true};
+  bool useHepMCOut{false};
+  double totCS;
+  double fidCS;
+  bool ignoreCSZ;
+  std::vector<TParticle> genParticles;
+  std::vector<std::vector<double>> nucCSYM;
+  std::vector<std::vector<double>> polCSRatio;
+  std::vector<double> binEdgesM, binEdgesZ, binEdgesY;
+
+  int pythiaVersion{-1};
+  bool isPythiaUsed{false};
+  bool doFSR{false};
+  bool doDecays{false};
+  int numThreads{1};
+  bool isPairProduction{false};
+  bool isSingleProduction{false};
+
+  // a very simple HepMC writer: particles only, no vertex information (as the reference's)
+  class WriterHepMC
+  {
+   public:
+    explicit WriterHepMC(const std::string& fname) { openFile(fname); }
+    ~WriterHepMC() { closeFile(); }
+    std::ofstream outfile;
+    void openFile(const std::string& fname)
+    {
+      outfile.open(fname);
+      outfile << "HepMC::Version 3.02.04\n" << "HepMC::Asciiv3-START_EVENT_LISTING\n";
+    }
+    void closeFile()
+    {
+      outfile << "HepMC::Asciiv3-END_EVENT_LISTING\n";
+      outfile.close();
+    }
+    void writeEventInfo(long int eventID, int nParticles, int nVertices = 0)
+    {
+      outfile << "E " << eventID << " " << nVertices << " " << nParticles << "\n" << "U GEV MM\n";
+    }
+    void writeParticleInfo(int id, int motherID, int pdg, double px, double py, double pz, double e, double m, int status)
+    {
+      outfile << std::setprecision(9) << "P " << id << " " << motherID << " " << pdg << " " << px << " " << py << " "
+              << pz << " " << e << " " << m << " " << status << "\n";
+    }
+  };
+  WriterHepMC* writerHepMC{nullptr};
+  void writeEvent(long int evt, const std::vector<int>& pdgs, const std::vector<int>& statuses,
+                  const std::vector<int>& mothers, const std::vector<TLorentzVector>& particles);
+
+  // block of candidates generated on the GPU and consumed by generateEvent()
+  struct Block {
+    std::vector<int> npart, pdg, status, mother;
+    std::vector<double> p4;
+    size_t pos{0}, n{0};
+  } block;
+  uint64_t nextCandidate{0};
+  void refillBlock();
+};
