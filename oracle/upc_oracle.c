@@ -720,6 +720,14 @@ return_error:
   return ret;
 }
 
+/* generic entry (used by the reference-shim build, oracle/refshim: gsl_integration_qags) */
+int upco_qags(double (*f)(double, void*), void* par, double a, double b, double epsabs, double epsrel, size_t limit,
+              double* result, double* abserr)
+{
+  int neval, last;
+  return qags(f, par, a, b, epsabs, epsrel, limit > QAGS_LIMIT ? QAGS_LIMIT : limit, result, abserr, &neval, &last);
+}
+
 /* analytic test integrands for pinning the QAGS restatement against scipy/QUADPACK */
 typedef struct { int kind; double alpha; } test_par;
 static double test_integrand(double x, void* vp)
