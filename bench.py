@@ -86,23 +86,52 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args):
-    """CPU arm: the oracle (kind 'port') on all host threads, bounded sample of the workload."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    from oracle import pyoracle
+def make_cpu_leg(workload, cores):
+    """Returns (step_fn, n_cells, kind, sample_text).  Preferred: the REFERENCE's own grid driver
+    (src/UpcCrossSection.cpp prepareTwoPhotonLumi, OpenMP static m-slabs, -nthreads = cores) from
+    oracle/_ref -- the reference's sources compiled against the GSL/ROOT shim -- on a coarser grid
+    over the SAME (m, y) ranges (bounded sample: the cost of a cell depends on (m, y) only).
+    Fallback: the oracle port on a strided sub-grid."""
+    import tempfile
+
+    from oracle import pyoracle, pyref
     from upcgen_b200.config import named_config
-    P = named_config(args.workload)
-    cores = os.cpu_count() or 1
+    P = named_config(workload)
+    if pyref.available() and P.proc_id in (11, 13, 15, 51):
+        nm_s, ny_s = 64, 11
+        Ps = named_config(workload, f"BINS_M {nm_s}\nBINS_Y {ny_s}\n")
+        ref = pyref.Reference(Ps, with_breakup_table=True)
+
+        def step():
+            with tempfile.TemporaryDirectory() as d:   # fresh directory: no cached lumi file
+                ref.grid_and_fold(d, nthreads=cores)
+
+        sample = (f"{nm_s}x{ny_s} = {nm_s * ny_s} cells over the same m and y ranges as the {P.nm}x{P.ny} grid; "
+                  f"the reference's prepareTwoPhotonLumi + calcNucCrossSectionYM (sources compiled against the "
+                  f"GSL/ROOT shim, oracle/_ref), {cores} OpenMP threads; table set-up excluded")
+        return step, nm_s * ny_s, "reference", sample
     o = pyoracle.Oracle(P, threads=cores)
-    # bounded sample: every im_step-th m row x every iy_step-th y column of the same grid
     im_step = max(1, P.nm // 64)
     iy_step = max(1, P.ny // 11)
     n_cells = len(range(0, P.nm, im_step)) * len(range(0, P.ny, iy_step))
 
     def step():
         o.fill_lumi(im_step=im_step, iy_step=iy_step)
+
+    sample = (f"{n_cells} cells = every {im_step}th m row x every {iy_step}th y column of the {P.nm}x{P.ny} grid; "
+              f"oracle/upc_oracle.c (port), {cores} OpenMP threads; lumi fill only")
+    return step, n_cells, "port", sample
+
+
+def reference_arm(args):
+    """CPU arm: the oracle (kind 'port') on all host threads, bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from upcgen_b200.config import named_config
+    P = named_config(args.workload)
+    cores = os.cpu_count() or 1
+    step, n_cells, kind, sample = make_cpu_leg(args.workload, cores)
 
     for _ in range(args.warmup):
         step()
@@ -111,17 +140,15 @@ def reference_arm(args):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     val = n_cells / dt
-    sample = (f"{n_cells} cells per step = every {im_step}th m row x every {iy_step}th y column of the "
-              f"{P.nm}x{P.ny} grid; lumi fill only (table set-up excluded)")
     line = {
         "impl": "reference", "metric": "lumi_cells_per_s", "value": val, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD_TEXT[args.workload], "cells": P.nm * P.ny},
-        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of the reference algorithm (oracle/upc_oracle.c, OpenMP static m-slabs); "
-                "the reference binary needs ROOT+GSL and cannot be built in this image",
+        "note": "the reference binary needs ROOT+GSL and cannot be built in this image; kind=reference runs the "
+                "reference's own sources against a GSL/ROOT shim, kind=port the oracle restatement",
     }
     print(json.dumps(line))
     return 0
@@ -286,21 +313,17 @@ def main():
     # ---- CPU baseline beside it (rank 0, N = 1, bounded sample) --------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import pyoracle
         cores = os.cpu_count() or 1
-        o = pyoracle.Oracle(P, threads=cores)
-        im_step = max(1, P.nm // 64); iy_step = max(1, P.ny // 11)
-        nc = len(range(0, P.nm, im_step)) * len(range(0, P.ny, iy_step))
-        o.fill_lumi(im_step=im_step * 4, iy_step=iy_step)  # warm caches/threads
+        cstep, nc, kind, sample = make_cpu_leg(args.workload, cores)
+        cstep()  # warm caches/threads
         t0 = time.perf_counter()
         reps = 0
         while time.perf_counter() - t0 < 10.0 and reps < 50:
-            o.fill_lumi(im_step=im_step, iy_step=iy_step)
+            cstep()
             reps += 1
         dt = (time.perf_counter() - t0) / reps
-        cpu = {"value": nc / dt, "unit": "cells/s", "cores": cores, "kind": "port",
-               "sample": f"{nc} cells (every {im_step}th m row x every {iy_step}th y column of the grid), "
-                         f"{reps} repetitions, lumi fill only; oracle/upc_oracle.c with OpenMP static m-slabs"}
+        cpu = {"value": nc / dt, "unit": "cells/s", "cores": cores, "kind": kind,
+               "sample": sample + f"; {reps} repetitions"}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
     if st["qags_evals"] > 0 and stage["ms_qags"] >= stage["ms_cells"]:

@@ -24,11 +24,47 @@ inline int gsl_spline_init(gsl_spline* s, const double* xa, const double* ya, si
   upco_cspline_init(s->x.data(), s->y.data(), (int)n, s->c.data());
   return 0;
 }
-inline double gsl_spline_eval(const gsl_spline* s, double x, gsl_interp_accel*)
+// gsl_interp_accel_find + cspline_eval: the cached interval is tried first, then a bisection on the
+// side of the miss (same interval as a plain bisection; same cost profile as GSL's).  The reference
+// shares one accelerator between its OpenMP threads; here each thread keeps its own cache slot.
+inline size_t gsl_shim_bsearch(const double* xa, double x, size_t lo, size_t hi)
+{
+  while (hi > lo + 1) {
+    size_t i = (hi + lo) / 2;
+    if (xa[i] > x) hi = i; else lo = i;
+  }
+  return lo;
+}
+inline double gsl_spline_eval(const gsl_spline* s, double x, gsl_interp_accel* a)
 {
   if (x < s->x.front() || x > s->x.back()) {
     std::fprintf(stderr, "gsl: interp.c: ERROR: interpolation error (x=%.17g outside [%.17g, %.17g])\n", x, s->x.front(), s->x.back());
     std::abort();
   }
-  return upco_cspline_eval(s->x.data(), s->y.data(), s->c.data(), (int)s->size, x);
+  static thread_local const gsl_spline* owner[4] = {nullptr, nullptr, nullptr, nullptr};
+  static thread_local size_t cache[4] = {0, 0, 0, 0};
+  int slot = 0;
+  for (; slot < 4; slot++) {
+    if (owner[slot] == s) break;
+    if (!owner[slot]) { owner[slot] = s; cache[slot] = 0; break; }
+  }
+  if (slot == 4) { slot = 0; owner[0] = s; cache[0] = 0; }
+  (void)a;
+  const double* xa = s->x.data();
+  const size_t n = s->size;
+  size_t idx = cache[slot];
+  if (idx > n - 2) idx = 0;
+  if (x < xa[idx]) idx = gsl_shim_bsearch(xa, x, 0, idx);
+  else if (x >= xa[idx + 1]) idx = gsl_shim_bsearch(xa, x, idx, n - 1);
+  cache[slot] = idx;
+  // cspline_eval on the found interval
+  const double x_lo = xa[idx], x_hi = xa[idx + 1];
+  const double dx = x_hi - x_lo;
+  const double y_lo = s->y[idx], y_hi = s->y[idx + 1];
+  const double dy = y_hi - y_lo;
+  const double delx = x - x_lo;
+  const double c_i = s->c[idx], c_ip1 = s->c[idx + 1];
+  const double b_i = (dy / dx) - dx * (c_ip1 + 2.0 * c_i) / 3.0;
+  const double d_i = (c_ip1 - c_i) / (3.0 * dx);
+  return y_lo + delx * (b_i + delx * (c_i + delx * d_i));
 }
