@@ -181,162 +181,217 @@ __device__ __forceinline__ GkOut gk21_tri(const F& f, double a, double b, double
   return o;
 }
 
-// Wynn epsilon table (integration/qelg.c)
-struct EpsTable {
-  int n;
-  int nres;
-  double rlist2[52];
-  double res3la[3];
-};
-
-__device__ __noinline__ void qelg(EpsTable& table, double& result, double& abserr)
-{
-  double* epstab = table.rlist2;
-  double* res3la = table.res3la;
-  const int n = table.n - 1;
-  const double current = epstab[n];
-  double absolute = DBL_MAX;
-  double relative = 5 * DBL_EPSILON * fabs(current);
-  const int newelm = n / 2;
-  const int n_orig = n;
-  int n_final = n;
-  const int nres_orig = table.nres;
-  result = current;
-  abserr = DBL_MAX;
-  if (n < 2) {
-    result = current;
-    abserr = fmax(absolute, relative);
-    return;
-  }
-  epstab[n + 2] = epstab[n];
-  epstab[n] = DBL_MAX;
-  for (int i = 0; i < newelm; i++) {
-    double res = epstab[n - 2 * i + 2];
-    double e0 = epstab[n - 2 * i - 2];
-    double e1 = epstab[n - 2 * i - 1];
-    double e2 = res;
-    double e1abs = fabs(e1);
-    double delta2 = e2 - e1;
-    double err2 = fabs(delta2);
-    double tol2 = fmax(fabs(e2), e1abs) * DBL_EPSILON;
-    double delta3 = e1 - e0;
-    double err3 = fabs(delta3);
-    double tol3 = fmax(e1abs, fabs(e0)) * DBL_EPSILON;
-    if (err2 <= tol2 && err3 <= tol3) {
-      result = res;
-      absolute = err2 + err3;
-      relative = 5 * DBL_EPSILON * fabs(res);
-      abserr = fmax(absolute, relative);
-      return;
-    }
-    double e3 = epstab[n - 2 * i];
-    epstab[n - 2 * i] = e1;
-    double delta1 = e1 - e3;
-    double err1 = fabs(delta1);
-    double tol1 = fmax(e1abs, fabs(e3)) * DBL_EPSILON;
-    if (err1 <= tol1 || err2 <= tol2 || err3 <= tol3) {
-      n_final = 2 * i;
-      break;
-    }
-    double ss = (1 / delta1 + 1 / delta2) - 1 / delta3;
-    if (fabs(ss * e1) <= 0.0001) {
-      n_final = 2 * i;
-      break;
-    }
-    res = e1 + 1 / ss;
-    epstab[n - 2 * i] = res;
-    {
-      const double error = err2 + fabs(res - e2) + err3;
-      if (error <= abserr) {
-        abserr = error;
-        result = res;
-      }
-    }
-  }
-  {
-    const int limexp = 50 - 1;
-    if (n_final == limexp) n_final = 2 * (limexp / 2);
-  }
-  if (n_orig % 2 == 1) {
-    for (int i = 0; i <= newelm; i++) epstab[1 + i * 2] = epstab[i * 2 + 3];
-  } else {
-    for (int i = 0; i <= newelm; i++) epstab[i * 2] = epstab[i * 2 + 2];
-  }
-  if (n_orig != n_final) {
-    for (int i = 0; i <= n_final; i++) epstab[i] = epstab[n_orig - n_final + i];
-  }
-  table.n = n_final + 1;
-  if (nres_orig < 3) {
-    res3la[nres_orig] = result;
-    abserr = DBL_MAX;
-  } else {
-    abserr = (fabs(result - res3la[2]) + fabs(result - res3la[1]) + fabs(result - res3la[0]));
-    res3la[0] = res3la[1];
-    res3la[1] = res3la[2];
-    res3la[2] = result;
-  }
-  table.nres = nres_orig + 1;
-  abserr = fmax(abserr, 5 * DBL_EPSILON * fabs(result));
-}
-
-// Per-lane QAGS state.  cap = capacity of the interval list (the reference allows 1000; every
-// integral met on this path needs < 20).  `limit` keeps the reference's value
-// (1000) in all the places where the algorithm's decisions depend on it (qpsrt's `top`,
-// increase_nrmax's `jupbnd`, the iteration cap); running out of CAP sets `overflow` and the
-// integral is redone by a second pass with cap = 1000.
-// interval-list storage: in-thread arrays (main pass) ...
+// Interval-list / epsilon-table storage.  The QAGS logic below is written against this small
+// interface so that the same code runs on in-thread arrays (test hooks), on a global-memory
+// workspace of the reference's full size (overflow pass) and on the strided shared-memory state of
+// the row-cooperative kernel (upc_qags_rows.cuh):
+//   R(k), E(k)          result / error estimate of interval k          (rlist, elist)
+//   ord(k), set_ord     the error-sorted permutation                   (order)
+//   lvl(k)              bisection level of interval k                  (level)
+//   get_iv / set_iv     bounds of interval k; set_iv returns false when the interval cannot be
+//                       represented (treated like running out of capacity)
+//   eps(k)              Wynn epsilon table entries                     (rlist2)
+//   sc(k), k < 11       the FP64 scalars of the driver (area, errsum, res_ext, ...)
+//   cap, eps_cap        capacities; exceeding either sets `overflow`
 template <int CAP>
 struct QagsLocalStore {
-  double alist[CAP], blist[CAP], rlist[CAP], elist[CAP];
-  short order[CAP], level[CAP];
+  double alist_[CAP], blist_[CAP], rlist_[CAP], elist_[CAP];
+  short order_[CAP], level_[CAP];
+  double eps_[52];
+  double sc_[11];
   static constexpr int cap = CAP;
+  static constexpr int eps_cap = 52;
+  __device__ __forceinline__ double& R(int k) { return rlist_[k]; }
+  __device__ __forceinline__ double& E(int k) { return elist_[k]; }
+  __device__ __forceinline__ int ord(int k) const { return order_[k]; }
+  __device__ __forceinline__ void set_ord(int k, int v) { order_[k] = (short)v; }
+  __device__ __forceinline__ int lvl(int k) const { return level_[k]; }
+  __device__ __forceinline__ void get_iv(int k, double& a, double& b) const { a = alist_[k]; b = blist_[k]; }
+  __device__ __forceinline__ bool set_iv(int k, double a, double b, int level)
+  {
+    alist_[k] = a; blist_[k] = b; level_[k] = (short)level;
+    return true;
+  }
+  __device__ __forceinline__ double& eps(int k) { return eps_[k]; }
+  __device__ __forceinline__ double& sc(int k) { return sc_[k]; }
 };
-// ... or a caller-provided global-memory workspace of the reference's full size (overflow pass)
+// caller-provided global-memory workspace of the reference's full size (overflow pass):
+// 4 x 1000 doubles, 2 x 1000 shorts, 52 doubles
 struct QagsGlobalStore {
-  double *alist, *blist, *rlist, *elist;
-  short *order, *level;
+  double *alist_, *blist_, *rlist_, *elist_, *eps_;
+  short *order_, *level_;
+  double sc_[11];
   static constexpr int cap = 1000;
+  static constexpr int eps_cap = 52;
+  __device__ __forceinline__ double& R(int k) { return rlist_[k]; }
+  __device__ __forceinline__ double& E(int k) { return elist_[k]; }
+  __device__ __forceinline__ int ord(int k) const { return order_[k]; }
+  __device__ __forceinline__ void set_ord(int k, int v) { order_[k] = (short)v; }
+  __device__ __forceinline__ int lvl(int k) const { return level_[k]; }
+  __device__ __forceinline__ void get_iv(int k, double& a, double& b) const { a = alist_[k]; b = blist_[k]; }
+  __device__ __forceinline__ bool set_iv(int k, double a, double b, int level)
+  {
+    alist_[k] = a; blist_[k] = b; level_[k] = (short)level;
+    return true;
+  }
+  __device__ __forceinline__ double& eps(int k) { return eps_[k]; }
+  __device__ __forceinline__ double& sc(int k) { return sc_[k]; }
 };
 
+// Per-lane QAGS state (integration/qags.c + qpsrt.c, qelg.c, util.c of GSL; QUADPACK dqagse).
+// `kLimit` keeps the reference's value (1000) in all the places where the algorithm's decisions
+// depend on it (qpsrt's `top`, increase_nrmax's `jupbnd`, the iteration cap); running out of the
+// store's capacity sets `overflow` and the integral is redone by a pass with the full workspace.
 template <class Store>
 struct Qags : Store {
   static constexpr int kLimit = 1000;
-  using Store::alist; using Store::blist; using Store::rlist; using Store::elist;
-  using Store::order; using Store::level; using Store::cap;
+  using Store::R; using Store::E; using Store::ord; using Store::set_ord; using Store::lvl;
+  using Store::get_iv; using Store::set_iv; using Store::eps; using Store::sc; using Store::cap; using Store::eps_cap;
   int size, nrmax, i, maximum_level;
   // driver state (integration/qags.c)
-  double a0, b0, epsabs, epsrel;
-  double area, errsum, res_ext, err_ext, resabs0, tolerance, ertest, error_over_large_intervals;
-  double reseps, abseps, correc;
+  // the reference's call: gsl_integration_qags(..., epsabs = 1e-4, epsrel = 1e-4, limit = 1000, ...),
+  // src/UpcCrossSection.cpp:209
+  static constexpr double epsabs = 1e-4, epsrel = 1e-4;
+  // the FP64 scalars of the driver live in the store (sc(0..10)): in the row-cooperative kernel
+  // that is shared memory, so that they do not occupy registers across the evaluation phases
+  __device__ __forceinline__ double& area() { return sc(0); }
+  __device__ __forceinline__ double& errsum() { return sc(1); }
+  __device__ __forceinline__ double& res_ext() { return sc(2); }
+  __device__ __forceinline__ double& err_ext() { return sc(3); }
+  __device__ __forceinline__ double& resabs0() { return sc(4); }
+  __device__ __forceinline__ double& ertest() { return sc(5); }
+  __device__ __forceinline__ double& error_over_large_intervals() { return sc(6); }
+  __device__ __forceinline__ double& correc() { return sc(7); }
+  __device__ __forceinline__ double& res3la0() { return sc(8); }
+  __device__ __forceinline__ double& res3la1() { return sc(9); }
+  __device__ __forceinline__ double& res3la2() { return sc(10); }
   int ktmin, roundoff_type1, roundoff_type2, roundoff_type3, error_type, error_type2, iteration;
   bool positive_integrand, extrapolate, disallow_extrapolation, overflow;
-  EpsTable table;
-  // pending bisection
-  double a1, b1, a2, b2, r_i, e_i;
-  int current_level;
+  // Wynn epsilon table (integration/qelg.c): entries in the store, bookkeeping here
+  int tab_n, tab_nres;
   // outputs
   double result, abserr;
   int ier, neval;
 
-  __device__ void begin(double a, double b, double ea, double er)
+  __device__ __forceinline__ void begin(double a, double b)
   {
-    a0 = a; b0 = b; epsabs = ea; epsrel = er;
     size = 0; nrmax = 0; i = 0; maximum_level = 0;
-    alist[0] = a; blist[0] = b; rlist[0] = 0; elist[0] = 0; order[0] = 0; level[0] = 0;
-    ertest = 0; error_over_large_intervals = 0; reseps = 0; abseps = 0; correc = 0;
+    set_iv(0, a, b, 0); R(0) = 0; E(0) = 0; set_ord(0, 0);
+    ertest() = 0; error_over_large_intervals() = 0; correc() = 0;
     ktmin = 0; roundoff_type1 = roundoff_type2 = roundoff_type3 = 0;
     error_type = 0; error_type2 = 0; iteration = 0;
     positive_integrand = false; extrapolate = false; disallow_extrapolation = false; overflow = false;
+    tab_n = 0; tab_nres = 0; res3la0() = res3la1() = res3la2() = 0;
+    area() = errsum() = res_ext() = err_ext() = resabs0() = 0;
     result = 0; abserr = 0; ier = 0; neval = 0;
   }
 
+  // append to the epsilon table; false when the store cannot hold what qelg will touch
+  __device__ __forceinline__ bool eps_push(double v)
+  {
+    if (tab_n + 2 >= eps_cap) return false;  // qelg writes entry n + 2 (n = index of the new one)
+    eps(tab_n++) = v;
+    return true;
+  }
+
+  // integration/qelg.c
+  __device__ __forceinline__ void qelg(double& result_, double& abserr_)
+  {
+    const int n = tab_n - 1;
+    const double current = eps(n);
+    double absolute = DBL_MAX;
+    double relative = 5 * DBL_EPSILON * fabs(current);
+    const int newelm = n / 2;
+    const int n_orig = n;
+    int n_final = n;
+    const int nres_orig = tab_nres;
+    result_ = current;
+    abserr_ = DBL_MAX;
+    if (n < 2) {
+      result_ = current;
+      abserr_ = fmax(absolute, relative);
+      return;
+    }
+    eps(n + 2) = eps(n);
+    eps(n) = DBL_MAX;
+    for (int ii = 0; ii < newelm; ii++) {
+      double res = eps(n - 2 * ii + 2);
+      double e0 = eps(n - 2 * ii - 2);
+      double e1 = eps(n - 2 * ii - 1);
+      double e2 = res;
+      double e1abs = fabs(e1);
+      double delta2 = e2 - e1;
+      double err2 = fabs(delta2);
+      double tol2 = fmax(fabs(e2), e1abs) * DBL_EPSILON;
+      double delta3 = e1 - e0;
+      double err3 = fabs(delta3);
+      double tol3 = fmax(e1abs, fabs(e0)) * DBL_EPSILON;
+      if (err2 <= tol2 && err3 <= tol3) {
+        result_ = res;
+        absolute = err2 + err3;
+        relative = 5 * DBL_EPSILON * fabs(res);
+        abserr_ = fmax(absolute, relative);
+        return;
+      }
+      double e3 = eps(n - 2 * ii);
+      eps(n - 2 * ii) = e1;
+      double delta1 = e1 - e3;
+      double err1 = fabs(delta1);
+      double tol1 = fmax(e1abs, fabs(e3)) * DBL_EPSILON;
+      if (err1 <= tol1 || err2 <= tol2 || err3 <= tol3) {
+        n_final = 2 * ii;
+        break;
+      }
+      double ss = (1 / delta1 + 1 / delta2) - 1 / delta3;
+      if (fabs(ss * e1) <= 0.0001) {
+        n_final = 2 * ii;
+        break;
+      }
+      res = e1 + 1 / ss;
+      eps(n - 2 * ii) = res;
+      {
+        const double error = err2 + fabs(res - e2) + err3;
+        if (error <= abserr_) {
+          abserr_ = error;
+          result_ = res;
+        }
+      }
+    }
+    {
+      const int limexp = 50 - 1;
+      if (n_final == limexp) n_final = 2 * (limexp / 2);
+    }
+    if (n_orig % 2 == 1) {
+      for (int ii = 0; ii <= newelm; ii++) eps(1 + ii * 2) = eps(ii * 2 + 3);
+    } else {
+      for (int ii = 0; ii <= newelm; ii++) eps(ii * 2) = eps(ii * 2 + 2);
+    }
+    if (n_orig != n_final) {
+      for (int ii = 0; ii <= n_final; ii++) eps(ii) = eps(n_orig - n_final + ii);
+    }
+    tab_n = n_final + 1;
+    if (nres_orig < 3) {
+      if (nres_orig == 0) res3la0() = result_;
+      else if (nres_orig == 1) res3la1() = result_;
+      else res3la2() = result_;
+      abserr_ = DBL_MAX;
+    } else {
+      abserr_ = (fabs(result_ - res3la2()) + fabs(result_ - res3la1()) + fabs(result_ - res3la0()));
+      res3la0() = res3la1();
+      res3la1() = res3la2();
+      res3la2() = result_;
+    }
+    tab_nres = nres_orig + 1;
+    abserr_ = fmax(abserr_, 5 * DBL_EPSILON * fabs(result_));
+  }
+
   // after the first GK21 on [a0,b0]; returns true when the integral is finished
-  __device__ bool post_first(const GkOut& g)
+  __device__ __forceinline__ bool post_first(const GkOut& g)
   {
     neval += 21;
-    size = 1; rlist[0] = g.result; elist[0] = g.abserr;
-    resabs0 = g.resabs;
-    tolerance = fmax(epsabs, epsrel * fabs(g.result));
+    size = 1; R(0) = g.result; E(0) = g.abserr;
+    resabs0() = g.resabs;
+    const double tolerance = fmax(epsabs, epsrel * fabs(g.result));
     if (g.abserr <= 100 * DBL_EPSILON * g.resabs && g.abserr > tolerance) {
       result = g.result; abserr = g.abserr; ier = 18;  // GSL_EROUND
       return true;
@@ -344,92 +399,98 @@ struct Qags : Store {
       result = g.result; abserr = g.abserr; ier = 0;
       return true;
     }
-    table.n = 0; table.nres = 0;
-    table.rlist2[table.n++] = g.result;
-    area = g.result;
-    errsum = g.abserr;
-    res_ext = g.result;
-    err_ext = DBL_MAX;
+    tab_n = 0; tab_nres = 0;
+    eps_push(g.result);
+    area() = g.result;
+    errsum() = g.abserr;
+    res_ext() = g.result;
+    err_ext() = DBL_MAX;
     positive_integrand = (fabs(g.result) >= (1 - 50 * DBL_EPSILON) * g.resabs);
     iteration = 1;
     return false;
   }
 
-  // choose the interval to bisect (top of the do-loop in qags())
-  __device__ void pre_step()
+  // choose the interval to bisect (top of the do-loop in qags()): [a1,b1] and [a2,b2] are its
+  // halves, `level` their bisection level
+  __device__ __forceinline__ void pre_step(double& a1, double& b1, double& a2, double& b2, int& level)
   {
-    double a_i = alist[i], b_i = blist[i];
-    r_i = rlist[i]; e_i = elist[i];
-    current_level = level[i] + 1;
+    double a_i, b_i;
+    get_iv(i, a_i, b_i);
+    level = lvl(i) + 1;
     a1 = a_i; b1 = 0.5 * (a_i + b_i); a2 = b1; b2 = b_i;
     iteration++;
   }
 
-  __device__ void qpsrt()
+  // integration/qpsrt.c
+  __device__ __forceinline__ void qpsrt()
   {
     const int last = size - 1;
     const int limit = kLimit;
     int i_nrmax = nrmax;
-    int i_maxerr = order[i_nrmax];
+    int i_maxerr = ord(i_nrmax);
     if (last < 2) {
-      order[0] = 0; order[1] = 1;
+      set_ord(0, 0); set_ord(1, 1);
       i = i_maxerr;
       return;
     }
-    double errmax = elist[i_maxerr];
-    while (i_nrmax > 0 && errmax > elist[order[i_nrmax - 1]]) {
-      order[i_nrmax] = order[i_nrmax - 1];
+    double errmax = E(i_maxerr);
+    while (i_nrmax > 0 && errmax > E(ord(i_nrmax - 1))) {
+      set_ord(i_nrmax, ord(i_nrmax - 1));
       i_nrmax--;
     }
     int top = (last < (limit / 2 + 2)) ? last : limit - last + 1;
     int ii = i_nrmax + 1;
-    while (ii < top && errmax < elist[order[ii]]) {
-      order[ii - 1] = order[ii];
+    while (ii < top && errmax < E(ord(ii))) {
+      set_ord(ii - 1, ord(ii));
       ii++;
     }
-    order[ii - 1] = (short)i_maxerr;
-    double errmin = elist[last];
+    set_ord(ii - 1, i_maxerr);
+    double errmin = E(last);
     int k = top - 1;
-    while (k > ii - 2 && errmin >= elist[order[k]]) {
-      order[k + 1] = order[k];
+    while (k > ii - 2 && errmin >= E(ord(k))) {
+      set_ord(k + 1, ord(k));
       k--;
     }
-    order[k + 1] = (short)last;
-    i_maxerr = order[i_nrmax];
+    set_ord(k + 1, last);
+    i_maxerr = ord(i_nrmax);
     i = i_maxerr;
     nrmax = i_nrmax;
   }
 
-  __device__ void update(double area1, double error1, double area2, double error2)
+  // integration/util.c update(): the half with the larger error stays at i_max
+  __device__ __forceinline__ void update(double a1, double b1, double a2, double b2, int current_level, double area1,
+                                         double error1, double area2, double error2)
   {
     const int i_max = i;
     const int i_new = size;
-    const int new_level = level[i_max] + 1;
+    const int new_level = current_level;  // = level[i_max] + 1
+    bool ok;
     if (error2 > error1) {
-      alist[i_max] = a2;
-      rlist[i_max] = area2; elist[i_max] = error2; level[i_max] = (short)new_level;
-      alist[i_new] = a1; blist[i_new] = b1; rlist[i_new] = area1; elist[i_new] = error1;
-      level[i_new] = (short)new_level;
+      ok = set_iv(i_max, a2, b2, new_level);
+      R(i_max) = area2; E(i_max) = error2;
+      ok &= set_iv(i_new, a1, b1, new_level);
+      R(i_new) = area1; E(i_new) = error1;
     } else {
-      blist[i_max] = b1;
-      rlist[i_max] = area1; elist[i_max] = error1; level[i_max] = (short)new_level;
-      alist[i_new] = a2; blist[i_new] = b2; rlist[i_new] = area2; elist[i_new] = error2;
-      level[i_new] = (short)new_level;
+      ok = set_iv(i_max, a1, b1, new_level);
+      R(i_max) = area1; E(i_max) = error1;
+      ok &= set_iv(i_new, a2, b2, new_level);
+      R(i_new) = area2; E(i_new) = error2;
     }
+    if (!ok) overflow = true;
     size++;
     if (new_level > maximum_level) maximum_level = new_level;
     qpsrt();
   }
 
-  __device__ bool increase_nrmax()
+  __device__ __forceinline__ bool increase_nrmax()
   {
     int id = nrmax;
     int last = size - 1;
     int jupbnd = (last > (1 + kLimit / 2)) ? kLimit + 1 - last : last;
     for (int k = id; k <= jupbnd; k++) {
-      int i_max = order[nrmax];
+      int i_max = ord(nrmax);
       i = i_max;
-      if (level[i_max] < maximum_level) return true;
+      if (lvl(i_max) < maximum_level) return true;
       nrmax++;
     }
     return false;
@@ -437,17 +498,31 @@ struct Qags : Store {
 
   // body of the do-loop after the two GK21 evaluations; returns true when finished
   // (result/abserr/ier set)
-  __device__ bool post_step(const GkOut& g1, const GkOut& g2)
+  __device__ __forceinline__ bool post_step(const GkOut& g1, const GkOut& g2)
+  {
+    const int act = step_core(g1, g2);
+    if (act == 0) return false;
+    return finish(act == 1);  // the only call site: everything stays in registers
+  }
+
+  // returns 0: continue, 1: finish with the plain sum, 2: finish with the extrapolated value
+  __device__ __forceinline__ int step_core(const GkOut& g1, const GkOut& g2)
   {
     neval += 42;
+    // the interval being bisected (chosen by pre_step; nothing has touched the list since)
+    double a1, b2;
+    get_iv(i, a1, b2);
+    const double b1 = 0.5 * (a1 + b2), a2 = b1;
+    const double r_i = R(i), e_i = E(i);
+    const int current_level = lvl(i) + 1;
     const double area1 = g1.result, area2 = g2.result;
     const double error1 = g1.abserr, error2 = g2.abserr;
     const double area12 = area1 + area2;
     const double error12 = error1 + error2;
     const double last_e_i = e_i;
-    errsum = errsum + error12 - e_i;
-    area = area + area12 - r_i;
-    tolerance = fmax(epsabs, epsrel * fabs(area));
+    errsum() = errsum() + error12 - e_i;
+    area() = area() + area12 - r_i;
+    const double tolerance = fmax(epsabs, epsrel * fabs(area()));
     if (g1.resasc != error1 && g2.resasc != error2) {
       double delta = r_i - area12;
       if (fabs(delta) <= 1.0e-5 * fabs(area12) && error12 >= 0.99 * e_i) {
@@ -461,87 +536,88 @@ struct Qags : Store {
       double tmp = (1 + 100 * DBL_EPSILON) * (fabs(a2) + 1000 * DBL_MIN);
       if (fabs(a1) <= tmp && fabs(b2) <= tmp) error_type = 4;
     }
-    update(area1, error1, area2, error2);
+    update(a1, b1, a2, b2, current_level, area1, error1, area2, error2);
 
-    if (errsum <= tolerance) return finish(true);
-    if (error_type) return finish(false);
-    if (iteration >= kLimit - 1) { error_type = 1; return finish(false); }
-    if (size >= cap) { overflow = true; error_type = 1; return finish(false); }
+    if (errsum() <= tolerance) return 1;
+    if (error_type) return 2;
+    if (iteration >= kLimit - 1) { error_type = 1; return 2; }
+    if (overflow || size >= cap) { overflow = true; error_type = 1; return 2; }
     if (iteration == 2) {
-      error_over_large_intervals = errsum;
-      ertest = tolerance;
-      table.rlist2[table.n++] = area;
-      return false;
+      error_over_large_intervals() = errsum();
+      ertest() = tolerance;
+      if (!eps_push(area())) { overflow = true; error_type = 1; return 2; }
+      return 0;
     }
-    if (disallow_extrapolation) return false;
-    error_over_large_intervals += -last_e_i;
-    if (current_level < maximum_level) error_over_large_intervals += error12;
+    if (disallow_extrapolation) return 0;
+    error_over_large_intervals() += -last_e_i;
+    if (current_level < maximum_level) error_over_large_intervals() += error12;
     if (!extrapolate) {
-      if (level[i] < maximum_level) return false;  // large_interval()
+      if (lvl(i) < maximum_level) return 0;  // large_interval()
       extrapolate = true;
       nrmax = 1;
     }
-    if (!error_type2 && error_over_large_intervals > ertest) {
-      if (increase_nrmax()) return false;
+    if (!error_type2 && error_over_large_intervals() > ertest()) {
+      if (increase_nrmax()) return 0;
     }
-    table.rlist2[table.n++] = area;
-    qelg(table, reseps, abseps);
+    if (!eps_push(area())) { overflow = true; error_type = 1; return 2; }
+    double reseps, abseps;
+    qelg(reseps, abseps);
     ktmin++;
-    if (ktmin > 5 && err_ext < 0.001 * errsum) error_type = 5;
-    if (abseps < err_ext) {
+    if (ktmin > 5 && err_ext() < 0.001 * errsum()) error_type = 5;
+    if (abseps < err_ext()) {
       ktmin = 0;
-      err_ext = abseps;
-      res_ext = reseps;
-      correc = error_over_large_intervals;
-      ertest = fmax(epsabs, epsrel * fabs(reseps));
-      if (err_ext <= ertest) return finish(false);
+      err_ext() = abseps;
+      res_ext() = reseps;
+      correc() = error_over_large_intervals();
+      ertest() = fmax(epsabs, epsrel * fabs(reseps));
+      if (err_ext() <= ertest()) return 2;
     }
-    if (table.n == 1) disallow_extrapolation = true;
-    if (error_type == 5) return finish(false);
-    nrmax = 0; i = order[0];  // reset_nrmax
+    if (tab_n == 1) disallow_extrapolation = true;
+    if (error_type == 5) return 2;
+    nrmax = 0; i = ord(0);  // reset_nrmax
     extrapolate = false;
-    error_over_large_intervals = errsum;
-    return false;
+    error_over_large_intervals() = errsum();
+    return 0;
   }
 
   // tail of qags(): choice between the extrapolated value and the plain sum
-  __device__ __noinline__ bool finish(bool direct_sum)
+  __device__ __forceinline__ bool finish(bool direct_sum)
   {
     bool compute = direct_sum;
     bool ret_err = false;
     if (!compute) {
-      result = res_ext;
-      abserr = err_ext;
-      if (err_ext == DBL_MAX) {
+      result = res_ext();
+      abserr = err_ext();
+      if (err_ext() == DBL_MAX) {
         compute = true;
       } else {
         if (error_type || error_type2) {
-          if (error_type2) err_ext += correc;
+          if (error_type2) err_ext() += correc();
           if (error_type == 0) error_type = 3;
-          if (res_ext != 0.0 && area != 0.0) {
-            if (err_ext / fabs(res_ext) > errsum / fabs(area)) compute = true;
-          } else if (err_ext > errsum) {
+          if (res_ext() != 0.0 && area() != 0.0) {
+            if (err_ext() / fabs(res_ext()) > errsum() / fabs(area())) compute = true;
+          } else if (err_ext() > errsum()) {
             compute = true;
-          } else if (area == 0.0) {
+          } else if (area() == 0.0) {
             ret_err = true;
           }
         }
         if (!compute && !ret_err) {
-          double max_area = fmax(fabs(res_ext), fabs(area));
-          if (!positive_integrand && max_area < 0.01 * resabs0) {
+          double max_area = fmax(fabs(res_ext()), fabs(area()));
+          if (!positive_integrand && max_area < 0.01 * resabs0()) {
             ret_err = true;
           } else {
-            double ratio = res_ext / area;
-            if (ratio < 0.01 || ratio > 100.0 || errsum > fabs(area)) error_type = 6;
+            double ratio = res_ext() / area();
+            if (ratio < 0.01 || ratio > 100.0 || errsum() > fabs(area())) error_type = 6;
           }
         }
       }
     }
     if (compute) {
       double s = 0;
-      for (int k = 0; k < size; k++) s += rlist[k];
+      for (int k = 0; k < size; k++) s += R(k);
       result = s;
-      abserr = errsum;
+      abserr = errsum();
     }
     if (error_type > 2) error_type--;
     ier = error_type;
