@@ -54,159 +54,173 @@ __device__ __forceinline__ double hot()
   return v;
 }
 
-struct D3 {
-  double a, b, c;
+// N evaluations side by side in one thread: every coefficient fetch feeds N independent DFMA chains
+template <int N>
+struct DV {
+  double v[N];
 };
+using D3 = DV<3>;
 
-// r = r*u + K[I] on three lanes-in-a-thread, descending I from I0+N-2 to I0
-template <int I0, int I>
-struct Horner3 {
-  static __device__ __forceinline__ void run(D3& r, const D3& u)
+#define UPC_FOR_N _Pragma("unroll") for (int i_ = 0; i_ < N; ++i_)
+
+// r = r*u + K[I] on N values, descending I from I0+N-2 to I0
+template <int N, int I0, int I>
+struct HornerN {
+  static __device__ __forceinline__ void run(DV<N>& r, const DV<N>& u)
   {
     const double k = hot<I0 + I>();
-    r.a = fma(r.a, u.a, k);
-    r.b = fma(r.b, u.b, k);
-    r.c = fma(r.c, u.c, k);
-    Horner3<I0, I - 1>::run(r, u);
+    UPC_FOR_N r.v[i_] = fma(r.v[i_], u.v[i_], k);
+    HornerN<N, I0, I - 1>::run(r, u);
   }
 };
-template <int I0>
-struct Horner3<I0, -1> {
-  static __device__ __forceinline__ void run(D3&, const D3&) {}
+template <int N, int I0>
+struct HornerN<N, I0, -1> {
+  static __device__ __forceinline__ void run(DV<N>&, const DV<N>&) {}
 };
-template <int I0, int N>
-__device__ __forceinline__ D3 horner3(const D3& u)
+template <int N, int I0, int LEN>
+__device__ __forceinline__ DV<N> hornerN(const DV<N>& u)
 {
-  const double top = hot<I0 + N - 1>();
-  D3 r{top, top, top};
-  Horner3<I0, N - 2>::run(r, u);
+  const double top = hot<I0 + LEN - 1>();
+  DV<N> r;
+  UPC_FOR_N r.v[i_] = top;
+  HornerN<N, I0, LEN - 2>::run(r, u);
   return r;
 }
 
-// sin/cos of three moderate arguments (see sincos_mid)
-__device__ __forceinline__ void sincos3(const D3& x, D3& s, D3& c)
+// sin/cos of N moderate arguments (see sincos_mid)
+template <int N>
+__device__ __forceinline__ void sincosN(const DV<N>& x, DV<N>& s, DV<N>& c)
 {
   const double kMagic = 6755399441055744.0;
-  const double two_over_pi = hot<H_SC + 0>();
-  const double qa = fma(x.a, two_over_pi, kMagic), qb = fma(x.b, two_over_pi, kMagic), qc = fma(x.c, two_over_pi, kMagic);
-  const int na = __double2loint(qa), nb = __double2loint(qb), nc = __double2loint(qc);
-  const double fa = qa - kMagic, fb = qb - kMagic, fc = qc - kMagic;
-  double ra, rb, rc;
+  DV<N> r, f;
+  int n[N];
+  {
+    const double two_over_pi = hot<H_SC + 0>();
+    UPC_FOR_N {
+      const double q = fma(x.v[i_], two_over_pi, kMagic);
+      n[i_] = __double2loint(q);
+      f.v[i_] = q - kMagic;
+    }
+  }
   {
     const double p = hot<H_SC + 1>();
-    ra = fma(-fa, p, x.a); rb = fma(-fb, p, x.b); rc = fma(-fc, p, x.c);
+    UPC_FOR_N r.v[i_] = fma(-f.v[i_], p, x.v[i_]);
   }
   {
     const double p = hot<H_SC + 2>();
-    ra = fma(-fa, p, ra); rb = fma(-fb, p, rb); rc = fma(-fc, p, rc);
+    UPC_FOR_N r.v[i_] = fma(-f.v[i_], p, r.v[i_]);
   }
   {
     const double p = hot<H_SC + 3>();
-    ra = fma(-fa, p, ra); rb = fma(-fb, p, rb); rc = fma(-fc, p, rc);
+    UPC_FOR_N r.v[i_] = fma(-f.v[i_], p, r.v[i_]);
   }
-  const D3 z{ra * ra, rb * rb, rc * rc};
+  DV<N> z;
+  UPC_FOR_N z.v[i_] = r.v[i_] * r.v[i_];
   // the table stores S6..S1 and C6..C1 in evaluation order (ascending index)
-  D3 sp, cp;
+  DV<N> sp, cp;
   {
     const double k6 = hot<H_SC + 4>(), k5 = hot<H_SC + 5>();
-    sp.a = fma(z.a, k6, k5); sp.b = fma(z.b, k6, k5); sp.c = fma(z.c, k6, k5);
+    UPC_FOR_N sp.v[i_] = fma(z.v[i_], k6, k5);
     const double k4 = hot<H_SC + 6>();
-    sp.a = fma(z.a, sp.a, k4); sp.b = fma(z.b, sp.b, k4); sp.c = fma(z.c, sp.c, k4);
+    UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k4);
     const double k3 = hot<H_SC + 7>();
-    sp.a = fma(z.a, sp.a, k3); sp.b = fma(z.b, sp.b, k3); sp.c = fma(z.c, sp.c, k3);
+    UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k3);
     const double k2 = hot<H_SC + 8>();
-    sp.a = fma(z.a, sp.a, k2); sp.b = fma(z.b, sp.b, k2); sp.c = fma(z.c, sp.c, k2);
+    UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k2);
     const double k1 = hot<H_SC + 9>();
-    sp.a = fma(z.a, sp.a, k1); sp.b = fma(z.b, sp.b, k1); sp.c = fma(z.c, sp.c, k1);
+    UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k1);
   }
   {
     const double k6 = hot<H_SC + 10>(), k5 = hot<H_SC + 11>();
-    cp.a = fma(z.a, k6, k5); cp.b = fma(z.b, k6, k5); cp.c = fma(z.c, k6, k5);
+    UPC_FOR_N cp.v[i_] = fma(z.v[i_], k6, k5);
     const double k4 = hot<H_SC + 12>();
-    cp.a = fma(z.a, cp.a, k4); cp.b = fma(z.b, cp.b, k4); cp.c = fma(z.c, cp.c, k4);
+    UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k4);
     const double k3 = hot<H_SC + 13>();
-    cp.a = fma(z.a, cp.a, k3); cp.b = fma(z.b, cp.b, k3); cp.c = fma(z.c, cp.c, k3);
+    UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k3);
     const double k2 = hot<H_SC + 14>();
-    cp.a = fma(z.a, cp.a, k2); cp.b = fma(z.b, cp.b, k2); cp.c = fma(z.c, cp.c, k2);
+    UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k2);
     const double k1 = hot<H_SC + 15>();
-    cp.a = fma(z.a, cp.a, k1); cp.b = fma(z.b, cp.b, k1); cp.c = fma(z.c, cp.c, k1);
+    UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k1);
   }
-  const double sra = fma(z.a * ra, sp.a, ra), srb = fma(z.b * rb, sp.b, rb), src = fma(z.c * rc, sp.c, rc);
-  const double cra = fma(z.a * z.a, cp.a, fma(z.a, -0.5, 1.0)), crb = fma(z.b * z.b, cp.b, fma(z.b, -0.5, 1.0)),
-               crc = fma(z.c * z.c, cp.c, fma(z.c, -0.5, 1.0));
-  auto quad = [](int n, double sr, double cr, double& so, double& co) {
-    const double a = (n & 1) ? cr : sr;
-    const double b = (n & 1) ? sr : cr;
-    so = (n & 2) ? -a : a;
-    co = ((n + 1) & 2) ? -b : b;
-  };
-  quad(na, sra, cra, s.a, c.a);
-  quad(nb, srb, crb, s.b, c.b);
-  quad(nc, src, crc, s.c, c.c);
+  UPC_FOR_N {
+    const double sr = fma(z.v[i_] * r.v[i_], sp.v[i_], r.v[i_]);
+    const double cr = fma(z.v[i_] * z.v[i_], cp.v[i_], fma(z.v[i_], -0.5, 1.0));
+    const double a = (n[i_] & 1) ? cr : sr;
+    const double b = (n[i_] & 1) ? sr : cr;
+    s.v[i_] = (n[i_] & 2) ? -a : a;
+    c.v[i_] = ((n[i_] + 1) & 2) ? -b : b;
+  }
 }
 
-// J1 on three arguments, all > 8 (modulus/phase form; see bessel_j1)
-__device__ __forceinline__ D3 j1_large3(const D3& x)
+// J1 on N arguments, all > 8 (modulus/phase form; see bessel_j1)
+template <int N>
+__device__ __forceinline__ DV<N> j1_largeN(const DV<N>& x)
 {
-  const D3 rx{1. / x.a, 1. / x.b, 1. / x.c};
+  DV<N> rx, u;
   const double k64 = 64.;
-  const D3 u{fma(2. * k64 * rx.a, rx.a, -1.), fma(2. * k64 * rx.b, rx.b, -1.), fma(2. * k64 * rx.c, rx.c, -1.)};
-  const D3 m = horner3<H_J1M, UPC_J1_M_N>(u);
-  const D3 t = horner3<H_J1T, UPC_J1_T_N>(u);
+  UPC_FOR_N {
+    rx.v[i_] = 1. / x.v[i_];
+    u.v[i_] = fma(2. * k64 * rx.v[i_], rx.v[i_], -1.);
+  }
+  const DV<N> m = hornerN<N, H_J1M, UPC_J1_M_N>(u);
+  const DV<N> t = hornerN<N, H_J1T, UPC_J1_T_N>(u);
   const double two_over_pi = hot<H_MISC + 1>();
-  const D3 ampl{m.a * sqrt(two_over_pi * rx.a), m.b * sqrt(two_over_pi * rx.b), m.c * sqrt(two_over_pi * rx.c)};
-  const D3 eps{t.a * rx.a, t.b * rx.b, t.c * rx.c};
-  D3 sy, cy;
-  sincos3(x, sy, cy);
-  const D3 e2{eps.a * eps.a, eps.b * eps.b, eps.c * eps.c};
-  D3 se, ce;
+  DV<N> ampl, eps, e2;
+  UPC_FOR_N {
+    ampl.v[i_] = m.v[i_] * sqrt(two_over_pi * rx.v[i_]);
+    eps.v[i_] = t.v[i_] * rx.v[i_];
+    e2.v[i_] = eps.v[i_] * eps.v[i_];
+  }
+  DV<N> sy, cy;
+  sincosN<N>(x, sy, cy);
+  DV<N> se, ce;
   {
     const double k9 = hot<H_EPS + 0>(), k7 = hot<H_EPS + 1>();
-    se.a = fma(e2.a, k9, k7); se.b = fma(e2.b, k9, k7); se.c = fma(e2.c, k9, k7);
+    UPC_FOR_N se.v[i_] = fma(e2.v[i_], k9, k7);
     const double k5 = hot<H_EPS + 2>();
-    se.a = fma(e2.a, se.a, k5); se.b = fma(e2.b, se.b, k5); se.c = fma(e2.c, se.c, k5);
+    UPC_FOR_N se.v[i_] = fma(e2.v[i_], se.v[i_], k5);
     const double k3 = hot<H_EPS + 3>();
-    se.a = fma(e2.a, se.a, k3); se.b = fma(e2.b, se.b, k3); se.c = fma(e2.c, se.c, k3);
-    se.a = eps.a * fma(e2.a, se.a, 1.); se.b = eps.b * fma(e2.b, se.b, 1.); se.c = eps.c * fma(e2.c, se.c, 1.);
+    UPC_FOR_N se.v[i_] = fma(e2.v[i_], se.v[i_], k3);
+    UPC_FOR_N se.v[i_] = eps.v[i_] * fma(e2.v[i_], se.v[i_], 1.);
     const double k8 = hot<H_EPS + 4>(), k6 = hot<H_EPS + 5>();
-    ce.a = fma(e2.a, k8, k6); ce.b = fma(e2.b, k8, k6); ce.c = fma(e2.c, k8, k6);
+    UPC_FOR_N ce.v[i_] = fma(e2.v[i_], k8, k6);
     const double k4 = hot<H_EPS + 6>();
-    ce.a = fma(e2.a, ce.a, k4); ce.b = fma(e2.b, ce.b, k4); ce.c = fma(e2.c, ce.c, k4);
-    ce.a = fma(e2.a, fma(e2.a, ce.a, -0.5), 1.); ce.b = fma(e2.b, fma(e2.b, ce.b, -0.5), 1.);
-    ce.c = fma(e2.c, fma(e2.c, ce.c, -0.5), 1.);
+    UPC_FOR_N ce.v[i_] = fma(e2.v[i_], ce.v[i_], k4);
+    UPC_FOR_N ce.v[i_] = fma(e2.v[i_], fma(e2.v[i_], ce.v[i_], -0.5), 1.);
   }
   const double inv_sqrt2 = hot<H_MISC + 2>();
-  D3 r;
-  r.a = ampl.a * fma(ce.a, sy.a - cy.a, se.a * (sy.a + cy.a)) * inv_sqrt2;
-  r.b = ampl.b * fma(ce.b, sy.b - cy.b, se.b * (sy.b + cy.b)) * inv_sqrt2;
-  r.c = ampl.c * fma(ce.c, sy.c - cy.c, se.c * (sy.c + cy.c)) * inv_sqrt2;
+  DV<N> r;
+  UPC_FOR_N r.v[i_] = ampl.v[i_] * fma(ce.v[i_], sy.v[i_] - cy.v[i_], se.v[i_] * (sy.v[i_] + cy.v[i_])) * inv_sqrt2;
   return r;
 }
 
-// J1 on three arguments, all in [0, 8]
-__device__ __forceinline__ D3 j1_small3(const D3& x)
+// J1 on N arguments, all in [0, 8]
+template <int N>
+__device__ __forceinline__ DV<N> j1_smallN(const DV<N>& x)
 {
   const double k32 = hot<H_MISC + 0>();
-  const D3 u{fma(x.a * x.a, k32, -1.), fma(x.b * x.b, k32, -1.), fma(x.c * x.c, k32, -1.)};
-  const D3 p = horner3<H_J1P, UPC_J1_P_N>(u);
-  return D3{x.a * p.a, x.b * p.b, x.c * p.c};
+  DV<N> u;
+  UPC_FOR_N u.v[i_] = fma(x.v[i_] * x.v[i_], k32, -1.);
+  const DV<N> p = hornerN<N, H_J1P, UPC_J1_P_N>(u);
+  DV<N> r;
+  UPC_FOR_N r.v[i_] = x.v[i_] * p.v[i_];
+  return r;
 }
 
 // J1 for three arbitrary non-negative arguments: each branch is evaluated for all three when any
 // of them needs it (arguments clamped into the branch's domain), then selected per argument.
 __device__ __forceinline__ D3 j1_3(const D3& x)
 {
-  const bool la = x.a > 8., lb = x.b > 8., lc = x.c > 8.;
-  D3 r{0., 0., 0.};
+  const bool la = x.v[0] > 8., lb = x.v[1] > 8., lc = x.v[2] > 8.;
+  D3 r{{0., 0., 0.}};
   if (la | lb | lc) {
-    const D3 v = j1_large3(D3{fmax(x.a, 8.), fmax(x.b, 8.), fmax(x.c, 8.)});
-    r = v;
+    r = j1_largeN<3>(D3{{fmax(x.v[0], 8.), fmax(x.v[1], 8.), fmax(x.v[2], 8.)}});
   }
   if (!(la & lb & lc)) {
-    const D3 v = j1_small3(D3{fmin(x.a, 8.), fmin(x.b, 8.), fmin(x.c, 8.)});
-    if (!la) r.a = v.a;
-    if (!lb) r.b = v.b;
-    if (!lc) r.c = v.c;
+    const D3 v = j1_smallN<3>(D3{{fmin(x.v[0], 8.), fmin(x.v[1], 8.), fmin(x.v[2], 8.)}});
+    if (!la) r.v[0] = v.v[0];
+    if (!lb) r.v[1] = v.v[1];
+    if (!lc) r.v[2] = v.v[2];
   }
   return r;
 }

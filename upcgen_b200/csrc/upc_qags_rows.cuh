@@ -29,8 +29,8 @@
 namespace upc {
 
 constexpr int kRcThreads = 512;
-constexpr int kRcGroups = 2;     // owner groups (one warpgroup each; 3 of its 4 warps own slots)
-constexpr int kRcSlots = 96;     // integrals in flight per group (multiple of 32: conflict-free strides)
+constexpr int kRcGroups = 4;     // owner groups of two warps (warpgroups 0 and 1)
+constexpr int kRcSlots = 64;     // integrals in flight per group (multiple of 32: conflict-free strides)
 constexpr int kRcEval = 256;     // evaluator threads
 constexpr int kRcCap = 16;       // interval-list capacity per integral (largest seen: 15)
 constexpr int kRcEps = 16;       // epsilon-table capacity (largest index touched so far: 12)
@@ -45,7 +45,7 @@ constexpr int kRcRegsOwner = 88, kRcRegsEval = 168;  // 256 * 88 + 256 * 168 = 6
 
 // state of one owner group
 struct RcGroup {
-  double fv[2][21][kRcSlots];          // integrand values [half][node][slot]
+  double gk[4][2][kRcSlots];           // GK21 sums of each task: result, abserr, resabs, resasc
   double rl[kRcCap][kRcSlots];         // QAGS interval list: integral estimates ...
   double el[kRcCap][kRcSlots];         // ... error estimates ...
   double ep[kRcEps][kRcSlots];         // Wynn epsilon table
@@ -60,11 +60,12 @@ struct RcGroup {
   short t_g[2][kRcSlots];              // cache entry of each pending interval (-1: uncached)
   unsigned char od[kRcCap][kRcSlots];  // ... and the error-sorted permutation
   unsigned char slot_ctx[kRcSlots];
-  unsigned char list[2][kRcSlots];     // compacted tasks of the round
+  int t_off[2][kRcSlots];              // position of the task's evaluations in the round's list (small << 16 | large)
+  unsigned char t_small[2][kRcSlots];  // number of nodes on J1's small-argument branch (255: no task)
   unsigned short newlist[kRcG];        // entries inserted this round (to be filled)
   int n_new[2];                        // by round parity
-  int cnt[3][kRcSlots / 32];           // per-warp counts of the round: A tasks, B tasks, idle slots
-  int n_task[2];                       // tasks handed to the evaluators (A, B)
+  int cnt[3][kRcSlots / 32];           // per-warp counts of the round: active slots, evaluations (packed), idle slots
+  int n_cls[2];                        // evaluations handed to the evaluators: large-argument, small-argument
   int fin;                             // the group has no more work
   // rows in flight: a row keeps its context (c0, cached intervals) until its last integral is done
   int ctx_left[kRcCtx];                // integrals of the row not finished yet (0: context free)
@@ -77,11 +78,20 @@ struct RcGroup {
 
 struct RcShared {
   RcGroup g[kRcGroups];
+  double fv[2][kRcSlots][21];          // integrand values of the group-round in service [half][slot][node] (odd stride:
+                                       // conflict-free both ways)
+  unsigned short elist[kRcSlots * 42]; // the evaluations of the group-round in service (slot | half << 6 | node << 7):
+                                       // J1 large-argument ones from the front, small-argument ones from the back
   double node[24];                     // signed GK21 abscissas (kGkNode)
+  double snode[24];                    // the same in ascending order ...
+  int sid[24];                         // ... and their index in kGkNode
 };
 
+static_assert(sizeof(RcShared) <= 227 * 1024, "shared memory of one SM");
+
 // named barriers (0 is __syncthreads)
-enum { kBarOwn0 = 1, kBarFull0 = 3, kBarDone0 = 5 };
+enum { kBarOwn0 = 1, kBarFull0 = 1 + kRcGroups, kBarDone0 = 1 + 2 * kRcGroups, kBarEval = 1 + 3 * kRcGroups };
+static_assert(kBarEval < 16, "named barriers");
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -184,6 +194,62 @@ __device__ __forceinline__ GkOut gk21_sums(const double* fv, int fv_stride, doub
   return o;
 }
 
+// The same sums split over two threads of a task (contiguous fv[0..20]), fully unrolled: role 0
+// forms the Kronrod, Gauss and |f| sums, role 1 re-forms the Kronrod sum (same operations, same
+// order: same bits) for the mean and then the |f - mean| sum; gk21_finish combines them (role 0,
+// after a shuffle).  The Gauss sum runs over the 5 Gauss pairs only, as in qk.c (the zero weights
+// of gk21_tri add +0.0: the same value).
+__device__ __forceinline__ void gk21_sums_pair(const double* fv, double half_length, int role, GkOut& o, double& asc)
+{
+  double f[21];
+#pragma unroll
+  for (int n = 0; n < 21; ++n) f[n] = fv[n];
+  const double f_center = f[20];
+  double result_kronrod = f_center * kGkWkC;
+  if (role == 0) {
+    double result_gauss = 0;
+    double result_abs = fabs(result_kronrod);
+#pragma unroll
+    for (int p = 0; p < 10; ++p) {
+      const double fsum = f[2 * p] + f[2 * p + 1];
+      if (p < 5) result_gauss += kGkWg[p] * fsum;
+      result_kronrod += kGkWk[p] * fsum;
+      result_abs += kGkWk[p] * (fabs(f[2 * p]) + fabs(f[2 * p + 1]));
+    }
+    o.abserr = (result_kronrod - result_gauss) * half_length;  // raw error, rescaled in gk21_finish
+    o.result = result_kronrod * half_length;
+    o.resabs = result_abs * fabs(half_length);
+  } else {
+#pragma unroll
+    for (int p = 0; p < 10; ++p) result_kronrod += kGkWk[p] * (f[2 * p] + f[2 * p + 1]);
+    const double mean = result_kronrod * 0.5;
+    double result_asc = kGkWkC * fabs(f_center - mean);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const int p = (j & 1) ? (j >> 1) : (5 + (j >> 1));
+      result_asc += kGkWk[p] * (fabs(f[2 * p] - mean) + fabs(f[2 * p + 1] - mean));
+    }
+    asc = result_asc * fabs(half_length);
+  }
+}
+
+// rescale_error of integration/qk.c
+__device__ __forceinline__ void gk21_finish(GkOut& o, double result_asc, double /*half_length*/)
+{
+  double err = fabs(o.abserr);
+  if (result_asc != 0 && err != 0) {
+    double s = 200 * err / result_asc;
+    double scale = s * sqrt(s);
+    err = scale < 1 ? result_asc * scale : result_asc;
+  }
+  if (o.resabs > DBL_MIN / (50 * DBL_EPSILON)) {
+    double min_err = 50 * DBL_EPSILON * o.resabs;
+    if (min_err > err) err = min_err;
+  }
+  o.abserr = err;
+  o.resasc = result_asc;
+}
+
 // look up / insert the interval (heap index) in the table of row context ctx; returns the entry
 // or -1 when the table is full or the interval too deep (the task is then evaluated uncached)
 __device__ __forceinline__ int rc_entry(RcGroup& sh, int parity, int ctx, int level, unsigned heap)
@@ -206,36 +272,53 @@ __device__ __forceinline__ int rc_entry(RcGroup& sh, int parity, int ctx, int le
 }
 
 // EVALUATORS: the integrand evaluations of one round of one owner group, flattened over the 256
-// evaluator threads: trip e -> (task, 3 consecutive nodes); A tasks first, then B tasks
-__device__ __forceinline__ void rc_eval(RcGroup& sh, const double* node, int etid, const double* __restrict__ gbuf,
-                                        const SplineSeg* __restrict__ ff, double ff_last)
+// evaluator threads whatever integral they belong to, three per thread and trip.  The owners have
+// sorted them by the branch of J1 they take (argument <= 8: polynomial; > 8: modulus/phase form),
+// so every warp runs one branch with all lanes.
+constexpr int kRcWide = 3;  // evaluations per evaluator thread and trip (independent DFMA chains)
+
+template <bool LARGE>
+__device__ __forceinline__ void rc_eval_trip(RcGroup& sh, double (*fv)[kRcSlots][21], const unsigned short* elist,
+                                             const double* node, int e, int n_ev, const double* __restrict__ gbuf,
+                                             const SplineSeg* __restrict__ ff, double ff_last)
 {
-  const int n_a = sh.n_task[0], n_t = n_a + sh.n_task[1];
-  const int n_trips = 7 * n_t;
+  constexpr int kLast = kRcSlots * 42 - 1;
+  constexpr int N = kRcWide;
+  int slot[N], half[N], nd[N], ent[N];
+  DV<N> g, x, z;
+  UPC_FOR_N {
+    const int idx = min(e + i_, n_ev - 1);  // tail: repeats (same value, same place)
+    const unsigned c = elist[LARGE ? idx : kLast - idx];
+    slot[i_] = c & 63; half[i_] = (c >> 6) & 1; nd[i_] = c >> 7;
+    ent[i_] = sh.t_g[half[i_]][slot[i_]];
+    // issued first: the L2 latency is covered by the J1 arithmetic below
+    if (ent[i_] >= 0) g.v[i_] = __ldcg(gbuf + ent[i_] * 21 + nd[i_]);
+  }
+  UPC_FOR_N {
+    x.v[i_] = fma(sh.t_half[half[i_]][slot[i_]], node[nd[i_]], sh.t_center[half[i_]][slot[i_]]);
+    if (ent[i_] < 0) g.v[i_] = rc_g(x.v[i_], sh.ctx_c0[sh.slot_ctx[slot[i_]]], ff, ff_last);
+    z.v[i_] = sh.beta[slot[i_]] * x.v[i_];
+  }
+  const DV<N> j = LARGE ? j1_largeN<N>(z) : j1_smallN<N>(z);
+  UPC_FOR_N fv[half[i_]][slot[i_]][nd[i_]] = g.v[i_] * j.v[i_];
+}
+
+// trips of kRcWide evaluations: the large-argument ones, padded to whole warps, then the small ones
+__device__ __forceinline__ void rc_eval_round(RcGroup& sh, double (*fv)[kRcSlots][21], const unsigned short* elist,
+                                              const double* node, int etid, int n_large, int n_small,
+                                              const double* __restrict__ gbuf, const SplineSeg* __restrict__ ff,
+                                              double ff_last)
+{
+  const int t_large = (n_large + kRcWide - 1) / kRcWide, t_small = (n_small + kRcWide - 1) / kRcWide;
+  const int t_pad = (t_large + 31) & ~31;
+  const int n_trips = t_pad + t_small;
 #pragma unroll 1
-  for (int e = etid; e < n_trips; e += kRcEval) {
-    const int q = e / n_t, rank = e - q * n_t;
-    const int half = rank >= n_a;
-    const int slot = sh.list[half][rank - (half ? n_a : 0)];
-    const int ent = sh.t_g[half][slot];
-    const int n = 3 * q;
-    double g0, g1, g2;
-    if (ent >= 0) {  // issued first: the L2 latency is covered by the J1 arithmetic below
-      const double* gv = gbuf + ent * 21 + n;
-      g0 = __ldcg(gv); g1 = __ldcg(gv + 1); g2 = __ldcg(gv + 2);
+  for (int t = etid; t < n_trips; t += kRcEval) {
+    if (t < t_pad) {  // warp-uniform
+      if (t < t_large) rc_eval_trip<true>(sh, fv, elist, node, kRcWide * t, n_large, gbuf, ff, ff_last);
+    } else {
+      rc_eval_trip<false>(sh, fv, elist, node, kRcWide * (t - t_pad), n_small, gbuf, ff, ff_last);
     }
-    const double center = sh.t_center[half][slot], hl = sh.t_half[half][slot];
-    const double beta = sh.beta[slot];
-    const double x0 = fma(hl, node[n], center), x1 = fma(hl, node[n + 1], center), x2 = fma(hl, node[n + 2], center);
-    if (ent < 0) {
-      const double c0 = sh.ctx_c0[sh.slot_ctx[slot]];
-      g0 = rc_g(x0, c0, ff, ff_last); g1 = rc_g(x1, c0, ff, ff_last); g2 = rc_g(x2, c0, ff, ff_last);
-    }
-    const D3 j = j1_3(D3{beta * x0, beta * x1, beta * x2});
-    double* fo = &sh.fv[half][n][slot];
-    fo[0] = g0 * j.a;
-    fo[kRcSlots] = g1 * j.b;
-    fo[2 * kRcSlots] = g2 * j.c;
   }
 }
 
@@ -284,7 +367,7 @@ __device__ __forceinline__ void rc_grant(RcGroup& sh, int n_idle, int n_rows, co
 
 // OWNERS: one group of 96 slots.  A slot whose integral is finished takes the next integral of the
 // row queue in the following round, so the rounds stay full until the queue runs dry.
-__device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, int grp, int ltid, int n_rows, int nb,
+__device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const double* snode, const int* sid, int grp, int ltid, int n_rows, int nb,
                                          const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
                                          const FluxConsts& fc, const SplineSeg* __restrict__ ff, double ff_last,
                                          double* __restrict__ W, int* __restrict__ neval_out,
@@ -353,8 +436,12 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, int gr
       bar_sync(bar_own, kRcSlots);
     }
 
-    // ---- R1 (thread = integral): pending intervals, cache entries, task counts ----
+    // ---- R1 (thread = integral): pending intervals, cache entries, evaluation counts ----
+    // z = beta * x is monotonic over the (ascending) nodes, so the evaluations of a task that take
+    // J1's small-argument branch (z <= 8, bessel_j1) are its first n_small nodes: a bisection with
+    // the very arithmetic of the evaluators
     bool has_b = false;
+    int small_a = 0, small_b = 0;
     if (active) {
       int level = 0;
       double a1 = 0., b1 = 10., a2 = 10., b2 = 10.;
@@ -363,31 +450,62 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, int gr
         has_b = true;
       }
       const unsigned heap = QagsSharedStore::heap_of(a1, level);
-      sh.t_center[0][ltid] = 0.5 * (a1 + b1);
-      sh.t_half[0][ltid] = 0.5 * (b1 - a1);
-      sh.t_g[0][ltid] = (short)rc_entry(sh, parity, my_ctx, level, heap);
+      const double beta = sh.beta[ltid];
+      {
+        const double c = 0.5 * (a1 + b1), h = 0.5 * (b1 - a1);
+        sh.t_center[0][ltid] = c;
+        sh.t_half[0][ltid] = h;
+        sh.t_g[0][ltid] = (short)rc_entry(sh, parity, my_ctx, level, heap);
+        int lo = 0, hi = 21;  // first node with z > 8
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (beta * fma(h, snode[mid], c) > 8.) hi = mid; else lo = mid + 1;
+        }
+        small_a = lo;
+      }
       if (has_b) {
-        sh.t_center[1][ltid] = 0.5 * (a2 + b2);
-        sh.t_half[1][ltid] = 0.5 * (b2 - a2);
+        const double c = 0.5 * (a2 + b2), h = 0.5 * (b2 - a2);
+        sh.t_center[1][ltid] = c;
+        sh.t_half[1][ltid] = h;
         sh.t_g[1][ltid] = (short)rc_entry(sh, parity, my_ctx, level, heap + 1);
+        int lo = 0, hi = 21;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (beta * fma(h, snode[mid], c) > 8.) hi = mid; else lo = mid + 1;
+        }
+        small_b = lo;
       }
     }
+    // packed (small << 16 | large) counts, inclusive warp scan
+    const int n_mine = active ? (has_b ? 42 : 21) : 0;
+    const int n_small = small_a + small_b;
+    const int packed = (n_small << 16) | (n_mine - n_small);
+    int incl = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += v;
+    }
     const unsigned bal_a = __ballot_sync(0xffffffffu, active);
-    const unsigned bal_b = __ballot_sync(0xffffffffu, has_b);
-    if (lane == 0) { sh.cnt[0][warp] = __popc(bal_a); sh.cnt[1][warp] = __popc(bal_b); }
+    if (lane == 31) { sh.cnt[0][warp] = __popc(bal_a); sh.cnt[1][warp] = incl; }
     bar_sync(bar_own, kRcSlots);
 
-    // ---- R2: compacted task lists (slot order), fill of the new table entries, hand-over ----
-    int n_a = 0, n_b = 0, base_a = 0, base_b = 0;
+    // ---- R2: this round's evaluation list, fill of the new table entries, hand-over ----
+    int n_a = 0, tot = 0, base = 0;
 #pragma unroll
     for (int w = 0; w < kRcSlots / 32; ++w) {
-      if (w < (int)warp) { base_a += sh.cnt[0][w]; base_b += sh.cnt[1][w]; }
+      if (w < (int)warp) base += sh.cnt[1][w];
       n_a += sh.cnt[0][w];
-      n_b += sh.cnt[1][w];
+      tot += sh.cnt[1][w];
     }
     if (n_a == 0) break;  // group-uniform: nothing in flight and nothing left to hand out
-    if (active) sh.list[0][base_a + __popc(bal_a & lt)] = (unsigned char)ltid;
-    if (has_b) sh.list[1][base_b + __popc(bal_b & lt)] = (unsigned char)ltid;
+    {
+      const int excl = base + incl - packed;  // (small << 16 | large) evaluations of the slots before this one
+      sh.t_small[0][ltid] = active ? (unsigned char)small_a : 255;
+      sh.t_off[0][ltid] = excl;
+      sh.t_small[1][ltid] = has_b ? (unsigned char)small_b : 255;
+      sh.t_off[1][ltid] = excl + ((small_a << 16) | (21 - small_a));
+    }
     {
       const int n_fill = sh.n_new[parity] * 21;
       for (int e = ltid; e < n_fill; e += kRcSlots) {
@@ -402,7 +520,7 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, int gr
       }
     }
     if (ltid == 0) {
-      sh.n_task[0] = n_a; sh.n_task[1] = n_b;
+      sh.n_cls[0] = tot & 0xffff; sh.n_cls[1] = tot >> 16;
       sh.n_new[parity ^ 1] = 0;  // last read one round ago, next used one round ahead
     }
     parity ^= 1;
@@ -410,15 +528,15 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, int gr
     bar_arrive(bar_full, kRcSlots + kRcEval);   // tasks published
     bar_sync(bar_done, kRcSlots + kRcEval);     // ... and evaluated
 
-    // ---- R4/R5 (thread = integral): GK21 sums in GSL's order, QAGS bookkeeping ----
+    // ---- R5 (thread = integral): QAGS bookkeeping on the GK21 sums the evaluators formed ----
     if (active) {
       bool done;
-      const GkOut ga = gk21_sums(&sh.fv[0][0][ltid], kRcSlots, sh.t_half[0][ltid]);
+      const GkOut ga{sh.gk[0][0][ltid], sh.gk[1][0][ltid], sh.gk[2][0][ltid], sh.gk[3][0][ltid]};
       if (first) {
         done = S.post_first(ga);
         first = false;
       } else {
-        const GkOut gb = gk21_sums(&sh.fv[1][0][ltid], kRcSlots, sh.t_half[1][ltid]);
+        const GkOut gb{sh.gk[0][1][ltid], sh.gk[1][1][ltid], sh.gk[2][1][ltid], sh.gk[3][1][ltid]};
         done = S.post_step(ga, gb);
       }
       if (done) {
@@ -461,33 +579,72 @@ k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const lon
   RcShared& sh = *reinterpret_cast<RcShared*>(rc_smem);
   const int tid = threadIdx.x;
   const int wg = tid >> 7;
-  if (tid < 21) sh.node[tid] = kGkNode[tid];
+  if (tid < 21) {
+    sh.node[tid] = kGkNode[tid];
+    const double v = kGkNode[tid];  // rank of node tid in ascending order (the abscissas are distinct)
+    int rank = 0;
+    for (int j = 0; j < 21; ++j) rank += kGkNode[j] < v;
+    sh.snode[rank] = v;
+    sh.sid[rank] = tid;
+  }
   __syncthreads();
   double* const gbuf = gbuf_all + (size_t)blockIdx.x * (kRcGroups * kRcG * 21);
 
-  if (wg < kRcGroups) {
+  if (wg < 2) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRcRegsOwner));
-    const int ltid = tid & 127;
-    if (ltid >= kRcSlots) return;  // the 4th warp of an owner warpgroup owns no slots
-    rc_owner(sh.g[wg], sh.node, wg, ltid, n_rows, nb, rows, item_off, fc, tab.ff_seg, tab.ff_last, W, neval_out, ctr,
-             overflow_items, gbuf + (size_t)wg * (kRcG * 21));
+    const int grp = tid / kRcSlots;
+    rc_owner(sh.g[grp], sh.node, sh.snode, sh.sid, grp, tid - grp * kRcSlots, n_rows, nb, rows, item_off, fc, tab.ff_seg, tab.ff_last, W,
+             neval_out, ctr, overflow_items, gbuf + (size_t)grp * (kRcG * 21));
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRcRegsEval));
-    const int etid = tid - kRcGroups * 128;
-    bool alive[kRcGroups] = {true, true};
+    const int etid = tid - 256;
+    unsigned alive = (1u << kRcGroups) - 1;
     int g = 0;
-    while (alive[0] || alive[1]) {
-      if (alive[g]) {
+    while (alive) {
+      if ((alive >> g) & 1) {
         bar_sync(kBarFull0 + g, kRcSlots + kRcEval);
         if (sh.g[g].fin) {
-          alive[g] = false;
+          alive &= ~(1u << g);
         } else {
-          rc_eval(sh.g[g], sh.node, etid, gbuf + (size_t)g * (kRcG * 21), tab.ff_seg, tab.ff_last);
+          RcGroup& G = sh.g[g];
+          const double* gb = gbuf + (size_t)g * (kRcG * 21);
+          // two evaluator threads per task (64 slots x 2 halves x 2 = 256)
+          const int role = etid & 1, task = etid >> 1;
+          const int half = task >= kRcSlots, slot = task - half * kRcSlots;
+          const int n_small = G.t_small[half][slot];
+          // expand the tasks into the class-sorted evaluation list: ascending nodes 0-10 / 11-20
+          if (n_small != 255) {
+            const int off = G.t_off[half][slot];
+            const unsigned code = slot | (half << 6);
+            const int j0 = role ? 11 : 0, j1 = role ? 21 : 11;
+            // node j of the task is its j-th small evaluation (j < n_small) or its (j - n_small)-th large one
+            const int base_s = kRcSlots * 42 - 1 - (off >> 16), base_l = (off & 0xffff) - n_small;
+            for (int j = j0; j < j1; ++j) {
+              const unsigned short c = (unsigned short)(code | (sh.sid[j] << 7));
+              if (j < n_small) sh.elist[base_s - j] = c; else sh.elist[base_l + j] = c;
+            }
+          }
+          bar_sync(kBarEval, kRcEval);
+          rc_eval_round(G, sh.fv, sh.elist, sh.node, etid, G.n_cls[0], G.n_cls[1], gb, tab.ff_seg, tab.ff_last);
+          bar_sync(kBarEval, kRcEval);
+          // GK21 sums in GSL's order, split over the two threads of the task
+          {
+            GkOut o{};
+            double asc = 0;
+            const bool live = n_small != 255;
+            if (live) gk21_sums_pair(&sh.fv[half][slot][0], G.t_half[half][slot], role, o, asc);
+            asc = __shfl_xor_sync(0xffffffffu, asc, 1);
+            if (live && role == 0) {
+              gk21_finish(o, asc, G.t_half[half][slot]);
+              G.gk[0][half][slot] = o.result; G.gk[1][half][slot] = o.abserr;
+              G.gk[2][half][slot] = o.resabs; G.gk[3][half][slot] = o.resasc;
+            }
+          }
           __threadfence_block();
           bar_arrive(kBarDone0 + g, kRcSlots + kRcEval);
         }
       }
-      g ^= 1;
+      g = g + 1 == kRcGroups ? 0 : g + 1;
     }
   }
 }
