@@ -54,6 +54,20 @@ __device__ __forceinline__ double hot()
   return v;
 }
 
+// where the coefficients come from: the __constant__ block (volatile ld.const, see above) ...
+struct HotConst {
+  template <int I>
+  __device__ __forceinline__ double at() const { return hot<I>(); }
+};
+// ... or a copy of it in shared memory: plain LDS into ordinary registers.  In a kernel that keeps
+// other FP64 constants in uniform registers the ld.const stream overflows the uniform register
+// file (R2UR / MOV.SPILL around the DFMAs); LDS broadcasts do not.
+struct HotShared {
+  const double* p;
+  template <int I>
+  __device__ __forceinline__ double at() const { return p[I]; }
+};
+
 // N evaluations side by side in one thread: every coefficient fetch feeds N independent DFMA chains
 template <int N>
 struct DV {
@@ -64,38 +78,38 @@ using D3 = DV<3>;
 #define UPC_FOR_N _Pragma("unroll") for (int i_ = 0; i_ < N; ++i_)
 
 // r = r*u + K[I] on N values, descending I from I0+N-2 to I0
-template <int N, int I0, int I>
+template <int N, int I0, int I, class H>
 struct HornerN {
-  static __device__ __forceinline__ void run(DV<N>& r, const DV<N>& u)
+  static __device__ __forceinline__ void run(DV<N>& r, const DV<N>& u, const H& h)
   {
-    const double k = hot<I0 + I>();
+    const double k = h.template at<I0 + I>();
     UPC_FOR_N r.v[i_] = fma(r.v[i_], u.v[i_], k);
-    HornerN<N, I0, I - 1>::run(r, u);
+    HornerN<N, I0, I - 1, H>::run(r, u, h);
   }
 };
-template <int N, int I0>
-struct HornerN<N, I0, -1> {
-  static __device__ __forceinline__ void run(DV<N>&, const DV<N>&) {}
+template <int N, int I0, class H>
+struct HornerN<N, I0, -1, H> {
+  static __device__ __forceinline__ void run(DV<N>&, const DV<N>&, const H&) {}
 };
-template <int N, int I0, int LEN>
-__device__ __forceinline__ DV<N> hornerN(const DV<N>& u)
+template <int N, int I0, int LEN, class H>
+__device__ __forceinline__ DV<N> hornerN(const DV<N>& u, const H& h)
 {
-  const double top = hot<I0 + LEN - 1>();
+  const double top = h.template at<I0 + LEN - 1>();
   DV<N> r;
   UPC_FOR_N r.v[i_] = top;
-  HornerN<N, I0, LEN - 2>::run(r, u);
+  HornerN<N, I0, LEN - 2, H>::run(r, u, h);
   return r;
 }
 
 // sin/cos of N moderate arguments (see sincos_mid)
-template <int N>
-__device__ __forceinline__ void sincosN(const DV<N>& x, DV<N>& s, DV<N>& c)
+template <int N, class H>
+__device__ __forceinline__ void sincosN(const DV<N>& x, DV<N>& s, DV<N>& c, const H& h)
 {
   const double kMagic = 6755399441055744.0;
   DV<N> r, f;
   int n[N];
   {
-    const double two_over_pi = hot<H_SC + 0>();
+    const double two_over_pi = h.template at<H_SC + 0>();
     UPC_FOR_N {
       const double q = fma(x.v[i_], two_over_pi, kMagic);
       n[i_] = __double2loint(q);
@@ -103,15 +117,15 @@ __device__ __forceinline__ void sincosN(const DV<N>& x, DV<N>& s, DV<N>& c)
     }
   }
   {
-    const double p = hot<H_SC + 1>();
+    const double p = h.template at<H_SC + 1>();
     UPC_FOR_N r.v[i_] = fma(-f.v[i_], p, x.v[i_]);
   }
   {
-    const double p = hot<H_SC + 2>();
+    const double p = h.template at<H_SC + 2>();
     UPC_FOR_N r.v[i_] = fma(-f.v[i_], p, r.v[i_]);
   }
   {
-    const double p = hot<H_SC + 3>();
+    const double p = h.template at<H_SC + 3>();
     UPC_FOR_N r.v[i_] = fma(-f.v[i_], p, r.v[i_]);
   }
   DV<N> z;
@@ -119,27 +133,27 @@ __device__ __forceinline__ void sincosN(const DV<N>& x, DV<N>& s, DV<N>& c)
   // the table stores S6..S1 and C6..C1 in evaluation order (ascending index)
   DV<N> sp, cp;
   {
-    const double k6 = hot<H_SC + 4>(), k5 = hot<H_SC + 5>();
+    const double k6 = h.template at<H_SC + 4>(), k5 = h.template at<H_SC + 5>();
     UPC_FOR_N sp.v[i_] = fma(z.v[i_], k6, k5);
-    const double k4 = hot<H_SC + 6>();
+    const double k4 = h.template at<H_SC + 6>();
     UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k4);
-    const double k3 = hot<H_SC + 7>();
+    const double k3 = h.template at<H_SC + 7>();
     UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k3);
-    const double k2 = hot<H_SC + 8>();
+    const double k2 = h.template at<H_SC + 8>();
     UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k2);
-    const double k1 = hot<H_SC + 9>();
+    const double k1 = h.template at<H_SC + 9>();
     UPC_FOR_N sp.v[i_] = fma(z.v[i_], sp.v[i_], k1);
   }
   {
-    const double k6 = hot<H_SC + 10>(), k5 = hot<H_SC + 11>();
+    const double k6 = h.template at<H_SC + 10>(), k5 = h.template at<H_SC + 11>();
     UPC_FOR_N cp.v[i_] = fma(z.v[i_], k6, k5);
-    const double k4 = hot<H_SC + 12>();
+    const double k4 = h.template at<H_SC + 12>();
     UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k4);
-    const double k3 = hot<H_SC + 13>();
+    const double k3 = h.template at<H_SC + 13>();
     UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k3);
-    const double k2 = hot<H_SC + 14>();
+    const double k2 = h.template at<H_SC + 14>();
     UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k2);
-    const double k1 = hot<H_SC + 15>();
+    const double k1 = h.template at<H_SC + 15>();
     UPC_FOR_N cp.v[i_] = fma(z.v[i_], cp.v[i_], k1);
   }
   UPC_FOR_N {
@@ -153,8 +167,8 @@ __device__ __forceinline__ void sincosN(const DV<N>& x, DV<N>& s, DV<N>& c)
 }
 
 // J1 on N arguments, all > 8 (modulus/phase form; see bessel_j1)
-template <int N>
-__device__ __forceinline__ DV<N> j1_largeN(const DV<N>& x)
+template <int N, class H>
+__device__ __forceinline__ DV<N> j1_largeN(const DV<N>& x, const H& h)
 {
   DV<N> rx, u;
   const double k64 = 64.;
@@ -162,9 +176,9 @@ __device__ __forceinline__ DV<N> j1_largeN(const DV<N>& x)
     rx.v[i_] = 1. / x.v[i_];
     u.v[i_] = fma(2. * k64 * rx.v[i_], rx.v[i_], -1.);
   }
-  const DV<N> m = hornerN<N, H_J1M, UPC_J1_M_N>(u);
-  const DV<N> t = hornerN<N, H_J1T, UPC_J1_T_N>(u);
-  const double two_over_pi = hot<H_MISC + 1>();
+  const DV<N> m = hornerN<N, H_J1M, UPC_J1_M_N>(u, h);
+  const DV<N> t = hornerN<N, H_J1T, UPC_J1_T_N>(u, h);
+  const double two_over_pi = h.template at<H_MISC + 1>();
   DV<N> ampl, eps, e2;
   UPC_FOR_N {
     ampl.v[i_] = m.v[i_] * sqrt(two_over_pi * rx.v[i_]);
@@ -172,36 +186,36 @@ __device__ __forceinline__ DV<N> j1_largeN(const DV<N>& x)
     e2.v[i_] = eps.v[i_] * eps.v[i_];
   }
   DV<N> sy, cy;
-  sincosN<N>(x, sy, cy);
+  sincosN<N>(x, sy, cy, h);
   DV<N> se, ce;
   {
-    const double k9 = hot<H_EPS + 0>(), k7 = hot<H_EPS + 1>();
+    const double k9 = h.template at<H_EPS + 0>(), k7 = h.template at<H_EPS + 1>();
     UPC_FOR_N se.v[i_] = fma(e2.v[i_], k9, k7);
-    const double k5 = hot<H_EPS + 2>();
+    const double k5 = h.template at<H_EPS + 2>();
     UPC_FOR_N se.v[i_] = fma(e2.v[i_], se.v[i_], k5);
-    const double k3 = hot<H_EPS + 3>();
+    const double k3 = h.template at<H_EPS + 3>();
     UPC_FOR_N se.v[i_] = fma(e2.v[i_], se.v[i_], k3);
     UPC_FOR_N se.v[i_] = eps.v[i_] * fma(e2.v[i_], se.v[i_], 1.);
-    const double k8 = hot<H_EPS + 4>(), k6 = hot<H_EPS + 5>();
+    const double k8 = h.template at<H_EPS + 4>(), k6 = h.template at<H_EPS + 5>();
     UPC_FOR_N ce.v[i_] = fma(e2.v[i_], k8, k6);
-    const double k4 = hot<H_EPS + 6>();
+    const double k4 = h.template at<H_EPS + 6>();
     UPC_FOR_N ce.v[i_] = fma(e2.v[i_], ce.v[i_], k4);
     UPC_FOR_N ce.v[i_] = fma(e2.v[i_], fma(e2.v[i_], ce.v[i_], -0.5), 1.);
   }
-  const double inv_sqrt2 = hot<H_MISC + 2>();
+  const double inv_sqrt2 = h.template at<H_MISC + 2>();
   DV<N> r;
   UPC_FOR_N r.v[i_] = ampl.v[i_] * fma(ce.v[i_], sy.v[i_] - cy.v[i_], se.v[i_] * (sy.v[i_] + cy.v[i_])) * inv_sqrt2;
   return r;
 }
 
 // J1 on N arguments, all in [0, 8]
-template <int N>
-__device__ __forceinline__ DV<N> j1_smallN(const DV<N>& x)
+template <int N, class H>
+__device__ __forceinline__ DV<N> j1_smallN(const DV<N>& x, const H& h)
 {
-  const double k32 = hot<H_MISC + 0>();
+  const double k32 = h.template at<H_MISC + 0>();
   DV<N> u;
   UPC_FOR_N u.v[i_] = fma(x.v[i_] * x.v[i_], k32, -1.);
-  const DV<N> p = hornerN<N, H_J1P, UPC_J1_P_N>(u);
+  const DV<N> p = hornerN<N, H_J1P, UPC_J1_P_N>(u, h);
   DV<N> r;
   UPC_FOR_N r.v[i_] = x.v[i_] * p.v[i_];
   return r;
@@ -211,13 +225,14 @@ __device__ __forceinline__ DV<N> j1_smallN(const DV<N>& x)
 // of them needs it (arguments clamped into the branch's domain), then selected per argument.
 __device__ __forceinline__ D3 j1_3(const D3& x)
 {
+  const HotConst h;
   const bool la = x.v[0] > 8., lb = x.v[1] > 8., lc = x.v[2] > 8.;
   D3 r{{0., 0., 0.}};
   if (la | lb | lc) {
-    r = j1_largeN<3>(D3{{fmax(x.v[0], 8.), fmax(x.v[1], 8.), fmax(x.v[2], 8.)}});
+    r = j1_largeN<3>(D3{{fmax(x.v[0], 8.), fmax(x.v[1], 8.), fmax(x.v[2], 8.)}}, h);
   }
   if (!(la & lb & lc)) {
-    const D3 v = j1_smallN<3>(D3{{fmin(x.v[0], 8.), fmin(x.v[1], 8.), fmin(x.v[2], 8.)}});
+    const D3 v = j1_smallN<3>(D3{{fmin(x.v[0], 8.), fmin(x.v[1], 8.), fmin(x.v[2], 8.)}}, h);
     if (!la) r.v[0] = v.v[0];
     if (!lb) r.v[1] = v.v[1];
     if (!lc) r.v[2] = v.v[2];

@@ -82,6 +82,7 @@ struct RcShared {
                                        // conflict-free both ways)
   unsigned short elist[kRcSlots * 42]; // the evaluations of the group-round in service (slot | half << 6 | node << 7):
                                        // J1 large-argument ones from the front, small-argument ones from the back
+  double hot[H_END];                   // the J1 / sincos coefficient block (upc_hot) for LDS access
   double node[24];                     // signed GK21 abscissas (kGkNode)
   double snode[24];                    // the same in ascending order ...
   int sid[24];                         // ... and their index in kGkNode
@@ -279,8 +280,9 @@ constexpr int kRcWide = 3;  // evaluations per evaluator thread and trip (indepe
 
 template <bool LARGE>
 __device__ __forceinline__ void rc_eval_trip(RcGroup& sh, double (*fv)[kRcSlots][21], const unsigned short* elist,
-                                             const double* node, int e, int n_ev, const double* __restrict__ gbuf,
-                                             const SplineSeg* __restrict__ ff, double ff_last)
+                                             const double* node, const HotShared& hs, int e, int n_ev,
+                                             const double* __restrict__ gbuf, const SplineSeg* __restrict__ ff,
+                                             double ff_last)
 {
   constexpr int kLast = kRcSlots * 42 - 1;
   constexpr int N = kRcWide;
@@ -299,13 +301,13 @@ __device__ __forceinline__ void rc_eval_trip(RcGroup& sh, double (*fv)[kRcSlots]
     if (ent[i_] < 0) g.v[i_] = rc_g(x.v[i_], sh.ctx_c0[sh.slot_ctx[slot[i_]]], ff, ff_last);
     z.v[i_] = sh.beta[slot[i_]] * x.v[i_];
   }
-  const DV<N> j = LARGE ? j1_largeN<N>(z) : j1_smallN<N>(z);
+  const DV<N> j = LARGE ? j1_largeN<N>(z, hs) : j1_smallN<N>(z, hs);
   UPC_FOR_N fv[half[i_]][slot[i_]][nd[i_]] = g.v[i_] * j.v[i_];
 }
 
 // trips of kRcWide evaluations: the large-argument ones, padded to whole warps, then the small ones
 __device__ __forceinline__ void rc_eval_round(RcGroup& sh, double (*fv)[kRcSlots][21], const unsigned short* elist,
-                                              const double* node, int etid, int n_large, int n_small,
+                                              const double* node, const HotShared& hs, int etid, int n_large, int n_small,
                                               const double* __restrict__ gbuf, const SplineSeg* __restrict__ ff,
                                               double ff_last)
 {
@@ -315,9 +317,9 @@ __device__ __forceinline__ void rc_eval_round(RcGroup& sh, double (*fv)[kRcSlots
 #pragma unroll 1
   for (int t = etid; t < n_trips; t += kRcEval) {
     if (t < t_pad) {  // warp-uniform
-      if (t < t_large) rc_eval_trip<true>(sh, fv, elist, node, kRcWide * t, n_large, gbuf, ff, ff_last);
+      if (t < t_large) rc_eval_trip<true>(sh, fv, elist, node, hs, kRcWide * t, n_large, gbuf, ff, ff_last);
     } else {
-      rc_eval_trip<false>(sh, fv, elist, node, kRcWide * (t - t_pad), n_small, gbuf, ff, ff_last);
+      rc_eval_trip<false>(sh, fv, elist, node, hs, kRcWide * (t - t_pad), n_small, gbuf, ff, ff_last);
     }
   }
 }
@@ -579,6 +581,7 @@ k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const lon
   RcShared& sh = *reinterpret_cast<RcShared*>(rc_smem);
   const int tid = threadIdx.x;
   const int wg = tid >> 7;
+  for (int e = tid; e < H_END; e += kRcThreads) sh.hot[e] = upc_hot[e];
   if (tid < 21) {
     sh.node[tid] = kGkNode[tid];
     const double v = kGkNode[tid];  // rank of node tid in ascending order (the abscissas are distinct)
@@ -625,7 +628,7 @@ k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const lon
             }
           }
           bar_sync(kBarEval, kRcEval);
-          rc_eval_round(G, sh.fv, sh.elist, sh.node, etid, G.n_cls[0], G.n_cls[1], gb, tab.ff_seg, tab.ff_last);
+          rc_eval_round(G, sh.fv, sh.elist, sh.node, HotShared{sh.hot}, etid, G.n_cls[0], G.n_cls[1], gb, tab.ff_seg, tab.ff_last);
           bar_sync(kBarEval, kRcEval);
           // GK21 sums in GSL's order, split over the two threads of the task
           {
