@@ -44,7 +44,8 @@ class CParams(C.Structure):
 
 class CTableInfo(C.Structure):
     _fields_ = [("rho0", C.c_double), ("sigma_nn", C.c_double), ("factor", C.c_double),
-                ("breakup_p20", C.c_double), ("n_breakup_energy_knots", C.c_int)]
+                ("breakup_p20", C.c_double), ("n_breakup_energy_knots", C.c_int),
+                ("gaa_zero_below", C.c_double)]
 
 
 class CFillStats(C.Structure):

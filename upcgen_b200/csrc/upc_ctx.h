@@ -16,6 +16,7 @@ struct DevTables {
   const SplineSeg* gaa_seg;
   double gaa_inv_db;  // 199/20
   double gaa_db;
+  double b_in2;       // G_AA's spline is <= 1e-30 in magnitude on [0, sqrt(b_in2)]: (b1, b2) pairs that stay below contribute nothing
   // breakup: knots b_i = 1e-6 + db*i, i < nbk (covers [0, 20.2]); seg[nbk-1] = {P20,0,0,0}
   const SplineSeg* bk_seg;
   int bk_n;      // number of real segments (index clamp = bk_n)

@@ -7,6 +7,8 @@
 #include <cstdio>
 
 #include "upc_ctx.h"
+#include <vector>
+
 #include "upc_internal.h"
 
 namespace upc {
@@ -480,6 +482,23 @@ int prepare_tables(upcgpu_ctx* c)
   } else {
     c->info.n_breakup_energy_knots = 0;
     c->tab.bk_n = 0;
+  }
+  {
+    // inner cut of the cell quadrature: the leading G_AA segments whose magnitude is bounded by
+    // 1e-30 on the whole segment (|y| + |b| h + |c| h^2 + |d| h^3); P(b) <= 1
+    std::vector<SplineSeg> hseg(kNB);
+    UPC_CUDA(c, cudaMemcpy(hseg.data(), c->gaa_seg, kNB * sizeof(SplineSeg), cudaMemcpyDeviceToHost));
+    const double hh = 20. / (kNB - 1);
+    int n_zero = 0;
+    while (n_zero < kNB - 1) {
+      const SplineSeg& sg = hseg[n_zero];
+      const double bound = fabs(sg.y) + hh * (fabs(sg.b) + hh * (fabs(sg.c) + hh * fabs(sg.d)));
+      if (!(bound <= 1e-30)) break;
+      ++n_zero;
+    }
+    const double b_in = n_zero * hh;
+    c->tab.b_in2 = b_in * b_in;
+    c->info.gaa_zero_below = b_in;
   }
   c->tab.gaa_seg = c->gaa_seg;
   c->tab.gaa_db = 20. / (kNB - 1);
