@@ -35,6 +35,10 @@ WORKLOAD_TEXT = {
     "cfg5": "cfg5: Xe-Xe 5.44 TeV ALP PROC_ID 51, NON_ZERO_GAM_PT 1, 0N0N, 1001x121 grid, 1e7 events",
 }
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
+# `ncu --set full` captures (profiles/r01_v9_ncu_qags_cfg2.txt, profiles/r01_v2_ncu_cells_cfg2.txt)
+NCU_TRAFFIC = {("cfg2", "k_flux_qags_rows"): 52.0e6 + 50.0e6, ("cfg2", "k_cells"): 235.9e6 + 5.9e6}
+
 # algorithmic work per unit
 FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegrand
 FLOP_CELL = {(0, 0): 1.19e6, (0, 1): 1.91e6, (1, 0): 1.30e6, (1, 1): 2.05e6}  # (pol, breakup) per cell
@@ -189,7 +193,12 @@ def main():
     pol, bk = int(P.use_pol), int(P.breakup_mode > 1)
 
     # host plug-in values (elementary sigma(m)), computed once: they are inputs of the step
-    if pol:
+    # (cfg3, light-by-light with USE_POLARIZED_CS 1, is defined at the lumi-table level only -- SURVEY Q5: the
+    # reference's fold multiplies by LbyL's identically-zero polarised sigma -- so its step has no fold)
+    fold = not (pol and P.proc_id in (22, 111))
+    if not fold:
+        sig = {}
+    elif pol:
         sig = dict(sig_s=capi.elem_sigma_m(P, 1), sig_p=capi.elem_sigma_m(P, 2))
     else:
         sig = dict(sig_m=capi.elem_sigma_m(P, 0))
@@ -204,7 +213,8 @@ def main():
         gpu.invalidate_tables()
         gpu.prepare_tables()
         udist.fill_lumi_distributed(gpu, rank, world, dev)
-        gpu.fold_sigma(download=False, **sig)
+        if fold:
+            gpu.fold_sigma(download=False, **sig)
 
     # ---- device-resident timing ---------------------------------------------------------
     for _ in range(args.warmup):
@@ -253,7 +263,9 @@ def main():
 
         def step_e2e():
             gpu.invalidate_tables()
-            if pol:
+            if not fold:
+                gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
+            elif pol:
                 gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
                 gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, None, vp(host_sig["sig_s"]), vp(host_sig["sig_p"]),
                                                  vp(host_cs), vp(host_ratio), C.byref(tot)))
@@ -274,8 +286,8 @@ def main():
         dt = (time.perf_counter() - t0) / args.steps
         e2e = {"value": n_cells / dt, "unit": "cells/s", "ms_per_step": dt * 1e3,
                "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in host_sig.values())),
-               "d2h_bytes_per_step": int(n_tab * n_cells * 8 + n_cells * 8 * (2 if pol else 1) + 8),
-               "api": "upcgpu_fill_lumi + upcgpu_fold_sigma (include/upcgpu.h), pinned host buffers",
+               "d2h_bytes_per_step": int(n_tab * n_cells * 8 + (n_cells * 8 * (2 if pol else 1) + 8 if fold else 0)),
+               "api": "upcgpu_fill_lumi" + (" + upcgpu_fold_sigma" if fold else "") + " (include/upcgpu.h), pinned host buffers",
                "total_cross_section_mb": tot.value}
 
     # ---- event stage ----------------------------------------------------------------------
@@ -339,7 +351,8 @@ def main():
         units = f"{cells_rank} cells x {FLOP_CELL[(pol, bk)]:.3g} flop"
     achieved = work / t_k / 1e12 if t_k > 0 else 0.0
     roofline = {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+                "frac": achieved / peak_tf if peak_tf else None,
+                "traffic": NCU_TRAFFIC.get((args.workload, kern)) if world == 1 else None,
                 "peak_source": "measured live: upcgpu_fp64_peak DFMA loop (MEASURED_PEAKS.json has no FP64 figure; "
                                "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
                 "algorithmic_work": units, "kernel_ms": t_k * 1e3}

@@ -16,12 +16,14 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 events = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 P = named_config(cfg)
 g = capi.UpcGpu(P, 0)
-sig = dict(sig_s=capi.elem_sigma_m(P, 1), sig_p=capi.elem_sigma_m(P, 2)) if P.use_pol else dict(sig_m=capi.elem_sigma_m(P, 0))
+fold = not (P.use_pol and P.proc_id in (22, 111))  # cfg3: lumi tables only
+sig = {} if not fold else dict(sig_s=capi.elem_sigma_m(P, 1), sig_p=capi.elem_sigma_m(P, 2)) if P.use_pol else dict(sig_m=capi.elem_sigma_m(P, 0))
 for i in range(warm + steps):
     g.invalidate_tables()
     g.prepare_tables()
     g.fill_lumi_shard(0, 1)
-    g.fold_sigma(download=False, **sig)
+    if fold:
+        g.fold_sigma(download=False, **sig)
     print("step", i, g.fill_stats())
 if events:
     g.sampler_build(cszm=None if P.ignore_csz else capi.elem_cs_zm(P, 0))
