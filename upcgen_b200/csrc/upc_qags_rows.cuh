@@ -30,10 +30,10 @@
 
 namespace upc {
 
-constexpr int kRcThreads = 512;
+constexpr int kRcThreads = 640;
 constexpr int kRcGroups = 4;     // owner groups of two warps (warpgroups 0 and 1)
 constexpr int kRcSlots = 64;     // integrals in flight per group (multiple of 32: conflict-free strides)
-constexpr int kRcEval = 256;     // evaluator threads
+constexpr int kRcEval = 384;     // evaluator threads (three warpgroups)
 constexpr int kRcCap = 16;       // interval-list capacity per integral (largest seen: 15)
 constexpr int kRcEps = 16;       // epsilon-table capacity (largest index touched so far: 12)
 constexpr int kRcCtx = 8;        // rows in flight per group
@@ -43,7 +43,7 @@ constexpr int kRcGE = 64;        // cached intervals per row in flight
 constexpr int kRcG = kRcCtx * kRcGE;  // cached (row, interval) entries per group
 constexpr int kRcMaxLevel = 26;  // deeper intervals are evaluated uncached
 constexpr unsigned kRcEmpty = 0xffffffffu;
-constexpr int kRcRegsOwner = 88, kRcRegsEval = 168;  // 256 * 88 + 256 * 168 = 64 K registers
+constexpr int kRcRegsOwner = 72, kRcRegsEval = 112;  // 256 * 72 + 384 * 112 = 60 K registers (launched with 96)
 
 // state of one owner group
 struct RcGroup {
@@ -278,7 +278,9 @@ __device__ __forceinline__ int rc_entry(RcGroup& sh, int parity, int ctx, int le
 // evaluator threads whatever integral they belong to, three per thread and trip.  The owners have
 // sorted them by the branch of J1 they take (argument <= 8: polynomial; > 8: modulus/phase form),
 // so every warp runs one branch with all lanes.
-constexpr int kRcWide = 3;  // evaluations per evaluator thread and trip (independent DFMA chains)
+constexpr int kRcWide = 2;  // evaluations per evaluator thread and trip.  Measured on cfg2 (8 evaluator warps): 1: 40.8 ms,
+                            // 2: 34.2, 3: 36.7, 4: 43.0, 6: 60; with 12 warps x 2: 32.1, 16 warps x 1: 33.2 -- short
+                            // trips quantise better over the ~2700 evaluations of a group-round
 
 template <bool LARGE>
 __device__ __forceinline__ void rc_eval_trip(RcGroup& sh, double (*fv)[kRcSlots][21], const unsigned short* elist,
@@ -616,7 +618,7 @@ k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const lon
           // two evaluator threads per task (64 slots x 2 halves x 2 = 256)
           const int role = etid & 1, task = etid >> 1;
           const int half = task >= kRcSlots, slot = task - half * kRcSlots;
-          const int n_small = G.t_small[half][slot];
+          const int n_small = task < 2 * kRcSlots ? G.t_small[half][slot] : 255;
           // expand the tasks into the class-sorted evaluation list: ascending nodes 0-10 / 11-20
           if (n_small != 255) {
             const int off = G.t_off[half][slot];
