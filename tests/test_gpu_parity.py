@@ -465,3 +465,48 @@ def test_sharded_fill_equals_monolithic_form_factor(get_gpu):
     assert np.array_equal(g.lumi_download(0), full)
     from upcgen_b200 import dist as udist
     assert np.array_equal(udist.unpack_host(allp, P.nm, P.ny, world), full)
+
+
+def test_full_grid_reflection_symmetry(get_gpu):
+    """Size-independent property at BASELINE's full size (cfg2, 1001 x 121): with identical beams
+    lumi(M, -Y) = lumi(M, Y) (k1 <-> k2 swaps the two b integrals).  The y grid of lower edges is
+    symmetric about 0 for iy <-> ny - iy, so columns iy and ny - iy of the table must agree to the
+    rounding of y itself (1 ulp of y moves k by 1e-16 relative)."""
+    P, g = get_gpu("cfg2")
+    table = g.fill_lumi()
+    ny = P.ny
+    a, b = table[:, 1:ny], table[:, ny - 1:0:-1]
+    e = np.max(np.abs(a - b) / np.maximum(a, 1e-300))
+    print("cfg2 reflection symmetry, max rel:", e)
+    assert e < 1e-11
+    # and the table falls monotonically in M at fixed Y over the whole grid (no cell lost or misplaced)
+    assert np.all(np.diff(table[:, ny // 2]) < 0)
+
+
+def test_cfg4_full_size_properties(get_gpu, capi):
+    """BASELINE config 4 at its full size (10001 x 1201 = 12 M cells, form-factor flux, slabs of m rows):
+    finite and positive where the reference's Bessel functions do not underflow (Q7), reflection
+    symmetry, sharded == monolithic on a row subset, and the golden sub-grid (oracle) is reproduced."""
+    P, g = get_gpu("cfg4")
+    table = g.fill_lumi()
+    st = g.fill_stats()
+    print("cfg4 fill:", {k: st[k] for k in ("qags_integrals", "qags_evals", "band_pairs", "ms_flux", "ms_cells")})
+    assert st["qags_errors"] == 0 and st["qags_overflow"] == 0
+    assert table.shape == (P.nm, P.ny) and np.all(np.isfinite(table)) and np.all(table >= 0)
+    ny = P.ny
+    a, b = table[:, 1:ny], table[:, ny - 1:0:-1]
+    m = a > 1e-250
+    e = np.max(np.abs(a[m] - b[m]) / a[m])
+    print("cfg4 reflection symmetry, max rel:", e)
+    assert e < 1e-10
+    gold = np.load(_os.path.join(_GOLD, "cfg4_subgrid.npz"))
+    im, iy = gold["im"], gold["iy"]
+    ref = gold["lumi"] * float(gold["dm"]) * float(gold["dy"])   # the table stores lumi * dm * dy (:546-550)
+    sel = ref > 1e-250
+    eg = np.max(np.abs(table[np.ix_(im, iy)][sel] - ref[sel]) / ref[sel])
+    print("cfg4 golden sub-grid, max rel:", eg)
+    assert eg < RTOL_FF
+    # rows 5 mod 7 recomputed as shard 5 of 7 are the same numbers
+    g.fill_lumi_shard(5, 7)
+    part = g.lumi_download(0)
+    assert np.array_equal(part[5::7], table[5::7])
