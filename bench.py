@@ -36,8 +36,8 @@ WORKLOAD_TEXT = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-# `ncu --set full` captures (profiles/r01_v9_ncu_qags_cfg2.txt, profiles/r01_v2_ncu_cells_cfg2.txt)
-NCU_TRAFFIC = {("cfg2", "k_flux_qags_rows"): 52.0e6 + 50.0e6, ("cfg2", "k_cells"): 235.9e6 + 5.9e6}
+# `ncu --set full` captures (profiles/r01_v10_ncu_qags_cfg2.txt, profiles/r01_v2_ncu_cells_cfg2.txt)
+NCU_TRAFFIC = {("cfg2", "k_flux_qags_rows"): 52.7e6 + 50.6e6, ("cfg2", "k_cells"): 235.9e6 + 5.9e6}
 
 # algorithmic work per unit
 FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegrand

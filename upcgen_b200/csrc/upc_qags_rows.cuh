@@ -5,7 +5,7 @@
 // the first factor ("g") depends on the ROW (photon energy k) only, the Bessel factor on the
 // integral (b).  Every integral starts on [0, 10] and QAGS bisects, so all intervals are dyadic
 // and the ~30-100 integrals of a row visit the same ~20-30 of them (measured: 1100 GK21 rules per
-// row on 29 distinct intervals).  One CTA per SM, 512 threads in four warpgroups:
+// row on 29 distinct intervals).  One CTA per SM, 640 threads in five warpgroups:
 //   * OWNERS (warpgroups 0 and 1 = four groups of 64 threads, one integral per thread): the QAGS
 //     bookkeeping, which follows gsl_integration_qags decision for decision (upc_qags.cuh).
 //     Interval lists, epsilon tables and the FP64 driver scalars live in SHARED memory, strided by
@@ -13,12 +13,12 @@
 //     look-ups that was latency-bound on L2 while that state sat in local memory.  A slot whose
 //     integral is finished takes the next one of the global row queue.  Owners publish the 1-2
 //     pending intervals of each integral as tasks.
-//   * EVALUATORS (warpgroups 2 and 3): the integrand evaluations of a round (21 per task),
-//     flattened over 256 threads whatever integral they belong to, three nodes per thread and
+//   * EVALUATORS (warpgroups 2 to 4): the integrand evaluations of a round (21 per task),
+//     flattened over 384 threads whatever integral they belong to, two nodes per thread and
 //     trip, sorted by the branch of J1 they take, followed by the GK21 sums in GSL's summation
 //     order.  They serve the owner groups in turn, so that the bookkeeping of three groups runs
 //     under the evaluations of the fourth and the FP64 pipe always has dense, convergent J1 work.
-//     Register budgets follow the roles (setmaxnreg: 88 / 168).
+//     Register budgets follow the roles (setmaxnreg: 72 / 112).
 //   * g on the 21 GK nodes of an interval is evaluated ONCE per (row, interval) -- the 10^6-knot
 //     form-factor spline gather and the division leave the hot loop -- into an L2-resident
 //     per-group table keyed by the interval's heap index (level, position).
