@@ -181,6 +181,102 @@ __device__ __forceinline__ GkOut gk21_tri(const F& f, double a, double b, double
   return o;
 }
 
+// GK21 sums from the 21 stored integrand values (node order of kGkNode), in GSL's order
+// (integration/qk.c); same arithmetic as the tail of gk21_tri.
+__device__ __forceinline__ GkOut gk21_sums(const double* fv, int fv_stride, double half_length)
+{
+  const double abs_half_length = fabs(half_length);
+  const double f_center = fv[20 * fv_stride];
+  double result_gauss = 0;
+  double result_kronrod = f_center * kGkWkC;
+  double result_abs = fabs(result_kronrod);
+#pragma unroll 1
+  for (int p = 0; p < 10; ++p) {
+    const double fval1 = fv[(2 * p) * fv_stride], fval2 = fv[(2 * p + 1) * fv_stride];
+    const double fsum = fval1 + fval2;
+    result_gauss += kGkWg[p] * fsum;
+    result_kronrod += kGkWk[p] * fsum;
+    result_abs += kGkWk[p] * (fabs(fval1) + fabs(fval2));
+  }
+  const double mean = result_kronrod * 0.5;
+  double result_asc = kGkWkC * fabs(f_center - mean);
+#pragma unroll 1
+  for (int j = 0; j < 10; ++j) {
+    const int p = (j & 1) ? (j >> 1) : (5 + (j >> 1));
+    result_asc += kGkWk[p] * (fabs(fv[(2 * p) * fv_stride] - mean) + fabs(fv[(2 * p + 1) * fv_stride] - mean));
+  }
+  double err = (result_kronrod - result_gauss) * half_length;
+  result_kronrod *= half_length;
+  result_abs *= abs_half_length;
+  result_asc *= abs_half_length;
+  err = fabs(err);
+  if (result_asc != 0 && err != 0) {
+    double s = 200 * err / result_asc;
+    double scale = s * sqrt(s);
+    err = scale < 1 ? result_asc * scale : result_asc;
+  }
+  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
+    double min_err = 50 * DBL_EPSILON * result_abs;
+    if (min_err > err) err = min_err;
+  }
+  GkOut o;
+  o.result = result_kronrod;
+  o.abserr = err;
+  o.resabs = result_abs;
+  o.resasc = result_asc;
+  return o;
+}
+
+// The same sums fully unrolled (weights and indices are compile-time), values at fv[n * STRIDE].  The
+// Gauss sum runs over the 5 Gauss pairs only, as in qk.c (the zero weights above add +0.0: the same
+// value).
+template <int STRIDE>
+__device__ __forceinline__ GkOut gk21_sums_strided(const double* fv, double half_length)
+{
+  double f[21];
+#pragma unroll
+  for (int n = 0; n < 21; ++n) f[n] = fv[n * STRIDE];
+  const double f_center = f[20];
+  double result_gauss = 0;
+  double result_kronrod = f_center * kGkWkC;
+  double result_abs = fabs(result_kronrod);
+#pragma unroll
+  for (int p = 0; p < 10; ++p) {
+    const double fsum = f[2 * p] + f[2 * p + 1];
+    if (p < 5) result_gauss += kGkWg[p] * fsum;
+    result_kronrod += kGkWk[p] * fsum;
+    result_abs += kGkWk[p] * (fabs(f[2 * p]) + fabs(f[2 * p + 1]));
+  }
+  const double mean = result_kronrod * 0.5;
+  double result_asc = kGkWkC * fabs(f_center - mean);
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    const int p = (j & 1) ? (j >> 1) : (5 + (j >> 1));
+    result_asc += kGkWk[p] * (fabs(f[2 * p] - mean) + fabs(f[2 * p + 1] - mean));
+  }
+  const double abs_half_length = fabs(half_length);
+  double err = (result_kronrod - result_gauss) * half_length;
+  result_kronrod *= half_length;
+  result_abs *= abs_half_length;
+  result_asc *= abs_half_length;
+  err = fabs(err);
+  if (result_asc != 0 && err != 0) {
+    double s = 200 * err / result_asc;
+    double scale = s * sqrt(s);
+    err = scale < 1 ? result_asc * scale : result_asc;
+  }
+  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
+    double min_err = 50 * DBL_EPSILON * result_abs;
+    if (min_err > err) err = min_err;
+  }
+  GkOut o;
+  o.result = result_kronrod;
+  o.abserr = err;
+  o.resabs = result_abs;
+  o.resasc = result_asc;
+  return o;
+}
+
 // Interval-list / epsilon-table storage.  The QAGS logic below is written against this small
 // interface so that the same code runs on in-thread arrays (test hooks), on a global-memory
 // workspace of the reference's full size (overflow pass) and on the strided shared-memory state of

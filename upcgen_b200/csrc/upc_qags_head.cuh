@@ -1,0 +1,249 @@
+// upc_qags_head.cuh -- stage A.3a: the predictable head of every form-factor flux integral.
+//
+// gsl_integration_qags on [0, 10] with this integrand (src/UpcCrossSection.cpp:181-212) always
+// starts the same way: the 21-point rule on [0, 10], then bisection of [0, 10], of [0, 5], of
+// [0, 2.5], of [0, 1.25], of [0, 0.625] -- the integrand lives at small k_perp, so the leftmost
+// interval carries the largest error estimate.  Measured with the oracle over the cfg2 and cfg4
+// grids: bisections 1-3 always, 4 in all but 1 of 56 061, 5 in 98.8 % of the integrals that get
+// that far; these six rounds hold 79 % of all integrand evaluations.  They need no scheduling:
+// one thread per integral walks them here in the reference's order (same Qags<> state machine,
+// same arithmetic, g cached per row as in the row-cooperative kernel), all lanes of a warp on
+// the same interval at the same time.  An integral that converges inside the head is finished
+// here; one whose next bisection is not the predicted interval, or that is still running after
+// the head, is handed to k_flux_qags_rows with its complete QAGS state (HeadState).  Nothing is
+// speculated: every evaluation made here is one the reference makes.
+#pragma once
+#include "upc_hot.cuh"
+#include "upc_qags.cuh"
+
+namespace upc {
+
+constexpr int kHdThreads = 128;           // integrals of one row (nb <= 128)
+constexpr int kHdBis = 5;                 // predicted bisections
+constexpr int kHdIv = 1 + 2 * kHdBis;     // intervals of the head: [0,10], then (left, right) of each bisection
+constexpr int kHdCap = 8;                 // interval-list capacity while in the head (size <= 1 + kHdBis)
+constexpr int kHdEps = 10;                // epsilon-table capacity while in the head (<= 1 + kHdBis entries + 2 scratch)
+
+// QAGS state of an integral leaving the head (everything Qags<Store> holds; see upc_qags.cuh)
+struct HeadState {
+  double sc[11];
+  double eps[8];
+  double rl[kHdCap], el[kHdCap];
+  unsigned hp[kHdCap];
+  unsigned char od[kHdCap];
+  int size, nrmax, i, maximum_level, ktmin, roundoff_type1, roundoff_type2, roundoff_type3, error_type, error_type2,
+      iteration, tab_n, tab_nres, flags, neval, pad;
+};
+static_assert(sizeof(HeadState) == 384, "HeadState layout");
+enum { kHdPositive = 1, kHdExtrapolate = 2, kHdDisallow = 4 };
+
+struct HdShared {
+  double fv[21][kHdThreads];            // GK21 function values [node][thread]
+  double rl[kHdCap][kHdThreads], el[kHdCap][kHdThreads];
+  double ep[kHdEps][kHdThreads];
+  double sc[11][kHdThreads];
+  double xs[kHdIv][21];                 // nodes of the head intervals (the same for every row)
+  double half[kHdIv];
+  unsigned hp[kHdCap][kHdThreads];
+  unsigned char od[kHdCap][kHdThreads];
+};
+
+// strided shared-memory store (same interval encoding as QagsSharedStore: heap indices)
+struct QagsHeadStore {
+  HdShared* sh;
+  int slot;
+  static constexpr int cap = kHdCap;
+  static constexpr int eps_cap = kHdEps;
+  __device__ __forceinline__ double& R(int k) { return sh->rl[k][slot]; }
+  __device__ __forceinline__ double& E(int k) { return sh->el[k][slot]; }
+  __device__ __forceinline__ int ord(int k) const { return sh->od[k][slot]; }
+  __device__ __forceinline__ void set_ord(int k, int v) { sh->od[k][slot] = (unsigned char)v; }
+  __device__ __forceinline__ int lvl(int k) const { return 31 - __clz(sh->hp[k][slot]); }
+  static __device__ __forceinline__ double pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+  __device__ __forceinline__ void get_iv(int k, double& a, double& b) const
+  {
+    const unsigned heap = sh->hp[k][slot];
+    const int level = 31 - __clz(heap);
+    const unsigned pos = heap - (1u << level);
+    const double width = 10. * pow2(-level);
+    a = pos * width;
+    b = (pos + 1.) * width;
+  }
+  __device__ __forceinline__ bool set_iv(int k, double a, double /*b*/, int level)
+  {
+    sh->hp[k][slot] = (1u << level) + __double2uint_rn(a * (0.1 * pow2(level)));
+    return true;
+  }
+  __device__ __forceinline__ double& eps(int k) { return sh->ep[k][slot]; }
+  __device__ __forceinline__ double& sc(int k) { return sh->sc[k][slot]; }
+};
+
+// bounds of head interval iv: 0 -> [0, 10]; 2k-1 -> [0, 10/2^k]; 2k -> [10/2^k, 10/2^(k-1)]
+__host__ __device__ __forceinline__ void head_interval(int iv, double& a, double& b)
+{
+  if (iv == 0) { a = 0.; b = 10.; return; }
+  const int k = (iv + 1) >> 1;
+  double w = 10.;
+  for (int j = 0; j < k; ++j) w *= 0.5;  // exact
+  if (iv & 1) { a = 0.; b = w; } else { a = w; b = 2. * w; }
+}
+
+__device__ __forceinline__ double head_g(double x, double c0, const SplineSeg* __restrict__ ff, double ff_last)
+{
+  const double x2 = x * x;
+  const double t = x2 + c0;
+  double F = ff_last;
+  if (t < kQ2max) {
+    int idx = (int)((t - kQ2min) * (1. / kDQ2));
+    idx = max(0, min(idx, kNQ2 - 2));
+    const double delx = t - fma((double)idx, kDQ2, kQ2min);
+    F = seg_eval(ld_seg(ff + idx), delx);
+  }
+  return x2 * F / t;
+}
+
+// g on the 231 head nodes of every row: hg[node][row]; and the row of every integral
+__global__ void k_head_tables(int n_rows, const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
+                              double g1, DevTables tab, double* __restrict__ hg, int* __restrict__ item_row)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;  // interval * 21 + node
+  if (row >= n_rows) return;
+  const RowInfo ri = rows[row];
+  const double k = ri.k;
+  const double c0 = k * k / g1 / g1;  // w*w/g/g, :187
+  if (e < ri.nq) item_row[item_off[row] + e] = row;
+  const int iv = e / 21, n = e - iv * 21;
+  double a, b;
+  head_interval(iv, a, b);
+  const double x = fma(0.5 * (b - a), kGkNode[n], 0.5 * (a + b));
+  hg[(size_t)e * n_rows + row] = head_g(x, c0, tab.ff_seg, tab.ff_last);
+}
+
+// GK21 rule on head interval iv for this thread's integral: f = g * J1(beta x), three nodes at a time
+__device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double beta, const double* __restrict__ g, size_t g_stride,
+                                           int tid)
+{
+  const double* gi = g + (size_t)(iv * 21) * g_stride;
+#pragma unroll 1
+  for (int n = 0; n < 21; n += 3) {
+    const double g0 = gi[n * g_stride], g1 = gi[(n + 1) * g_stride], g2 = gi[(n + 2) * g_stride];
+    const D3 j = j1_3(D3{{beta * sh.xs[iv][n], beta * sh.xs[iv][n + 1], beta * sh.xs[iv][n + 2]}});
+    sh.fv[n][tid] = g0 * j.v[0];
+    sh.fv[n + 1][tid] = g1 * j.v[1];
+    sh.fv[n + 2][tid] = g2 * j.v[2];
+  }
+  return gk21_sums(&sh.fv[0][tid], kHdThreads, sh.half[iv]);
+}
+
+struct HeadCounters {
+  unsigned long long evals;  // integrand evaluations of integrals finished in the head
+  unsigned long long errors;
+  unsigned long long left;   // integrals handed over
+};
+
+// One thread per integral, in queue order (consecutive b of a row, row after row): the lanes of a warp
+// read the same g (a broadcast) and sit on the same node.
+__global__ void __launch_bounds__(kHdThreads, 3)
+k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restrict__ rows,
+                 const long long* __restrict__ item_off, const int* __restrict__ item_row, const double* __restrict__ hg,
+                 FluxConsts fc, double* __restrict__ W,
+                 int* __restrict__ neval_out, HeadCounters* __restrict__ ctr, HeadState* __restrict__ state,
+                 unsigned char* __restrict__ done_flag)
+{
+  extern __shared__ __align__(16) unsigned char hd_smem[];
+  HdShared& sh = *reinterpret_cast<HdShared*>(hd_smem);
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31;
+  for (int e = tid; e < kHdIv * 21; e += kHdThreads) {
+    const int iv = e / 21, n = e - iv * 21;
+    double a, b;
+    head_interval(iv, a, b);
+    sh.xs[iv][n] = fma(0.5 * (b - a), kGkNode[n], 0.5 * (a + b));
+    if (n == 0) sh.half[iv] = 0.5 * (b - a);
+  }
+  __syncthreads();
+
+  const long long item = (long long)blockIdx.x * kHdThreads + tid;
+  double my_evals = 0;
+  unsigned my_err = 0, my_left = 0;
+  if (item < n_items) {
+    const int row = item_row[item];
+    const int i = (int)(item - item_off[row]);
+    const RowInfo ri = rows[row];
+    const double* g = hg + row;
+    const size_t gs = (size_t)n_rows;
+    double b, w;
+    grid_point(ri, i, b, w);
+    const double beta = b * (1. / kHc);
+    Qags<QagsHeadStore> S;
+    S.sh = &sh;
+    S.slot = tid;
+    S.begin(0., 10.);                                  // :209
+    bool done = S.post_first(head_gk21(sh, 0, beta, g, gs, tid));
+#pragma unroll 1
+    for (int k = 1; k <= kHdBis && !done; ++k) {
+      // the head continues only while QAGS bisects [0, 10 / 2^(k-1)]
+      if (sh.hp[S.i][tid] != (1u << (k - 1))) break;
+      double a1, b1, a2, b2;
+      int level;
+      S.pre_step(a1, b1, a2, b2, level);
+      const GkOut ga = head_gk21(sh, 2 * k - 1, beta, g, gs, tid);
+      const GkOut gb = head_gk21(sh, 2 * k, beta, g, gs, tid);
+      done = S.post_step(ga, gb);
+    }
+    done_flag[item] = done ? 1 : 0;
+    if (done) {
+      const double Q = S.result / fc.A;                  // :214
+      const double flux = fc.factor * Q * Q / ri.k;      // :215
+      W[(size_t)row * nb + i] = flux * (b * w);
+      if (neval_out) neval_out[(size_t)row * nb + i] = S.neval;
+      my_evals += S.neval;
+      if (S.ier != 0) my_err++;
+    } else {
+      HeadState& hs = state[item];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) hs.sc[k] = sh.sc[k][tid];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hs.eps[k] = sh.ep[k][tid];
+#pragma unroll
+      for (int k = 0; k < kHdCap; ++k) {
+        hs.rl[k] = sh.rl[k][tid]; hs.el[k] = sh.el[k][tid];
+        hs.hp[k] = sh.hp[k][tid]; hs.od[k] = sh.od[k][tid];
+      }
+      hs.size = S.size; hs.nrmax = S.nrmax; hs.i = S.i; hs.maximum_level = S.maximum_level; hs.ktmin = S.ktmin;
+      hs.roundoff_type1 = S.roundoff_type1; hs.roundoff_type2 = S.roundoff_type2; hs.roundoff_type3 = S.roundoff_type3;
+      hs.error_type = S.error_type; hs.error_type2 = S.error_type2; hs.iteration = S.iteration;
+      hs.tab_n = S.tab_n; hs.tab_nres = S.tab_nres;
+      hs.flags = (S.positive_integrand ? kHdPositive : 0) | (S.extrapolate ? kHdExtrapolate : 0) |
+                 (S.disallow_extrapolation ? kHdDisallow : 0);
+      hs.neval = S.neval;
+      my_left++;
+    }
+  }
+  const double ev = warp_sum(my_evals);
+  const unsigned er = __reduce_add_sync(0xffffffffu, my_err);
+  const unsigned lf = __reduce_add_sync(0xffffffffu, my_left);
+  if (lane == 0) {
+    if (ev > 0) atomicAdd(&ctr->evals, (unsigned long long)ev);
+    if (er) atomicAdd(&ctr->errors, (unsigned long long)er);
+    if (lf) atomicAdd(&ctr->left, (unsigned long long)lf);
+  }
+}
+
+// the integrals of each row the head hands over, in order of b
+__global__ void k_head_compact(int n_rows, const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
+                               const unsigned char* __restrict__ done_flag, int* __restrict__ left_idx,
+                               int* __restrict__ nq_left)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  const long long i0 = item_off[row];
+  const int nq = rows[row].nq;
+  int n = 0;
+  for (int i = 0; i < nq; ++i)
+    if (!done_flag[i0 + i]) left_idx[i0 + n++] = i;
+  nq_left[row] = n;
+}
+
+}  // namespace upc

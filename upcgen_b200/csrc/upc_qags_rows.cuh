@@ -27,6 +27,7 @@
 #pragma once
 #include "upc_hot.cuh"
 #include "upc_qags.cuh"
+#include "upc_qags_head.cuh"
 
 namespace upc {
 
@@ -149,52 +150,6 @@ __device__ __forceinline__ double rc_g(double x, double c0, const SplineSeg* __r
     F = seg_eval(ld_seg(ff + idx), delx);
   }
   return x2 * F / t;
-}
-
-// GK21 sums from the 21 stored integrand values (node order of kGkNode), in GSL's order
-// (integration/qk.c); same arithmetic as the tail of gk21_tri.
-__device__ __forceinline__ GkOut gk21_sums(const double* fv, int fv_stride, double half_length)
-{
-  const double abs_half_length = fabs(half_length);
-  const double f_center = fv[20 * fv_stride];
-  double result_gauss = 0;
-  double result_kronrod = f_center * kGkWkC;
-  double result_abs = fabs(result_kronrod);
-#pragma unroll 1
-  for (int p = 0; p < 10; ++p) {
-    const double fval1 = fv[(2 * p) * fv_stride], fval2 = fv[(2 * p + 1) * fv_stride];
-    const double fsum = fval1 + fval2;
-    result_gauss += kGkWg[p] * fsum;
-    result_kronrod += kGkWk[p] * fsum;
-    result_abs += kGkWk[p] * (fabs(fval1) + fabs(fval2));
-  }
-  const double mean = result_kronrod * 0.5;
-  double result_asc = kGkWkC * fabs(f_center - mean);
-#pragma unroll 1
-  for (int j = 0; j < 10; ++j) {
-    const int p = (j & 1) ? (j >> 1) : (5 + (j >> 1));
-    result_asc += kGkWk[p] * (fabs(fv[(2 * p) * fv_stride] - mean) + fabs(fv[(2 * p + 1) * fv_stride] - mean));
-  }
-  double err = (result_kronrod - result_gauss) * half_length;
-  result_kronrod *= half_length;
-  result_abs *= abs_half_length;
-  result_asc *= abs_half_length;
-  err = fabs(err);
-  if (result_asc != 0 && err != 0) {
-    double s = 200 * err / result_asc;
-    double scale = s * sqrt(s);
-    err = scale < 1 ? result_asc * scale : result_asc;
-  }
-  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
-    double min_err = 50 * DBL_EPSILON * result_abs;
-    if (min_err > err) err = min_err;
-  }
-  GkOut o;
-  o.result = result_kronrod;
-  o.abserr = err;
-  o.resabs = result_abs;
-  o.resasc = result_asc;
-  return o;
 }
 
 // The same sums split over two threads of a task (contiguous fv[0..20]), fully unrolled: role 0
@@ -331,7 +286,7 @@ __device__ __forceinline__ void rc_eval_round(RcGroup& sh, double (*fv)[kRcSlots
 // OWNERS, single thread: hand the next integrals of the row queue to this round's idle slots.
 // Rows are taken in order; a row entering service gets a free context (its table is cleared by
 // the group afterwards); if none is free the remaining idle slots wait for a later round.
-__device__ __forceinline__ void rc_grant(RcGroup& sh, int n_idle, int n_rows, const RowInfo* __restrict__ rows,
+__device__ __forceinline__ void rc_grant(RcGroup& sh, int n_idle, int n_rows, const int* __restrict__ nq_left,
                                          QagsCounters* __restrict__ ctr)
 {
   int n_grant = 0, clear_mask = 0, given = 0;
@@ -343,7 +298,7 @@ __device__ __forceinline__ void rc_grant(RcGroup& sh, int n_idle, int n_rows, co
       if (r0 >= n_rows) { sh.exhausted = 1; break; }
       sh.chunk_row0 = (int)r0;
       sh.chunk_n = (int)min((long long)kRcChunk, n_rows - r0);
-      for (int j = 0; j < sh.chunk_n; ++j) sh.chunk_nq[j] = rows[r0 + j].nq;
+      for (int j = 0; j < sh.chunk_n; ++j) sh.chunk_nq[j] = nq_left[r0 + j];  // integrals the head handed over
       sh.cur_row = 0; sh.cur_i = 0; sh.cur_ctx = -1;
     }
     const int nq = sh.chunk_nq[sh.cur_row];
@@ -378,7 +333,8 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
                                          const FluxConsts& fc, const SplineSeg* __restrict__ ff, double ff_last,
                                          double* __restrict__ W, int* __restrict__ neval_out,
                                          QagsCounters* __restrict__ ctr, long long* __restrict__ overflow_items,
-                                         double* __restrict__ gbuf)
+                                         double* __restrict__ gbuf, const HeadState* __restrict__ head_state,
+                                         const int* __restrict__ left_idx, const int* __restrict__ nq_left)
 {
   const unsigned lane = ltid & 31, warp = ltid >> 5;
   const unsigned lt = (1u << lane) - 1;
@@ -389,7 +345,7 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
   double my_evals = 0;
   unsigned my_err = 0;
   int parity = 0;
-  bool active = false, first = false;
+  bool active = false;
   int my_ctx = 0, my_row = 0, my_i = 0;
   if (ltid == 0) {
     sh.n_new[0] = 0; sh.n_new[1] = 0; sh.fin = 0;
@@ -409,7 +365,7 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
       n_idle += sh.cnt[2][w];
     }
     if (n_idle > 0) {  // group-uniform
-      if (ltid == 0) rc_grant(sh, n_idle, n_rows, rows, ctr);
+      if (ltid == 0) rc_grant(sh, n_idle, n_rows, nq_left, ctr);
       bar_sync(bar_own, kRcSlots);
       const int clear_mask = sh.clear_mask;
       if (clear_mask) {
@@ -423,7 +379,9 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
           const int r0 = sh.grant_rank0[j];
           if (rank >= r0 && rank < r0 + sh.grant_n[j]) {
             my_row = sh.grant_row[j];
-            my_i = sh.grant_i0[j] + (rank - r0);
+            const int pos = sh.grant_i0[j] + (rank - r0);  // position among the row's handed-over integrals
+            const long long item0 = item_off[my_row];
+            my_i = left_idx[item0 + pos];
             my_ctx = sh.grant_ctx[j];
             const RowInfo ri = rows[my_row];
             double b, w;
@@ -432,10 +390,29 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
             sh.bw_cur[ltid] = b * w;
             sh.beta[ltid] = b * (1. / kHc);
             sh.slot_ctx[ltid] = (unsigned char)my_ctx;
-            if (my_i == 0) sh.ctx_c0[my_ctx] = ri.k * ri.k / fc.g1 / fc.g1;  // w*w/g/g, :187
-            S.begin(0., 10.);                                              // :209
+            if (pos == 0) sh.ctx_c0[my_ctx] = ri.k * ri.k / fc.g1 / fc.g1;  // w*w/g/g, :187
+            // the QAGS state the head left (upc_qags_head.cuh)
+            const HeadState& hs = head_state[item0 + my_i];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) sh.sc[k][ltid] = hs.sc[k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sh.ep[k][ltid] = hs.eps[k];
+#pragma unroll
+            for (int k = 0; k < kHdCap; ++k) {
+              sh.rl[k][ltid] = hs.rl[k]; sh.el[k][ltid] = hs.el[k];
+              sh.hp[k][ltid] = hs.hp[k]; sh.od[k][ltid] = hs.od[k];
+            }
+            S.size = hs.size; S.nrmax = hs.nrmax; S.i = hs.i; S.maximum_level = hs.maximum_level; S.ktmin = hs.ktmin;
+            S.roundoff_type1 = hs.roundoff_type1; S.roundoff_type2 = hs.roundoff_type2;
+            S.roundoff_type3 = hs.roundoff_type3; S.error_type = hs.error_type; S.error_type2 = hs.error_type2;
+            S.iteration = hs.iteration; S.tab_n = hs.tab_n; S.tab_nres = hs.tab_nres;
+            S.positive_integrand = (hs.flags & kHdPositive) != 0;
+            S.extrapolate = (hs.flags & kHdExtrapolate) != 0;
+            S.disallow_extrapolation = (hs.flags & kHdDisallow) != 0;
+            S.overflow = false;
+            S.neval = hs.neval;
+            S.result = 0; S.abserr = 0; S.ier = 0;
             active = true;
-            first = true;
           }
         }
       }
@@ -449,12 +426,10 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
     bool has_b = false;
     int small_a = 0, small_b = 0;
     if (active) {
-      int level = 0;
-      double a1 = 0., b1 = 10., a2 = 10., b2 = 10.;
-      if (!first) {
-        S.pre_step(a1, b1, a2, b2, level);
-        has_b = true;
-      }
+      int level;
+      double a1, b1, a2, b2;
+      S.pre_step(a1, b1, a2, b2, level);
+      has_b = true;
       const unsigned heap = QagsSharedStore::heap_of(a1, level);
       const double beta = sh.beta[ltid];
       {
@@ -538,13 +513,8 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
     if (active) {
       bool done;
       const GkOut ga{sh.gk[0][0][ltid], sh.gk[1][0][ltid], sh.gk[2][0][ltid], sh.gk[3][0][ltid]};
-      if (first) {
-        done = S.post_first(ga);
-        first = false;
-      } else {
-        const GkOut gb{sh.gk[0][1][ltid], sh.gk[1][1][ltid], sh.gk[2][1][ltid], sh.gk[3][1][ltid]};
-        done = S.post_step(ga, gb);
-      }
+      const GkOut gb{sh.gk[0][1][ltid], sh.gk[1][1][ltid], sh.gk[2][1][ltid], sh.gk[3][1][ltid]};
+      done = S.post_step(ga, gb);
       if (done) {
         const double Q = S.result / fc.A;                         // :214
         const double flux = fc.factor * Q * Q / sh.k_cur[ltid];   // :215
@@ -579,7 +549,9 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
 __global__ void __launch_bounds__(kRcThreads, 1)
 k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
                  FluxConsts fc, DevTables tab, double* __restrict__ W, int* __restrict__ neval_out,
-                 QagsCounters* __restrict__ ctr, long long* __restrict__ overflow_items, double* __restrict__ gbuf_all)
+                 QagsCounters* __restrict__ ctr, long long* __restrict__ overflow_items, double* __restrict__ gbuf_all,
+                 const HeadState* __restrict__ head_state, const int* __restrict__ left_idx,
+                 const int* __restrict__ nq_left)
 {
   extern __shared__ __align__(16) unsigned char rc_smem[];
   RcShared& sh = *reinterpret_cast<RcShared*>(rc_smem);
@@ -601,7 +573,7 @@ k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const lon
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRcRegsOwner));
     const int grp = tid / kRcSlots;
     rc_owner(sh.g[grp], sh.node, sh.snode, sh.sid, grp, tid - grp * kRcSlots, n_rows, nb, rows, item_off, fc, tab.ff_seg, tab.ff_last, W,
-             neval_out, ctr, overflow_items, gbuf + (size_t)grp * (kRcG * 21));
+             neval_out, ctr, overflow_items, gbuf + (size_t)grp * (kRcG * 21), head_state, left_idx, nq_left);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRcRegsEval));
     const int etid = tid - 256;
