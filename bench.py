@@ -36,8 +36,9 @@ WORKLOAD_TEXT = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-# `ncu --set full` captures (profiles/r01_v10_ncu_qags_cfg2.txt, profiles/r01_v2_ncu_cells_cfg2.txt)
-NCU_TRAFFIC = {("cfg2", "k_flux_qags_rows"): 52.7e6 + 50.6e6, ("cfg2", "k_cells"): 235.9e6 + 5.9e6}
+# `ncu --set full` captures (profiles/r01_v11_ncu_qags_head_cfg2.txt, r01_v11_ncu_qags_rows_cfg2.txt,
+# r01_v2_ncu_cells_cfg2.txt)
+NCU_TRAFFIC = {("cfg2", "k_flux_qags_head"): 472.5e6 + 2346.1e6, ("cfg2", "k_flux_qags_rows"): 2730.4e6 + 187.6e6, ("cfg2", "k_cells"): 235.9e6 + 5.9e6}
 
 # algorithmic work per unit
 FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegrand
@@ -357,11 +358,20 @@ def main():
                "sample": sample + f"; {reps} repetitions"}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
+    ms_head = st.get("ms_qags_head", 0.0)
     if st["qags_evals"] > 0 and stage["ms_qags"] >= stage["ms_cells"]:
-        work = FLOP_PER_QAGS_EVAL * st["qags_evals"]
-        t_k = stage["ms_qags"] * 1e-3
-        kern = "k_flux_qags_rows"
-        units = f"{st['qags_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
+        # the QAGS stage is two kernels; the head (first GK21 rule + the 5 predictable bisections of every integral)
+        # is the longer one and holds ~80 % of the evaluations
+        if ms_head > 0.5 * stage["ms_qags"]:
+            work = FLOP_PER_QAGS_EVAL * st["qags_head_evals"]
+            t_k = ms_head * 1e-3
+            kern = "k_flux_qags_head"
+            units = f"{st['qags_head_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
+        else:
+            work = FLOP_PER_QAGS_EVAL * (st["qags_evals"] - st["qags_head_evals"])
+            t_k = (stage["ms_qags"] - ms_head) * 1e-3
+            kern = "k_flux_qags_rows"
+            units = f"{st['qags_evals'] - st['qags_head_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
     else:
         cells_rank = len(udist.cyclic_rows(P.nm, rank, world)) * P.ny
         work = FLOP_CELL[(pol, bk)] * cells_rank
@@ -374,7 +384,10 @@ def main():
                 "traffic": NCU_TRAFFIC.get((args.workload, kern)) if world == 1 else None,
                 "peak_source": "measured live: upcgpu_fp64_peak DFMA loop (MEASURED_PEAKS.json has no FP64 figure; "
                                "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
-                "algorithmic_work": units, "kernel_ms": t_k * 1e3}
+                "algorithmic_work": units, "kernel_ms": t_k * 1e3,
+                "qags_stage": {"ms": stage["ms_qags"], "ms_head": ms_head, "evals": st["qags_evals"],
+                               "tflops": FLOP_PER_QAGS_EVAL * st["qags_evals"] / (stage["ms_qags"] * 1e-3) / 1e12
+                               if stage["ms_qags"] > 0 else None}}
 
     if rank == 0:
         line = {

@@ -85,7 +85,10 @@ typedef struct {
   long long flux_rows;        /* photon-energy rows tabulated */
   long long band_pairs;       /* (b1,b2) pairs with some b < 20 fm that were evaluated */
   double ms_tables, ms_flux, ms_cells, ms_total; /* device time of the stages, CUDA events */
-  double ms_qags;             /* of ms_flux: the persistent QAGS kernel alone */
+  double ms_qags;             /* of ms_flux: the QAGS kernels (head + row-cooperative) */
+  double ms_qags_head;        /* of ms_qags: k_flux_qags_head alone (the predictable first 6 rounds) */
+  long long qags_head_evals;  /* integrand evaluations made by k_flux_qags_head */
+  long long qags_head_done;   /* integrals that converged inside the head */
 } upcgpu_fill_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -52,7 +52,8 @@ class CFillStats(C.Structure):
     _fields_ = [("qags_integrals", C.c_longlong), ("qags_evals", C.c_longlong), ("qags_overflow", C.c_longlong),
                 ("qags_errors", C.c_longlong), ("flux_rows", C.c_longlong), ("band_pairs", C.c_longlong),
                 ("ms_tables", C.c_double), ("ms_flux", C.c_double), ("ms_cells", C.c_double), ("ms_total", C.c_double),
-                ("ms_qags", C.c_double)]
+                ("ms_qags", C.c_double), ("ms_qags_head", C.c_double), ("qags_head_evals", C.c_longlong),
+                ("qags_head_done", C.c_longlong)]
 
 
 # every symbol include/upcgpu.h declares (tests check that the library exports all of them)

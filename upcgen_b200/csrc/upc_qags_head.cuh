@@ -140,6 +140,7 @@ struct HeadCounters {
   unsigned long long evals;  // integrand evaluations of integrals finished in the head
   unsigned long long errors;
   unsigned long long left;   // integrals handed over
+  unsigned long long evals_left;  // evaluations the head made for them
 };
 
 // One thread per integral, in queue order (consecutive b of a row, row after row): the lanes of a warp
@@ -165,7 +166,7 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
   __syncthreads();
 
   const long long item = (long long)blockIdx.x * kHdThreads + tid;
-  double my_evals = 0;
+  double my_evals = 0, my_evals_left = 0;
   unsigned my_err = 0, my_left = 0;
   if (item < n_items) {
     const int row = item_row[item];
@@ -219,15 +220,17 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
                  (S.disallow_extrapolation ? kHdDisallow : 0);
       hs.neval = S.neval;
       my_left++;
+      my_evals_left += S.neval;
     }
   }
-  const double ev = warp_sum(my_evals);
+  const double ev = warp_sum(my_evals), evl = warp_sum(my_evals_left);
   const unsigned er = __reduce_add_sync(0xffffffffu, my_err);
   const unsigned lf = __reduce_add_sync(0xffffffffu, my_left);
   if (lane == 0) {
     if (ev > 0) atomicAdd(&ctr->evals, (unsigned long long)ev);
     if (er) atomicAdd(&ctr->errors, (unsigned long long)er);
     if (lf) atomicAdd(&ctr->left, (unsigned long long)lf);
+    if (evl > 0) atomicAdd(&ctr->evals_left, (unsigned long long)evl);
   }
 }
 
