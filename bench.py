@@ -291,6 +291,39 @@ def main():
                "api": "upcgpu_fill_lumi" + (" + upcgpu_fold_sigma" if fold else "") + " (include/upcgpu.h), pinned host buffers",
                "total_cross_section_mb": tot.value}
 
+    else:
+        # N > 1: the sharded fill, the NCCL all-gather, then on EVERY rank the read-back of the lumi table(s)
+        # (upcgpu_lumi_download) and the fold with its sigma table read-back (upcgpu_fold_sigma), host buffers
+        kinds = (1, 2) if pol else (0,)
+
+        def step_e2e_dist():
+            gpu.invalidate_tables()
+            gpu.prepare_tables()
+            udist.fill_lumi_distributed(gpu, rank, world, dev)
+            for which in kinds:
+                gpu.lumi_download(which)
+            return gpu.fold_sigma(download=True, **sig)[2] if fold else 0.0
+
+        step_e2e_dist()
+        dts = []
+        for _ in range(args.steps):
+            l2_flush.fill_(1)
+            barrier()
+            t0 = time.perf_counter()
+            tot_mb = step_e2e_dist()
+            torch.cuda.synchronize(dev)
+            dts.append(time.perf_counter() - t0)
+        t = torch.tensor([float(np.mean(dts))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        n_tab = 2 if pol else 1
+        e2e = {"value": n_cells / dt, "unit": "cells/s", "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(sum(np.asarray(v).size * 8 for v in sig.values())),
+               "d2h_bytes_per_step": int(n_tab * n_cells * 8 + (n_cells * 8 * (2 if pol else 1) + 8 if fold else 0)),
+               "api": "per rank: upcgpu_fill_lumi_shard + NCCL all-gather + upcgpu_lumi_unpack + upcgpu_lumi_download"
+                      + (" + upcgpu_fold_sigma" if fold else "") + " (host buffers; bytes are per rank; max over ranks)",
+               "total_cross_section_mb": tot_mb}
+
     # ---- event stage ----------------------------------------------------------------------
     events = None
     if args.workload in ("cfg1", "cfg2", "cfg5"):

@@ -120,11 +120,50 @@ __global__ void k_head_tables(int n_rows, const RowInfo* __restrict__ rows, cons
   hg[(size_t)e * n_rows + row] = head_g(x, c0, tab.ff_seg, tab.ff_last);
 }
 
-// GK21 rule on head interval iv for this thread's integral: f = g * J1(beta x), three nodes at a time
+// J1 on the head nodes of the COMMON b grid.  bmax = max(5 g1 hc / k, 5R) (:228-229) is 5R for every
+// photon energy k >= g1 hc / R, so all those rows (34-38 % of the rows, 47-51 % of the integrals of the
+// cfg2 / cfg4 grids: they are the rows with the most b <= 2R points) share one b grid, and with it the
+// arguments beta_i * x of J1 on the 231 head nodes.  j1h[node][i] holds these values, formed by the same
+// instruction sequence as head_gk21's own evaluation (same j1_3 site, same products), so a row of the
+// common grid multiplies g by a table entry instead of evaluating J1: same bits, ~1/100 of the work.
+constexpr int kJ1hStride = 128;           // i stride of j1h (nb <= 128)
+
+__global__ void k_head_j1_table(int nb, double R, double* __restrict__ j1h)
+{
+  const int i = threadIdx.x;
+  const int iv = blockIdx.x;
+  if (i >= nb) return;
+  RowInfo ri;  // the common grid, formed as k_rows_setup forms it when bmax = 5R
+  ri.k = 0.; ri.bmin = 0.05 * R; ri.ld = (log(5. * R) - log(ri.bmin)) / nb; ri.nq = nb; ri.pad = 1;
+  double b, w;
+  grid_point(ri, i, b, w);
+  const double beta = b * (1. / kHc);
+  double a, bb;
+  head_interval(iv, a, bb);
+  double xs[21];
+#pragma unroll
+  for (int n = 0; n < 21; ++n) xs[n] = fma(0.5 * (bb - a), kGkNode[n], 0.5 * (a + bb));
+#pragma unroll 1
+  for (int n = 0; n < 21; n += 3) {
+    const D3 j = j1_3(D3{{beta * xs[n], beta * xs[n + 1], beta * xs[n + 2]}});
+    j1h[(size_t)(iv * 21 + n) * kJ1hStride + i] = j.v[0];
+    j1h[(size_t)(iv * 21 + n + 1) * kJ1hStride + i] = j.v[1];
+    j1h[(size_t)(iv * 21 + n + 2) * kJ1hStride + i] = j.v[2];
+  }
+}
+
+// GK21 rule on head interval iv for this thread's integral: f = g * J1(beta x), three nodes at a time;
+// jt != nullptr: the row is on the common b grid, J1 comes from the table (jt = j1h + i)
 __device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double beta, const double* __restrict__ g, size_t g_stride,
-                                           int tid)
+                                           const double* __restrict__ jt, int tid)
 {
   const double* gi = g + (size_t)(iv * 21) * g_stride;
+  if (jt) {
+    const double* ji = jt + (size_t)(iv * 21) * kJ1hStride;
+#pragma unroll
+    for (int n = 0; n < 21; ++n) sh.fv[n][tid] = gi[n * g_stride] * ji[n * kJ1hStride];
+    return gk21_sums(&sh.fv[0][tid], kHdThreads, sh.half[iv]);
+  }
 #pragma unroll 1
   for (int n = 0; n < 21; n += 3) {
     const double g0 = gi[n * g_stride], g1 = gi[(n + 1) * g_stride], g2 = gi[(n + 2) * g_stride];
@@ -148,7 +187,7 @@ struct HeadCounters {
 __global__ void __launch_bounds__(kHdThreads, 3)
 k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restrict__ rows,
                  const long long* __restrict__ item_off, const int* __restrict__ item_row, const double* __restrict__ hg,
-                 FluxConsts fc, double* __restrict__ W,
+                 const double* __restrict__ j1h, FluxConsts fc, double* __restrict__ W,
                  int* __restrict__ neval_out, HeadCounters* __restrict__ ctr, HeadState* __restrict__ state,
                  unsigned char* __restrict__ done_flag)
 {
@@ -177,21 +216,30 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
     double b, w;
     grid_point(ri, i, b, w);
     const double beta = b * (1. / kHc);
+    const double* jt = ri.pad ? j1h + i : nullptr;     // row on the common b grid
     Qags<QagsHeadStore> S;
     S.sh = &sh;
     S.slot = tid;
     S.begin(0., 10.);                                  // :209
-    bool done = S.post_first(head_gk21(sh, 0, beta, g, gs, tid));
+    // ONE GK21 site for all eleven rules of the head (the kernel's code must stay inside the 32 KB
+    // instruction cache: with three inlined sites `no_instruction` was the largest stall).  Rule 0 is
+    // [0, 10]; rules 2k-1 and 2k are the halves of bisection k.
+    bool done = false;
+    GkOut ga{};
 #pragma unroll 1
-    for (int k = 1; k <= kHdBis && !done; ++k) {
-      // the head continues only while QAGS bisects [0, 10 / 2^(k-1)]
-      if (sh.hp[S.i][tid] != (1u << (k - 1))) break;
-      double a1, b1, a2, b2;
-      int level;
-      S.pre_step(a1, b1, a2, b2, level);
-      const GkOut ga = head_gk21(sh, 2 * k - 1, beta, g, gs, tid);
-      const GkOut gb = head_gk21(sh, 2 * k, beta, g, gs, tid);
-      done = S.post_step(ga, gb);
+    for (int iv = 0; iv < kHdIv; ++iv) {
+      if (iv & 1) {
+        // the head continues only while QAGS bisects [0, 10 / 2^(k-1)], k = (iv + 1) / 2
+        if (sh.hp[S.i][tid] != (1u << (iv >> 1))) break;
+        double a1, b1, a2, b2;
+        int level;
+        S.pre_step(a1, b1, a2, b2, level);
+      }
+      const GkOut gk = head_gk21(sh, iv, beta, g, gs, jt, tid);
+      if (iv == 0) done = S.post_first(gk);
+      else if (iv & 1) ga = gk;
+      else done = S.post_step(ga, gk);
+      if (done) break;
     }
     done_flag[item] = done ? 1 : 0;
     if (done) {
