@@ -471,7 +471,10 @@ def test_full_grid_reflection_symmetry(get_gpu):
     """Size-independent property at BASELINE's full size (cfg2, 1001 x 121): with identical beams
     lumi(M, -Y) = lumi(M, Y) (k1 <-> k2 swaps the two b integrals).  The y grid of lower edges is
     symmetric about 0 for iy <-> ny - iy, so columns iy and ny - iy of the table must agree to the
-    rounding of y itself (1 ulp of y moves k by 1e-16 relative)."""
+    rounding of y itself (1 ulp of y moves k by 1e-16 relative).  The cell kernel USES this identity (columns
+    above ny/2 are written from their mirror images), so here the columns are equal; that the mirrored
+    columns equal the reference's own evaluation of them is what the golden sub-grids check (their iy sets
+    contain both halves: 80, 100, 120 / 900, 1200) and test_mirrored_cells_equal_direct_evaluation below."""
     P, g = get_gpu("cfg2")
     table = g.fill_lumi()
     ny = P.ny
@@ -481,6 +484,22 @@ def test_full_grid_reflection_symmetry(get_gpu):
     assert e < 1e-11
     # and the table falls monotonically in M at fixed Y over the whole grid (no cell lost or misplaced)
     assert np.all(np.diff(table[:, ny // 2]) < 0)
+
+
+def test_mirrored_cells_equal_direct_evaluation(get_gpu):
+    """Columns iy > ny/2 of the grid fill are mirror images (cell (im, ny-iy) with b1 <-> b2).  upcgpu_lumi_cells
+    evaluates any (M, Y) directly, without the reflection: both must agree to summation-order rounding."""
+    P, g = get_gpu("cfg2")
+    table = g.fill_lumi()
+    dm, dy = (P.mmax - P.mmin) / P.nm, (P.ymax - P.ymin) / P.ny
+    im = np.array([0, 1, 250, 500, 777, 1000])
+    iy = np.array([61, 62, 75, 90, 110, 119, 120])
+    M = (P.mmin + dm * im)[:, None] + 0 * iy[None, :]
+    Y = (P.ymin + dy * iy)[None, :] + 0 * im[:, None]
+    direct = g.lumi_cells(M, Y) * dm * dy
+    e = np.max(np.abs(table[np.ix_(im, iy)] - direct) / direct)
+    print("mirrored vs direct, max rel:", e)
+    assert e < 1e-12
 
 
 def test_cfg4_full_size_properties(get_gpu, capi):
