@@ -355,6 +355,10 @@ static void qk21(integrand_fn f, void* par, double a, double b, double* result, 
 }
 
 #define QAGS_LIMIT 1000
+/* analysis aid (tools/qags_interval_stats.py): the sequence of bisected intervals of the last qags()
+   call of this thread, as (level << 24 | position) with [a, b] = [pos, pos + 1] * (b0 - a0) / 2^level */
+static __thread unsigned* qags_trace_buf = 0;
+static __thread int qags_trace_cap = 0, qags_trace_n = 0;
 typedef struct {
   size_t limit, size, nrmax, i, maximum_level;
   double alist[QAGS_LIMIT], blist[QAGS_LIMIT], rlist[QAGS_LIMIT], elist[QAGS_LIMIT];
@@ -616,6 +620,11 @@ static int qags(integrand_fn f, void* par, double a, double b, double epsabs, do
     current_level = w->level[w->i] + 1;
     a1 = a_i; b1 = 0.5 * (a_i + b_i); a2 = b1; b2 = b_i;
     iteration++;
+    if (qags_trace_buf && qags_trace_n < qags_trace_cap) {
+      unsigned lv = (unsigned)(current_level - 1);
+      double wdt = (b - a) / (double)(1ull << lv);
+      qags_trace_buf[qags_trace_n++] = (lv << 24) | (unsigned)((a_i - a) / wdt + 0.5);
+    }
 
     qk21(f, par, a1, b1, &area1, &error1, &resabs1, &resasc1, neval);
     qk21(f, par, a2, b2, &area2, &error2, &resabs2, &resasc2, neval);
@@ -1190,6 +1199,17 @@ double upco_qags_fluxform(upco_ctx* c, double b, double k, double* abserr, int* 
   double res;
   *ier = qags(fluxFormIntegrand, &fp, 0., 10., 1e-4, 1e-4, QAGS_LIMIT, &res, abserr, neval, last);
   return res;
+}
+
+/* analysis aid: as upco_qags_fluxform, also returning the bisected intervals in order */
+int upco_qags_fluxform_trace(upco_ctx* c, double b, double k, unsigned* trace, int cap, int* neval)
+{
+  double err;
+  int last, ier;
+  qags_trace_buf = trace; qags_trace_cap = cap; qags_trace_n = 0;
+  upco_qags_fluxform(c, b, k, &err, neval, &last, &ier);
+  qags_trace_buf = 0;
+  return qags_trace_n;
 }
 
 /* src/UpcCrossSection.cpp:194-218 */

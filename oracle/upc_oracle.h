@@ -75,6 +75,8 @@ double upco_cspline_eval(const double* x, const double* y, const double* c, int 
 /* QAGS with GK21 on f(x) = x^2 F(t)/t J1(b x/hc), the fluxForm integrand; returns result and
    fills neval/last/abserr/ier */
 double upco_qags_fluxform(upco_ctx*, double b, double k, double* abserr, int* neval, int* last, int* ier);
+/* analysis aid: the bisected intervals of that integral, in order, as (level << 24 | position) */
+int upco_qags_fluxform_trace(upco_ctx*, double b, double k, unsigned* trace, int cap, int* neval);
 /* generic QAGS (GK21) on a C callback; returns the GSL error code */
 int upco_qags(double (*f)(double, void*), void* par, double a, double b, double epsabs, double epsrel, size_t limit,
               double* result, double* abserr);

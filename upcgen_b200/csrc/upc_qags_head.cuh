@@ -1,16 +1,18 @@
-// upc_qags_head.cuh -- stage A.3a: the predictable head of every form-factor flux integral.
+// upc_qags_head.cuh -- stage A.3a: the form-factor flux integrals, one thread per integral, for as long as
+// gsl_integration_qags stays on the intervals it almost always visits.
 //
-// gsl_integration_qags on [0, 10] with this integrand (src/UpcCrossSection.cpp:181-212) always
-// starts the same way: the 21-point rule on [0, 10], then bisection of [0, 10], of [0, 5], of
-// [0, 2.5], of [0, 1.25], of [0, 0.625] -- the integrand lives at small k_perp, so the leftmost
-// interval carries the largest error estimate.  Measured with the oracle over the cfg2 and cfg4
-// grids: bisections 1-3 always, 4 in all but 1 of 56 061, 5 in 98.8 % of the integrals that get
-// that far; these six rounds hold 79 % of all integrand evaluations.  They need no scheduling:
-// one thread per integral walks them here in the reference's order (same Qags<> state machine,
-// same arithmetic, g cached per row as in the row-cooperative kernel), all lanes of a warp on
-// the same interval at the same time.  An integral that converges inside the head is finished
-// here; one whose next bisection is not the predicted interval, or that is still running after
-// the head, is handed to k_flux_qags_rows with its complete QAGS state (HeadState).  Nothing is
+// gsl_integration_qags on [0, 10] with this integrand (src/UpcCrossSection.cpp:181-212) is very regular.
+// The integrand lives at small k_perp, so QAGS bisects [0, 10], [0, 5], [0, 2.5], [0, 1.25] and (98.9 %)
+// [0, 0.625]; after that the oracle's trace over the cfg2 grid (tools/qags_interval_stats.py: 87 253
+// integrals, 163 642 later bisections) shows 14 distinct intervals in all, nine of which take 99.65 % of
+// the bisections: (level, position) = (5,0) 30 %, (4,1) 26 %, (6,0) 19 %, (7,0) 10 %, (5,1) 5 %, (8,0) 4 %,
+// (5,2) 3 %, (1,1) 1 %, (9,0) 1 %.  So g -- the row-only factor of the integrand -- is tabulated once per row
+// on the GK21 nodes of the 29 intervals these 14 bisections can produce (k_head_tables), and every integral
+// runs the reference's QAGS in its own thread (same Qags<> state machine, state in shared memory strided by
+// thread) for as long as the interval it bisects next is one of the 14 and its interval list fits
+// (kHdCap: up to 9 bisections, 92 % of the integrals).  The lanes of a warp are consecutive b of one row:
+// they read the same few g entries and evaluate J1 on their own arguments.  An integral that needs
+// anything else (8 %) is handed to k_flux_qags_rows with its complete QAGS state (HeadState).  Nothing is
 // speculated: every evaluation made here is one the reference makes.
 #pragma once
 #include "upc_hot.cuh"
@@ -18,23 +20,48 @@
 
 namespace upc {
 
-constexpr int kHdThreads = 128;           // integrals of one row (nb <= 128)
-constexpr int kHdBis = 5;                 // predicted bisections
-constexpr int kHdIv = 1 + 2 * kHdBis;     // intervals of the head: [0,10], then (left, right) of each bisection
-constexpr int kHdCap = 8;                 // interval-list capacity while in the head (size <= 1 + kHdBis)
-constexpr int kHdEps = 10;                // epsilon-table capacity while in the head (<= 1 + kHdBis entries + 2 scratch)
+constexpr int kHdThreads = 128;
+constexpr int kHdPar = 14;                // bisections the head knows (parents of tabulated intervals)
+constexpr int kHdIv = 1 + 2 * kHdPar;     // tabulated intervals: [0,10], then (left, right) of each known bisection
+constexpr int kHdG = kHdIv * 21;          // g values per row
+constexpr int kHdCap = 11;                // interval-list capacity in the head: up to 9 bisections
+constexpr int kHdEps = 13;                // epsilon-table capacity in the head (1 + 9 entries + 2 scratch, +1)
+
+// heap index ((1 << level) + position) of the known bisections, in table order: interval 1 + 2j is the left
+// half of parent j, 2 + 2j the right half
+__constant__ unsigned kHdParent[kHdPar] = {1, 2, 4, 8, 16, 17, 32, 64, 128, 33, 256, 34, 3, 512};
+__host__ __device__ __forceinline__ int head_child_slot(unsigned heap)
+{
+  switch (heap) {
+    case 1: return 1;
+    case 2: return 3;
+    case 4: return 5;
+    case 8: return 7;
+    case 16: return 9;
+    case 17: return 11;
+    case 32: return 13;
+    case 64: return 15;
+    case 128: return 17;
+    case 33: return 19;
+    case 256: return 21;
+    case 34: return 23;
+    case 3: return 25;
+    case 512: return 27;
+    default: return -1;
+  }
+}
 
 // QAGS state of an integral leaving the head (everything Qags<Store> holds; see upc_qags.cuh)
 struct HeadState {
   double sc[11];
-  double eps[8];
+  double eps[kHdEps];
   double rl[kHdCap], el[kHdCap];
   unsigned hp[kHdCap];
-  unsigned char od[kHdCap];
+  unsigned char od[kHdCap + 1];
   int size, nrmax, i, maximum_level, ktmin, roundoff_type1, roundoff_type2, roundoff_type3, error_type, error_type2,
       iteration, tab_n, tab_nres, flags, neval, pad;
 };
-static_assert(sizeof(HeadState) == 384, "HeadState layout");
+static_assert(sizeof(HeadState) % 8 == 0, "HeadState layout");
 enum { kHdPositive = 1, kHdExtrapolate = 2, kHdDisallow = 4 };
 
 struct HdShared {
@@ -42,11 +69,10 @@ struct HdShared {
   double rl[kHdCap][kHdThreads], el[kHdCap][kHdThreads];
   double ep[kHdEps][kHdThreads];
   double sc[11][kHdThreads];
-  double xs[kHdIv][21];                 // nodes of the head intervals (the same for every row)
-  double half[kHdIv];
   unsigned hp[kHdCap][kHdThreads];
   unsigned char od[kHdCap][kHdThreads];
 };
+static_assert(3 * (sizeof(HdShared) + 1024) <= 227 * 1024, "three CTAs per SM");
 
 // strided shared-memory store (same interval encoding as QagsSharedStore: heap indices)
 struct QagsHeadStore {
@@ -78,14 +104,15 @@ struct QagsHeadStore {
   __device__ __forceinline__ double& sc(int k) { return sh->sc[k][slot]; }
 };
 
-// bounds of head interval iv: 0 -> [0, 10]; 2k-1 -> [0, 10/2^k]; 2k -> [10/2^k, 10/2^(k-1)]
-__host__ __device__ __forceinline__ void head_interval(int iv, double& a, double& b)
+// bounds of tabulated interval iv (exact: dyadic sub-intervals of [0, 10])
+__device__ __forceinline__ void head_interval(int iv, double& a, double& b)
 {
-  if (iv == 0) { a = 0.; b = 10.; return; }
-  const int k = (iv + 1) >> 1;
-  double w = 10.;
-  for (int j = 0; j < k; ++j) w *= 0.5;  // exact
-  if (iv & 1) { a = 0.; b = w; } else { a = w; b = 2. * w; }
+  const unsigned heap = iv == 0 ? 1u : 2u * kHdParent[(iv - 1) >> 1] + ((iv - 1) & 1);
+  const int level = 31 - __clz(heap);
+  const unsigned pos = heap - (1u << level);
+  const double width = 10. * QagsHeadStore::pow2(-level);
+  a = pos * width;
+  b = (pos + 1.) * width;
 }
 
 __device__ __forceinline__ double head_g(double x, double c0, const SplineSeg* __restrict__ ff, double ff_last)
@@ -102,28 +129,28 @@ __device__ __forceinline__ double head_g(double x, double c0, const SplineSeg* _
   return x2 * F / t;
 }
 
-// g on the 231 head nodes of every row: hg[node][row]; and the row of every integral
+// g on the kHdG tabulated nodes of every row: hg[row][interval * 21 + node]; and the row of every integral
 __global__ void k_head_tables(int n_rows, const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
                               double g1, DevTables tab, double* __restrict__ hg, int* __restrict__ item_row)
 {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  const int e = blockIdx.y;  // interval * 21 + node
-  if (row >= n_rows) return;
+  const int row = blockIdx.x;
   const RowInfo ri = rows[row];
   const double k = ri.k;
   const double c0 = k * k / g1 / g1;  // w*w/g/g, :187
-  if (e < ri.nq) item_row[item_off[row] + e] = row;
-  const int iv = e / 21, n = e - iv * 21;
-  double a, b;
-  head_interval(iv, a, b);
-  const double x = fma(0.5 * (b - a), kGkNode[n], 0.5 * (a + b));
-  hg[(size_t)e * n_rows + row] = head_g(x, c0, tab.ff_seg, tab.ff_last);
+  for (int e = threadIdx.x; e < kHdG; e += blockDim.x) {
+    if (e < ri.nq) item_row[item_off[row] + e] = row;
+    const int iv = e / 21, n = e - iv * 21;
+    double a, b;
+    head_interval(iv, a, b);
+    const double x = fma(0.5 * (b - a), kGkNode[n], 0.5 * (a + b));
+    hg[(size_t)row * kHdG + e] = head_g(x, c0, tab.ff_seg, tab.ff_last);
+  }
 }
 
-// J1 on the head nodes of the COMMON b grid.  bmax = max(5 g1 hc / k, 5R) (:228-229) is 5R for every
+// J1 on the tabulated nodes of the COMMON b grid.  bmax = max(5 g1 hc / k, 5R) (:228-229) is 5R for every
 // photon energy k >= g1 hc / R, so all those rows (34-38 % of the rows, 47-51 % of the integrals of the
 // cfg2 / cfg4 grids: they are the rows with the most b <= 2R points) share one b grid, and with it the
-// arguments beta_i * x of J1 on the 231 head nodes.  j1h[node][i] holds these values, formed by the same
+// arguments beta_i * x of J1 on the tabulated nodes.  j1h[node][i] holds these values, formed by the same
 // instruction sequence as head_gk21's own evaluation (same j1_3 site, same products), so a row of the
 // common grid multiplies g by a table entry instead of evaluating J1: same bits, ~1/100 of the work.
 constexpr int kJ1hStride = 128;           // i stride of j1h (nb <= 128)
@@ -140,39 +167,40 @@ __global__ void k_head_j1_table(int nb, double R, double* __restrict__ j1h)
   const double beta = b * (1. / kHc);
   double a, bb;
   head_interval(iv, a, bb);
-  double xs[21];
-#pragma unroll
-  for (int n = 0; n < 21; ++n) xs[n] = fma(0.5 * (bb - a), kGkNode[n], 0.5 * (a + bb));
+  const double center = 0.5 * (a + bb), half = 0.5 * (bb - a);
 #pragma unroll 1
   for (int n = 0; n < 21; n += 3) {
-    const D3 j = j1_3(D3{{beta * xs[n], beta * xs[n + 1], beta * xs[n + 2]}});
+    const D3 j = j1_3(D3{{beta * fma(half, kGkNode[n], center), beta * fma(half, kGkNode[n + 1], center),
+                          beta * fma(half, kGkNode[n + 2], center)}});
     j1h[(size_t)(iv * 21 + n) * kJ1hStride + i] = j.v[0];
     j1h[(size_t)(iv * 21 + n + 1) * kJ1hStride + i] = j.v[1];
     j1h[(size_t)(iv * 21 + n + 2) * kJ1hStride + i] = j.v[2];
   }
 }
 
-// GK21 rule on head interval iv for this thread's integral: f = g * J1(beta x), three nodes at a time;
+// GK21 rule on tabulated interval iv = [center - half, center + half] for this thread's integral:
+// f = g * J1(beta x), three nodes at a time; g = the row's table + 21 iv;
 // jt != nullptr: the row is on the common b grid, J1 comes from the table (jt = j1h + i)
-__device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double beta, const double* __restrict__ g, size_t g_stride,
-                                           const double* __restrict__ jt, int tid)
+__device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double center, double half, double beta,
+                                           const double* __restrict__ g, const double* __restrict__ jt, int tid)
 {
-  const double* gi = g + (size_t)(iv * 21) * g_stride;
+  const double* gi = g + iv * 21;
   if (jt) {
     const double* ji = jt + (size_t)(iv * 21) * kJ1hStride;
 #pragma unroll
-    for (int n = 0; n < 21; ++n) sh.fv[n][tid] = gi[n * g_stride] * ji[n * kJ1hStride];
-    return gk21_sums(&sh.fv[0][tid], kHdThreads, sh.half[iv]);
+    for (int n = 0; n < 21; ++n) sh.fv[n][tid] = gi[n] * ji[n * kJ1hStride];
+    return gk21_sums(&sh.fv[0][tid], kHdThreads, half);
   }
 #pragma unroll 1
   for (int n = 0; n < 21; n += 3) {
-    const double g0 = gi[n * g_stride], g1 = gi[(n + 1) * g_stride], g2 = gi[(n + 2) * g_stride];
-    const D3 j = j1_3(D3{{beta * sh.xs[iv][n], beta * sh.xs[iv][n + 1], beta * sh.xs[iv][n + 2]}});
+    const double g0 = gi[n], g1 = gi[n + 1], g2 = gi[n + 2];
+    const D3 j = j1_3(D3{{beta * fma(half, kGkNode[n], center), beta * fma(half, kGkNode[n + 1], center),
+                          beta * fma(half, kGkNode[n + 2], center)}});
     sh.fv[n][tid] = g0 * j.v[0];
     sh.fv[n + 1][tid] = g1 * j.v[1];
     sh.fv[n + 2][tid] = g2 * j.v[2];
   }
-  return gk21_sums(&sh.fv[0][tid], kHdThreads, sh.half[iv]);
+  return gk21_sums(&sh.fv[0][tid], kHdThreads, half);
 }
 
 struct HeadCounters {
@@ -183,7 +211,7 @@ struct HeadCounters {
 };
 
 // One thread per integral, in queue order (consecutive b of a row, row after row): the lanes of a warp
-// read the same g (a broadcast) and sit on the same node.
+// read the same g entries (broadcasts) and walk the same rounds.
 __global__ void __launch_bounds__(kHdThreads, 3)
 k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restrict__ rows,
                  const long long* __restrict__ item_off, const int* __restrict__ item_row, const double* __restrict__ hg,
@@ -195,14 +223,6 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
   HdShared& sh = *reinterpret_cast<HdShared*>(hd_smem);
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
-  for (int e = tid; e < kHdIv * 21; e += kHdThreads) {
-    const int iv = e / 21, n = e - iv * 21;
-    double a, b;
-    head_interval(iv, a, b);
-    sh.xs[iv][n] = fma(0.5 * (b - a), kGkNode[n], 0.5 * (a + b));
-    if (n == 0) sh.half[iv] = 0.5 * (b - a);
-  }
-  __syncthreads();
 
   const long long item = (long long)blockIdx.x * kHdThreads + tid;
   double my_evals = 0, my_evals_left = 0;
@@ -211,8 +231,7 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
     const int row = item_row[item];
     const int i = (int)(item - item_off[row]);
     const RowInfo ri = rows[row];
-    const double* g = hg + row;
-    const size_t gs = (size_t)n_rows;
+    const double* g = hg + (size_t)row * kHdG;
     double b, w;
     grid_point(ri, i, b, w);
     const double beta = b * (1. / kHc);
@@ -221,25 +240,32 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
     S.sh = &sh;
     S.slot = tid;
     S.begin(0., 10.);                                  // :209
-    // ONE GK21 site for all eleven rules of the head (the kernel's code must stay inside the 32 KB
-    // instruction cache: with three inlined sites `no_instruction` was the largest stall).  Rule 0 is
-    // [0, 10]; rules 2k-1 and 2k are the halves of bisection k.
+    // ONE GK21 site for every rule (the kernel's code must stay inside the 32 KB instruction cache: with
+    // three inlined sites `no_instruction` was the largest stall).  phase 0: the rule on [0, 10];
+    // phase 1 / 2: the left / right half of the interval being bisected.
     bool done = false;
     GkOut ga{};
+    int iv = 0, phase = 0;
+    double center = 5., half = 5., c2 = 0., h2 = 0.;
 #pragma unroll 1
-    for (int iv = 0; iv < kHdIv; ++iv) {
-      if (iv & 1) {
-        // the head continues only while QAGS bisects [0, 10 / 2^(k-1)], k = (iv + 1) / 2
-        if (sh.hp[S.i][tid] != (1u << (iv >> 1))) break;
-        double a1, b1, a2, b2;
-        int level;
-        S.pre_step(a1, b1, a2, b2, level);
+    while (true) {
+      const GkOut gk = head_gk21(sh, iv, center, half, beta, g, jt, tid);
+      if (phase == 1) {
+        ga = gk;
+        ++iv; center = c2; half = h2; phase = 2;
+        continue;
       }
-      const GkOut gk = head_gk21(sh, iv, beta, g, gs, jt, tid);
-      if (iv == 0) done = S.post_first(gk);
-      else if (iv & 1) ga = gk;
-      else done = S.post_step(ga, gk);
+      done = phase == 0 ? S.post_first(gk) : S.post_step(ga, gk);
       if (done) break;
+      // the head goes on while QAGS bisects an interval whose halves are tabulated and the state fits
+      const int cs = head_child_slot(sh.hp[S.i][tid]);
+      if (cs < 0 || S.size + 1 >= kHdCap || S.tab_n + 2 >= kHdEps) break;
+      double a1, b1, a2, b2;
+      int level;
+      S.pre_step(a1, b1, a2, b2, level);
+      iv = cs; phase = 1;
+      center = 0.5 * (a1 + b1); half = 0.5 * (b1 - a1);
+      c2 = 0.5 * (a2 + b2); h2 = 0.5 * (b2 - a2);
     }
     done_flag[item] = done ? 1 : 0;
     if (done) {
@@ -254,7 +280,7 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
 #pragma unroll
       for (int k = 0; k < 11; ++k) hs.sc[k] = sh.sc[k][tid];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) hs.eps[k] = sh.ep[k][tid];
+      for (int k = 0; k < kHdEps; ++k) hs.eps[k] = sh.ep[k][tid];
 #pragma unroll
       for (int k = 0; k < kHdCap; ++k) {
         hs.rl[k] = sh.rl[k][tid]; hs.el[k] = sh.el[k][tid];

@@ -396,7 +396,7 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
 #pragma unroll
             for (int k = 0; k < 11; ++k) sh.sc[k][ltid] = hs.sc[k];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sh.ep[k][ltid] = hs.eps[k];
+            for (int k = 0; k < kHdEps; ++k) sh.ep[k][ltid] = hs.eps[k];
 #pragma unroll
             for (int k = 0; k < kHdCap; ++k) {
               sh.rl[k][ltid] = hs.rl[k]; sh.el[k][ltid] = hs.el[k];
