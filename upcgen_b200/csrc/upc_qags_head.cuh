@@ -129,23 +129,45 @@ __device__ __forceinline__ double head_g(double x, double c0, const SplineSeg* _
   return x2 * F / t;
 }
 
-// g on the kHdG tabulated nodes of every row: hg[row][interval * 21 + node]; and the row of every integral
-__global__ void k_head_tables(int n_rows, const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
-                              double g1, DevTables tab, double* __restrict__ hg, int* __restrict__ item_row)
+// g on the kHdG tabulated nodes of every row.  Layout hg[ir][e][iml] (row = iml * rows_per_m + ir): the lanes of a
+// head warp are the same grid point i of 32 consecutive m rows at one y row ir, so a load of node e is one
+// contiguous 256 B segment.
+__global__ void k_head_tables(int n_m, int rows_per_m, const RowInfo* __restrict__ rows, double g1, DevTables tab,
+                              double* __restrict__ hg)
 {
-  const int row = blockIdx.x;
-  const RowInfo ri = rows[row];
-  const double k = ri.k;
+  const int iml = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ir = blockIdx.y;
+  if (iml >= n_m) return;
+  const double k = rows[(size_t)iml * rows_per_m + ir].k;
   const double c0 = k * k / g1 / g1;  // w*w/g/g, :187
-  for (int e = threadIdx.x; e < kHdG; e += blockDim.x) {
-    if (e < ri.nq) item_row[item_off[row] + e] = row;
-    const int iv = e / 21, n = e - iv * 21;
+  double* out = hg + (size_t)ir * kHdG * n_m + iml;
+#pragma unroll 1
+  for (int iv = 0; iv < kHdIv; ++iv) {
     double a, b;
     head_interval(iv, a, b);
-    const double x = fma(0.5 * (b - a), kGkNode[n], 0.5 * (a + b));
-    hg[(size_t)row * kHdG + e] = head_g(x, c0, tab.ff_seg, tab.ff_last);
+    const double center = 0.5 * (a + b), half = 0.5 * (b - a);
+#pragma unroll 3
+    for (int n = 0; n < 21; ++n)
+      out[(size_t)(iv * 21 + n) * n_m] = head_g(fma(half, kGkNode[n], center), c0, tab.ff_seg, tab.ff_last);
   }
 }
+
+// The order in which the head takes the integrals: flat index q = (ir * nb + i) * n_m + iml, i.e. for one y row ir
+// and one grid point i the integrals of consecutive m rows are neighbours.  M changes by dm from one m row to the
+// next (0.1-1 % of k), so the 32 integrals of a warp have almost the same photon energy and the same b index:
+// the same number of QAGS rounds, the same intervals, the same branch of J1 (lanes that are consecutive b of
+// ONE row differ by a factor 3 in b: 66 % of the lanes were busy, here 9x %).  Selected: i < nq(row).
+struct HeadItemValid {
+  const int* nq;
+  int n_m, nb, rows_per_m;
+  __device__ __forceinline__ bool operator()(unsigned q) const
+  {
+    const unsigned per_ir = (unsigned)nb * (unsigned)n_m;
+    const unsigned ir = q / per_ir, rem = q - ir * per_ir;
+    const unsigned i = rem / (unsigned)n_m, iml = rem - i * (unsigned)n_m;
+    return (int)i < nq[(size_t)iml * rows_per_m + ir];
+  }
+};
 
 // J1 on the tabulated nodes of the COMMON b grid.  bmax = max(5 g1 hc / k, 5R) (:228-229) is 5R for every
 // photon energy k >= g1 hc / R, so all those rows (34-38 % of the rows, 47-51 % of the integrals of the
@@ -182,18 +204,18 @@ __global__ void k_head_j1_table(int nb, double R, double* __restrict__ j1h)
 // f = g * J1(beta x), three nodes at a time; g = the row's table + 21 iv;
 // jt != nullptr: the row is on the common b grid, J1 comes from the table (jt = j1h + i)
 __device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double center, double half, double beta,
-                                           const double* __restrict__ g, const double* __restrict__ jt, int tid)
+                                           const double* __restrict__ g, size_t gs, const double* __restrict__ jt, int tid)
 {
-  const double* gi = g + iv * 21;
+  const double* gi = g + (size_t)(iv * 21) * gs;
   if (jt) {
     const double* ji = jt + (size_t)(iv * 21) * kJ1hStride;
 #pragma unroll
-    for (int n = 0; n < 21; ++n) sh.fv[n][tid] = gi[n] * ji[n * kJ1hStride];
+    for (int n = 0; n < 21; ++n) sh.fv[n][tid] = gi[n * gs] * ji[n * kJ1hStride];
     return gk21_sums(&sh.fv[0][tid], kHdThreads, half);
   }
 #pragma unroll 1
   for (int n = 0; n < 21; n += 3) {
-    const double g0 = gi[n], g1 = gi[n + 1], g2 = gi[n + 2];
+    const double g0 = gi[n * gs], g1 = gi[(n + 1) * gs], g2 = gi[(n + 2) * gs];
     const D3 j = j1_3(D3{{beta * fma(half, kGkNode[n], center), beta * fma(half, kGkNode[n + 1], center),
                           beta * fma(half, kGkNode[n + 2], center)}});
     sh.fv[n][tid] = g0 * j.v[0];
@@ -210,11 +232,10 @@ struct HeadCounters {
   unsigned long long evals_left;  // evaluations the head made for them
 };
 
-// One thread per integral, in queue order (consecutive b of a row, row after row): the lanes of a warp
-// read the same g entries (broadcasts) and walk the same rounds.
+// One thread per integral, in the order of HeadItemValid (order[]: the selected flat indices).
 __global__ void __launch_bounds__(kHdThreads, 3)
-k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restrict__ rows,
-                 const long long* __restrict__ item_off, const int* __restrict__ item_row, const double* __restrict__ hg,
+k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowInfo* __restrict__ rows,
+                 const long long* __restrict__ item_off, const unsigned* __restrict__ order, const double* __restrict__ hg,
                  const double* __restrict__ j1h, FluxConsts fc, double* __restrict__ W,
                  int* __restrict__ neval_out, HeadCounters* __restrict__ ctr, HeadState* __restrict__ state,
                  unsigned char* __restrict__ done_flag)
@@ -224,14 +245,19 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
 
-  const long long item = (long long)blockIdx.x * kHdThreads + tid;
+  const long long t = (long long)blockIdx.x * kHdThreads + tid;
   double my_evals = 0, my_evals_left = 0;
   unsigned my_err = 0, my_left = 0;
-  if (item < n_items) {
-    const int row = item_row[item];
-    const int i = (int)(item - item_off[row]);
+  if (t < n_items) {
+    const unsigned q = order[t];
+    const unsigned per_ir = (unsigned)nb * (unsigned)n_m;
+    const unsigned ir = q / per_ir, rem = q - ir * per_ir;
+    const int i = (int)(rem / (unsigned)n_m), iml = (int)(rem - (unsigned)i * (unsigned)n_m);
+    const size_t row = (size_t)iml * rows_per_m + ir;
+    const long long item = item_off[row] + i;          // row-major index: done_flag, state (k_flux_qags_rows)
     const RowInfo ri = rows[row];
-    const double* g = hg + (size_t)row * kHdG;
+    const double* g = hg + (size_t)ir * kHdG * n_m + iml;
+    const size_t gs = (size_t)n_m;
     double b, w;
     grid_point(ri, i, b, w);
     const double beta = b * (1. / kHc);
@@ -249,7 +275,7 @@ k_flux_qags_head(long long n_items, int n_rows, int nb, const RowInfo* __restric
     double center = 5., half = 5., c2 = 0., h2 = 0.;
 #pragma unroll 1
     while (true) {
-      const GkOut gk = head_gk21(sh, iv, center, half, beta, g, jt, tid);
+      const GkOut gk = head_gk21(sh, iv, center, half, beta, g, gs, jt, tid);
       if (phase == 1) {
         ga = gk;
         ++iv; center = c2; half = h2; phase = 2;
