@@ -207,22 +207,23 @@ __device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double center, 
                                            const double* __restrict__ g, size_t gs, const double* __restrict__ jt, int tid)
 {
   const double* gi = g + (size_t)(iv * 21) * gs;
+  double* fvp = &sh.fv[0][tid];
   if (jt) {
     const double* ji = jt + (size_t)(iv * 21) * kJ1hStride;
 #pragma unroll
-    for (int n = 0; n < 21; ++n) sh.fv[n][tid] = gi[n * gs] * ji[n * kJ1hStride];
-    return gk21_sums(&sh.fv[0][tid], kHdThreads, half);
-  }
+    for (int n = 0; n < 21; ++n) fvp[n * kHdThreads] = gi[n * gs] * ji[n * kJ1hStride];
+  } else {
 #pragma unroll 1
-  for (int n = 0; n < 21; n += 3) {
-    const double g0 = gi[n * gs], g1 = gi[(n + 1) * gs], g2 = gi[(n + 2) * gs];
-    const D3 j = j1_3(D3{{beta * fma(half, kGkNode[n], center), beta * fma(half, kGkNode[n + 1], center),
-                          beta * fma(half, kGkNode[n + 2], center)}});
-    sh.fv[n][tid] = g0 * j.v[0];
-    sh.fv[n + 1][tid] = g1 * j.v[1];
-    sh.fv[n + 2][tid] = g2 * j.v[2];
+    for (int n = 0; n < 21; n += 3, gi += 3 * gs, fvp += 3 * kHdThreads) {
+      const double g0 = gi[0], g1 = gi[gs], g2 = gi[2 * gs];
+      const D3 j = j1_3(D3{{beta * fma(half, kGkNode[n], center), beta * fma(half, kGkNode[n + 1], center),
+                            beta * fma(half, kGkNode[n + 2], center)}});
+      fvp[0] = g0 * j.v[0];
+      fvp[kHdThreads] = g1 * j.v[1];
+      fvp[2 * kHdThreads] = g2 * j.v[2];
+    }
   }
-  return gk21_sums(&sh.fv[0][tid], kHdThreads, half);
+  return gk21_sums_strided<kHdThreads>(&sh.fv[0][tid], half);  // one site, fully unrolled
 }
 
 struct HeadCounters {
