@@ -112,26 +112,41 @@ __constant__ double kJ1C[12] = {
   1. / 40320., -1. / 720., 1. / 24., 0., 0.};         // 7..9: cos(eps) series
 
 // J1(x), x >= 0.  Replaces gsl_sf_bessel_J1 at src/UpcCrossSection.cpp:189.
-// x <= 8: x * P(x^2/32 - 1); x > 8: modulus/phase form with sin(x - pi/4 + eps) expanded (as
-// GSL's bessel_sin_pi4 does) so that only x itself goes through the large-argument sincos.
+// x <= 8: x * P(x^2/32 - 1); x > 8: modulus/phase form sqrt(2/(pi x)) M sin(x - pi/4 + eps) with the
+// whole angle reduced at once (see j1_largeN in upc_hot.cuh).
 __device__ __forceinline__ double bessel_j1(double x)
 {
   if (x <= 8.) {
     return x * horner(UPC_J1_P, fma(x * x, kJ1C[0], -1.));
   }
-  double rx = 1. / x;
-  double w = 64. * rx * rx;
-  double u = fma(2., w, -1.);
-  double ampl = horner(UPC_J1_M, u) * sqrt(kJ1C[1] * rx);  // sqrt(2/(pi x))
-  double eps = horner(UPC_J1_T, u) * rx;
-  double sy, cy;
-  sincos_mid(x, sy, cy);
-  // |eps| <= 0.047: short Taylor series are exact to < 1e-22
-  double e2 = eps * eps;
-  double seps = eps * fma(e2, fma(e2, fma(e2, fma(e2, kJ1C[3], kJ1C[4]), kJ1C[5]), kJ1C[6]), 1.);
-  double ceps = fma(e2, fma(e2, fma(e2, fma(e2, kJ1C[7], kJ1C[8]), kJ1C[9]), -0.5), 1.);
-  double s = sy + cy, d = sy - cy;
-  return ampl * fma(ceps, d, seps * s) * kJ1C[2];
+  // same formulation as j1_largeN (upc_hot.cuh)
+  const double rs = rsqrt(x);
+  const double rx = rs * rs;
+  const double u = fma(128. * rx, rx, -1.);
+  const double ampl = horner(UPC_J1_M, u) * (rs * 0.79788456080286535588);  // sqrt(2/(pi x))
+  const double eps = horner(UPC_J1_T, u) * rx;
+  const double kMagic = 6755399441055744.0;
+  const double q = fma(x + eps, kSinCosC[0], -0.5) + kMagic;
+  const int n = __double2loint(q);
+  const double f = (q - kMagic) + 0.5;
+  double r = fma(-f, kSinCosC[1], x);
+  r = fma(-f, kSinCosC[2], r);
+  r = fma(-f, kSinCosC[3], r) + eps;
+  const double z = r * r;
+  double ps = fma(z, kSinCosC[4], kSinCosC[5]);
+  ps = fma(z, ps, kSinCosC[6]);
+  ps = fma(z, ps, kSinCosC[7]);
+  ps = fma(z, ps, kSinCosC[8]);
+  ps = fma(z, ps, kSinCosC[9]);
+  const double sr = fma(z * r, ps, r);
+  double pc = fma(z, kSinCosC[10], kSinCosC[11]);
+  pc = fma(z, pc, kSinCosC[12]);
+  pc = fma(z, pc, kSinCosC[13]);
+  pc = fma(z, pc, kSinCosC[14]);
+  pc = fma(z, pc, kSinCosC[15]);
+  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const double a = (n & 1) ? cr : sr;
+  return ampl * ((n & 2) ? -a : a);
 }
 
 // ROOT TMath::BesselI1 / BesselK1 polynomials (A&S 9.8.3-9.8.8), used by calcBreakupProb
