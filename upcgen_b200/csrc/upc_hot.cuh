@@ -22,7 +22,7 @@ enum HotOff {
   H_J1M = H_J1P + UPC_J1_P_N,        // 14: modulus
   H_J1T = H_J1M + UPC_J1_M_N,        // 16: phase
   H_SC = H_J1T + UPC_J1_T_N,         // 16: sincos (see kSinCosC)
-  H_EPS = H_SC + 16,                 // 8 : sin/cos(eps) series
+  H_EPS = H_SC + 16,                 // 8 : 3/8, spare
   H_MISC = H_EPS + 8,                // 8 : 1/32, 2/pi, 1/sqrt2, Q2min, 1/dQ2, dQ2, 64, sqrt(2/pi)
   H_END = H_MISC + 8
 };
@@ -38,8 +38,8 @@ __constant__ double upc_hot[upc::H_END] = {
   -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
   -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
   2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
-  // eps series: sin: 1/9!, -1/7!, 1/5!, -1/3!; cos: 1/8!, -1/6!, 1/4!, (pad)
-  1. / 362880., -1. / 5040., 1. / 120., -1. / 6., 1. / 40320., -1. / 720., 1. / 24., 0.,
+  // 3/8 (rsqrt refinement), 7 spare
+  0.375, 0., 0., 0., 0., 0., 0., 0.,
   // misc
   1. / 32., 0.63661977236758134308, 0.70710678118654752440, upc::kQ2min, 1. / upc::kDQ2, upc::kDQ2, 64.,
   0.79788456080286535588 /* sqrt(2/pi) */};
@@ -114,8 +114,19 @@ __device__ __forceinline__ DV<N> j1_largeN(const DV<N>& x, const H& h)
 {
   DV<N> rs, rx, u;
   const double k128 = 128.;
+  {
+    // 1/sqrt(x): MUFU.RSQ64H seed (~2^-22) + one third-order step, the sequence rsqrt() itself uses, without
+    // its special-case branch (x is positive and normal here; an argument that belongs to the other branch
+    // of J1 may give inf/NaN in a lane whose value is discarded)
+    const double k375 = h.template at<H_EPS + 0>();
+    UPC_FOR_N {
+      double y;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x.v[i_]));
+      const double e = fma(-x.v[i_], y * y, 1.);
+      rs.v[i_] = fma(fma(e, k375, 0.5), y * e, y);
+    }
+  }
   UPC_FOR_N {
-    rs.v[i_] = rsqrt(x.v[i_]);
     rx.v[i_] = rs.v[i_] * rs.v[i_];
     u.v[i_] = fma(k128 * rx.v[i_], rx.v[i_], -1.);
   }
@@ -179,8 +190,8 @@ __device__ __forceinline__ DV<N> j1_largeN(const DV<N>& x, const H& h)
   UPC_FOR_N {
     const double sr = fma(z.v[i_] * r.v[i_], sp.v[i_], r.v[i_]);
     const double cr = fma(z.v[i_] * z.v[i_], cp.v[i_], fma(z.v[i_], -0.5, 1.0));
-    const double a = (n[i_] & 1) ? cr : sr;     // sin(r + n pi/2)
-    res.v[i_] = ampl.v[i_] * ((n[i_] & 2) ? -a : a);
+    const double a = (n[i_] & 1) ? cr : sr;     // sin(r + n pi/2): sign flipped in quadrants 2 and 3
+    res.v[i_] = ampl.v[i_] * __hiloint2double(__double2hiint(a) ^ ((n[i_] & 2) << 30), __double2loint(a));
   }
   return res;
 }
@@ -198,18 +209,23 @@ __device__ __forceinline__ DV<N> j1_smallN(const DV<N>& x, const H& h)
   return r;
 }
 
-// J1 for three arbitrary non-negative arguments: each branch is evaluated for all three when any
-// of them needs it (arguments clamped into the branch's domain), then selected per argument.
+// J1 for three arbitrary positive arguments: each branch is evaluated for all three when any of them needs
+// it, then selected per argument.  An argument outside a branch's domain gives a meaningless (possibly
+// non-finite) value in that branch, which the selection drops: no clamping.  The class test is an integer
+// comparison of the bit patterns (x > 8 for positive x), off the FP64 pipe.
+__device__ __forceinline__ bool j1_is_large(double x)
+{
+  return (unsigned long long)__double_as_longlong(x) > 0x4020000000000000ull;
+}
+
 __device__ __forceinline__ D3 j1_3(const D3& x)
 {
   const HotConst h;
-  const bool la = x.v[0] > 8., lb = x.v[1] > 8., lc = x.v[2] > 8.;
+  const bool la = j1_is_large(x.v[0]), lb = j1_is_large(x.v[1]), lc = j1_is_large(x.v[2]);
   D3 r{{0., 0., 0.}};
-  if (la | lb | lc) {
-    r = j1_largeN<3>(D3{{fmax(x.v[0], 8.), fmax(x.v[1], 8.), fmax(x.v[2], 8.)}}, h);
-  }
-  if (!(la & lb & lc)) {
-    const D3 v = j1_smallN<3>(D3{{fmin(x.v[0], 8.), fmin(x.v[1], 8.), fmin(x.v[2], 8.)}}, h);
+  if (la || lb || lc) r = j1_largeN<3>(x, h);
+  if (!(la && lb && lc)) {
+    const D3 v = j1_smallN<3>(x, h);
     if (!la) r.v[0] = v.v[0];
     if (!lb) r.v[1] = v.v[1];
     if (!lc) r.v[2] = v.v[2];

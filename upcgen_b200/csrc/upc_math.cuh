@@ -120,7 +120,10 @@ __device__ __forceinline__ double bessel_j1(double x)
     return x * horner(UPC_J1_P, fma(x * x, kJ1C[0], -1.));
   }
   // same formulation as j1_largeN (upc_hot.cuh)
-  const double rs = rsqrt(x);
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y * y, 1.);
+  const double rs = fma(fma(e, 0.375, 0.5), y * e, y);
   const double rx = rs * rs;
   const double u = fma(128. * rx, rx, -1.);
   const double ampl = horner(UPC_J1_M, u) * (rs * 0.79788456080286535588);  // sqrt(2/(pi x))
@@ -146,7 +149,7 @@ __device__ __forceinline__ double bessel_j1(double x)
   pc = fma(z, pc, kSinCosC[15]);
   const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
   const double a = (n & 1) ? cr : sr;
-  return ampl * ((n & 2) ? -a : a);
+  return ampl * __hiloint2double(__double2hiint(a) ^ ((n & 2) << 30), __double2loint(a));
 }
 
 // ROOT TMath::BesselI1 / BesselK1 polynomials (A&S 9.8.3-9.8.8), used by calcBreakupProb
