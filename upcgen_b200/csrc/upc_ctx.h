@@ -31,6 +31,8 @@ struct upcgpu_ctx_impl {
   upcgpu_params p;
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux[2] = {nullptr, nullptr};   // side streams: the three lookup tables are built concurrently
+  cudaEvent_t aux_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   cudaDeviceProp prop;
   bool tables_ready = false;

@@ -422,20 +422,33 @@ int prepare_tables(upcgpu_ctx* c)
   c->info.sigma_nn = csNN;
   c->info.factor = p.Z * p.Z * kAlpha / M_PI / M_PI / kHc / kHc;  // :120
 
+  // T2 (G_AA), T3 (form factor) and T4 (breakup) are independent chains of small, latency-bound kernels:
+  // G_AA stays on the main stream, the other two run beside it on side streams (T3 needs rho0 only)
+  if (!c->aux[0]) {
+    for (int i = 0; i < 2; ++i) UPC_CUDA(c, cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) UPC_CUDA(c, cudaEventCreateWithFlags(&c->aux_ev[i], cudaEventDisableTiming));
+  }
+  cudaStream_t st_ff = c->aux[0], st_bk = c->aux[1];
+  cudaEventRecord(c->aux_ev[0], st);
+  cudaStreamWaitEvent(st_bk, c->aux_ev[0], 0);
+
   Gl5 gl = make_gl5(false);
   UPC_K(c), k_rho0<<<1, 256, 0, st>>>(p.R, p.a, p.A, c->d_scal);
+  cudaEventRecord(c->aux_ev[1], st);
+  cudaStreamWaitEvent(st_ff, c->aux_ev[1], 0);
   UPC_K(c), k_ta<<<kNB, 256, 0, st>>>(p.R, p.a, c->d_scal, c->gaa_x, c->ta_y);
   UPC_K(c), k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->ta_y, kNB, c->ta_c);
   UPC_K(c), k_gaa<<<kNB, 256, 0, st>>>(c->gaa_x, c->ta_y, c->ta_c, csNN, gl, c->gaa_y);
   UPC_K(c), k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->gaa_y, kNB, c->gaa_c);
   UPC_K(c), k_segs_from_arrays<<<1, 256, 0, st>>>(c->gaa_x, c->gaa_y, c->gaa_c, kNB, c->gaa_seg, 1.0);
 
-  UPC_K(c), k_ff_y<<<(kNQ2 + 255) / 256, 256, 0, st>>>(p.R, p.a, c->d_scal, c->ff_y);
+  UPC_K(c), k_ff_y<<<(kNQ2 + 255) / 256, 256, 0, st_ff>>>(p.R, p.a, c->d_scal, c->ff_y);
   {
     int nthr = (kNQ2 - 2 + kSpChunk - 1) / kSpChunk;
-    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kQ2min, kDQ2, c->ff_y, kNQ2, c->ff_c);
+    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st_ff>>>(kQ2min, kDQ2, c->ff_y, kNQ2, c->ff_c);
   }
-  UPC_K(c), k_segs_uniform<<<(kNQ2 + 255) / 256, 256, 0, st>>>(kQ2min, kDQ2, c->ff_y, c->ff_c, kNQ2, c->ff_seg, kNQ2 - 1);
+  UPC_K(c), k_segs_uniform<<<(kNQ2 + 255) / 256, 256, 0, st_ff>>>(kQ2min, kDQ2, c->ff_y, c->ff_c, kNQ2, c->ff_seg, kNQ2 - 1);
+  cudaEventRecord(c->aux_ev[2], st_ff);
 
   int use_bk = p.breakup_mode > 1;
   if (use_bk) {
@@ -447,14 +460,17 @@ int prepare_tables(upcgpu_ctx* c)
     UPC_CUDA(c, cudaMalloc(&c->bk_seg, (size_t)(c->bk_nknots + 1) * sizeof(SplineSeg)));
     UPC_CUDA(c, cudaMalloc(&c->bk_table, sizeof(BkTable)));
     }
-    UPC_K(c), k_bk_init<<<1, 1, 0, st>>>(p.g1, (BkTable*)c->bk_table);
-    UPC_K(c), k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
+    UPC_K(c), k_bk_init<<<1, 1, 0, st_bk>>>(p.g1, (BkTable*)c->bk_table);
+    UPC_K(c), k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st_bk>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
                                                           c->bk_y);
     int nthr = (c->bk_nknots - 2 + kSpChunk - 1) / kSpChunk;
-    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
-    UPC_K(c), k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
+    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st_bk>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
+    UPC_K(c), k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st_bk>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
                                                               c->bk_seg, c->bk_nknots - 1);
   }
+  cudaEventRecord(c->aux_ev[3], st_bk);
+  cudaStreamWaitEvent(st, c->aux_ev[2], 0);
+  cudaStreamWaitEvent(st, c->aux_ev[3], 0);
   UPC_K(c), k_table_scalars<<<1, 1, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, c->d_scal + 1);
   cudaEventRecord(e1, st);
   UPC_CUDA(c, cudaStreamSynchronize(st));
