@@ -35,10 +35,12 @@ WORKLOAD_TEXT = {
     "cfg5": "cfg5: Xe-Xe 5.44 TeV ALP PROC_ID 51, NON_ZERO_GAM_PT 1, 0N0N, 1001x121 grid, 1e7 events",
 }
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed
-# `ncu --set full` captures (profiles/r01_v11_ncu_qags_head_cfg2.txt, r01_v11_ncu_qags_rows_cfg2.txt,
-# r01_v2_ncu_cells_cfg2.txt)
-NCU_TRAFFIC = {("cfg2", "k_flux_qags_head"): 472.5e6 + 2346.1e6, ("cfg2", "k_flux_qags_rows"): 2730.4e6 + 187.6e6, ("cfg2", "k_cells"): 235.9e6 + 5.9e6}
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, and its FP64-pipe activity, from
+# the committed `ncu --set full` captures (profiles/r01_v12_ncu_flux_qags_head_cfg2.txt, ..._flux_qags_rows_...,
+# ..._cells_...)
+NCU_TRAFFIC = {("cfg2", "k_flux_qags_head"): 542.0e6 + 415.7e6, ("cfg2", "k_flux_qags_rows"): 406.7e6 + 24.8e6,
+               ("cfg2", "k_cells"): 235.5e6 + 4.8e6}
+NCU_FP64_PIPE_PCT = {("cfg2", "k_flux_qags_head"): 59.3, ("cfg2", "k_flux_qags_rows"): 13.8, ("cfg2", "k_cells"): 50.4}
 
 # algorithmic work per unit
 FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegrand
@@ -391,15 +393,23 @@ def main():
                "sample": sample + f"; {reps} repetitions"}
 
     # ---- roofline of the dominant kernel ----------------------------------------------------
+    # `achieved` is ALGORITHMIC work (what the reference's algorithm does per unit, no shortcut
+    # deducted) over the kernel's measured time.  The kernels do less than that: J1 of the rows on the common b grid
+    # comes from a table, cells above ny/2 are mirror images, far (b >= 20 fm) pairs are a closed sum.  `executed`
+    # repeats the figure with only the work the kernel really performed (from its own counters), which is what the
+    # FP64 pipe sees; the ncu pipe-activity figure of the committed capture stands beside it.
     ms_head = st.get("ms_qags_head", 0.0)
+    executed = None
     if st["qags_evals"] > 0 and stage["ms_qags"] >= stage["ms_cells"]:
-        # the QAGS stage is two kernels; the head (first GK21 rule + the 5 predictable bisections of every integral)
-        # is the longer one and holds ~80 % of the evaluations
+        # the QAGS stage is two kernels; the head (one thread per integral on tabulated intervals) holds ~98 % of it
         if ms_head > 0.5 * stage["ms_qags"]:
             work = FLOP_PER_QAGS_EVAL * st["qags_head_evals"]
             t_k = ms_head * 1e-3
             kern = "k_flux_qags_head"
             units = f"{st['qags_head_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
+            ex = st["qags_head_evals"] - st["qags_table_evals"]
+            executed = {"flop": FLOP_PER_QAGS_EVAL * ex, "what": f"{ex} evaluations with J1 computed "
+                        f"({st['qags_table_evals']} took J1 from the common-grid table: a multiplication each)"}
         else:
             work = FLOP_PER_QAGS_EVAL * (st["qags_evals"] - st["qags_head_evals"])
             t_k = (stage["ms_qags"] - ms_head) * 1e-3
@@ -411,13 +421,22 @@ def main():
         t_k = stage["ms_cells"] * 1e-3
         kern = "k_cells"
         units = f"{cells_rank} cells x {FLOP_CELL[(pol, bk)]:.3g} flop"
+        # per evaluated (b1,b2) pair: 5 phi x (15, +10 with breakup, +2 polarised) + 5; per evaluated cell: rows + fluxes
+        per_triplet = 15 + (10 if bk else 0) + (2 if pol else 0)
+        ex_flop = st["band_pairs"] * (5 * per_triplet + 5) + st["cells_evaluated"] * (360 + 120 * 120 * 2)
+        executed = {"flop": float(ex_flop), "what": f"{st['band_pairs']} (b1,b2) pairs evaluated point by point in "
+                    f"{st['cells_evaluated']} cells (the other pairs are a closed sum, the other cells mirror images)"}
     achieved = work / t_k / 1e12 if t_k > 0 else 0.0
+    if executed is not None and t_k > 0:
+        executed["tflops"] = executed["flop"] / t_k / 1e12
+        executed["frac"] = executed["tflops"] / peak_tf if peak_tf else None
     roofline = {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf if peak_tf else None,
                 "traffic": NCU_TRAFFIC.get((args.workload, kern)) if world == 1 else None,
                 "peak_source": "measured live: upcgpu_fp64_peak DFMA loop (MEASURED_PEAKS.json has no FP64 figure; "
                                "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
-                "algorithmic_work": units, "kernel_ms": t_k * 1e3,
+                "algorithmic_work": units, "kernel_ms": t_k * 1e3, "executed": executed,
+                "ncu_fp64_pipe_active_pct": NCU_FP64_PIPE_PCT.get((args.workload, kern)),
                 "qags_stage": {"ms": stage["ms_qags"], "ms_head": ms_head, "evals": st["qags_evals"],
                                "tflops": FLOP_PER_QAGS_EVAL * st["qags_evals"] / (stage["ms_qags"] * 1e-3) / 1e12
                                if stage["ms_qags"] > 0 else None}}
@@ -429,6 +448,7 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "cells": n_cells, "grid": [P.nm, P.ny],
                        "l2": "flushed between timed steps (256 MiB device write)",
+                       "reflection": "columns iy > ny/2 of a y grid symmetric about 0 are written from their mirror images",
                        "parallelism": f"m rows cyclic over {world} GPU(s); NCCL all-gather of the table" if world > 1
                        else "single GPU"},
             "sigma_table_ms": ms,

@@ -86,9 +86,11 @@ typedef struct {
   long long band_pairs;       /* (b1,b2) pairs with some b < 20 fm that were evaluated */
   double ms_tables, ms_flux, ms_cells, ms_total; /* device time of the stages, CUDA events */
   double ms_qags;             /* of ms_flux: the QAGS kernels (head + row-cooperative) */
-  double ms_qags_head;        /* of ms_qags: k_flux_qags_head alone (the predictable first 6 rounds) */
+  double ms_qags_head;        /* of ms_qags: k_flux_qags_head alone (one thread per integral on tabulated intervals) */
   long long qags_head_evals;  /* integrand evaluations made by k_flux_qags_head */
   long long qags_head_done;   /* integrals that converged inside the head */
+  long long qags_table_evals; /* of qags_head_evals: those whose J1 factor came from the common-grid table */
+  long long cells_evaluated;  /* cells the quadrature kernel evaluated (the others are mirror images, Y -> -Y) */
 } upcgpu_fill_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------ */

@@ -53,7 +53,7 @@ class CFillStats(C.Structure):
                 ("qags_errors", C.c_longlong), ("flux_rows", C.c_longlong), ("band_pairs", C.c_longlong),
                 ("ms_tables", C.c_double), ("ms_flux", C.c_double), ("ms_cells", C.c_double), ("ms_total", C.c_double),
                 ("ms_qags", C.c_double), ("ms_qags_head", C.c_double), ("qags_head_evals", C.c_longlong),
-                ("qags_head_done", C.c_longlong)]
+                ("qags_head_done", C.c_longlong), ("qags_table_evals", C.c_longlong), ("cells_evaluated", C.c_longlong)]
 
 
 # every symbol include/upcgpu.h declares (tests check that the library exports all of them)

@@ -231,6 +231,7 @@ struct HeadCounters {
   unsigned long long errors;
   unsigned long long left;   // integrals handed over
   unsigned long long evals_left;  // evaluations the head made for them
+  unsigned long long evals_tab;   // evaluations (of both kinds) whose J1 came from the common-grid table
 };
 
 // One thread per integral, in the order of HeadItemValid (order[]: the selected flat indices).
@@ -247,7 +248,7 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
   const unsigned lane = tid & 31;
 
   const long long t = (long long)blockIdx.x * kHdThreads + tid;
-  double my_evals = 0, my_evals_left = 0;
+  double my_evals = 0, my_evals_left = 0, my_evals_tab = 0;
   unsigned my_err = 0, my_left = 0;
   if (t < n_items) {
     const unsigned q = order[t];
@@ -295,6 +296,7 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
       c2 = 0.5 * (a2 + b2); h2 = 0.5 * (b2 - a2);
     }
     done_flag[item] = done ? 1 : 0;
+    if (jt) my_evals_tab = S.neval;
     if (done) {
       const double Q = S.result / fc.A;                  // :214
       const double flux = fc.factor * Q * Q / ri.k;      // :215
@@ -324,7 +326,7 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
       my_evals_left += S.neval;
     }
   }
-  const double ev = warp_sum(my_evals), evl = warp_sum(my_evals_left);
+  const double ev = warp_sum(my_evals), evl = warp_sum(my_evals_left), evt = warp_sum(my_evals_tab);
   const unsigned er = __reduce_add_sync(0xffffffffu, my_err);
   const unsigned lf = __reduce_add_sync(0xffffffffu, my_left);
   if (lane == 0) {
@@ -332,6 +334,7 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
     if (er) atomicAdd(&ctr->errors, (unsigned long long)er);
     if (lf) atomicAdd(&ctr->left, (unsigned long long)lf);
     if (evl > 0) atomicAdd(&ctr->evals_left, (unsigned long long)evl);
+    if (evt > 0) atomicAdd(&ctr->evals_tab, (unsigned long long)evt);
   }
 }
 
