@@ -329,10 +329,13 @@ def main():
     # ---- event stage ----------------------------------------------------------------------
     events = None
     if args.workload in ("cfg1", "cfg2", "cfg5"):
-        if not P.ignore_csz:
-            gpu.sampler_build(cszm=capi.elem_cs_zm(P, 0))
-        else:
-            gpu.sampler_build()
+        cszm = None if P.ignore_csz else capi.elem_cs_zm(P, 0)
+        gpu.sampler_build(cszm=cszm)          # warm-up (allocations)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        gpu.sampler_build(cszm=cszm)          # S1: the CDFs of the (y, m) table and of the nm z tables
+        torch.cuda.synchronize(dev)
+        ms_sampler = (time.perf_counter() - t0) * 1e3
         n_ev = args.events or min(P.n_events, 1 << 20) // world
         n_ev = max(n_ev, 1 << 14)
         first = rank * n_ev
@@ -349,7 +352,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_ev = float(t.item())
         events = {"events_per_s": world * n_ev / (ms_ev * 1e-3), "candidates": world * n_ev, "accepted_rank0": int(acc),
-                  "ms": ms_ev, "sharding": "Philox counter ranges, no collective"}
+                  "ms": ms_ev, "sharding": "Philox counter ranges, no collective", "sampler_build_ms": ms_sampler}
         if world == 1:
             # the same through upcgpu_generate with pinned host buffers for every output array
             import ctypes as C

@@ -120,14 +120,54 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
 
 // ---------------------------------------------------------------------------------------------
 // S1: gsl_histogram2d_pdf_init.  The running mean and the cumulative sum are sequential
-// recurrences whose rounding the bin selection depends on: one thread walks them in the
-// reference's order.  (The per-bin divisions bin/mean/n have no dependency and run in parallel.)
-__global__ void k_running_mean(const double* __restrict__ bin, size_t n, double* __restrict__ mean_out)
+// recurrences whose rounding the bin selection depends on: they are walked in the reference's order by
+// ONE lane, while the other lanes of its warp keep it fed -- bins staged in shared memory by coalesced
+// loads and the reciprocals 1/(i+1) formed in parallel.  (The per-bin divisions bin/mean/n have no
+// dependency and run in parallel.)
+//
+// x / d with d = i + 1 and y = RN(1/d) given: q0 = RN(x y); one residual correction makes it faithful, the second
+// (Markstein: q faithful, r = x - d q exact by FMA, y correctly rounded => RN(q + r y) = RN(x / d)) makes it the
+// correctly rounded quotient -- the value __ddiv_rn returns, on a dependent chain half as long.
+__device__ __forceinline__ double div_by_known(double x, double d, double y)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double q = __dmul_rn(x, y);
+  q = __fma_rn(__fma_rn(-q, d, x), y, q);
+  q = __fma_rn(__fma_rn(-q, d, x), y, q);
+  return q;
+}
+
+constexpr int kSeqChunk = 1024;
+
+__global__ void __launch_bounds__(32) k_running_mean(const double* __restrict__ bin, size_t n, double* __restrict__ mean_out)
+{
+  __shared__ double sb[2][kSeqChunk], sr[2][kSeqChunk];
+  const int lane = threadIdx.x;
   double mean = 0;
-  for (size_t i = 0; i < n; i++) mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn(bin[i], mean), (double)(i + 1)));
-  mean_out[0] = mean;
+  int buf = 0;
+  for (int j = lane; j < kSeqChunk && (size_t)j < n; j += 32) {
+    sb[0][j] = bin[j];
+    sr[0][j] = __drcp_rn((double)(j + 1));
+  }
+  __syncwarp();
+  for (size_t i0 = 0; i0 < n; i0 += kSeqChunk, buf ^= 1) {
+    const size_t nxt = i0 + kSeqChunk;
+    if (lane == 0) {
+      const int m = (int)min((size_t)kSeqChunk, n - i0);
+      const double* b = sb[buf];
+      const double* r = sr[buf];
+#pragma unroll 4
+      for (int j = 0; j < m; ++j)   // mean += (bin[i] - mean) / (i + 1)
+        mean = __dadd_rn(mean, div_by_known(__dsub_rn(b[j], mean), (double)(i0 + j + 1), r[j]));
+    } else {
+      // lanes 1..31 stage the next chunk meanwhile
+      for (size_t j = nxt + (lane - 1); j < nxt + kSeqChunk && j < n; j += 31) {
+        sb[buf ^ 1][j - nxt] = bin[j];
+        sr[buf ^ 1][j - nxt] = __drcp_rn((double)(j + 1));
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) mean_out[0] = mean;
 }
 
 __global__ void k_pdf_terms(const double* __restrict__ bin, size_t n, const double* __restrict__ mean,
@@ -137,14 +177,31 @@ __global__ void k_pdf_terms(const double* __restrict__ bin, size_t n, const doub
   if (i < n) term[i] = __ddiv_rn(__ddiv_rn(bin[i], mean[0]), (double)n);  // (bin/mean)/n
 }
 
-__global__ void k_seq_cumsum(const double* __restrict__ term, size_t n, double* __restrict__ sum)
+__global__ void __launch_bounds__(32) k_seq_cumsum(const double* __restrict__ term, size_t n, double* __restrict__ sum)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ double st[2][kSeqChunk], so[kSeqChunk];
+  const int lane = threadIdx.x;
   double s = 0;
-  sum[0] = 0;
-  for (size_t i = 0; i < n; i++) {
-    s = __dadd_rn(s, term[i]);
-    sum[i + 1] = s;
+  int buf = 0;
+  if (lane == 0) sum[0] = 0;
+  for (int j = lane; j < kSeqChunk && (size_t)j < n; j += 32) st[0][j] = term[j];
+  __syncwarp();
+  for (size_t i0 = 0; i0 < n; i0 += kSeqChunk, buf ^= 1) {
+    const size_t nxt = i0 + kSeqChunk;
+    const int m = (int)min((size_t)kSeqChunk, n - i0);
+    if (lane == 0) {
+      const double* t = st[buf];
+#pragma unroll 8
+      for (int j = 0; j < m; ++j) {
+        s = __dadd_rn(s, t[j]);
+        so[j] = s;
+      }
+    } else {
+      for (size_t j = nxt + (lane - 1); j < nxt + kSeqChunk && j < n; j += 31) st[buf ^ 1][j - nxt] = term[j];
+    }
+    __syncwarp();
+    for (int j = lane; j < m; j += 32) sum[i0 + j + 1] = so[j];
+    __syncwarp();
   }
 }
 
@@ -196,9 +253,9 @@ int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const dou
   double *term = nullptr, *mean = nullptr;
   UPC_CUDA(c, cudaMalloc(&term, n * sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&mean, sizeof(double)));
-  UPC_K(c), k_running_mean<<<1, 1, 0, st>>>(c->cs, n, mean);
+  UPC_K(c), k_running_mean<<<1, 32, 0, st>>>(c->cs, n, mean);
   UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->cs, n, mean, term);
-  UPC_K(c), k_seq_cumsum<<<1, 1, 0, st>>>(term, n, c->sum2d);
+  UPC_K(c), k_seq_cumsum<<<1, 32, 0, st>>>(term, n, c->sum2d);
   // z samplers
   const size_t nzm = (size_t)p.nm * p.nz, nsz = (size_t)p.nm * (p.nz + 1);
   double* dz_in = nullptr;
@@ -309,9 +366,9 @@ int hist_pdf_init(upcgpu_ctx* c, const double* bins, size_t n, double* sum)
   UPC_CUDA(c, cudaMalloc(&dm, sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&ds, (n + 1) * sizeof(double)));
   UPC_CUDA(c, cudaMemcpyAsync(db, bins, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  UPC_K(c), k_running_mean<<<1, 1, 0, c->stream>>>(db, n, dm);
+  UPC_K(c), k_running_mean<<<1, 32, 0, c->stream>>>(db, n, dm);
   UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(db, n, dm, dt);
-  UPC_K(c), k_seq_cumsum<<<1, 1, 0, c->stream>>>(dt, n, ds);
+  UPC_K(c), k_seq_cumsum<<<1, 32, 0, c->stream>>>(dt, n, ds);
   UPC_CUDA(c, cudaMemcpyAsync(sum, ds, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   UPC_CUDA(c, cudaGetLastError());
