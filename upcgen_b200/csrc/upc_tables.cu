@@ -316,10 +316,58 @@ __device__ inline double calc_breakup(const BkTable* __restrict__ T, double b, i
   return prob;
 }
 
-__global__ void k_bk_prob(const BkTable* T, int mode, int n, double* y)
+// the table of P(b): one WARP per knot.  The lanes form K1 at the energy knots and the trapezoid terms in parallel
+// (the same expressions as calc_breakup), then lane 0 adds the terms in the reference's order -- the sum keeps its
+// rounding, the ~600 Bessel evaluations of a knot are spread over 32 lanes (one thread per knot left 4 warps per SM
+// busy for 0.34 ms; this is the critical path of the table stage).
+constexpr int kBkWarps = 4;
+__global__ void __launch_bounds__(32 * kBkWarps) k_bk_prob(const BkTable* __restrict__ T, int mode, int n, double* __restrict__ y)
 {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = calc_breakup(T, knot(kBkBmin, kBkDb, i), mode);
+  __shared__ double sg[kBkWarps][700];   // K1 at knot k, then the term of step k
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * kBkWarps + w;
+  if (i >= n) return;
+  const double b = knot(kBkBmin, kBkDb, i);
+  const double hbarcmev = 197.3269718;
+  const double* ee = T->ee;
+  const double* se = T->se;
+  const double gammatarg = T->gammatarg, zcon = T->zcon;
+  const double omax = fmin(T->omaxx, 4. * gammatarg * (hbarcmev) / b);
+  if (omax < T->o0) {
+    if (lane == 0) y[i] = 0.;
+    return;
+  }
+  // K = first k >= 2 with ee[k] >= omax: the loop of calc_breakup stops there (ee[n + 1] is a sentinel above any omax)
+  const int nk = T->n;
+  int kmin = nk + 1;
+  for (int k = 2 + lane; k <= nk; k += 32)
+    if (!(ee[k] < omax)) kmin = min(kmin, k);
+  const int K = __reduce_min_sync(0xffffffffu, kmin);
+  double* g = sg[w];
+  for (int k = 1 + lane; k < K; k += 32) g[k] = tmath_bessel_k1(ee[k] * b / ((hbarcmev)*gammatarg));
+  __syncwarp();
+  double term[20];  // terms of k = 2 + lane + 32 j (K <= 700: at most 22 per lane; bounded below)
+  int nt = 0;
+  for (int k = 2 + lane; k < K && nt < 20; k += 32, ++nt) {
+    const double gk1m = g[k - 1], gk1 = g[k];
+    const double t1 = __dmul_rn(__dmul_rn(__dmul_rn(se[k - 1], ee[k - 1]), gk1m), gk1m);
+    const double t2 = __dmul_rn(__dmul_rn(__dmul_rn(se[k], ee[k]), gk1), gk1);
+    term[nt] = __dmul_rn(__dmul_rn(__dmul_rn(zcon, __dsub_rn(ee[k], ee[k - 1])), .5), __dadd_rn(t1, t2));
+  }
+  __syncwarp();
+  nt = 0;
+  for (int k = 2 + lane; k < K && nt < 20; k += 32, ++nt) g[k] = term[nt];
+  __syncwarp();
+  if (lane == 0) {
+    double pxn = 0.;
+    for (int k = 2; k < K; ++k) pxn = __dadd_rn(pxn, g[k]);
+    double prob = 0.;
+    if (mode == 1) prob = 1.;
+    if (mode == 2) prob = (1 - exp(-1 * pxn)) * (1 - exp(-1 * pxn));
+    if (mode == 3) prob = exp(-2 * pxn);
+    if (mode == 4) prob = 2. * exp(-pxn) * (1. - exp(-pxn));
+    y[i] = prob;
+  }
 }
 
 __global__ void k_bk_raw(const BkTable* T, const double* b, int mode, size_t n, double* out)
@@ -461,7 +509,7 @@ int prepare_tables(upcgpu_ctx* c)
     UPC_CUDA(c, cudaMalloc(&c->bk_table, sizeof(BkTable)));
     }
     UPC_K(c), k_bk_init<<<1, 1, 0, st_bk>>>(p.g1, (BkTable*)c->bk_table);
-    UPC_K(c), k_bk_prob<<<(c->bk_nknots + 127) / 128, 128, 0, st_bk>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
+    UPC_K(c), k_bk_prob<<<(c->bk_nknots + kBkWarps - 1) / kBkWarps, 32 * kBkWarps, 0, st_bk>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
                                                           c->bk_y);
     int nthr = (c->bk_nknots - 2 + kSpChunk - 1) / kSpChunk;
     UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st_bk>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
