@@ -160,7 +160,7 @@ __global__ void k_ff_y(double R, double a, const double* rho0p, double* y)
 // strictly diagonally dominant, so the influence of a far knot decays as (2-sqrt 3)^distance
 // (1e-37 after 64 knots): each thread solves the system on its chunk plus a 64-knot halo with
 // the same LDL^T recurrences GSL uses and keeps the chunk.
-constexpr int kSpChunk = 192;
+constexpr int kSpChunk = 48;   // short chunks: the kernel is a latency chain per thread (192: 0.33 ms for the 10^6-knot table)
 constexpr int kSpHalo = 64;
 __global__ void k_spline_windowed(double x0, double dx, const double* ya, int size, double* c)
 {
