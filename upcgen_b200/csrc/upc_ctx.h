@@ -46,6 +46,8 @@ struct upcgpu_ctx_impl {
   double *bk_y = nullptr, *bk_c = nullptr;
   int bk_nknots = 0;
   void* bk_table = nullptr;  // photo-nuclear energy table of calcBreakupProb (device)
+  double bk_table_g1 = -1.;  // beam gamma the energy table was built for (the reference builds it once per process:
+                             // function-local statics, src/UpcCrossSection.cpp:853-969)
   SplineSeg *gaa_seg = nullptr, *ff_seg = nullptr, *bk_seg = nullptr;
   double* d_scal = nullptr;  // small device scratch for scalars
   DevTables tab{};

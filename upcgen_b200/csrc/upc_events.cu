@@ -116,41 +116,61 @@ __device__ __forceinline__ double ff_lookup(const SplineSeg* __restrict__ ff, do
   return seg_eval(ff[idx], t - fma((double)idx, kDQ2, kQ2min));
 }
 
+constexpr int kPtPerThread = (kPtBins + 255) / 256;  // 20 bins per thread
+constexpr int kPtRunPad = kPtPerThread + 1;          // runs padded to 21 doubles in shared memory (2-way conflicts)
+
 __global__ void __launch_bounds__(256) k_pt_tables(int n_keys, const int* __restrict__ keys, const double* e_direct,
                                                    const SplineSeg* __restrict__ ff, double gtot, double R,
                                                    double* __restrict__ cdf)
 {
+  // The pdf is evaluated and the cdf stored with bin = base + thread (neighbouring threads gather neighbouring
+  // form-factor segments and write neighbouring doubles); the prefix sum goes through shared memory: each thread
+  // sums a RUN of 20 consecutive bins serially and ONE block scan ranks the runs (a block scan per 256 bins -- 20
+  // of them, two barriers each -- was 60 % of this kernel's instructions).
   typedef cub::BlockScan<double, 256> Scan;
   __shared__ typename Scan::TempStorage tmp;
-  __shared__ double carry_s;
+  __shared__ double sp[256 * kPtRunPad];
   const int kidx = blockIdx.x;
   if (kidx >= n_keys) return;
+  const int tid = threadIdx.x;
   const double e = e_direct ? e_direct[kidx] : (keys[kidx] + 0.5) * 1e-3;
   const double ereds = (e * e) / (gtot * gtot);
   const double pi2x4 = 4 * kPi * kPi;
   double* out = cdf + (size_t)kidx * (kPtBins + 1);
-  if (threadIdx.x == 0) { carry_s = 0; out[0] = 0; }
-  __syncthreads();
-  for (int base = 0; base < kPtBins; base += 256) {
-    const int bin = base + threadIdx.x + 1;  // 1..5000
+#pragma unroll 4
+  for (int it = 0; it < kPtPerThread; ++it) {
+    const int b0 = it * 256 + tid;           // 0-based bin
     double prob = 0;
-    if (bin <= kPtBins) {
-      const double pt = 6. * kHc / R / kPtBins * bin;  // upper bin edge, :1033
+    if (b0 < kPtBins) {
+      const double pt = 6. * kHc / R / kPtBins * (b0 + 1);  // upper bin edge, :1033
       const double arg = pt * pt + ereds;
       const double f = ff_lookup(ff, arg);
       prob = (f * f) * pt * pt * pt / (pi2x4 * arg * arg);
     }
-    double incl, total;
-    Scan(tmp).InclusiveSum(prob, incl, total);
-    const double carry = carry_s;
-    if (bin <= kPtBins) out[bin] = carry + incl;
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + total;
-    __syncthreads();
+    sp[(b0 / kPtPerThread) * kPtRunPad + b0 % kPtPerThread] = prob;
   }
-  const double tot = carry_s;
-  if (tot != 0)
-    for (int bin = 1 + threadIdx.x; bin <= kPtBins; bin += 256) out[bin] /= tot;
+  __syncthreads();
+  double acc = 0;
+  double* run = sp + tid * kPtRunPad;
+#pragma unroll
+  for (int j = 0; j < kPtPerThread; ++j) {
+    acc += run[j];
+    run[j] = acc;
+  }
+  double before, tot;
+  Scan(tmp).ExclusiveSum(acc, before, tot);
+  run[kPtPerThread] = before;                // the pad slot carries the run's offset
+  __syncthreads();
+  if (tid == 0) out[0] = 0;
+#pragma unroll 4
+  for (int it = 0; it < kPtPerThread; ++it) {
+    const int b0 = it * 256 + tid;
+    if (b0 < kPtBins) {
+      const int r = b0 / kPtPerThread;
+      const double v = sp[r * kPtRunPad + kPtPerThread] + sp[r * kPtRunPad + b0 % kPtPerThread];
+      out[b0 + 1] = tot != 0 ? v / tot : v;
+    }
+  }
 }
 
 // TH1::GetRandom on a tabulated integral

@@ -508,7 +508,10 @@ int prepare_tables(upcgpu_ctx* c)
     UPC_CUDA(c, cudaMalloc(&c->bk_seg, (size_t)(c->bk_nknots + 1) * sizeof(SplineSeg)));
     UPC_CUDA(c, cudaMalloc(&c->bk_table, sizeof(BkTable)));
     }
-    UPC_K(c), k_bk_init<<<1, 1, 0, st_bk>>>(p.g1, (BkTable*)c->bk_table);
+    if (c->bk_table_g1 != p.g1) {  // depends on the beam gamma only; built once, like the reference's statics
+      UPC_K(c), k_bk_init<<<1, 1, 0, st_bk>>>(p.g1, (BkTable*)c->bk_table);
+      c->bk_table_g1 = p.g1;
+    }
     UPC_K(c), k_bk_prob<<<(c->bk_nknots + kBkWarps - 1) / kBkWarps, 32 * kBkWarps, 0, st_bk>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
                                                           c->bk_y);
     int nthr = (c->bk_nknots - 2 + kSpChunk - 1) / kSpChunk;
