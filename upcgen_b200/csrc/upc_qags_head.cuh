@@ -21,15 +21,17 @@
 namespace upc {
 
 constexpr int kHdThreads = 128;
-constexpr int kHdPar = 14;                // bisections the head knows (parents of tabulated intervals)
+constexpr int kHdPar = 15;                // bisections the head knows (parents of tabulated intervals)
 constexpr int kHdIv = 1 + 2 * kHdPar;     // tabulated intervals: [0,10], then (left, right) of each known bisection
 constexpr int kHdG = kHdIv * 21;          // g values per row
-constexpr int kHdCap = 11;                // interval-list capacity in the head: up to 9 bisections
-constexpr int kHdEps = 13;                // epsilon-table capacity in the head (1 + 9 entries + 2 scratch, +1)
+constexpr int kHdCap = 11;                // interval-list capacity of the first pass: up to 9 bisections
+constexpr int kHdEps = 13;                // epsilon-table capacity of the first pass (1 + 9 entries + 2 scratch, +1)
+constexpr int kHsCap = 16;                // ... of the second pass (and of HeadState): up to 14 bisections
+constexpr int kHsEps = 16;
 
 // heap index ((1 << level) + position) of the known bisections, in table order: interval 1 + 2j is the left
 // half of parent j, 2 + 2j the right half
-__constant__ unsigned kHdParent[kHdPar] = {1, 2, 4, 8, 16, 17, 32, 64, 128, 33, 256, 34, 3, 512};
+__constant__ unsigned kHdParent[kHdPar] = {1, 2, 4, 8, 16, 17, 32, 64, 128, 33, 256, 34, 3, 512, 1024};
 __host__ __device__ __forceinline__ int head_child_slot(unsigned heap)
 {
   switch (heap) {
@@ -47,6 +49,7 @@ __host__ __device__ __forceinline__ int head_child_slot(unsigned heap)
     case 34: return 23;
     case 3: return 25;
     case 512: return 27;
+    case 1024: return 29;
     default: return -1;
   }
 }
@@ -54,32 +57,37 @@ __host__ __device__ __forceinline__ int head_child_slot(unsigned heap)
 // QAGS state of an integral leaving the head (everything Qags<Store> holds; see upc_qags.cuh)
 struct HeadState {
   double sc[11];
-  double eps[kHdEps];
-  double rl[kHdCap], el[kHdCap];
-  unsigned hp[kHdCap];
-  unsigned char od[kHdCap + 1];
+  double eps[kHsEps];
+  double rl[kHsCap], el[kHsCap];
+  unsigned hp[kHsCap];
+  unsigned char od[kHsCap];
   int size, nrmax, i, maximum_level, ktmin, roundoff_type1, roundoff_type2, roundoff_type3, error_type, error_type2,
       iteration, tab_n, tab_nres, flags, neval, pad;
 };
 static_assert(sizeof(HeadState) % 8 == 0, "HeadState layout");
 enum { kHdPositive = 1, kHdExtrapolate = 2, kHdDisallow = 4 };
 
-struct HdShared {
+template <int CAP, int EPS>
+struct HdSharedT {
   double fv[21][kHdThreads];            // GK21 function values [node][thread]
-  double rl[kHdCap][kHdThreads], el[kHdCap][kHdThreads];
-  double ep[kHdEps][kHdThreads];
+  double rl[CAP][kHdThreads], el[CAP][kHdThreads];
+  double ep[EPS][kHdThreads];
   double sc[11][kHdThreads];
-  unsigned hp[kHdCap][kHdThreads];
-  unsigned char od[kHdCap][kHdThreads];
+  unsigned hp[CAP][kHdThreads];
+  unsigned char od[CAP][kHdThreads];
 };
+using HdShared = HdSharedT<kHdCap, kHdEps>;   // first pass: three CTAs per SM
+using HdShared2 = HdSharedT<kHsCap, kHsEps>;  // second pass: two
 static_assert(3 * (sizeof(HdShared) + 1024) <= 227 * 1024, "three CTAs per SM");
+static_assert(2 * (sizeof(HdShared2) + 1024) <= 227 * 1024, "two CTAs per SM");
 
 // strided shared-memory store (same interval encoding as QagsSharedStore: heap indices)
-struct QagsHeadStore {
-  HdShared* sh;
+template <int CAP, int EPS>
+struct QagsHeadStoreT {
+  HdSharedT<CAP, EPS>* sh;
   int slot;
-  static constexpr int cap = kHdCap;
-  static constexpr int eps_cap = kHdEps;
+  static constexpr int cap = CAP;
+  static constexpr int eps_cap = EPS;
   __device__ __forceinline__ double& R(int k) { return sh->rl[k][slot]; }
   __device__ __forceinline__ double& E(int k) { return sh->el[k][slot]; }
   __device__ __forceinline__ int ord(int k) const { return sh->od[k][slot]; }
@@ -103,6 +111,7 @@ struct QagsHeadStore {
   __device__ __forceinline__ double& eps(int k) { return sh->ep[k][slot]; }
   __device__ __forceinline__ double& sc(int k) { return sh->sc[k][slot]; }
 };
+using QagsHeadStore = QagsHeadStoreT<kHdCap, kHdEps>;
 
 // bounds of tabulated interval iv (exact: dyadic sub-intervals of [0, 10])
 __device__ __forceinline__ void head_interval(int iv, double& a, double& b)
@@ -203,7 +212,8 @@ __global__ void k_head_j1_table(int nb, double R, double* __restrict__ j1h)
 // GK21 rule on tabulated interval iv = [center - half, center + half] for this thread's integral:
 // f = g * J1(beta x), three nodes at a time; g = the row's table + 21 iv;
 // jt != nullptr: the row is on the common b grid, J1 comes from the table (jt = j1h + i)
-__device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double center, double half, double beta,
+template <class SH>
+__device__ __forceinline__ GkOut head_gk21(SH& sh, int iv, double center, double half, double beta,
                                            const double* __restrict__ g, size_t gs, const double* __restrict__ jt, int tid)
 {
   const double* gi = g + (size_t)(iv * 21) * gs;
@@ -227,30 +237,38 @@ __device__ __forceinline__ GkOut head_gk21(HdShared& sh, int iv, double center, 
 }
 
 struct HeadCounters {
-  unsigned long long evals;  // integrand evaluations of integrals finished in the head
+  unsigned long long evals;       // total evaluations (S.neval) of the integrals finished by the head passes
   unsigned long long errors;
-  unsigned long long left;   // integrals handed over
-  unsigned long long evals_left;  // evaluations the head made for them
-  unsigned long long evals_tab;   // evaluations (of both kinds) whose J1 came from the common-grid table
+  unsigned long long left;        // integrals the LAST pass hands to k_flux_qags_rows
+  unsigned long long evals_made;  // evaluations made by the head passes themselves
+  unsigned long long evals_tab;   // ... of which J1 came from the common-grid table
+  unsigned long long left1;       // integrals the first pass hands to the second
 };
 
-// One thread per integral, in the order of HeadItemValid (order[]: the selected flat indices).
-__global__ void __launch_bounds__(kHdThreads, 3)
-k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowInfo* __restrict__ rows,
-                 const long long* __restrict__ item_off, const unsigned* __restrict__ order, const double* __restrict__ hg,
-                 const double* __restrict__ j1h, FluxConsts fc, double* __restrict__ W,
-                 int* __restrict__ neval_out, HeadCounters* __restrict__ ctr, HeadState* __restrict__ state,
-                 unsigned char* __restrict__ done_flag)
+// One thread per integral.  RESUME = false (first pass): all integrals, in the order of HeadItemValid (order[]: the
+// selected flat indices), interval list up to CAP = 11 (three CTAs per SM).  RESUME = true (second pass): the
+// integrals the first pass left (order[] compacted by its `left_flag`, *n_order of them), resumed from their
+// HeadState with the capacity of the reference-sized fallback (CAP = 16, two CTAs per SM).
+template <int CAP, int EPS, bool RESUME>
+__global__ void __launch_bounds__(kHdThreads, RESUME ? 2 : 3)
+k_flux_qags_head(long long n_items, const int* __restrict__ n_order, int n_m, int rows_per_m, int nb,
+                 const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
+                 const unsigned* __restrict__ order, const double* __restrict__ hg, const double* __restrict__ j1h,
+                 FluxConsts fc, double* __restrict__ W, int* __restrict__ neval_out, HeadCounters* __restrict__ ctr,
+                 HeadState* __restrict__ state, unsigned char* __restrict__ done_flag,
+                 unsigned char* __restrict__ left_flag)
 {
+  using SH = HdSharedT<CAP, EPS>;
   extern __shared__ __align__(16) unsigned char hd_smem[];
-  HdShared& sh = *reinterpret_cast<HdShared*>(hd_smem);
+  SH& sh = *reinterpret_cast<SH*>(hd_smem);
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
 
   const long long t = (long long)blockIdx.x * kHdThreads + tid;
-  double my_evals = 0, my_evals_left = 0, my_evals_tab = 0;
+  const long long n_mine = RESUME ? (long long)*n_order : n_items;
+  double my_evals = 0, my_made = 0, my_tab = 0;
   unsigned my_err = 0, my_left = 0;
-  if (t < n_items) {
+  if (t < n_mine) {
     const unsigned q = order[t];
     const unsigned per_ir = (unsigned)nb * (unsigned)n_m;
     const unsigned ir = q / per_ir, rem = q - ir * per_ir;
@@ -264,10 +282,9 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
     grid_point(ri, i, b, w);
     const double beta = b * (1. / kHc);
     const double* jt = ri.pad ? j1h + i : nullptr;     // row on the common b grid
-    Qags<QagsHeadStore> S;
+    Qags<QagsHeadStoreT<CAP, EPS>> S;
     S.sh = &sh;
     S.slot = tid;
-    S.begin(0., 10.);                                  // :209
     // ONE GK21 site for every rule (the kernel's code must stay inside the 32 KB instruction cache: with
     // three inlined sites `no_instruction` was the largest stall).  phase 0: the rule on [0, 10];
     // phase 1 / 2: the left / right half of the interval being bisected.
@@ -275,8 +292,48 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
     GkOut ga{};
     int iv = 0, phase = 0;
     double center = 5., half = 5., c2 = 0., h2 = 0.;
+    // the pass goes on while QAGS bisects an interval whose halves are tabulated and the state fits
+    auto next_step = [&]() -> bool {
+      const int cs = head_child_slot(sh.hp[S.i][tid]);
+      if (cs < 0 || S.size + 1 >= CAP || S.tab_n + 2 >= EPS) return false;
+      double a1, b1, a2, b2;
+      int level;
+      S.pre_step(a1, b1, a2, b2, level);
+      iv = cs; phase = 1;
+      center = 0.5 * (a1 + b1); half = 0.5 * (b1 - a1);
+      c2 = 0.5 * (a2 + b2); h2 = 0.5 * (b2 - a2);
+      return true;
+    };
+    bool go = true;
+    int neval_in = 0;
+    if (RESUME) {
+      const HeadState& hs = state[item];
+#pragma unroll
+      for (int k = 0; k < 11; ++k) sh.sc[k][tid] = hs.sc[k];
+#pragma unroll
+      for (int k = 0; k < kHdEps; ++k) sh.ep[k][tid] = hs.eps[k];
+#pragma unroll
+      for (int k = 0; k < kHdCap; ++k) {
+        sh.rl[k][tid] = hs.rl[k]; sh.el[k][tid] = hs.el[k];
+        sh.hp[k][tid] = hs.hp[k]; sh.od[k][tid] = hs.od[k];
+      }
+      S.size = hs.size; S.nrmax = hs.nrmax; S.i = hs.i; S.maximum_level = hs.maximum_level; S.ktmin = hs.ktmin;
+      S.roundoff_type1 = hs.roundoff_type1; S.roundoff_type2 = hs.roundoff_type2; S.roundoff_type3 = hs.roundoff_type3;
+      S.error_type = hs.error_type; S.error_type2 = hs.error_type2; S.iteration = hs.iteration;
+      S.tab_n = hs.tab_n; S.tab_nres = hs.tab_nres;
+      S.positive_integrand = (hs.flags & kHdPositive) != 0;
+      S.extrapolate = (hs.flags & kHdExtrapolate) != 0;
+      S.disallow_extrapolation = (hs.flags & kHdDisallow) != 0;
+      S.overflow = false;
+      S.neval = hs.neval;
+      S.result = 0; S.abserr = 0; S.ier = 0;
+      neval_in = hs.neval;
+      go = next_step();
+    } else {
+      S.begin(0., 10.);                                // :209
+    }
 #pragma unroll 1
-    while (true) {
+    while (go) {
       const GkOut gk = head_gk21(sh, iv, center, half, beta, g, gs, jt, tid);
       if (phase == 1) {
         ga = gk;
@@ -285,33 +342,27 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
       }
       done = phase == 0 ? S.post_first(gk) : S.post_step(ga, gk);
       if (done) break;
-      // the head goes on while QAGS bisects an interval whose halves are tabulated and the state fits
-      const int cs = head_child_slot(sh.hp[S.i][tid]);
-      if (cs < 0 || S.size + 1 >= kHdCap || S.tab_n + 2 >= kHdEps) break;
-      double a1, b1, a2, b2;
-      int level;
-      S.pre_step(a1, b1, a2, b2, level);
-      iv = cs; phase = 1;
-      center = 0.5 * (a1 + b1); half = 0.5 * (b1 - a1);
-      c2 = 0.5 * (a2 + b2); h2 = 0.5 * (b2 - a2);
+      go = next_step();
     }
     done_flag[item] = done ? 1 : 0;
-    if (jt) my_evals_tab = S.neval;
+    if (!RESUME) left_flag[t] = done ? 0 : 1;
+    my_made = S.neval - neval_in;
+    if (jt) my_tab = my_made;
     if (done) {
       const double Q = S.result / fc.A;                  // :214
       const double flux = fc.factor * Q * Q / ri.k;      // :215
       W[(size_t)row * nb + i] = flux * (b * w);
       if (neval_out) neval_out[(size_t)row * nb + i] = S.neval;
-      my_evals += S.neval;
+      my_evals = S.neval;
       if (S.ier != 0) my_err++;
     } else {
       HeadState& hs = state[item];
 #pragma unroll
       for (int k = 0; k < 11; ++k) hs.sc[k] = sh.sc[k][tid];
 #pragma unroll
-      for (int k = 0; k < kHdEps; ++k) hs.eps[k] = sh.ep[k][tid];
+      for (int k = 0; k < EPS; ++k) hs.eps[k] = sh.ep[k][tid];
 #pragma unroll
-      for (int k = 0; k < kHdCap; ++k) {
+      for (int k = 0; k < CAP; ++k) {
         hs.rl[k] = sh.rl[k][tid]; hs.el[k] = sh.el[k][tid];
         hs.hp[k] = sh.hp[k][tid]; hs.od[k] = sh.od[k][tid];
       }
@@ -323,17 +374,16 @@ k_flux_qags_head(long long n_items, int n_m, int rows_per_m, int nb, const RowIn
                  (S.disallow_extrapolation ? kHdDisallow : 0);
       hs.neval = S.neval;
       my_left++;
-      my_evals_left += S.neval;
     }
   }
-  const double ev = warp_sum(my_evals), evl = warp_sum(my_evals_left), evt = warp_sum(my_evals_tab);
+  const double ev = warp_sum(my_evals), evm = warp_sum(my_made), evt = warp_sum(my_tab);
   const unsigned er = __reduce_add_sync(0xffffffffu, my_err);
   const unsigned lf = __reduce_add_sync(0xffffffffu, my_left);
   if (lane == 0) {
     if (ev > 0) atomicAdd(&ctr->evals, (unsigned long long)ev);
     if (er) atomicAdd(&ctr->errors, (unsigned long long)er);
-    if (lf) atomicAdd(&ctr->left, (unsigned long long)lf);
-    if (evl > 0) atomicAdd(&ctr->evals_left, (unsigned long long)evl);
+    if (lf) atomicAdd(RESUME ? &ctr->left : &ctr->left1, (unsigned long long)lf);
+    if (evm > 0) atomicAdd(&ctr->evals_made, (unsigned long long)evm);
     if (evt > 0) atomicAdd(&ctr->evals_tab, (unsigned long long)evt);
   }
 }

@@ -92,6 +92,7 @@ struct RcShared {
 };
 
 static_assert(sizeof(RcShared) <= 227 * 1024, "shared memory of one SM");
+static_assert(kRcCap == kHsCap && kRcEps <= kHsEps, "the row-cooperative kernel takes the head's state as it is");
 
 // named barriers (0 is __syncthreads)
 enum { kBarOwn0 = 1, kBarFull0 = 1 + kRcGroups, kBarDone0 = 1 + 2 * kRcGroups, kBarEval = 1 + 3 * kRcGroups };
@@ -396,9 +397,9 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
 #pragma unroll
             for (int k = 0; k < 11; ++k) sh.sc[k][ltid] = hs.sc[k];
 #pragma unroll
-            for (int k = 0; k < kHdEps; ++k) sh.ep[k][ltid] = hs.eps[k];
+            for (int k = 0; k < kRcEps; ++k) sh.ep[k][ltid] = hs.eps[k];
 #pragma unroll
-            for (int k = 0; k < kHdCap; ++k) {
+            for (int k = 0; k < kRcCap; ++k) {
               sh.rl[k][ltid] = hs.rl[k]; sh.el[k][ltid] = hs.el[k];
               sh.hp[k][ltid] = hs.hp[k]; sh.od[k][ltid] = hs.od[k];
             }
