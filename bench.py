@@ -36,11 +36,10 @@ WORKLOAD_TEXT = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, and its FP64-pipe activity, from
-# the committed `ncu --set full` captures (profiles/r01_v12_ncu_flux_qags_head_cfg2.txt, ..._flux_qags_rows_...,
-# ..._cells_...)
-NCU_TRAFFIC = {("cfg2", "k_flux_qags_head"): 542.0e6 + 415.7e6, ("cfg2", "k_flux_qags_rows"): 406.7e6 + 24.8e6,
-               ("cfg2", "k_cells"): 235.5e6 + 4.8e6}
-NCU_FP64_PIPE_PCT = {("cfg2", "k_flux_qags_head"): 59.3, ("cfg2", "k_flux_qags_rows"): 13.8, ("cfg2", "k_cells"): 50.4}
+# the committed `ncu --set full` captures (profiles/r01_v13_ncu_qags_head_pass1_cfg2.txt, ..._qags_rows_..., ..._cells_...)
+NCU_TRAFFIC = {("cfg2", "k_flux_qags_head"): 669.7e6 + 497.6e6, ("cfg2", "k_flux_qags_rows"): 28.9e6 + 0.06e6,
+               ("cfg2", "k_cells"): 234.8e6 + 6.2e6}
+NCU_FP64_PIPE_PCT = {("cfg2", "k_flux_qags_head"): 59.0, ("cfg2", "k_flux_qags_rows"): 3.8, ("cfg2", "k_cells"): 50.4}
 
 # algorithmic work per unit
 FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegrand
@@ -404,7 +403,8 @@ def main():
     ms_head = st.get("ms_qags_head", 0.0)
     executed = None
     if st["qags_evals"] > 0 and stage["ms_qags"] >= stage["ms_cells"]:
-        # the QAGS stage is two kernels; the head (one thread per integral on tabulated intervals) holds ~98 % of it
+        # the QAGS stage is the head kernel (one thread per integral on tabulated intervals, two passes: ~100 % of the
+        # evaluations; ms_qags_head covers both) and the row-cooperative fallback
         if ms_head > 0.5 * stage["ms_qags"]:
             work = FLOP_PER_QAGS_EVAL * st["qags_head_evals"]
             t_k = ms_head * 1e-3
