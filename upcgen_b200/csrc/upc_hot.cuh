@@ -215,7 +215,9 @@ __device__ __forceinline__ DV<N> j1_smallN(const DV<N>& x, const H& h)
 // comparison of the bit patterns (x > 8 for positive x), off the FP64 pipe.
 __device__ __forceinline__ bool j1_is_large(double x)
 {
-  return (unsigned long long)__double_as_longlong(x) > 0x4020000000000000ull;
+  // x > 8 for positive x, on the two 32-bit halves (a 64-bit comparison makes ptxas form integer min/max chains)
+  const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
+  return hi > 0x40200000u || (hi == 0x40200000u && lo != 0u);
 }
 
 __device__ __forceinline__ D3 j1_3(const D3& x)
