@@ -72,8 +72,8 @@ typedef struct {
   double factor;     /* UpcCrossSection::factor         src/UpcCrossSection.cpp:120 */
   double breakup_p20;/* P(b=20): the clamp value of     src/UpcCrossSection.cpp:260 */
   int n_breakup_energy_knots;
-  double gaa_zero_below; /* b [fm] below which the G_AA spline is <= 1e-30 in magnitude: such (b1,b2,phi)
-                          * points are not evaluated by the cell quadrature (they add < 1e-30 relative) */
+  double gaa_zero_below; /* b [fm] below which the G_AA spline is <= 1e-20 in magnitude: such (b1,b2,phi)
+                          * points are not evaluated by the cell quadrature (they add < 1e-19 relative) */
 } upcgpu_table_info;
 
 /* Work counters of the last lumi fill (for the roofline arithmetic; not needed by callers). */

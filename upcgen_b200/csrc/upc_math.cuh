@@ -62,10 +62,10 @@ __device__ __forceinline__ void bessel_k0k1(double x, double& k0, double& k1)
   }
 }
 
-// sin and cos of a moderate argument (0 <= x < ~1e5; on this path x = b k/hc <= 700).
-// Cody-Waite reduction by pi/2 with three FMA steps, then the classic fdlibm minimax kernels on
-// |r| <= pi/4 (~1 ulp).  Unlike the library sincos() there is no Payne-Hanek slow path, which
-// keeps the QAGS kernel's code inside the instruction cache.
+// Constants of the angle reduction and of the sin / cos kernels used by J1 for x > 8 (0 <= x < ~1e5; on this path
+// x = b k/hc <= 700): Cody-Waite reduction by pi/2 with three FMA steps, then the classic fdlibm minimax kernels on
+// |r| <= pi/4 (~1 ulp).  There is no Payne-Hanek slow path, which keeps the QAGS kernels' code inside the
+// instruction cache.
 // (all FP64 constants of the hot loops live in __constant__ arrays: a 64-bit literal would be
 // materialised with two UMOVs per use, a __constant__ element is a free DFMA operand)
 __constant__ double kSinCosC[16] = {
@@ -78,38 +78,7 @@ __constant__ double kSinCosC[16] = {
   -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,  // 10..15: C6..C1
   2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
 
-__device__ __forceinline__ void sincos_mid(double x, double& s, double& c)
-{
-  const double kMagic = 6755399441055744.0;  // 2^52 + 2^51 (high word only: a 32-bit immediate)
-  const double qm = fma(x, kSinCosC[0], kMagic);
-  const int n = __double2loint(qm);
-  const double q = qm - kMagic;
-  double r = fma(-q, kSinCosC[1], x);
-  r = fma(-q, kSinCosC[2], r);
-  r = fma(-q, kSinCosC[3], r);
-  const double z = r * r;
-  double ps = fma(z, kSinCosC[4], kSinCosC[5]);
-  ps = fma(z, ps, kSinCosC[6]);
-  ps = fma(z, ps, kSinCosC[7]);
-  ps = fma(z, ps, kSinCosC[8]);
-  ps = fma(z, ps, kSinCosC[9]);
-  const double sr = fma(z * r, ps, r);
-  double pc = fma(z, kSinCosC[10], kSinCosC[11]);
-  pc = fma(z, pc, kSinCosC[12]);
-  pc = fma(z, pc, kSinCosC[13]);
-  pc = fma(z, pc, kSinCosC[14]);
-  pc = fma(z, pc, kSinCosC[15]);
-  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-  const double a = (n & 1) ? cr : sr;
-  const double b = (n & 1) ? sr : cr;
-  s = (n & 2) ? -a : a;
-  c = ((n + 1) & 2) ? -b : b;
-}
-
-__constant__ double kJ1C[12] = {
-  1. / 32., 0.63661977236758134308, 0.70710678118654752440,
-  1. / 362880., -1. / 5040., 1. / 120., -1. / 6.,     // 3..6: sin(eps) series
-  1. / 40320., -1. / 720., 1. / 24., 0., 0.};         // 7..9: cos(eps) series
+__constant__ double kJ1C[1] = {1. / 32.};
 
 // J1(x), x >= 0.  Replaces gsl_sf_bessel_J1 at src/UpcCrossSection.cpp:189.
 // x <= 8: x * P(x^2/32 - 1); x > 8: modulus/phase form sqrt(2/(pi x)) M sin(x - pi/4 + eps) with the

@@ -552,7 +552,9 @@ int prepare_tables(upcgpu_ctx* c)
   }
   {
     // inner cut of the cell quadrature: the leading G_AA segments whose magnitude is bounded by
-    // 1e-30 on the whole segment (|y| + |b| h + |c| h^2 + |d| h^3); P(b) <= 1
+    // 1e-20 on the whole segment (|y| + |b| h + |c| h^2 + |d| h^3); P(b) <= 1.  What is skipped adds less than
+    // 1e-19 of a cell's sum (the far pairs alone, with G_AA = 1, are a fifth of the total weight): four orders below
+    // one ulp.  (1e-30 put the cut at 10.6 fm for Pb-Pb 5.02 TeV, 1e-20 puts it at 12.4 fm: 20 % fewer look-ups.)
     std::vector<SplineSeg> hseg(kNB);
     UPC_CUDA(c, cudaMemcpy(hseg.data(), c->gaa_seg, kNB * sizeof(SplineSeg), cudaMemcpyDeviceToHost));
     const double hh = 20. / (kNB - 1);
@@ -560,7 +562,7 @@ int prepare_tables(upcgpu_ctx* c)
     while (n_zero < kNB - 1) {
       const SplineSeg& sg = hseg[n_zero];
       const double bound = fabs(sg.y) + hh * (fabs(sg.b) + hh * (fabs(sg.c) + hh * fabs(sg.d)));
-      if (!(bound <= 1e-30)) break;
+      if (!(bound <= 1e-20)) break;
       ++n_zero;
     }
     const double b_in = n_zero * hh;
