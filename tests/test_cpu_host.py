@@ -222,3 +222,38 @@ def test_cyclic_rows_cover_grid():
         seen = sorted(sum((udist.cyclic_rows(nm, r, w) for r in range(w)), []))
         assert seen == list(range(nm))
         assert max(len(udist.cyclic_rows(nm, r, w)) for r in range(w)) == udist.rows_per_shard(nm, w)
+
+
+def test_head_interval_table_covers_the_oracles_bisections(get_oracle):
+    """The CUDA head kernel (csrc/upc_qags_head.cuh) runs an integral for as long as QAGS bisects one of 15 tabulated
+    intervals.  The oracle's trace of a sample of cfg2 integrals must stay inside that set almost always, and the
+    first four bisections must be the leftmost interval every time (the statistic the kernel's table was chosen from;
+    tools/qags_interval_stats.py prints the full version)."""
+    import ctypes as C
+    P, o = get_oracle("cfg2")
+    L = o.L
+    L.upco_qags_fluxform_trace.restype = C.c_int
+    L.upco_qags_fluxform_trace.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_uint), C.c_int,
+                                           C.POINTER(C.c_int)]
+    # heap index (1 << level) + position of the tabulated parents, as in kHdParent
+    parents = {1, 2, 4, 8, 16, 17, 32, 64, 128, 33, 256, 34, 3, 512, 1024}
+    hc, nb = 0.1973269718, 120
+    buf = (C.c_uint * 64)()
+    ne = C.c_int()
+    total = inside = 0
+    rows = [(im, iy) for im in range(0, P.nm, 97) for iy in range(0, P.ny + 1, 13)]
+    for im, iy in rows:
+        k = (P.mmin + P.dm * im) / 2 * np.exp(P.ymin + P.dy * iy)
+        bmax = max(5 * P.g1 * hc / k, 5 * P.R)
+        ld = (np.log(bmax) - np.log(0.05 * P.R)) / nb
+        for i in range(0, nb, 7):
+            b = (0.05 * P.R * np.exp(i * ld) + 0.05 * P.R * np.exp((i + 1) * ld)) / 2
+            if b > 2 * P.R:
+                break
+            n = L.upco_qags_fluxform_trace(o.h, b, k, buf, 64, C.byref(ne))
+            assert ne.value == 21 * (1 + 2 * n)
+            heaps = [(1 << (buf[j] >> 24)) + (buf[j] & 0xFFFFFF) for j in range(n)]
+            assert heaps[:4] == [1, 2, 4, 8][:min(n, 4)]
+            total += n
+            inside += sum(h in parents for h in heaps)
+    assert total > 2000 and inside / total > 0.995, (inside, total)
