@@ -235,22 +235,27 @@ def test_lumi_grid_formfactor_breakup_vs_oracle(get_gpu, get_oracle):
     assert e.max() < RTOL_FF
 
 
-@pytest.mark.parametrize("extra,tol", [
-    ("YMIN -2\nYMAX 4\nBINS_M 20\nBINS_Y 9\n", RTOL_FF),                  # asymmetric y grid: no reflection, 2 ny rows per m
-    ("BINS_M 20\nBINS_Y 8\nMMIN 0.5\nMMAX 4\n", RTOL_FF),                  # even ny (self-mirrored centre column), low masses
+@pytest.mark.parametrize("base,extra,tol", [
+    ("cfg2", "YMIN -2\nYMAX 4\nBINS_M 20\nBINS_Y 9\n", RTOL_FF),          # asymmetric y grid: no reflection, 2 ny rows per m
+    ("cfg2", "BINS_M 20\nBINS_Y 8\nMMIN 0.5\nMMAX 4\n", RTOL_FF),          # even ny (self-mirrored centre column), low masses
+    ("cfg5", "FLUX_POINT 0\nBINS_M 12\nBINS_Y 9\n", RTOL_FF),               # Xe-Xe, 0N0N, form-factor flux at m ~ 1 GeV
+    ("cfg2", "USE_POLARIZED_CS 1\nBINS_M 10\nBINS_Y 7\n", RTOL_FF),         # polarised tables with the form-factor flux
 ])
-def test_small_grids_every_cell_vs_oracle(get_gpu, get_oracle, extra, tol):
+def test_small_grids_every_cell_vs_oracle(get_gpu, get_oracle, base, extra, tol):
     """Every cell of small form-factor + XNXN grids against the oracle: the grid shapes the row sharing and the
     reflection depend on (symmetric or not, odd or even ny) and photon energies far from the cfg2 range (the head's
     interval table is chosen from cfg2 statistics; integrals that leave it must come out the same through the
     fallback kernels)."""
-    P, g = get_gpu("cfg2", extra)
-    _, o = get_oracle("cfg2", extra)
+    P, g = get_gpu(base, extra)
+    _, o = get_oracle(base, extra)
     table = g.fill_lumi()
     st = g.fill_stats()
     assert st["qags_errors"] == 0
-    ref, ne = o.fill_lumi(with_neval=True)
-    e = np.max(np.abs(table - ref) / ref)
+    ref = o.fill_lumi()
+    if P.use_pol:
+        e = max(np.max(np.abs(table[0] - ref[0]) / ref[0]), np.max(np.abs(table[1] - ref[1]) / ref[1]))
+    else:
+        e = np.max(np.abs(table - ref) / ref)
     print("grid", P.nm, "x", P.ny, "max rel", e, "integrals", st["qags_integrals"], "finished in the head", st["qags_head_done"])
     assert e < tol
     # (the QAGS decisions themselves are pinned by test_qags_follows_the_oracle_on_the_whole_grid and by the neval
