@@ -136,7 +136,8 @@ int upcgpu_flux_form(upcgpu_ctx* ctx, const double* b, const double* k, size_t n
  * whole grid, values already multiplied by dm*dy (:546-550).  Unpolarised: lumi[nm*ny];
  * polarised (use_pol): lumi_s, lumi_p.  Unused pointers may be NULL.  Host buffers. */
 int upcgpu_fill_lumi(upcgpu_ctx* ctx, double* lumi, double* lumi_s, double* lumi_p);
-/* Same, but computes only the m-rows im = shard, shard+nshards, ... (cyclic), keeps the result
+/* Same, but computes only the m-rows of one shard -- blocks of B consecutive rows dealt round-robin: row im belongs
+ * to shard (im / B) % nshards, B = 32 or, on small grids, the largest power of two with nm >= 2 B nshards -- keeps the result
  * on the device (see upcgpu_lumi_device) and copies nothing.  One rank per GPU calls this with
  * its rank; the exchange between ranks is the caller's (NCCL all-gather of the packed shard). */
 int upcgpu_fill_lumi_shard(upcgpu_ctx* ctx, int shard, int nshards);
@@ -147,8 +148,8 @@ int upcgpu_lumi_cells(upcgpu_ctx* ctx, const double* M, const double* Y, size_t 
 int upcgpu_get_fill_stats(const upcgpu_ctx* ctx, upcgpu_fill_stats* st);
 
 /* Device-resident buffers for the multi-GPU exchange (device pointers as integers so that no
- * CUDA type appears here).  packed shard: [rows_per_shard][ny] per table, rows im=shard+i*nshards
- * (rows_per_shard = ceil(nm/nshards), padding rows zero).  which: 0 unpol, 1 scalar, 2 pseudo. */
+ * CUDA type appears here).  packed shard: [rows_per_shard][ny] per table, the shard's rows in ascending
+ * im (rows_per_shard = the row count of shard 0, the largest; padding rows zero).  which: 0 unpol, 1 scalar, 2 pseudo. */
 int upcgpu_lumi_shard_buffer(upcgpu_ctx* ctx, int which, uint64_t* dev_ptr, size_t* n_doubles);
 /* gathered buffer [nshards][rows_per_shard][ny] to be filled by the caller's all-gather, then
  * un-permuted into the full [nm][ny] device table by upcgpu_lumi_unpack */

@@ -468,11 +468,11 @@ def test_qags_follows_the_oracle_on_the_whole_grid(get_gpu):
 
 
 def test_sharded_fill_equals_monolithic_form_factor(get_gpu):
-    """Shards (cyclic m rows) assembled through the gather/unpack path reproduce the single-shot
-    table bit for bit (form-factor + breakup, 3 shards, one device)."""
+    """Shards (blocks of m rows dealt round-robin) assembled through the gather/unpack path reproduce the single-shot
+    table bit for bit (form-factor + breakup, 3 shards of 8-row blocks, one device)."""
     import ctypes as C
     from upcgen_b200.config import named_config
-    extra = "BINS_M 23\nBINS_Y 10\n"
+    extra = "BINS_M 53\nBINS_Y 10\n"
     P, g = get_gpu("cfg2", extra)
     full = g.fill_lumi()
     cudart = C.CDLL("libcudart.so.12")
@@ -555,4 +555,6 @@ def test_cfg4_full_size_properties(get_gpu, capi):
     # rows 5 mod 7 recomputed as shard 5 of 7 are the same numbers
     g.fill_lumi_shard(5, 7)
     part = g.lumi_download(0)
-    assert np.array_equal(part[5::7], table[5::7])
+    from upcgen_b200 import dist as udist
+    mine = udist.cyclic_rows(P.nm, 5, 7)
+    assert np.array_equal(part[mine], table[mine])

@@ -144,21 +144,20 @@ __device__ __forceinline__ double head_g(double x, double c0, const SplineSeg* _
 __global__ void k_head_tables(int n_m, int rows_per_m, const RowInfo* __restrict__ rows, double g1, DevTables tab,
                               double* __restrict__ hg)
 {
+  // one thread per (m row, y row, interval): 21 values each (a thread per row with all 651 values in sequence took
+  // 0.33 ms however few rows there were -- it is a chain of dependent gathers -- and did not shrink with the shard)
   const int iml = blockIdx.x * blockDim.x + threadIdx.x;
   const int ir = blockIdx.y;
+  const int iv = blockIdx.z;
   if (iml >= n_m) return;
   const double k = rows[(size_t)iml * rows_per_m + ir].k;
   const double c0 = k * k / g1 / g1;  // w*w/g/g, :187
-  double* out = hg + (size_t)ir * kHdG * n_m + iml;
-#pragma unroll 1
-  for (int iv = 0; iv < kHdIv; ++iv) {
-    double a, b;
-    head_interval(iv, a, b);
-    const double center = 0.5 * (a + b), half = 0.5 * (b - a);
+  double* out = hg + ((size_t)ir * kHdG + (size_t)iv * 21) * n_m + iml;
+  double a, b;
+  head_interval(iv, a, b);
+  const double center = 0.5 * (a + b), half = 0.5 * (b - a);
 #pragma unroll 3
-    for (int n = 0; n < 21; ++n)
-      out[(size_t)(iv * 21 + n) * n_m] = head_g(fma(half, kGkNode[n], center), c0, tab.ff_seg, tab.ff_last);
-  }
+  for (int n = 0; n < 21; ++n) out[(size_t)n * n_m] = head_g(fma(half, kGkNode[n], center), c0, tab.ff_seg, tab.ff_last);
 }
 
 // The order in which the head takes the integrals: flat index q = (ir * nb + i) * n_m + iml, i.e. for one y row ir

@@ -1,6 +1,6 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch).
 
-The (y, m) grid shards by m rows, cyclically (rank r owns im = r, r+G, ...).
+The (y, m) grid shards by m rows, block-cyclically (blocks of 32 consecutive rows dealt round-robin).
 Cells are independent, so the only exchange on the table path is one all-gather of the packed
 shards, after which every rank un-permutes the rows into its full device table and folds it
 locally.  Event sampling shards by Philox counter ranges and needs no collective at all.
@@ -27,13 +27,26 @@ def as_tensor(ptr: int, n: int, device):
     return torch.as_tensor(_DevBuf(ptr, n), device=device)
 
 
+def shard_block(nm: int, world: int) -> int:
+    """shard_block() of csrc/upc_lumi.cu: 32 rows when every shard still gets two blocks, else a smaller power of 2."""
+    b = 32
+    while b > 1 and nm < 2 * b * world:
+        b >>= 1
+    return b
+
+
 def cyclic_rows(nm: int, rank: int, world: int):
-    """m rows owned by `rank` (host-side logic shared with the CPU tests)."""
-    return list(range(rank, nm, world))
+    """m rows owned by `rank` (host-side logic shared with the CPU tests): blocks of shard_block() consecutive rows
+    dealt round-robin, row im belongs to shard (im // block) % world; ascending."""
+    blk = shard_block(nm, world)
+    return [im for im in range(nm) if (im // blk) % world == rank]
 
 
 def rows_per_shard(nm: int, world: int) -> int:
-    return (nm + world - 1) // world
+    """Rows of the packed shard buffer = the row count of shard 0, the largest."""
+    blk = shard_block(nm, world)
+    cyc = blk * world
+    return (nm // cyc) * blk + min(nm % cyc, blk)
 
 
 def unpack_host(gathered: np.ndarray, nm: int, ny: int, world: int) -> np.ndarray:
@@ -76,12 +89,21 @@ def fill_lumi_distributed(gpu, rank: int, world: int, device=None):
         return
     import torch
     import torch.distributed as dist
-    kinds = (1, 2) if gpu.P.use_pol else (0,)
-    for which in kinds:
-        sptr, sn = gpu.lumi_shard_buffer(which)
-        gptr, gn = gpu.lumi_gather_buffer(which, world)
-        src = as_tensor(sptr, sn, device)
-        dst = as_tensor(gptr, gn, device)
-        dist.all_gather_into_tensor(dst, src)
-    torch.cuda.current_stream().synchronize()
+    # the library's shard / gather buffers live as long as the context: the zero-copy views are made once
+    views = getattr(gpu, "_dist_views", None)
+    if views is None or views[0] != world:
+        kinds = (1, 2) if gpu.P.use_pol else (0,)
+        pairs = []
+        for which in kinds:
+            sptr, sn = gpu.lumi_shard_buffer(which)
+            gptr, gn = gpu.lumi_gather_buffer(which, world)
+            pairs.append((as_tensor(sptr, sn, device), as_tensor(gptr, gn, device)))
+        # the collective is issued on the library's own stream: the un-permute kernel that follows on that stream is
+        # ordered behind it without a host synchronisation in between
+        ext = torch.cuda.ExternalStream(gpu.stream_handle(), device=device)
+        views = (world, pairs, ext)
+        gpu._dist_views = views
+    with torch.cuda.stream(views[2]):
+        for src, dst in views[1]:
+            dist.all_gather_into_tensor(dst, src)
     gpu.lumi_unpack(world)
