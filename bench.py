@@ -46,6 +46,15 @@ FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegr
 FLOP_CELL = {(0, 0): 1.19e6, (0, 1): 1.91e6, (1, 0): 1.30e6, (1, 1): 2.05e6}  # (pol, breakup) per cell
 
 
+def make_config(workload, P, world):
+    """The `config` object of the JSON line (the same for both arms)."""
+    return {"workload": WORKLOAD_TEXT[workload], "cells": P.nm * P.ny, "grid": [P.nm, P.ny],
+            "l2": "flushed between timed steps (256 MiB device write)",
+            "reflection": "columns iy > ny/2 of a y grid symmetric about 0 are written from their mirror images",
+            "parallelism": f"m rows in blocks of 32 dealt round-robin over {world} GPU(s); NCCL all-gather of the table"
+            if world > 1 else "single GPU"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -150,7 +159,7 @@ def reference_arm(args):
         "impl": "reference", "metric": "lumi_cells_per_s", "value": val, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_TEXT[args.workload], "cells": P.nm * P.ny},
+        "config": make_config(args.workload, P, args.gpus),
         "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference binary needs ROOT+GSL and cannot be built in this image; kind=reference runs the "
@@ -449,11 +458,7 @@ def main():
             "metric": "lumi_cells_per_s", "value": n_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_TEXT[args.workload], "cells": n_cells, "grid": [P.nm, P.ny],
-                       "l2": "flushed between timed steps (256 MiB device write)",
-                       "reflection": "columns iy > ny/2 of a y grid symmetric about 0 are written from their mirror images",
-                       "parallelism": f"m rows cyclic over {world} GPU(s); NCCL all-gather of the table" if world > 1
-                       else "single GPU"},
+            "config": make_config(args.workload, P, world),
             "sigma_table_ms": ms,
             "stage_ms": stage, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "events": events,
