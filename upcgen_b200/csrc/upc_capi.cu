@@ -58,7 +58,7 @@ void upcgpu_destroy(upcgpu_ctx* c)
   cudaSetDevice(c->device);
   cudaFree(c->gaa_x); cudaFree(c->gaa_y); cudaFree(c->gaa_c); cudaFree(c->ta_y); cudaFree(c->ta_c);
   cudaFree(c->ff_y); cudaFree(c->ff_c); cudaFree(c->bk_y); cudaFree(c->bk_c);
-  cudaFree(c->gaa_seg); cudaFree(c->ff_seg); cudaFree(c->bk_seg); cudaFree(c->d_scal); cudaFree(c->bk_table);
+  cudaFree(c->gaa_seg); cudaFree(c->ff_seg); cudaFree(c->bk_seg); cudaFree(c->d_scal); cudaFree(c->bk_table); cudaFree(c->fold_ws);
   for (int w = 0; w < 3; w++) { cudaFree(c->lumi[w]); cudaFree(c->shard[w]); cudaFree(c->gather[w]); }
   cudaFree(c->cs); cudaFree(c->ratio); cudaFree(c->sum2d); cudaFree(c->sumz); cudaFree(c->sumz_ps);
   cudaFree(c->edges_y); cudaFree(c->edges_m); cudaFree(c->edges_z);

@@ -65,6 +65,8 @@ struct upcgpu_ctx_impl {
   double *sum2d = nullptr, *sumz = nullptr, *sumz_ps = nullptr;
   double *edges_y = nullptr, *edges_m = nullptr, *edges_z = nullptr;
   bool fold_ready = false, sampler_ready = false;
+  double* fold_ws = nullptr;  // scratch of fold_sigma: 3 x nm sigma values + the block sums of the total (kept: a
+                              // cudaMalloc / cudaFree pair per call costs more than the fold itself)
 
   // event stage scratch (grown on demand)
   void* ev = nullptr;

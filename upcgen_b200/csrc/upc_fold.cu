@@ -79,8 +79,9 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
   cudaStream_t st = c->stream;
   if (!c->cs) UPC_CUDA(c, cudaMalloc(&c->cs, n * sizeof(double)));
   if (p.use_pol && !c->ratio) UPC_CUDA(c, cudaMalloc(&c->ratio, n * sizeof(double)));
-  double* dsig = nullptr;
-  UPC_CUDA(c, cudaMalloc(&dsig, 3 * (size_t)p.nm * sizeof(double)));
+  const size_t nb0 = (n + 4095) / 4096, nb1 = (nb0 + 4095) / 4096;
+  if (!c->fold_ws) UPC_CUDA(c, cudaMalloc(&c->fold_ws, (3 * (size_t)p.nm + nb0 + nb1) * sizeof(double)));
+  double* dsig = c->fold_ws;
   if (sig_m) UPC_CUDA(c, cudaMemcpyAsync(dsig, sig_m, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
   if (sig_s) UPC_CUDA(c, cudaMemcpyAsync(dsig + p.nm, sig_s, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
   if (sig_p) UPC_CUDA(c, cudaMemcpyAsync(dsig + 2 * p.nm, sig_p, p.nm * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -91,10 +92,7 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
   double total = 0;
   {
     size_t cur = n;
-    double *a = c->cs, *b0 = nullptr, *b1 = nullptr;
-    size_t nb0 = (n + 4095) / 4096;
-    UPC_CUDA(c, cudaMalloc(&b0, nb0 * sizeof(double)));
-    UPC_CUDA(c, cudaMalloc(&b1, ((nb0 + 4095) / 4096) * sizeof(double)));
+    double *a = c->cs, *b0 = c->fold_ws + 3 * (size_t)p.nm, *b1 = b0 + nb0;
     double* outb = b0;
     while (true) {
       size_t nblk = (cur + 4095) / 4096;
@@ -106,14 +104,11 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
     }
     UPC_CUDA(c, cudaMemcpyAsync(&total, outb, sizeof(double), cudaMemcpyDeviceToHost, st));
     UPC_CUDA(c, cudaStreamSynchronize(st));
-    cudaFree(b0);
-    cudaFree(b1);
   }
   UPC_CUDA(c, cudaGetLastError());
   if (totcs_mb) *totcs_mb = total * 1e-6;  // :696
   if (cs) UPC_CUDA(c, cudaMemcpy(cs, c->cs, n * sizeof(double), cudaMemcpyDeviceToHost));
   if (ratio && p.use_pol) UPC_CUDA(c, cudaMemcpy(ratio, c->ratio, n * sizeof(double), cudaMemcpyDeviceToHost));
-  cudaFree(dsig);
   c->fold_ready = true;
   return UPCGPU_OK;
 }
