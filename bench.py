@@ -36,7 +36,7 @@ WORKLOAD_TEXT = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, and its FP64-pipe activity, from
-# the committed `ncu --set full` captures (profiles/r01_v14_ncu_qags_head_pass1_cfg2.txt, r01_v13_ncu_qags_rows_cfg2.txt, r01_v14_ncu_cells_cfg2.txt)
+# the committed `ncu --set full` captures (profiles/r01_v15_ncu_qags_head_pass1_cfg2.txt, r01_v13_ncu_qags_rows_cfg2.txt, r01_v15_ncu_cells_cfg2.txt)
 NCU_TRAFFIC = {("cfg2", "k_flux_qags_head"): 670.9e6 + 495.1e6, ("cfg2", "k_flux_qags_rows"): 28.9e6 + 0.06e6,
                ("cfg2", "k_cells"): 234.8e6 + 4.9e6}
 NCU_FP64_PIPE_PCT = {("cfg2", "k_flux_qags_head"): 60.5, ("cfg2", "k_flux_qags_rows"): 3.8, ("cfg2", "k_cells"): 52.3}
