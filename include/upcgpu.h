@@ -168,8 +168,10 @@ int upcgpu_fold_sigma(upcgpu_ctx* ctx, const double* sig_m, const double* sig_s,
                       double* cs, double* ratio, double* totcs_mb);
 
 /* ---- elementary-process plug-ins P1 (host code) -------------------------------------- */
-/* C access to the built-in plug-ins UpcTwoPhotonDilep (proc_id 11/13/15) and UpcTwoPhotonALP (51)
- * (reference src/UpcTwoPhotonDilep.cpp:46-134, src/UpcTwoPhotonALP.cpp:28-33), for callers that
+/* C access to the built-in plug-ins UpcTwoPhotonDilep (proc_id 11/13/15), UpcTwoPhotonALP (51) and the
+ * file-based UpcTwoPhotonLbyL (22) / UpcTwoPhotonDipion (111), which read the reference's histograms from
+ * $UPCGEN_CROSS_SEC_DIR/{lbyl,pi0pi0}/cross_section_{m,zm}.root (UPCGPU_EINVAL if they cannot be read)
+ * (reference src/UpcTwoPhotonDilep.cpp:46-134, src/UpcTwoPhotonALP.cpp:28-33, src/UpcTwoPhotonLbyL.cpp:32-80), for callers that
  * cannot instantiate the C++ classes.  which: 0 calcCrossSectionM, 1 ...MPolS, 2 ...MPolPS. */
 int upcgpu_elem_sigma_m(int proc_id, double a_lep, double alp_mass, double alp_width, int which, const double* m,
                         size_t n, double* out);

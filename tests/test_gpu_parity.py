@@ -43,6 +43,11 @@ def get_gpu(capi):
     _GPUS.clear()
 
 
+def pyoracle_pdf_init(cs):
+    from oracle import pyoracle
+    return pyoracle.pdf_init(cs)
+
+
 def relerr(a, b, floor=0.0):
     a = np.asarray(a, float); b = np.asarray(b, float)
     return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor + 1e-300))
@@ -395,6 +400,41 @@ def test_events_alp_single_production_and_decay(get_gpu, get_oracle):
     assert np.all(ev["npart"] == 3) and np.all(ev["pdg"][:, 0] == 51) and np.all(ev["pdg"][:, 1:3] == 22)
     # four-momentum conservation in the decay
     assert np.max(np.abs(ev["p4"][:, 0] - ev["p4"][:, 1] - ev["p4"][:, 2])) < 1e-9 * np.abs(ev["p4"][:, 0]).max()
+
+
+def test_lbyl_unpolarised_fold_and_events(get_gpu, get_oracle):
+    """BASELINE config 3's process (light-by-light, PROC_ID 22) with USE_POLARIZED_CS 0 -- the fold the reference
+    defines for it.  sigma(m) and dsigma/dz are the reference's histograms, read by the product's ROOT-less
+    reader (tests/test_root_hist.py) and committed as a derived fixture (tools/gen_lbyl_fixture.py): the lumi table
+    against the oracle, the fold bit for bit, photon pairs against the oracle's event restatement."""
+    extra = "USE_POLARIZED_CS 0\n"
+    P, g = get_gpu("cfg3", extra)
+    _, o = get_oracle("cfg3", extra)
+    fx = np.load(_os.path.join(_GOLD, "lbyl_elem.npz"))
+    assert (P.nm, P.nz) == (int(fx["nm"]), int(fx["nz"])) and P.mmin == float(fx["mmin"]) and P.zmax == float(fx["zmax"])
+    lumi = g.fill_lumi()
+    ref = o.fill_lumi(im_step=100, iy_step=12)
+    sel = np.isfinite(ref)
+    assert np.max(np.abs(lumi[sel] - ref[sel]) / ref[sel]) < RTOL_POINT
+    sig = fx["sig_m"]
+    cs, _, tot = g.fold_sigma(sig_m=sig)
+    assert np.array_equal(cs, (lumi * sig[:, None]).T)          # cs[iy][im] = sigma(m_im) * lumi[im][iy], :647-648
+    assert tot == pytest.approx(cs.sum() * 1e-6, rel=1e-12) and tot > 0
+    print("LbyL total cross section [mb]", tot)
+    # z samplers from the stored rows of the dsigma/dz table (row im uses the nearest stored row below it)
+    cszm = fx["cszm_rows"][np.searchsorted(fx["im_rows"], np.arange(P.nm), side="right") - 1]
+    g.sampler_build(cszm=cszm)
+    s2, sz, _ = g.sampler_cdf()
+    assert np.array_equal(s2, pyoracle_pdf_init(cs))
+    worst, nacc = _compare_events(P, g, o, 4242, 300, s2, sz)
+    print("LbyL events: worst rel p4 diff", worst, "accepted", nacc)
+    assert worst < 1e-9 and nacc > 0
+    ev = g.generate(4242, 100, 300)
+    acc = ev["npart"] == 2
+    assert np.all(ev["pdg"][acc][:, :2] == 22) and np.all(ev["status"][acc][:, :2] == 23)
+    p4 = ev["p4"][acc][:, :2]
+    mass2 = p4[..., 3] ** 2 - (p4[..., :3] ** 2).sum(-1)
+    assert np.max(np.abs(mass2)) < 1e-9 * np.max(p4[..., 3] ** 2)      # massless photons
 
 
 def test_events_distributions_independent_of_batching(get_gpu, get_oracle):

@@ -7,6 +7,7 @@
 #include "../host/UpcPhysConstants.h"
 #include "../host/UpcTwoPhotonALP.h"
 #include "../host/UpcTwoPhotonDilep.h"
+#include "../host/UpcTwoPhotonTabulated.h"
 
 static std::unique_ptr<UpcElemProcess> make_process(int proc_id, double a_lep, double alp_mass, double alp_width)
 {
@@ -20,6 +21,15 @@ static std::unique_ptr<UpcElemProcess> make_process(int proc_id, double a_lep, d
       return p;
     }
     case 51: return std::make_unique<UpcTwoPhotonALP>(alp_mass, alp_width);
+    case 22:
+    case 111: {
+      // histograms from $UPCGEN_CROSS_SEC_DIR/{lbyl,pi0pi0} (no DO_M_CUT workaround through this entry point)
+      std::unique_ptr<UpcTwoPhotonTabulated> p;
+      if (proc_id == 22) p = std::make_unique<UpcTwoPhotonLbyL>(false, 0., 9999.);
+      else p = std::make_unique<UpcTwoPhotonDipion>(false, 0., 9999.);
+      if (!p->ok) return nullptr;
+      return p;
+    }
     default: return nullptr;
   }
 }

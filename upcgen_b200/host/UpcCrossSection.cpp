@@ -1,6 +1,7 @@
 // UpcCrossSection over the CUDA C-ABI.  Method-by-method counterpart of the reference's
 // src/UpcCrossSection.cpp; every numeric kernel of that file runs on the GPU here.
 #include "UpcCrossSection.h"
+#include "UpcTwoPhotonTabulated.h"
 
 #include <cmath>
 #include <cstdint>
@@ -56,12 +57,23 @@ void UpcCrossSection::setElemProcess(int procID)
       elemProcess = new UpcTwoPhotonALP(alpMass, alpWidth);
       break;
     case 22:
-    case 111:
+    case 111: {
+      // cross sections from the reference's ROOT files (cross_sections/lbyl, cross_sections/pi0pi0)
+      auto* tab = procID == 22 ? (UpcTwoPhotonTabulated*)new UpcTwoPhotonLbyL(doMassCut, lowMCut, hiMCut)
+                               : (UpcTwoPhotonTabulated*)new UpcTwoPhotonDipion(doMassCut, lowMCut, hiMCut);
+      if (!tab->ok) {
+        PLOG_FATAL << "Cannot read the elementary cross sections: " << tab->error
+                   << " (set UPCGEN_CROSS_SEC_DIR to the reference's cross_sections directory). Exiting...";
+        std::_Exit(-1);
+      }
+      elemProcess = tab;
+      break;
+    }
     case 443:
     case 100443:
     case 553:
-      PLOG_FATAL << "Process " << procID << " needs ROOT input files / the vector-meson path, which are outside the "
-                 << "GPU build (see DESIGN.md, out of scope). Exiting...";
+      PLOG_FATAL << "Process " << procID << " needs the vector-meson path, which is outside the GPU build (see DESIGN.md, "
+                 << "out of scope). Exiting...";
       std::_Exit(-1);
     default:
       PLOG_FATAL << "Unknown process ID! Check manual and enter a correct ID! Exiting...";

@@ -159,6 +159,31 @@ void UpcGenerator::init()
   ignoreCSZ = false;
   auto* cs = nucProcessCS;
   // process-specific set-up, src/UpcGenerator.cpp:69-140
+  if (procID == 22 || procID == 111) {
+    // the elementary cross sections come from files with a fixed (z, m) grid: the grid is set explicitly (:69-103)
+    isPairProduction = true;
+    PLOG_WARNING << "For this process grid sizes along Z and M are fixed -- see parameters check";
+    if (procID == 22) {
+      cs->zmin = -0.99; cs->zmax = 0.99; cs->nz = 198;
+      cs->mmin = 0.05; cs->mmax = 50.; cs->nm = 1000;
+    } else {
+      cs->zmin = -1; cs->zmax = 1; cs->nz = 100;
+      cs->mmin = 0.275; cs->mmax = 5.; cs->nm = 91;
+    }
+    if (usePolarizedCS) {
+      // The reference clears only the generator's flag here and leaves the cross-section object's set, which makes it
+      // fold the polarised luminosities with cross sections that are identically 0 and write a ratio table that was never
+      // sized.  Both flags are cleared here: the process is run unpolarised, as the warning says.
+      PLOG_WARNING << "For this process polarized cross section is not available";
+      usePolarizedCS = false;
+      cs->usePolarizedCS = false;
+    }
+    if (procID == 111) {
+      PLOG_FATAL << "pi0 pi0: the two pi0 -> gamma gamma decays of the event stage are not part of the GPU build; the cross "
+                 << "sections are available through UpcTwoPhotonDipion. Exiting...";
+      std::_Exit(-1);
+    }
+  }
   if (procID == 51) {
     ignoreCSZ = true; // cos(theta) uniform for the ALP
     isSingleProduction = true;
