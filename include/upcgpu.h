@@ -180,6 +180,14 @@ int upcgpu_elem_sigma_m(int proc_id, double a_lep, double alp_mass, double alp_w
 int upcgpu_elem_fill_cs_zm(int proc_id, double a_lep, double alp_mass, double alp_width, int flag, double zmin,
                            double zmax, int nz, double mmin, double mmax, int nm, double* out);
 
+/* Reads a TH1D / TH2D from a ROOT file without ROOT (upcgen_b200/host/UpcRootHist.cpp): the reference's elementary
+ * cross-section histograms and its luminosity caches twoPhotonLumi[Pol].root (hD2LDMDY[_s,_p]: bin (im + 1, iy + 1)
+ * holds table[im][iy], src/UpcCrossSection.cpp:503-506, :564-571).  cells: (nx + 2) x (ny + 2) doubles (x fastest,
+ * under-/overflow cells included; ny = 0 and one row for a TH1D), or NULL to query the sizes only.  No GPU is
+ * involved.  Returns UPCGPU_EINVAL if the file or object cannot be read or `cap` is too small. */
+int upcgpu_root_hist_read(const char* path, const char* name, int* dim, int* nx, double* xlo, double* xhi, int* ny,
+                          double* ylo, double* yhi, double* cells, size_t cap, size_t* n_cells);
+
 /* ---- samplers S1-S3 ------------------------------------------------------------------ */
 /* replaces the UpcSampler2D / UpcSampler1D constructors (include/UpcSampler.h:40-59, :81-109,
  * i.e. gsl_histogram[2d]_pdf_init) built in UpcGenerator::computeNuclXsection

@@ -165,3 +165,19 @@ def test_missing_directory_is_an_error(lib):
         assert lib.upcgpu_elem_sigma_m(22, 0., 0., 0., 0, m.ctypes.data, 1, out.ctypes.data) != 0
     finally:
         os.environ["UPCGEN_CROSS_SEC_DIR"] = REF
+
+
+def test_c_abi_reader_equals_python_parse():
+    """upcgpu_root_hist_read (the entry point a luminosity-cache comparison uses, tools/compare_lumi_root.py) against the
+    independent Python parse: axes and every cell, under- and overflow included."""
+    from upcgen_b200 import capi
+    for sub, nm_ in (("lbyl", "hCrossSectionZM"), ("pi0pi0", "hCrossSectionZM")):
+        path = f"{REF}/{sub}/cross_section_zm.root"
+        cl, ax, ay, cells = py_read_hist(path, nm_)
+        h = capi.root_hist_read(path, nm_)
+        assert h["dim"] == 2 and (h["nx"], h["xlo"], h["xhi"]) == ax and (h["ny"], h["ylo"], h["yhi"]) == ay
+        assert np.array_equal(h["cells"].ravel(), cells)
+    h1 = capi.root_hist_read(f"{REF}/lbyl/cross_section_m.root", "hCrossSectionM")
+    assert h1["dim"] == 1 and h1["cells"].shape == (1002,)
+    with pytest.raises(capi.UpcGpuError):
+        capi.root_hist_read(f"{REF}/lbyl/cross_section_m.root", "noSuchObject")

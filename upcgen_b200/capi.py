@@ -66,7 +66,7 @@ SYMBOLS = [
     "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_device",
     "upcgpu_photon_pt_cdf", "upcgpu_philox", "upcgpu_invalidate_tables", "upcgpu_fp64_peak",
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
-    "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d",
+    "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
 ]
 
 
@@ -402,6 +402,27 @@ def elem_cs_zm(P: UpcParams, flag=0):
                                       P.mmin, P.mmax, P.nm, _p(out))
     if rc != OK:
         raise UpcGpuError(rc, "elem_cs_zm: process not built in")
+    return out
+
+
+def root_hist_read(path: str, name: str):
+    """TH1D / TH2D `name` of the ROOT file `path`, read without ROOT (host/UpcRootHist.cpp).  Returns a dict with
+    dim, the axes (nx, xlo, xhi[, ny, ylo, yhi]) and `cells`: [ny + 2][nx + 2] (TH2D) or [nx + 2] (TH1D), under- and
+    overflow cells included, as ROOT stores them."""
+    L = lib()
+    L.upcgpu_root_hist_read.argtypes = [C.c_char_p, C.c_char_p] + [C.c_void_p] * 8 + [C.c_size_t, C.c_void_p]
+    dim, nx, ny = C.c_int(), C.c_int(), C.c_int()
+    xlo, xhi, ylo, yhi = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    n = C.c_size_t()
+    args = [path.encode(), name.encode(), C.byref(dim), C.byref(nx), C.byref(xlo), C.byref(xhi), C.byref(ny), C.byref(ylo),
+            C.byref(yhi)]
+    if L.upcgpu_root_hist_read(*args, None, 0, C.byref(n)) != OK:
+        raise UpcGpuError(EINVAL, f"root_hist_read: cannot read {name} from {path}")
+    cells = np.zeros(n.value)
+    if L.upcgpu_root_hist_read(*args, _p(cells), cells.size, C.byref(n)) != OK:
+        raise UpcGpuError(EINVAL, f"root_hist_read: cannot read {name} from {path}")
+    out = dict(dim=dim.value, nx=nx.value, xlo=xlo.value, xhi=xhi.value, ny=ny.value, ylo=ylo.value, yhi=yhi.value)
+    out["cells"] = cells.reshape(ny.value + 2, nx.value + 2) if dim.value == 2 else cells
     return out
 
 

@@ -66,4 +66,26 @@ int upcgpu_elem_fill_cs_zm(int proc_id, double a_lep, double alp_mass, double al
   return UPCGPU_OK;
 }
 
+int upcgpu_root_hist_read(const char* path, const char* name, int* dim, int* nx, double* xlo, double* xhi, int* ny,
+                          double* ylo, double* yhi, double* cells, size_t cap, size_t* n_cells)
+{
+  if (!path || !name) return UPCGPU_EINVAL;
+  UpcRootHist h;
+  std::string err;
+  if (!h.Read(path, name, err)) return UPCGPU_EINVAL;
+  if (dim) *dim = h.dim;
+  if (nx) *nx = h.fXaxis.fNbins;
+  if (xlo) *xlo = h.fXaxis.fXmin;
+  if (xhi) *xhi = h.fXaxis.fXmax;
+  if (ny) *ny = h.dim == 2 ? h.fYaxis.fNbins : 0;
+  if (ylo) *ylo = h.fYaxis.fXmin;
+  if (yhi) *yhi = h.fYaxis.fXmax;
+  if (n_cells) *n_cells = h.fArray.size();
+  if (cells) {
+    if (cap < h.fArray.size()) return UPCGPU_EINVAL;
+    for (size_t i = 0; i < h.fArray.size(); ++i) cells[i] = h.fArray[i];
+  }
+  return UPCGPU_OK;
+}
+
 } // extern "C"
