@@ -7,13 +7,20 @@
 // integrals, 163 642 later bisections) shows 14 distinct intervals in all, nine of which take 99.65 % of
 // the bisections: (level, position) = (5,0) 30 %, (4,1) 26 %, (6,0) 19 %, (7,0) 10 %, (5,1) 5 %, (8,0) 4 %,
 // (5,2) 3 %, (1,1) 1 %, (9,0) 1 %.  So g -- the row-only factor of the integrand -- is tabulated once per row
-// on the GK21 nodes of the 29 intervals these 14 bisections can produce (k_head_tables), and every integral
+// on the GK21 nodes of the 31 intervals that 15 such bisections produce (k_head_tables), and every integral
 // runs the reference's QAGS in its own thread (same Qags<> state machine, state in shared memory strided by
-// thread) for as long as the interval it bisects next is one of the 14 and its interval list fits
-// (kHdCap: up to 9 bisections, 92 % of the integrals).  The lanes of a warp are consecutive b of one row:
-// they read the same few g entries and evaluate J1 on their own arguments.  An integral that needs
-// anything else (8 %) is handed to k_flux_qags_rows with its complete QAGS state (HeadState).  Nothing is
-// speculated: every evaluation made here is one the reference makes.
+// thread) for as long as the interval it bisects next is one of the 15 and its state fits.
+//
+// Two passes of one kernel template: pass 1 takes all integrals with an 11-interval state (9 bisections: 92 %
+// finish; three CTAs per SM), pass 2 resumes the others from their HeadState with the 16-interval state of the
+// fallback (two CTAs per SM).  What pass 2 leaves (an interval outside the table: 0.1 %) goes to
+// k_flux_qags_rows with its complete QAGS state.  Nothing is speculated: every evaluation made here is one the
+// reference makes, in the reference's order.
+//
+// The lanes of a warp are the same b index of 32 neighbouring m rows at one y row (HeadItemValid): nearly the
+// same photon energy and b, so the same rounds, intervals and branch of J1; the g table is laid out
+// [y row][node][m row] so that their loads coalesce.  Rows with k >= g1 hc / R share one b grid: their J1
+// values on the tabulated nodes come from a table (k_head_j1_table).
 #pragma once
 #include "upc_hot.cuh"
 #include "upc_qags.cuh"
