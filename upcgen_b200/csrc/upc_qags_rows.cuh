@@ -1,5 +1,10 @@
-// upc_qags_rows.cuh -- stage A.3, the form-factor flux rows (F2/F3: fluxFormIntegrand / fluxForm,
+// upc_qags_rows.cuh -- stage A.3b, the form-factor flux rows (F2/F3: fluxFormIntegrand / fluxForm,
 // src/UpcCrossSection.cpp:181-218) as a row-cooperative, warp-specialised persistent kernel.
+//
+// Role today: the general fallback.  It takes the integrals the head passes (upc_qags_head.cuh) hand over --
+// QAGS wants an interval outside the head's table, or more than 14 bisections: 0.1 % of the cfg2 grid -- and,
+// unlike the head, caches g for ANY dyadic interval.  It was written when it carried the whole stage (DESIGN.md
+// section 7, v3-v11), which is why it is built for throughput.
 //
 // The reference's integrand is   x^2 F(x^2 + (k/gamma)^2) / (x^2 + (k/gamma)^2) * J1(b x / hc):
 // the first factor ("g") depends on the ROW (photon energy k) only, the Bessel factor on the
