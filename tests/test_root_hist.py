@@ -18,7 +18,20 @@ import numpy as np
 import pytest
 
 REF = "/root/reference/cross_sections"
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's cross_sections directory is not mounted")
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's cross_sections directory is not mounted")
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lookup_semantics_cpp(tmp_path):
+    """tests/cpp/roothist_check.cpp: FindBin on uniform and variable-width axes, edges, under-/overflow, clamping."""
+    import subprocess
+    exe = tmp_path / "roothist_check"
+    host = os.path.join(ROOT_DIR, "upcgen_b200", "host")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", host, "-o", str(exe),
+                           os.path.join(ROOT_DIR, "tests", "cpp", "roothist_check.cpp"),
+                           os.path.join(host, "UpcRootHist.cpp"), "-lz"])
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "ROOTHIST_OK" in r.stdout, r.stdout + r.stderr
 
 
 def py_read_hist(path, name):
@@ -111,6 +124,7 @@ def sigma_m(L, proc, m, which=0):
     return out
 
 
+@needs_ref
 @pytest.mark.parametrize("proc,sub,nz,zlo,zhi,nm,mlo,mhi", [
     (22, "lbyl", 198, -0.99, 0.99, 1000, 0.05, 50.0),      # the grid src/UpcGenerator.cpp:74-79 forces
     (111, "pi0pi0", 100, -1.0, 1.0, 100, 0.0, 5.0),
@@ -158,6 +172,7 @@ def test_histograms_and_lookups(lib, proc, sub, nz, zlo, zhi, nm, mlo, mhi):
     assert r.std() / r.mean() < 1e-3
 
 
+@needs_ref
 def test_missing_directory_is_an_error(lib):
     os.environ["UPCGEN_CROSS_SEC_DIR"] = "/nonexistent"
     try:
@@ -167,6 +182,7 @@ def test_missing_directory_is_an_error(lib):
         os.environ["UPCGEN_CROSS_SEC_DIR"] = REF
 
 
+@needs_ref
 def test_c_abi_reader_equals_python_parse():
     """upcgpu_root_hist_read (the entry point a luminosity-cache comparison uses, tools/compare_lumi_root.py) against the
     independent Python parse: axes and every cell, under- and overflow included."""
