@@ -265,3 +265,19 @@ def test_head_interval_table_covers_the_oracles_bisections(get_oracle):
             total += n
             inside += sum(h in parents for h in heaps)
     assert total > 2000 and inside / total > 0.995, (inside, total)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's
+    keys, the same metric / unit / config object as the GPU arm, and a cpu_baseline describing the run."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "lumi_cells_per_s" and line["unit"] == "cells/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["value"] > 0
+    assert set(line["config"]) >= {"workload", "cells", "grid"} and line["config"]["grid"] == [1001, 121]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
