@@ -21,7 +21,7 @@ enum HotOff {
   H_J1P = 0,                         // 17: J1(x)/x on x <= 8, centred in x^2/32 - 1
   H_J1M = H_J1P + UPC_J1_P_N,        // 14: modulus
   H_J1T = H_J1M + UPC_J1_M_N,        // 16: phase
-  H_SC = H_J1T + UPC_J1_T_N,         // 16: sincos (see kSinCosC)
+  H_SC = H_J1T + UPC_J1_T_N,         // 16: angle reduction by pi/2 and the fdlibm sin / cos kernels
   H_EPS = H_SC + 16,                 // 8 : 3/8, spare
   H_MISC = H_EPS + 8,                // 8 : 1/32, 2/pi, 1/sqrt2, Q2min, 1/dQ2, dQ2, 64, sqrt(2/pi)
   H_END = H_MISC + 8

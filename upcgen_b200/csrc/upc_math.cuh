@@ -62,64 +62,7 @@ __device__ __forceinline__ void bessel_k0k1(double x, double& k0, double& k1)
   }
 }
 
-// Constants of the angle reduction and of the sin / cos kernels used by J1 for x > 8 (0 <= x < ~1e5; on this path
-// x = b k/hc <= 700): Cody-Waite reduction by pi/2 with three FMA steps, then the classic fdlibm minimax kernels on
-// |r| <= pi/4 (~1 ulp).  There is no Payne-Hanek slow path, which keeps the QAGS kernels' code inside the
-// instruction cache.
-// (all FP64 constants of the hot loops live in __constant__ arrays: a 64-bit literal would be
-// materialised with two UMOVs per use, a __constant__ element is a free DFMA operand)
-__constant__ double kSinCosC[16] = {
-  0.63661977236758134308,       // 0: 2/pi
-  1.57079632679489655800e+00,   // 1: pi/2 high
-  6.12323399573676603587e-17,   // 2: pi/2 mid
-  -1.49738490485916983693e-33,  // 3: pi/2 low
-  1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,   // 4..9: S6..S1
-  -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
-  -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,  // 10..15: C6..C1
-  2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02};
-
-__constant__ double kJ1C[1] = {1. / 32.};
-
-// J1(x), x >= 0.  Replaces gsl_sf_bessel_J1 at src/UpcCrossSection.cpp:189.
-// x <= 8: x * P(x^2/32 - 1); x > 8: modulus/phase form sqrt(2/(pi x)) M sin(x - pi/4 + eps) with the
-// whole angle reduced at once (see j1_largeN in upc_hot.cuh).
-__device__ __forceinline__ double bessel_j1(double x)
-{
-  if (x <= 8.) {
-    return x * horner(UPC_J1_P, fma(x * x, kJ1C[0], -1.));
-  }
-  // same formulation as j1_largeN (upc_hot.cuh)
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x, y * y, 1.);
-  const double rs = fma(fma(e, 0.375, 0.5), y * e, y);
-  const double rx = rs * rs;
-  const double u = fma(128. * rx, rx, -1.);
-  const double ampl = horner(UPC_J1_M, u) * (rs * 0.79788456080286535588);  // sqrt(2/(pi x))
-  const double eps = horner(UPC_J1_T, u) * rx;
-  const double kMagic = 6755399441055744.0;
-  const double q = fma(x + eps, kSinCosC[0], -0.5) + kMagic;
-  const int n = __double2loint(q);
-  const double f = (q - kMagic) + 0.5;
-  double r = fma(-f, kSinCosC[1], x);
-  r = fma(-f, kSinCosC[2], r);
-  r = fma(-f, kSinCosC[3], r) + eps;
-  const double z = r * r;
-  double ps = fma(z, kSinCosC[4], kSinCosC[5]);
-  ps = fma(z, ps, kSinCosC[6]);
-  ps = fma(z, ps, kSinCosC[7]);
-  ps = fma(z, ps, kSinCosC[8]);
-  ps = fma(z, ps, kSinCosC[9]);
-  const double sr = fma(z * r, ps, r);
-  double pc = fma(z, kSinCosC[10], kSinCosC[11]);
-  pc = fma(z, pc, kSinCosC[12]);
-  pc = fma(z, pc, kSinCosC[13]);
-  pc = fma(z, pc, kSinCosC[14]);
-  pc = fma(z, pc, kSinCosC[15]);
-  const double cr = fma(z * z, pc, fma(z, -0.5, 1.0));
-  const double a = (n & 1) ? cr : sr;
-  return ampl * __hiloint2double(__double2hiint(a) ^ ((n & 2) << 30), __double2loint(a));
-}
+// (J1, which replaces gsl_sf_bessel_J1 at src/UpcCrossSection.cpp:189, lives in upc_hot.cuh: j1_3 and its two branches.)
 
 // ROOT TMath::BesselI1 / BesselK1 polynomials (A&S 9.8.3-9.8.8), used by calcBreakupProb
 // (src/UpcCrossSection.cpp:982-999).  H2: these 1e-7-accurate forms ARE the reference.

@@ -42,71 +42,6 @@ struct GkOut {
   double result, abserr, resabs, resasc;
 };
 
-// gsl_integration_qk (integration/qk.c) specialised to the 21-point rule.
-//   F provides  void pair(double x1, double x2, double& f1, double& f2)  -- two integrand
-//   evaluations through ONE inlined call site (two interleaved instruction streams for ILP, and
-//   a kernel whose hot loop stays small enough for the instruction cache).
-//   fv: per-thread scratch of 20 doubles at fv[j * fv_stride] (shared memory, lane-interleaved).
-// Summation order: the centre term first, then the pairs in GSL's order; result_asc in GSL's
-// index order.  The centre is evaluated by the same pair() site (its second slot re-evaluates
-// the centre: one redundant evaluation in 22).
-template <class F>
-__device__ __forceinline__ GkOut gk21(const F& f, double a, double b, double* fv, int fv_stride)
-{
-  const double center = 0.5 * (a + b);
-  const double half_length = 0.5 * (b - a);
-  const double abs_half_length = fabs(half_length);
-  double f_center = 0, result_gauss = 0, result_kronrod = 0, result_abs = 0;
-#pragma unroll 1
-  for (int it = 0; it < 11; ++it) {
-    const int p = it == 0 ? 10 : it - 1;  // visiting order: centre (10), then pairs 0..9
-    const double abscissa = half_length * kGkX[p];
-    double fval1, fval2;
-    f.pair(center - abscissa, center + abscissa, fval1, fval2);
-    if (p == 10) {
-      f_center = fval1;
-      result_kronrod = f_center * kGkWkC;
-      result_abs = fabs(result_kronrod);
-    } else {
-      const double fsum = fval1 + fval2;
-      fv[(2 * p) * fv_stride] = fval1;
-      fv[(2 * p + 1) * fv_stride] = fval2;
-      result_gauss += kGkWg[p] * fsum;
-      result_kronrod += kGkWk[p] * fsum;
-      result_abs += kGkWk[p] * (fabs(fval1) + fabs(fval2));
-    }
-  }
-  const double mean = result_kronrod * 0.5;
-  double result_asc = kGkWkC * fabs(f_center - mean);
-  // GSL sums j = 0..9 in xgk index order: j even -> pair 5 + j/2, j odd -> pair (j-1)/2
-#pragma unroll 1
-  for (int j = 0; j < 10; ++j) {
-    const int p = (j & 1) ? (j >> 1) : (5 + (j >> 1));
-    result_asc += kGkWk[p] * (fabs(fv[(2 * p) * fv_stride] - mean) + fabs(fv[(2 * p + 1) * fv_stride] - mean));
-  }
-  double err = (result_kronrod - result_gauss) * half_length;
-  result_kronrod *= half_length;
-  result_abs *= abs_half_length;
-  result_asc *= abs_half_length;
-  // rescale_error
-  err = fabs(err);
-  if (result_asc != 0 && err != 0) {
-    double s = 200 * err / result_asc;
-    double scale = s * sqrt(s);  // pow(s, 1.5)
-    err = scale < 1 ? result_asc * scale : result_asc;
-  }
-  if (result_abs > DBL_MIN / (50 * DBL_EPSILON)) {
-    double min_err = 50 * DBL_EPSILON * result_abs;
-    if (min_err > err) err = min_err;
-  }
-  GkOut o;
-  o.result = result_kronrod;
-  o.abserr = err;
-  o.resabs = result_abs;
-  o.resasc = result_asc;
-  return o;
-}
-
 // signed abscissas of the 21 nodes in storage order: node 2p = -x_p, node 2p+1 = +x_p (pairs p in
 // the order of kGkX), node 20 = centre
 __constant__ double kGkNode[21] = {
@@ -121,7 +56,8 @@ __constant__ double kGkNode[21] = {
   -0.562757134668604683339000099272694, 0.562757134668604683339000099272694,
   -0.294392862701460198131126603103866, 0.294392862701460198131126603103866, 0.0};
 
-// The same 21-point rule with the integrand evaluated three nodes at a time (F::tri) -- 7 trips,
+// gsl_integration_qk (integration/qk.c) specialised to the 21-point rule, with the integrand evaluated three nodes
+// at a time (F::tri) -- 7 trips,
 // no redundant evaluation -- into fv[0..20] (node order of kGkNode), followed by the weighted
 // sums in GSL's order.  fv: per-thread scratch of 21 doubles at fv[n * fv_stride].
 template <class F>

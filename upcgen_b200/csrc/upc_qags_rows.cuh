@@ -427,7 +427,7 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
 
     // ---- R1 (thread = integral): pending intervals, cache entries, evaluation counts ----
     // z = beta * x is monotonic over the (ascending) nodes, so the evaluations of a task that take
-    // J1's small-argument branch (z <= 8, bessel_j1) are its first n_small nodes: a bisection with
+    // J1's small-argument branch (z <= 8, j1_smallN) are its first n_small nodes: a bisection with
     // the very arithmetic of the evaluators
     bool has_b = false;
     int small_a = 0, small_b = 0;
