@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed, see upcgen_b200/build/nvcc.log")
-    subprocess.check_call([NVCC, "-shared", "-o", SO, *objs, "-lcudart", "-lz", "-ccbin", "/usr/bin/g++"])
+    subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", SO, *objs, "-lcudart", "-lz", "-ccbin", "/usr/bin/g++"])
     return SO
 
 
