@@ -37,9 +37,14 @@ WORKLOAD_TEXT = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, and its FP64-pipe activity, from
 # the committed `ncu --set full` captures (profiles/r01_v15_ncu_qags_head_pass1_cfg2.txt, r01_v13_ncu_qags_rows_cfg2.txt, r01_v15_ncu_cells_cfg2.txt)
-NCU_TRAFFIC = {("cfg2", "k_flux_qags_head"): 670.9e6 + 495.1e6, ("cfg2", "k_flux_qags_rows"): 28.9e6 + 0.06e6,
-               ("cfg2", "k_cells"): 234.8e6 + 4.9e6}
-NCU_FP64_PIPE_PCT = {("cfg2", "k_flux_qags_head"): 60.5, ("cfg2", "k_flux_qags_rows"): 3.8, ("cfg2", "k_cells"): 52.3}
+NCU_QUOTED = {
+    ("cfg2", "k_flux_qags_head"): {"traffic": 670.9e6 + 495.1e6, "fp64_pipe_pct": 60.5,
+                                   "source": "profiles/r01_v15_ncu_qags_head_pass1_cfg2.txt"},
+    ("cfg2", "k_flux_qags_rows"): {"traffic": 28.9e6 + 0.06e6, "fp64_pipe_pct": 3.8,
+                                   "source": "profiles/r01_v13_ncu_qags_rows_cfg2.txt"},
+    ("cfg2", "k_cells"): {"traffic": 234.8e6 + 4.9e6, "fp64_pipe_pct": 52.3,
+                          "source": "profiles/r01_v15_ncu_cells_cfg2.txt"},
+}
 
 # algorithmic work per unit
 FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegrand
@@ -169,6 +174,266 @@ def reference_arm(args):
     return 0
 
 
+class Bench:
+    """One workload on this rank's GPU: context, plug-in inputs, and the timed legs."""
+
+    def __init__(self, workload, rank, local, world, dev):
+        import torch
+
+        from upcgen_b200 import capi
+        from upcgen_b200.config import named_config
+        self.torch, self.capi = torch, capi
+        self.workload, self.rank, self.local, self.world, self.dev = workload, rank, local, world, dev
+        self.P = P = named_config(workload)
+        self.gpu = capi.UpcGpu(P, local)
+        self.ext_stream = torch.cuda.ExternalStream(self.gpu.stream_handle(), device=dev)
+        self.n_cells = P.nm * P.ny
+        self.pol, self.bk = int(P.use_pol), int(P.breakup_mode > 1)
+        # host plug-in values (elementary sigma(m)), computed once: they are inputs of the step
+        # (cfg3, light-by-light with USE_POLARIZED_CS 1, is defined at the lumi-table level only -- SURVEY Q5: the
+        # reference's fold multiplies by LbyL's identically-zero polarised sigma -- so its step has no fold)
+        self.fold = not (self.pol and P.proc_id in (22, 111))
+        if not self.fold:
+            self.sig = {}
+        elif self.pol:
+            self.sig = dict(sig_s=capi.elem_sigma_m(P, 1), sig_p=capi.elem_sigma_m(P, 2))
+        else:
+            self.sig = dict(sig_m=capi.elem_sigma_m(P, 0))
+
+    def close(self):
+        self.gpu.close()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        import torch.distributed as dist
+        t = self.torch.tensor([float(x)], device=self.dev, dtype=self.torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device(self):
+        from upcgen_b200 import dist as udist
+        gpu = self.gpu
+        gpu.invalidate_tables()
+        gpu.prepare_tables()
+        udist.fill_lumi_distributed(gpu, self.rank, self.world, self.dev)
+        if self.fold:
+            gpu.fold_sigma(download=False, **self.sig)   # the step's one host wait
+        else:
+            gpu.fill_stats()                             # no fold: collect the queued fill
+
+    def time_device(self, steps, warmup, l2_flush, clocks=None):
+        """Device-resident step: CUDA events on the library's stream, L2 flushed between steps, max over ranks."""
+        import numpy as np
+        torch, gpu = self.torch, self.gpu
+        for _ in range(warmup):
+            self.step_device()
+        stage = {"ms_tables": 0.0, "ms_flux": 0.0, "ms_qags": 0.0, "ms_cells": 0.0}
+        ms_steps = []
+        launches0 = gpu.launch_count()
+        self.barrier()
+        if clocks:
+            clocks.start()
+        for _ in range(steps):
+            l2_flush.fill_(1)                 # flush L2 between timed iterations (126 MB L2 < 256 MiB)
+            self.barrier()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(self.ext_stream)
+            self.step_device()
+            e1.record(self.ext_stream)
+            self.barrier()
+            ms_steps.append(e0.elapsed_time(e1))
+            st = gpu.fill_stats()
+            for k in stage:
+                stage[k] += st[k] / steps
+        clk = clocks.stop() if clocks else None
+        launches = gpu.launch_count() - launches0
+        ms = self.max_over_ranks(float(np.mean(ms_steps)))
+        return ms, stage, clk, launches, gpu.fill_stats()
+
+    def time_e2e(self, steps, l2_flush):
+        """The same step through the host-buffer C-ABI calls, pinned host buffers, copies inside the timed region."""
+        import ctypes as C
+
+        import numpy as np
+
+        from upcgen_b200 import dist as udist
+        torch, gpu, P, pol, fold, sig = self.torch, self.gpu, self.P, self.pol, self.fold, self.sig
+        n_cells, world = self.n_cells, self.world
+        n_tab = 2 if pol else 1
+        d2h = int(n_tab * n_cells * 8 + (n_cells * 8 * (2 if pol else 1) + 8 if fold else 0))
+        h2d = int(sum(np.asarray(v).size * 8 for v in sig.values()))
+        if world == 1:
+            host_lumi = [torch.empty((P.nm, P.ny), dtype=torch.float64).pin_memory() for _ in range(n_tab)]
+            host_cs = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory()
+            host_ratio = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory() if pol else None
+            host_sig = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in sig.items()}
+            tot = C.c_double()
+
+            def vp(t):
+                return None if t is None else C.c_void_p(t.data_ptr())
+
+            def step():
+                gpu.invalidate_tables()
+                if not fold:
+                    gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
+                elif pol:
+                    gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
+                    gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, None, vp(host_sig["sig_s"]), vp(host_sig["sig_p"]),
+                                                     vp(host_cs), vp(host_ratio), C.byref(tot)))
+                else:
+                    gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, vp(host_lumi[0]), None, None))
+                    gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, vp(host_sig["sig_m"]), None, None, vp(host_cs), None,
+                                                     C.byref(tot)))
+                return tot.value
+            api = ("upcgpu_fill_lumi" + (" + upcgpu_fold_sigma" if fold else "")
+                   + " (include/upcgpu.h), pinned host buffers")
+        else:
+            # N > 1: the sharded fill, the NCCL all-gather, then on EVERY rank the read-back of the lumi table(s)
+            # (upcgpu_lumi_download) and the fold with its sigma table read-back (upcgpu_fold_sigma), host buffers
+            kinds = (1, 2) if pol else (0,)
+
+            def step():
+                gpu.invalidate_tables()
+                gpu.prepare_tables()
+                udist.fill_lumi_distributed(gpu, self.rank, world, self.dev)
+                for which in kinds:
+                    gpu.lumi_download(which)
+                return gpu.fold_sigma(download=True, **sig)[2] if fold else 0.0
+            api = ("per rank: upcgpu_fill_lumi_shard + NCCL all-gather + upcgpu_lumi_unpack + upcgpu_lumi_download"
+                   + (" + upcgpu_fold_sigma" if fold else "") + " (host buffers; bytes are per rank; max over ranks)")
+        tot_mb = step()
+        dts = []
+        for _ in range(steps):
+            l2_flush.fill_(1)
+            self.barrier()
+            t0 = time.perf_counter()
+            tot_mb = step()
+            torch.cuda.synchronize(self.dev)
+            dts.append(time.perf_counter() - t0)
+        dt = self.max_over_ranks(float(np.mean(dts)))
+        return {"value": n_cells / dt, "unit": "cells/s", "ms_per_step": dt * 1e3, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "api": api, "total_cross_section_mb": tot_mb}
+
+    def time_events(self, n_total, e2e_cap=1 << 18):
+        """Event stage: S1 (sampler build) and E1-E5 on n_total candidates split over the ranks by Philox counter
+        ranges (no collective); needs the folded sigma table of this context on the device."""
+        import ctypes as C
+        torch, gpu, P, capi, world, rank = self.torch, self.gpu, self.P, self.capi, self.world, self.rank
+        cszm = None if P.ignore_csz else capi.elem_cs_zm(P, 0)
+        gpu.sampler_build(cszm=cszm)          # warm-up (allocations)
+        torch.cuda.synchronize(self.dev)
+        t0 = time.perf_counter()
+        gpu.sampler_build(cszm=cszm)          # S1: the CDFs of the (y, m) table and of the nm z tables
+        torch.cuda.synchronize(self.dev)
+        ms_sampler = (time.perf_counter() - t0) * 1e3
+        n_ev = max(n_total // world, 1 << 14)
+        first = rank * n_ev
+        gpu.generate_device(12345, first, min(n_ev, 1 << 20))  # warm-up: the scratch buffers grow on demand
+        self.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(self.ext_stream)
+        acc = gpu.generate_device(12345, first, n_ev)
+        e1.record(self.ext_stream)
+        self.barrier()
+        ms_ev = self.max_over_ranks(e0.elapsed_time(e1))
+        acc_all = acc
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([float(acc)], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            acc_all = int(t.item())
+        ev = {"events_per_s": world * n_ev / (ms_ev * 1e-3), "candidates": world * n_ev, "accepted": int(acc_all),
+              "ms": ms_ev, "sharding": "Philox counter ranges, no collective", "sampler_build_ms": ms_sampler}
+        # the same through upcgpu_generate with pinned host buffers for every output array (per rank; max over ranks)
+        n_small = min(n_ev, e2e_cap)
+        mp = capi.MAX_PART
+        hb = {"npart": torch.empty(n_small, dtype=torch.int32).pin_memory(),
+              "pdg": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
+              "status": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
+              "mother": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
+              "p4": torch.empty((n_small, mp, 4), dtype=torch.float64).pin_memory()}
+        nacc = C.c_uint64()
+
+        def gen_e2e():
+            gpu._chk(gpu.L.upcgpu_generate(gpu.h, 12345, first, n_small, C.c_void_p(hb["npart"].data_ptr()),
+                                           C.c_void_p(hb["pdg"].data_ptr()), C.c_void_p(hb["status"].data_ptr()),
+                                           C.c_void_p(hb["mother"].data_ptr()), C.c_void_p(hb["p4"].data_ptr()), None,
+                                           C.byref(nacc)))
+
+        gen_e2e()
+        self.barrier()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            gen_e2e()
+        dt = self.max_over_ranks((time.perf_counter() - t0) / reps)
+        ev["e2e_events_per_s"] = world * n_small / dt
+        ev["e2e_candidates_per_rank"] = n_small
+        ev["e2e_d2h_bytes"] = int(sum(t.numel() * t.element_size() for t in hb.values()))
+        return ev
+
+    def roofline(self, stage, st, peak_tf):
+        """Roofline of the dominant kernel.  `achieved` is ALGORITHMIC work (what the reference's
+        algorithm does per unit, no shortcut deducted) over the kernel's measured time.  The kernels do less than that:
+        J1 of the rows on the common b grid comes from a table, cells above ny/2 are mirror images, far (b >= 20 fm)
+        pairs are a closed sum.  `executed` repeats the figure with only the work the kernel really performed (from its
+        own counters), which is what the FP64 pipe sees; the ncu pipe-activity figure of the committed capture stands
+        beside it (quoted from profiles/, not measured in this run)."""
+        from upcgen_b200 import dist as udist
+        P, pol, bk = self.P, self.pol, self.bk
+        ms_head = st.get("ms_qags_head", 0.0)
+        executed = None
+        if st["qags_evals"] > 0 and stage["ms_qags"] >= stage["ms_cells"]:
+            if ms_head > 0.5 * stage["ms_qags"]:
+                work = FLOP_PER_QAGS_EVAL * st["qags_head_evals"]
+                t_k = ms_head * 1e-3
+                kern = "k_flux_qags_head"
+                units = f"{st['qags_head_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
+                ex = st["qags_head_evals"] - st["qags_table_evals"]
+                executed = {"flop": FLOP_PER_QAGS_EVAL * ex, "what": f"{ex} evaluations with J1 computed "
+                            f"({st['qags_table_evals']} took J1 from the common-grid table: a multiplication each)"}
+            else:
+                work = FLOP_PER_QAGS_EVAL * (st["qags_evals"] - st["qags_head_evals"])
+                t_k = (stage["ms_qags"] - ms_head) * 1e-3
+                kern = "k_flux_qags_rows"
+                units = f"{st['qags_evals'] - st['qags_head_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
+        else:
+            cells_rank = len(udist.cyclic_rows(P.nm, self.rank, self.world)) * P.ny
+            work = FLOP_CELL[(pol, bk)] * cells_rank
+            t_k = stage["ms_cells"] * 1e-3
+            kern = "k_cells"
+            units = f"{cells_rank} cells x {FLOP_CELL[(pol, bk)]:.3g} flop"
+            # per evaluated (b1,b2) pair: 5 phi x (15, +10 with breakup, +2 polarised) + 5; per evaluated cell: rows + fluxes
+            per_triplet = 15 + (10 if bk else 0) + (2 if pol else 0)
+            ex_flop = st["band_pairs"] * (5 * per_triplet + 5) + st["cells_evaluated"] * (360 + 120 * 120 * 2)
+            executed = {"flop": float(ex_flop), "what": f"{st['band_pairs']} (b1,b2) pairs evaluated point by point in "
+                        f"{st['cells_evaluated']} cells (the other pairs are a closed sum, the other cells mirror images)"}
+        achieved = work / t_k / 1e12 if t_k > 0 else 0.0
+        if executed is not None and t_k > 0:
+            executed["tflops"] = executed["flop"] / t_k / 1e12
+            executed["frac"] = executed["tflops"] / peak_tf if peak_tf else None
+        ncu = NCU_QUOTED.get((self.workload, kern)) if self.world == 1 else None
+        return {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf if peak_tf else None,
+                "traffic": ncu["traffic"] if ncu else None,
+                "traffic_source": ncu["source"] + " (ncu --set full capture of this kernel, quoted; not measured in this run)"
+                if ncu else None,
+                "peak_source": "measured live: upcgpu_fp64_peak DFMA loop (MEASURED_PEAKS.json has no FP64 figure; "
+                               "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
+                "algorithmic_work": units, "kernel_ms": t_k * 1e3, "executed": executed,
+                "ncu_fp64_pipe_active_pct": ncu["fp64_pipe_pct"] if ncu else None,
+                "qags_stage": {"ms": stage["ms_qags"], "ms_head": ms_head, "evals": st["qags_evals"],
+                               "tflops": FLOP_PER_QAGS_EVAL * st["qags_evals"] / (stage["ms_qags"] * 1e-3) / 1e12
+                               if stage["ms_qags"] > 0 else None}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,17 +441,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOAD_TEXT))
-    ap.add_argument("--events", type=int, default=None, help="events per rank for the event-stage timing")
+    ap.add_argument("--events", type=int, default=None, help="total candidates of the event-stage timing")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the cfg4 fill leg and the cfg5 10^7-event leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
 
-    import numpy as np
     import torch
 
-    from upcgen_b200 import capi, dist as udist
-    from upcgen_b200.config import named_config
+    from upcgen_b200 import dist as udist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
@@ -196,197 +460,24 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist
-
-    P = named_config(args.workload)
-    gpu = capi.UpcGpu(P, local)
-    ext_stream = torch.cuda.ExternalStream(gpu.stream_handle(), device=dev)
-    n_cells = P.nm * P.ny
-    pol, bk = int(P.use_pol), int(P.breakup_mode > 1)
-
-    # host plug-in values (elementary sigma(m)), computed once: they are inputs of the step
-    # (cfg3, light-by-light with USE_POLARIZED_CS 1, is defined at the lumi-table level only -- SURVEY Q5: the
-    # reference's fold multiplies by LbyL's identically-zero polarised sigma -- so its step has no fold)
-    fold = not (pol and P.proc_id in (22, 111))
-    if not fold:
-        sig = {}
-    elif pol:
-        sig = dict(sig_s=capi.elem_sigma_m(P, 1), sig_p=capi.elem_sigma_m(P, 2))
-    else:
-        sig = dict(sig_m=capi.elem_sigma_m(P, 0))
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def step_device():
-        gpu.invalidate_tables()
-        gpu.prepare_tables()
-        udist.fill_lumi_distributed(gpu, rank, world, dev)
-        if fold:
-            gpu.fold_sigma(download=False, **sig)
-
-    # ---- device-resident timing ---------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
+    # ---- the headline workload (cfg2 unless --workload says otherwise) -------------------------------
+    B = Bench(args.workload, rank, local, world, dev)
+    P, gpu = B.P, B.gpu
+    for _ in range(2):
+        B.step_device()                       # first touch: allocations, the integral-count cache
     peak_tf, _ = gpu.fp64_peak(400000)
-    clocks = ClockSampler(local)
-    stage = {"ms_tables": 0.0, "ms_flux": 0.0, "ms_qags": 0.0, "ms_cells": 0.0}
-    ms_steps = []
-    launches0 = gpu.launch_count()
-    barrier()
-    clocks.start()
-    for _ in range(args.steps):
-        l2_flush.fill_(1)                 # flush L2 between timed iterations (126 MB L2 < 256 MiB)
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(ext_stream)
-        step_device()
-        e1.record(ext_stream)
-        barrier()
-        ms_steps.append(e0.elapsed_time(e1))
-        st = gpu.fill_stats()
-        for k in stage:
-            stage[k] += st[k] / args.steps
-    clk = clocks.stop()
-    launches = gpu.launch_count() - launches0
-    ms = float(np.mean(ms_steps))
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    st = gpu.fill_stats()
-
-    # ---- end-to-end through the host-buffer C-ABI (N = 1 only: the call fills the whole grid) ----
-    e2e = None
-    if world == 1:
-        n_tab = 2 if pol else 1
-        host_lumi = [torch.empty((P.nm, P.ny), dtype=torch.float64).pin_memory() for _ in range(n_tab)]
-        host_cs = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory()
-        host_ratio = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory() if pol else None
-        host_sig = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in sig.items()}
-        import ctypes as C
-        tot = C.c_double()
-
-        def vp(t):
-            return None if t is None else C.c_void_p(t.data_ptr())
-
-        def step_e2e():
-            gpu.invalidate_tables()
-            if not fold:
-                gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
-            elif pol:
-                gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
-                gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, None, vp(host_sig["sig_s"]), vp(host_sig["sig_p"]),
-                                                 vp(host_cs), vp(host_ratio), C.byref(tot)))
-            else:
-                gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, vp(host_lumi[0]), None, None))
-                gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, vp(host_sig["sig_m"]), None, None, vp(host_cs), None,
-                                                 C.byref(tot)))
-            return tot.value
-
-        step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            l2_flush.fill_(1)
-            torch.cuda.synchronize(dev)
-            step_e2e()
-        torch.cuda.synchronize(dev)
-        dt = (time.perf_counter() - t0) / args.steps
-        e2e = {"value": n_cells / dt, "unit": "cells/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in host_sig.values())),
-               "d2h_bytes_per_step": int(n_tab * n_cells * 8 + (n_cells * 8 * (2 if pol else 1) + 8 if fold else 0)),
-               "api": "upcgpu_fill_lumi" + (" + upcgpu_fold_sigma" if fold else "") + " (include/upcgpu.h), pinned host buffers",
-               "total_cross_section_mb": tot.value}
-
-    else:
-        # N > 1: the sharded fill, the NCCL all-gather, then on EVERY rank the read-back of the lumi table(s)
-        # (upcgpu_lumi_download) and the fold with its sigma table read-back (upcgpu_fold_sigma), host buffers
-        kinds = (1, 2) if pol else (0,)
-
-        def step_e2e_dist():
-            gpu.invalidate_tables()
-            gpu.prepare_tables()
-            udist.fill_lumi_distributed(gpu, rank, world, dev)
-            for which in kinds:
-                gpu.lumi_download(which)
-            return gpu.fold_sigma(download=True, **sig)[2] if fold else 0.0
-
-        step_e2e_dist()
-        dts = []
-        for _ in range(args.steps):
-            l2_flush.fill_(1)
-            barrier()
-            t0 = time.perf_counter()
-            tot_mb = step_e2e_dist()
-            torch.cuda.synchronize(dev)
-            dts.append(time.perf_counter() - t0)
-        t = torch.tensor([float(np.mean(dts))], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        n_tab = 2 if pol else 1
-        e2e = {"value": n_cells / dt, "unit": "cells/s", "ms_per_step": dt * 1e3,
-               "h2d_bytes_per_step": int(sum(np.asarray(v).size * 8 for v in sig.values())),
-               "d2h_bytes_per_step": int(n_tab * n_cells * 8 + (n_cells * 8 * (2 if pol else 1) + 8 if fold else 0)),
-               "api": "per rank: upcgpu_fill_lumi_shard + NCCL all-gather + upcgpu_lumi_unpack + upcgpu_lumi_download"
-                      + (" + upcgpu_fold_sigma" if fold else "") + " (host buffers; bytes are per rank; max over ranks)",
-               "total_cross_section_mb": tot_mb}
-
-    # ---- event stage ----------------------------------------------------------------------
+    ms, stage, clk, launches, st = B.time_device(args.steps, args.warmup, l2_flush, ClockSampler(local))
+    e2e = B.time_e2e(args.steps, l2_flush)
     events = None
     if args.workload in ("cfg1", "cfg2", "cfg5"):
-        cszm = None if P.ignore_csz else capi.elem_cs_zm(P, 0)
-        gpu.sampler_build(cszm=cszm)          # warm-up (allocations)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        gpu.sampler_build(cszm=cszm)          # S1: the CDFs of the (y, m) table and of the nm z tables
-        torch.cuda.synchronize(dev)
-        ms_sampler = (time.perf_counter() - t0) * 1e3
-        n_ev = args.events or min(P.n_events, 1 << 20) // world
-        n_ev = max(n_ev, 1 << 14)
-        first = rank * n_ev
-        gpu.generate_device(12345, first, n_ev)  # warm-up at full size: the scratch buffers grow on demand
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(ext_stream)
-        acc = gpu.generate_device(12345, first, n_ev)
-        e1.record(ext_stream)
-        barrier()
-        ms_ev = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms_ev], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_ev = float(t.item())
-        events = {"events_per_s": world * n_ev / (ms_ev * 1e-3), "candidates": world * n_ev, "accepted_rank0": int(acc),
-                  "ms": ms_ev, "sharding": "Philox counter ranges, no collective", "sampler_build_ms": ms_sampler}
-        if world == 1:
-            # the same through upcgpu_generate with pinned host buffers for every output array
-            import ctypes as C
-            n_small = min(n_ev, 1 << 18)
-            mp = capi.MAX_PART
-            hb = {"npart": torch.empty(n_small, dtype=torch.int32).pin_memory(),
-                  "pdg": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
-                  "status": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
-                  "mother": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
-                  "p4": torch.empty((n_small, mp, 4), dtype=torch.float64).pin_memory()}
-            nacc = C.c_uint64()
-
-            def gen_e2e():
-                gpu._chk(gpu.L.upcgpu_generate(gpu.h, 12345, 0, n_small, C.c_void_p(hb["npart"].data_ptr()),
-                                               C.c_void_p(hb["pdg"].data_ptr()), C.c_void_p(hb["status"].data_ptr()),
-                                               C.c_void_p(hb["mother"].data_ptr()), C.c_void_p(hb["p4"].data_ptr()), None,
-                                               C.byref(nacc)))
-
-            gen_e2e()
-            t0 = time.perf_counter()
-            reps = 3
-            for _ in range(reps):
-                gen_e2e()
-            dt = (time.perf_counter() - t0) / reps
-            events["e2e_events_per_s"] = n_small / dt
-            events["e2e_d2h_bytes"] = int(sum(t.numel() * t.element_size() for t in hb.values()))
+        events = B.time_events(args.events or min(P.n_events, 1 << 20))
+    roofline = B.roofline(stage, st, peak_tf)
+    device_name = gpu.device_name()
+    work = {"qags_integrals": st["qags_integrals"], "qags_evals": st["qags_evals"],
+            "band_pairs": st["band_pairs"], "flux_rows": st["flux_rows"]}
+    B.close()
 
     # ---- CPU baseline beside it (rank 0, N = 1, bounded sample) --------------------------
     cpu = None
@@ -403,71 +494,39 @@ def main():
         cpu = {"value": nc / dt, "unit": "cells/s", "cores": cores, "kind": kind,
                "sample": sample + f"; {reps} repetitions"}
 
-    # ---- roofline of the dominant kernel ----------------------------------------------------
-    # `achieved` is ALGORITHMIC work (what the reference's algorithm does per unit, no shortcut
-    # deducted) over the kernel's measured time.  The kernels do less than that: J1 of the rows on the common b grid
-    # comes from a table, cells above ny/2 are mirror images, far (b >= 20 fm) pairs are a closed sum.  `executed`
-    # repeats the figure with only the work the kernel really performed (from its own counters), which is what the
-    # FP64 pipe sees; the ncu pipe-activity figure of the committed capture stands beside it.
-    ms_head = st.get("ms_qags_head", 0.0)
-    executed = None
-    if st["qags_evals"] > 0 and stage["ms_qags"] >= stage["ms_cells"]:
-        # the QAGS stage is the head kernel (one thread per integral on tabulated intervals, two passes: ~100 % of the
-        # evaluations; ms_qags_head covers both) and the row-cooperative fallback
-        if ms_head > 0.5 * stage["ms_qags"]:
-            work = FLOP_PER_QAGS_EVAL * st["qags_head_evals"]
-            t_k = ms_head * 1e-3
-            kern = "k_flux_qags_head"
-            units = f"{st['qags_head_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
-            ex = st["qags_head_evals"] - st["qags_table_evals"]
-            executed = {"flop": FLOP_PER_QAGS_EVAL * ex, "what": f"{ex} evaluations with J1 computed "
-                        f"({st['qags_table_evals']} took J1 from the common-grid table: a multiplication each)"}
-        else:
-            work = FLOP_PER_QAGS_EVAL * (st["qags_evals"] - st["qags_head_evals"])
-            t_k = (stage["ms_qags"] - ms_head) * 1e-3
-            kern = "k_flux_qags_rows"
-            units = f"{st['qags_evals'] - st['qags_head_evals']} integrand evaluations x {FLOP_PER_QAGS_EVAL:.0f} flop"
-    else:
-        cells_rank = len(udist.cyclic_rows(P.nm, rank, world)) * P.ny
-        work = FLOP_CELL[(pol, bk)] * cells_rank
-        t_k = stage["ms_cells"] * 1e-3
-        kern = "k_cells"
-        units = f"{cells_rank} cells x {FLOP_CELL[(pol, bk)]:.3g} flop"
-        # per evaluated (b1,b2) pair: 5 phi x (15, +10 with breakup, +2 polarised) + 5; per evaluated cell: rows + fluxes
-        per_triplet = 15 + (10 if bk else 0) + (2 if pol else 0)
-        ex_flop = st["band_pairs"] * (5 * per_triplet + 5) + st["cells_evaluated"] * (360 + 120 * 120 * 2)
-        executed = {"flop": float(ex_flop), "what": f"{st['band_pairs']} (b1,b2) pairs evaluated point by point in "
-                    f"{st['cells_evaluated']} cells (the other pairs are a closed sum, the other cells mirror images)"}
-    achieved = work / t_k / 1e12 if t_k > 0 else 0.0
-    if executed is not None and t_k > 0:
-        executed["tflops"] = executed["flop"] / t_k / 1e12
-        executed["frac"] = executed["tflops"] / peak_tf if peak_tf else None
-    roofline = {"bound": "fp64", "kernel": kern, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": NCU_TRAFFIC.get((args.workload, kern)) if world == 1 else None,
-                "peak_source": "measured live: upcgpu_fp64_peak DFMA loop (MEASURED_PEAKS.json has no FP64 figure; "
-                               "nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2)",
-                "algorithmic_work": units, "kernel_ms": t_k * 1e3, "executed": executed,
-                "ncu_fp64_pipe_active_pct": NCU_FP64_PIPE_PCT.get((args.workload, kern)),
-                "qags_stage": {"ms": stage["ms_qags"], "ms_head": ms_head, "evals": st["qags_evals"],
-                               "tflops": FLOP_PER_QAGS_EVAL * st["qags_evals"] / (stage["ms_qags"] * 1e-3) / 1e12
-                               if stage["ms_qags"] > 0 else None}}
+    # ---- the north-star target beside it: cfg4 (10001 x 1201 cells) fill and cfg5 (10^7 events) ------
+    cfg4 = ev5 = None
+    if args.workload == "cfg2" and not args.no_legs:
+        B4 = Bench("cfg4", rank, local, world, dev)
+        B4.step_device()                      # first touch
+        k4 = max(1, min(args.steps, 2))
+        ms4, stage4, _, launches4, st4 = B4.time_device(k4, 1, l2_flush)
+        e2e4 = B4.time_e2e(1, l2_flush)
+        cfg4 = {"workload": WORKLOAD_TEXT["cfg4"], "cells": B4.n_cells, "grid": [B4.P.nm, B4.P.ny], "steps": k4,
+                "warmup": 2, "ms_per_step": ms4, "cells_per_s": B4.n_cells / (ms4 * 1e-3), "stage_ms": stage4,
+                "e2e": e2e4, "gpu_launches": int(launches4), "roofline": B4.roofline(stage4, st4, peak_tf),
+                "work": {"qags_integrals": st4["qags_integrals"], "qags_evals": st4["qags_evals"],
+                         "band_pairs": st4["band_pairs"], "flux_rows": st4["flux_rows"]}}
+        B4.close()
+        B5 = Bench("cfg5", rank, local, world, dev)
+        B5.step_device()                      # tables, lumi table, fold: the sigma table the samplers are built from
+        ev5 = B5.time_events(10_000_000, e2e_cap=1 << 21)
+        ev5["workload"] = WORKLOAD_TEXT["cfg5"]
+        B5.close()
 
     if rank == 0:
         line = {
-            "metric": "lumi_cells_per_s", "value": n_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
+            "metric": "lumi_cells_per_s", "value": B.n_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": make_config(args.workload, P, world),
             "sigma_table_ms": ms,
             "stage_ms": stage, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "events": events,
-            "work": {"qags_integrals": st["qags_integrals"], "qags_evals": st["qags_evals"],
-                     "band_pairs": st["band_pairs"], "flux_rows": st["flux_rows"]},
-            "device": gpu.device_name(),
+            "work": work, "cfg4": cfg4, "events_cfg5": ev5,
+            "device": device_name,
         }
         print(json.dumps(line))
-    gpu.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

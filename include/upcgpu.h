@@ -145,7 +145,7 @@ int upcgpu_fill_lumi_shard(upcgpu_ctx* ctx, int shard, int nshards);
  * (M,Y) -> out (unpol) or out_s/out_p, NOT multiplied by dm*dy */
 int upcgpu_lumi_cells(upcgpu_ctx* ctx, const double* M, const double* Y, size_t n, double* out,
                       double* out_s, double* out_p);
-int upcgpu_get_fill_stats(const upcgpu_ctx* ctx, upcgpu_fill_stats* st);
+int upcgpu_get_fill_stats(upcgpu_ctx* ctx, upcgpu_fill_stats* st);
 
 /* Device-resident buffers for the multi-GPU exchange (device pointers as integers so that no
  * CUDA type appears here).  packed shard: [rows_per_shard][ny] per table, the shard's rows in ascending

@@ -93,6 +93,8 @@ def lib():
         L.upco_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, dp, dp]
         L.upco_generate_event.restype = i
         L.upco_generate_event.argtypes = [p, C.c_uint64, C.c_uint64, p, p, p, p, ip, p, p, p, p, p]
+        L.upco_generate_event_u.restype = i
+        L.upco_generate_event_u.argtypes = [p, p, p, p, p, p, ip, p, p, p, p, p]
         _LIB = L
     return _LIB
 
@@ -247,6 +249,19 @@ class Oracle:
         acc = self.L.upco_generate_event(self.h, seed, cand, _ptr(cs_sum), _ptr(z_sum), _ptr(z_sum_ps),
                                          _ptr(ratio), C.byref(npart), _ptr(pdg), _ptr(st), _ptr(mo),
                                          _ptr(p4), _ptr(aux))
+        n = npart.value
+        return acc, pdg[:n].copy(), st[:n].copy(), mo[:n].copy(), p4[:n].copy(), aux
+
+
+    def generate_event_u(self, u, cs_sum, z_sum, z_sum_ps=None, ratio=None):
+        """generateEvent with the twelve uniforms of the slot map injected (see upco_generate_event_u)."""
+        u = np.ascontiguousarray(u, float)
+        assert u.size == 12
+        npart = C.c_int()
+        pdg = np.zeros(4, np.int32); st = np.zeros(4, np.int32); mo = np.zeros(4, np.int32)
+        p4 = np.zeros((4, 4)); aux = np.zeros(5)
+        acc = self.L.upco_generate_event_u(self.h, _ptr(u), _ptr(cs_sum), _ptr(z_sum), _ptr(z_sum_ps), _ptr(ratio),
+                                           C.byref(npart), _ptr(pdg), _ptr(st), _ptr(mo), _ptr(p4), _ptr(aux))
         n = npart.value
         return acc, pdg[:n].copy(), st[:n].copy(), mo[:n].copy(), p4[:n].copy(), aux
 

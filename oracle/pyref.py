@@ -1,7 +1,7 @@
 """ctypes loader for oracle/_ref/libupcref.so: the REFERENCE's own src/UpcCrossSection.cpp,
-src/UpcTwoPhotonDilep.cpp and src/UpcTwoPhotonALP.cpp compiled unmodified against the GSL/ROOT
-shim (oracle/refshim).  TEST INFRASTRUCTURE ONLY.  One instance per process (the reference keeps
-its splines in file-scope globals)."""
+src/UpcTwoPhotonDilep.cpp, src/UpcTwoPhotonALP.cpp, src/UpcGenerator.cpp and include/UpcSampler.h compiled
+unmodified against the GSL/ROOT shim (oracle/refshim).  TEST INFRASTRUCTURE ONLY.  One instance per process (the
+reference keeps its splines in file-scope globals)."""
 import ctypes as C
 import os
 
@@ -61,3 +61,124 @@ class Reference:
         ratio = np.zeros((self.P.ny, self.P.nm))
         tot = self.L.upcref_grid_and_fold(nthreads, directory.encode(), cs.ctypes.data, ratio.ctypes.data)
         return cs, ratio, tot
+
+
+class RefGenerator:
+    """The reference's own UpcGenerator, driven as main.cpp drives it (setParFile, configGeneratorFromFile, init,
+    generateEvent), with the two-photon luminosity cache injected: the table is placed into the shim's in-memory
+    twoPhotonLumi[Pol].root, so UpcCrossSection::prepareTwoPhotonLumi takes its "found pre-calculated luminosity"
+    branch (src/UpcCrossSection.cpp:481-491) and calcNucCrossSectionYM folds THAT table.  Everything after it --
+    fillCrossSectionZM, the UpcSampler constructors, generateEvent with getPairMomentum / getPhotonPt, pair / single
+    production, the uniform decay, the cuts, the HepMC writer -- is the reference's code with its own MT19937 streams.
+
+    par_text: parameters.in text (BREAKUP_MODE only matters to the lumi table, which is injected: pass 1 to skip the
+    minute-long prepareBreakupProb).  lumi / (lumi_s, lumi_p): [nm][ny] tables, already multiplied by dm * dy."""
+
+    def __init__(self, par_text, workdir, lumi=None, lumi_s=None, lumi_p=None, grid=None):
+        self.L = L = C.CDLL(SO)
+        d, i, p, lg = C.c_double, C.c_int, C.c_void_p, C.c_long
+        L.upcrefgen_put_lumi.argtypes = [C.c_char_p, i, i, i, d, d, d, d, p, p, p]
+        L.upcrefgen_create.argtypes = [C.c_char_p, C.c_char_p]
+        L.upcrefgen_totcs.restype = d
+        L.upcrefgen_grid.argtypes = [C.POINTER(i)] * 3
+        L.upcrefgen_cs.argtypes = [p, p]
+        L.upcrefgen_cdfs.argtypes = [p, p]
+        L.upcrefgen_generate.restype = lg
+        L.upcrefgen_generate.argtypes = [lg, p, p, p, p, p]
+        L.upcrefgen_sample_ym.argtypes = [lg, p, p, p, p]
+        L.upcrefgen_sample_z.argtypes = [i, lg, p]
+        L.upcrefgen_photon_pt.argtypes = [d, lg, p]
+        L.upcrefgen_tape.argtypes = [i]
+        L.upcrefgen_tape_read.restype = lg
+        L.upcrefgen_tape_read.argtypes = [p, p, lg]
+        L.upcrefgen_generate_events_hepmc.argtypes = [lg]
+        L.upcrefgen_generate_events_tree.restype = lg
+        L.upcrefgen_generate_events_tree.argtypes = [lg, p, lg]
+        os.makedirs(workdir, exist_ok=True)
+        self.workdir = workdir
+        parfile = os.path.join(workdir, "parameters.in")
+        with open(parfile, "w") as fh:
+            fh.write(par_text)
+        nm, ny, mmin, mmax, ymin, ymax = grid
+        pol = lumi is None
+        tabs = [None if t is None else np.ascontiguousarray(t, float) for t in (lumi, lumi_s, lumi_p)]
+        for t in tabs:
+            assert t is None or t.shape == (nm, ny)
+        ptr = [None if t is None else t.ctypes.data for t in tabs]
+        assert L.upcrefgen_put_lumi(workdir.encode(), int(pol), nm, ny, mmin, mmax, ymin, ymax, *ptr) == 0
+        assert L.upcrefgen_create(parfile.encode(), workdir.encode()) == 0
+        a, b, c = i(), i(), i()
+        L.upcrefgen_grid(C.byref(a), C.byref(b), C.byref(c))
+        self.nm, self.ny, self.nz = a.value, b.value, c.value
+        assert (self.nm, self.ny) == (nm, ny), "grid of the injected table != grid the reference derived"
+
+    def totcs(self):
+        return self.L.upcrefgen_totcs()
+
+    def cs(self):
+        cs, ratio = np.zeros((self.ny, self.nm)), np.zeros((self.ny, self.nm))
+        self.L.upcrefgen_cs(cs.ctypes.data, ratio.ctypes.data)
+        return cs, ratio
+
+    def cdfs(self, with_z=True):
+        s2 = np.zeros(self.ny * self.nm + 1)
+        sz = np.zeros((self.nm, self.nz + 1)) if with_z else None
+        self.L.upcrefgen_cdfs(s2.ctypes.data, None if sz is None else sz.ctypes.data)
+        return s2, sz
+
+    def generate(self, n):
+        npart = np.zeros(n, np.int32)
+        pdg = np.zeros((n, 4), np.int32); st = np.zeros((n, 4), np.int32); mo = np.zeros((n, 4), np.int32)
+        p4 = np.zeros((n, 4, 4))
+        acc = self.L.upcrefgen_generate(n, npart.ctypes.data, pdg.ctypes.data, st.ctypes.data, mo.ctypes.data,
+                                        p4.ctypes.data)
+        return dict(npart=npart, pdg=pdg, status=st, mother=mo, p4=p4, n_accepted=acc)
+
+    def sample_ym(self, n):
+        y, m = np.zeros(n), np.zeros(n)
+        yb, mb = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        self.L.upcrefgen_sample_ym(n, y.ctypes.data, m.ctypes.data, yb.ctypes.data, mb.ctypes.data)
+        return y, m, yb, mb
+
+    def sample_z(self, mbin, n):
+        z = np.zeros(n)
+        self.L.upcrefgen_sample_z(mbin, n, z.ctypes.data)
+        return z
+
+    def photon_pt(self, e, n):
+        pt = np.zeros(n)
+        self.L.upcrefgen_photon_pt(float(e), n, pt.ctypes.data)
+        return pt
+
+    def tape(self, on):
+        self.L.upcrefgen_tape(int(on))
+
+    def tape_read(self):
+        n = self.L.upcrefgen_tape_read(None, None, 0)
+        v, t = np.zeros(n), np.zeros(n, np.int32)
+        self.L.upcrefgen_tape_read(v.ctypes.data, t.ctypes.data, n)
+        return v, t
+
+    def generate_events_hepmc(self, n_events):
+        """UpcGenerator::generateEvents with USE_HEPMC_OUTPUT: returns the text of events.hepmc."""
+        cwd = os.getcwd()
+        os.chdir(self.workdir)
+        try:
+            self.L.upcrefgen_generate_events_hepmc(n_events)
+            with open("events.hepmc") as fh:
+                return fh.read()
+        finally:
+            os.chdir(cwd)
+
+    def generate_events_tree(self, n_events):
+        """... with USE_ROOT_OUTPUT: the rows filled into the `particles` tree, [n_rows][9] in branch order
+        (eventNumber, pdgCode, particleID, statusID, motherID, px, py, pz, e)."""
+        cwd = os.getcwd()
+        os.chdir(self.workdir)
+        try:
+            cap = int(n_events) * 4 + 16
+            out = np.zeros((cap, 9))
+            rows = self.L.upcrefgen_generate_events_tree(n_events, out.ctypes.data, cap)
+            return out[:rows]
+        finally:
+            os.chdir(cwd)

@@ -5,6 +5,7 @@
 #include <fcntl.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -12,6 +13,8 @@
 #include <random>
 #include <string>
 #include <vector>
+
+#include "../shim_tape.h"
 
 extern "C" double upco_tmath_besselK1(double x);
 
@@ -63,7 +66,12 @@ class TRandom
  public:
   virtual ~TRandom() {}
   virtual void SetSeed(unsigned long s = 0) { rng.seed(s); }
-  virtual double Rndm() { return (rng() >> 11) * (1.0 / 9007199254740992.0); }
+  virtual double Rndm()
+  {
+    const double u = (rng() >> 11) * (1.0 / 9007199254740992.0);
+    shim_tape().put(u, 0);
+    return u;
+  }
   double Uniform(double a, double b) { return a + (b - a) * Rndm(); }
   double Uniform(double b = 1) { return b * Rndm(); }
   std::mt19937_64 rng{4357};
@@ -77,12 +85,19 @@ class TObject
   virtual ~TObject() {}
 };
 
-class TH1D : public TObject
+class TH1 : public TObject
+{
+ public:
+  static void AddDirectory(bool) {}
+};
+
+class TH1D : public TH1
 {
  public:
   TH1D() = default;
   TH1D(const char* name, const char*, int nb, double lo, double hi) : name_(name), n(nb), xlo(lo), xhi(hi), c(nb + 2, 0.) {}
   void SetDirectory(void*) {}
+  int Write() { return 0; }
   void SetBinContent(int bin, double v) { c[bin] = v; integral.clear(); }
   double GetBinContent(int bin) const { return c[bin]; }
   int GetNbinsX() const { return n; }
@@ -115,6 +130,20 @@ class TH2D : public TObject
 {
  public:
   TH2D(const char* name, const char*, int nx_, double, double, int ny_, double, double) : name_(name), nx(nx_), ny(ny_), c((size_t)(nx_ + 2) * (ny_ + 2), 0.) {}
+  TH2D(const char* name, const char*, int nx_, const double*, int ny_, const double*) : name_(name), nx(nx_), ny(ny_), c((size_t)(nx_ + 2) * (ny_ + 2), 0.) {}
+  // debug-only projections of UpcGenerator::generateEvents (src/UpcGenerator.cpp:902-908)
+  TH1D* ProjectionX() const
+  {
+    auto* h = new TH1D((name_ + "_px").c_str(), "", nx, 0., 1.);
+    for (int ix = 0; ix <= nx + 1; ix++) { double a = 0; for (int iy = 0; iy <= ny + 1; iy++) a += GetBinContent(ix, iy); h->SetBinContent(ix, a); }
+    return h;
+  }
+  TH1D* ProjectionY() const
+  {
+    auto* h = new TH1D((name_ + "_py").c_str(), "", ny, 0., 1.);
+    for (int iy = 0; iy <= ny + 1; iy++) { double a = 0; for (int ix = 0; ix <= nx + 1; ix++) a += GetBinContent(ix, iy); h->SetBinContent(iy, a); }
+    return h;
+  }
   void SetBinContent(int ix, int iy, double v) { c[(size_t)iy * (nx + 2) + ix] = v; }
   double GetBinContent(int ix, int iy) const { return c[(size_t)iy * (nx + 2) + ix]; }
   TObject* Clone(const char* newname) const { auto* h = new TH2D(*this); h->name_ = newname; return h; }
@@ -175,20 +204,163 @@ namespace ROOT
 inline void EnableThreadSafety() {}
 }
 
+// TVector3 / TLorentzVector with ROOT's arithmetic (math/physics/src/TVector3.cxx, TLorentzVector.cxx), the members the
+// reference's event stage calls (src/UpcGenerator.cpp:388-423, :526-587, :770-775; src/UpcCrossSection.cpp:1053-1074)
+class TVector3
+{
+ public:
+  TVector3() = default;
+  TVector3(double x, double y, double z) : fX(x), fY(y), fZ(z) {}
+  double X() const { return fX; }
+  double Y() const { return fY; }
+  double Z() const { return fZ; }
+  double Mag2() const { return fX * fX + fY * fY + fZ * fZ; }
+  double Mag() const { return std::sqrt(Mag2()); }
+  double Perp() const { return std::sqrt(fX * fX + fY * fY); }
+  double CosTheta() const { const double ptot = Mag(); return ptot == 0.0 ? 1.0 : fZ / ptot; }
+  double PseudoRapidity() const
+  {
+    const double cosTheta = CosTheta();
+    if (cosTheta * cosTheta < 1) return -0.5 * std::log((1.0 - cosTheta) / (1.0 + cosTheta));
+    if (fZ == 0) return 0;
+    if (fZ > 0) return 10e10;
+    return -10e10;
+  }
+  void SetMagThetaPhi(double mag, double theta, double phi)
+  {
+    const double amag = std::fabs(mag);
+    fX = amag * std::sin(theta) * std::cos(phi);
+    fY = amag * std::sin(theta) * std::sin(phi);
+    fZ = amag * std::cos(theta);
+  }
+  TVector3 Unit() const
+  {
+    const double tot2 = Mag2();
+    const double tot = (tot2 > 0) ? 1.0 / std::sqrt(tot2) : 1.0;
+    return TVector3(fX * tot, fY * tot, fZ * tot);
+  }
+  TVector3 operator-() const { return TVector3(-fX, -fY, -fZ); }
+  void RotateUz(const TVector3& nu)
+  {
+    const double u1 = nu.fX, u2 = nu.fY, u3 = nu.fZ;
+    double up = u1 * u1 + u2 * u2;
+    if (up) {
+      up = std::sqrt(up);
+      const double px = fX, py = fY, pz = fZ;
+      fX = (u1 * u3 * px - u2 * py + u1 * up * pz) / up;
+      fY = (u2 * u3 * px + u1 * py + u2 * up * pz) / up;
+      fZ = (u3 * u3 * px - px + u3 * up * pz) / up;
+    } else if (u3 < 0.) {
+      fX = -fX;
+      fZ = -fZ;
+    }
+  }
+  double fX{0}, fY{0}, fZ{0};
+};
+
 class TLorentzVector
 {
  public:
-  void SetPxPyPzE(double x, double y, double z, double e) { fX = x; fY = y; fZ = z; fE = e; }
-  double Px() const { return fX; }
-  double Py() const { return fY; }
-  double Pz() const { return fZ; }
+  void SetPxPyPzE(double x, double y, double z, double e) { fP = TVector3(x, y, z); fE = e; }
+  void SetXYZT(double x, double y, double z, double t) { SetPxPyPzE(x, y, z, t); }
+  void SetXYZM(double x, double y, double z, double m)
+  {
+    if (m >= 0) SetXYZT(x, y, z, std::sqrt(x * x + y * y + z * z + m * m));
+    else SetXYZT(x, y, z, std::sqrt(std::max((x * x + y * y + z * z - m * m), 0.)));
+  }
+  void SetVectM(const TVector3& v, double m) { SetXYZM(v.X(), v.Y(), v.Z(), m); }
+  double Px() const { return fP.fX; }
+  double Py() const { return fP.fY; }
+  double Pz() const { return fP.fZ; }
   double E() const { return fE; }
-  double fX{0}, fY{0}, fZ{0}, fE{0};
+  double X() const { return fP.fX; }
+  double Y() const { return fP.fY; }
+  double Z() const { return fP.fZ; }
+  double T() const { return fE; }
+  TVector3 Vect() const { return fP; }
+  double Mag2() const { return fE * fE - fP.Mag2(); }
+  double Mag() const { const double mm = Mag2(); return mm < 0.0 ? -std::sqrt(-mm) : std::sqrt(mm); }
+  double M() const { return Mag(); }
+  double Pt() const { return fP.Perp(); }
+  double Eta() const { return fP.PseudoRapidity(); }
+  TVector3 BoostVector() const { return TVector3(X() / T(), Y() / T(), Z() / T()); }
+  void Boost(const TVector3& b) { Boost(b.X(), b.Y(), b.Z()); }
+  void Boost(double bx, double by, double bz)
+  {
+    const double b2 = bx * bx + by * by + bz * bz;
+    const double gamma = 1.0 / std::sqrt(1.0 - b2);
+    const double bp = bx * X() + by * Y() + bz * Z();
+    const double gamma2 = b2 > 0 ? (gamma - 1.0) / b2 : 0.0;
+    const double nx = X() + gamma2 * bp * bx + gamma * bx * T();
+    const double ny = Y() + gamma2 * bp * by + gamma * by * T();
+    const double nz = Z() + gamma2 * bp * bz + gamma * bz * T();
+    const double nt = gamma * (T() + bp);
+    fP = TVector3(nx, ny, nz);
+    fE = nt;
+  }
+  void RotateUz(const TVector3& nu) { fP.RotateUz(nu); }
+  TVector3 fP;
+  double fE{0};
 };
 class TF1 {};
 class TGraph {};
 class TGraph2D {};
 class TSpline3 {};
-class TTree {};
-class TClonesArray {};
-class TParticle {};
+// the output tree of generateEvents (src/UpcGenerator.cpp:842-857): branch addresses are recorded and every Fill()
+// appends the current values, so that tests can read back what the reference would have written to events.root
+class TTree
+{
+ public:
+  TTree(const char* = "", const char* = "") {}
+  struct Br { std::string name; void* addr; char type; };
+  void Branch(const char* name, void* addr, const char* leaflist)
+  {
+    std::string l(leaflist);
+    br.push_back(Br{name, addr, l.empty() ? 'D' : l.back()});
+    cols.emplace_back();
+  }
+  int Fill()
+  {
+    for (size_t i = 0; i < br.size(); i++) {
+      // "/I" leaves are 32-bit ints (eventNumber/I is bound to a long: ROOT reads its low 4 bytes -- Q10)
+      cols[i].push_back(br[i].type == 'I' ? (double)*(int*)br[i].addr : *(double*)br[i].addr);
+    }
+    return 1;
+  }
+  void SetAutoSave(long long) {}
+  int Write() { return 0; }
+  std::vector<Br> br;
+  std::vector<std::vector<double>> cols;
+};
+class TClonesArray
+{
+ public:
+  TClonesArray(const char* = "") {}
+  int GetEntriesFast() const { return 0; }
+  TObject* At(int) const { return nullptr; }
+};
+class TParticle : public TObject
+{
+ public:
+  TParticle() = default;
+  TParticle(int pdg, int status, int mother1, int mother2, int daughter1, int daughter2, double px, double py, double pz,
+            double etot, double vx, double vy, double vz, double time)
+      : fPdgCode(pdg), fStatusCode(status), fPx(px), fPy(py), fPz(pz), fE(etot)
+  {
+    fMother[0] = mother1; fMother[1] = mother2; fDaughter[0] = daughter1; fDaughter[1] = daughter2;
+    (void)vx; (void)vy; (void)vz; (void)time;
+  }
+  int GetPdgCode() const { return fPdgCode; }
+  int GetStatusCode() const { return fStatusCode; }
+  int GetFirstMother() const { return fMother[0]; }
+  int GetFirstDaughter() const { return fDaughter[0]; }
+  int GetLastDaughter() const { return fDaughter[1]; }
+  double Px() const { return fPx; }
+  double Py() const { return fPy; }
+  double Pz() const { return fPz; }
+  double Energy() const { return fE; }
+  void Momentum(TLorentzVector& v) const { v.SetPxPyPzE(fPx, fPy, fPz, fE); }
+  void Print() const {}
+  int fPdgCode{0}, fStatusCode{0}, fMother[2]{0, 0}, fDaughter[2]{0, 0};
+  double fPx{0}, fPy{0}, fPz{0}, fE{0};
+};

@@ -1636,9 +1636,12 @@ static double lv_eta(const lv* v)
    dependent); the product uses the key's lower edge + 0.5 MeV. */
 static double key_energy(int key) { return (key + 0.5) * 1e-3; }
 
-int upco_generate_event(upco_ctx* c, uint64_t seed, uint64_t cand, const double* cs_sum,
-                        const double* z_sum, const double* z_sum_ps, const double* ratio, int* npart,
-                        int* pdg, int* status, int* mother, double* p4, double* aux)
+/* generateEvent with the twelve uniforms of the slot map injected (u[2 j], u[2 j + 1] = block j of SURVEY.md appendix
+   B): the form the tests use to replay an event of the reference's own generateEvent (oracle/refshim/gen_capi.cpp
+   records the uniforms it drew) */
+int upco_generate_event_u(upco_ctx* c, const double* u, const double* cs_sum,
+                          const double* z_sum, const double* z_sum_ps, const double* ratio, int* npart,
+                          int* pdg, int* status, int* mother, double* p4, double* aux)
 {
   const upco_params* p = &c->p;
   const int nm = p->nm, ny = p->ny, nz = p->nz;
@@ -1649,8 +1652,6 @@ int upco_generate_event(upco_ctx* c, uint64_t seed, uint64_t cand, const double*
   for (int i = 0; i <= nm; i++) me[i] = p->mmin + dm * i; /* UpcGenerator.cpp:675-682 */
   for (int i = 0; i <= nz; i++) ze[i] = p->zmin + dz * i;
   for (int i = 0; i <= ny; i++) ye[i] = p->ymin + dy * i;
-  double u[12];
-  for (uint32_t b = 0; b < 6; b++) upco_philox(seed, cand, b, &u[2 * b], &u[2 * b + 1]);
   int n = 0, accepted = 1;
   lv parts[4];
 
@@ -1761,4 +1762,14 @@ int upco_generate_event(upco_ctx* c, uint64_t seed, uint64_t cand, const double*
   if (aux) { aux[0] = yPair; aux[1] = mPair; aux[2] = cost; aux[3] = pt1; aux[4] = pt2; }
   free(ye); free(me); free(ze);
   return accepted;
+}
+
+/* the same with the uniforms of candidate `cand` of the Philox4x32-10 stream keyed by `seed` (the GPU's slot map) */
+int upco_generate_event(upco_ctx* c, uint64_t seed, uint64_t cand, const double* cs_sum,
+                        const double* z_sum, const double* z_sum_ps, const double* ratio, int* npart,
+                        int* pdg, int* status, int* mother, double* p4, double* aux)
+{
+  double u[12];
+  for (uint32_t b = 0; b < 6; b++) upco_philox(seed, cand, b, &u[2 * b], &u[2 * b + 1]);
+  return upco_generate_event_u(c, u, cs_sum, z_sum, z_sum_ps, ratio, npart, pdg, status, mother, p4, aux);
 }

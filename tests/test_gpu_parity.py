@@ -519,7 +519,8 @@ def test_sharded_fill_equals_monolithic_form_factor(get_gpu):
     world = 3
     parts = []
     for r in range(world):
-        g.fill_lumi_shard(r, world)
+        g.fill_lumi_shard(r, world)   # queued, not waited for
+        g.fill_stats()                # ... collected here
         ptr, n = g.lumi_shard_buffer(0)
         host = np.zeros(n)
         assert cudart.cudaMemcpy(C.c_void_p(host.ctypes.data), C.c_void_p(ptr), C.c_size_t(n * 8), 2) == 0

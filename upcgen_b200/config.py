@@ -244,6 +244,11 @@ CONFIG_OVERRIDES = {
 }
 
 
+def config_text(name: str, extra: str = "") -> str:
+    """The parameters.in text of cfg1..cfg5 (+ extra lines): what `named_config` parses."""
+    return _BASE + CONFIG_OVERRIDES[name] + extra
+
+
 def named_config(name: str, extra: str = "") -> UpcParams:
     """One of cfg1..cfg5, optionally with extra 'KEY value' lines appended (later wins)."""
     return UpcParams.from_text(_BASE + CONFIG_OVERRIDES[name] + extra).init()

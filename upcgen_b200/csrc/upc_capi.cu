@@ -1,4 +1,5 @@
 // upc_capi.cu -- the extern "C" boundary declared in include/upcgpu.h.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -12,6 +13,14 @@ static thread_local std::string g_create_err;
 #define CHECK_CTX(c)                 \
   if (!(c)) return UPCGPU_EINVAL;    \
   cudaSetDevice((c)->device);
+
+// entry points that read results on the host (or free / reuse the fill's scratch) first collect a queued fill
+#define CHECK_CTX_SYNC(c)                         \
+  CHECK_CTX(c);                                   \
+  if ((c)->fill_pending) {                        \
+    int _rc = finish_fill(c);                     \
+    if (_rc) return _rc;                          \
+  }
 
 extern "C" {
 
@@ -42,6 +51,7 @@ int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out)
   if (!c) { g_create_err = "upcgpu_create: out of memory"; return UPCGPU_EINVAL; }
   c->p = p;
   c->device = device;
+  if (const char* e = std::getenv("UPCGPU_TEST_HEAD_POOL")) c->test_head_pool = std::atoll(e);
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     g_create_err = std::string("upcgpu_create: ") + cudaGetErrorString(cudaGetLastError());
@@ -56,8 +66,10 @@ void upcgpu_destroy(upcgpu_ctx* c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->gaa_x); cudaFree(c->gaa_y); cudaFree(c->gaa_c); cudaFree(c->ta_y); cudaFree(c->ta_c);
   cudaFree(c->ff_y); cudaFree(c->ff_c); cudaFree(c->bk_y); cudaFree(c->bk_c);
+  if (c->h_scal) cudaFreeHost(c->h_scal);
   cudaFree(c->gaa_seg); cudaFree(c->ff_seg); cudaFree(c->bk_seg); cudaFree(c->d_scal); cudaFree(c->bk_table); cudaFree(c->fold_ws);
   for (int w = 0; w < 3; w++) { cudaFree(c->lumi[w]); cudaFree(c->shard[w]); cudaFree(c->gather[w]); }
   cudaFree(c->cs); cudaFree(c->ratio); cudaFree(c->sum2d); cudaFree(c->sumz); cudaFree(c->sumz_ps);
@@ -66,6 +78,7 @@ void upcgpu_destroy(upcgpu_ctx* c)
   free_lumi_scratch(c);
   for (int i = 0; i < 2; ++i) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   for (int i = 0; i < 4; ++i) if (c->aux_ev[i]) cudaEventDestroy(c->aux_ev[i]);
+  for (int i = 0; i < 2; ++i) if (c->fill_ev[i]) cudaEventDestroy(c->fill_ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -103,7 +116,7 @@ int upcgpu_invalidate_tables(upcgpu_ctx* c)
 
 int upcgpu_fp64_peak(upcgpu_ctx* c, int iters, double* tflops, double* ms)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   return fp64_peak(c, iters, tflops, ms);
 }
 
@@ -116,7 +129,7 @@ int upcgpu_get_table_info(const upcgpu_ctx* c, upcgpu_table_info* info)
 
 int upcgpu_get_table(upcgpu_ctx* c, int which, size_t i0, size_t n, double* x, double* y, double* cc)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!c->tables_ready) { c->err = "get_table: tables not prepared"; return UPCGPU_EINVAL; }
   const double *dy = nullptr, *dc = nullptr;
   size_t size = 0;
@@ -146,7 +159,7 @@ int upcgpu_get_table(upcgpu_ctx* c, int which, size_t i0, size_t n, double* x, d
 
 int upcgpu_eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, double* out)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!c->tables_ready || !x || !out) { c->err = "eval_table: bad state/argument"; return UPCGPU_EINVAL; }
   if (n == 0) return UPCGPU_OK;
   return eval_table(c, which, x, n, out);
@@ -154,7 +167,7 @@ int upcgpu_eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, doubl
 
 int upcgpu_breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!c->tables_ready || !c->bk_seg) { c->err = "breakup_raw: breakup table not prepared (BREAKUP_MODE 1?)"; return UPCGPU_EINVAL; }
   if (n == 0) return UPCGPU_OK;
   return breakup_raw(c, b, mode, n, out);
@@ -162,7 +175,7 @@ int upcgpu_breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, doubl
 
 int upcgpu_flux_point(upcgpu_ctx* c, const double* b, const double* k, size_t n, double* out)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!b || !k || !out) return UPCGPU_EINVAL;
   if (n == 0) return UPCGPU_OK;
   return flux_points(c, b, k, n, 1, out, nullptr);
@@ -170,7 +183,7 @@ int upcgpu_flux_point(upcgpu_ctx* c, const double* b, const double* k, size_t n,
 
 int upcgpu_flux_form(upcgpu_ctx* c, const double* b, const double* k, size_t n, double* out, int* neval)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!b || !k || !out) return UPCGPU_EINVAL;
   if (n == 0) return UPCGPU_OK;
   return flux_points(c, b, k, n, 0, out, neval);
@@ -179,35 +192,38 @@ int upcgpu_flux_form(upcgpu_ctx* c, const double* b, const double* k, size_t n, 
 int upcgpu_fill_lumi_shard(upcgpu_ctx* c, int shard, int nshards)
 {
   CHECK_CTX(c);
-  return fill_lumi_rows(c, shard, nshards);
+  return fill_lumi_rows(c, shard, nshards, /*wait=*/false);
 }
 
 int upcgpu_lumi_download(upcgpu_ctx* c, int which, double* host)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (which < 0 || which > 2 || !host || !c->lumi[which]) { c->err = "lumi_download: table not available"; return UPCGPU_EINVAL; }
-  UPC_CUDA(c, cudaMemcpy(host, c->lumi[which], (size_t)c->p.nm * c->p.ny * sizeof(double), cudaMemcpyDeviceToHost));
+  // on the context's stream: upcgpu_lumi_unpack and the fill are queued there and do not wait
+  UPC_CUDA(c, cudaMemcpyAsync(host, c->lumi[which], (size_t)c->p.nm * c->p.ny * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   return UPCGPU_OK;
 }
 
 int upcgpu_lumi_upload(upcgpu_ctx* c, int which, const double* host)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (which < 0 || which > 2 || !host) return UPCGPU_EINVAL;
   if ((which == 0) == (c->p.use_pol != 0)) { c->err = "lumi_upload: table kind does not match use_pol"; return UPCGPU_EINVAL; }
   int rc = ensure_lumi_buffers(c, 0);
   if (rc) return rc;
-  UPC_CUDA(c, cudaMemcpy(c->lumi[which], host, (size_t)c->p.nm * c->p.ny * sizeof(double), cudaMemcpyHostToDevice));
+  UPC_CUDA(c, cudaMemcpyAsync(c->lumi[which], host, (size_t)c->p.nm * c->p.ny * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   c->lumi_ready = true;
   return UPCGPU_OK;
 }
 
 int upcgpu_fill_lumi(upcgpu_ctx* c, double* lumi, double* lumi_s, double* lumi_p)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   int rc = upcgpu_prepare_tables(c);
   if (rc) return rc;
-  rc = fill_lumi_rows(c, 0, 1);
+  rc = fill_lumi_rows(c, 0, 1, /*wait=*/true);
   if (rc) return rc;
   if (!c->p.use_pol) {
     if (lumi) rc = upcgpu_lumi_download(c, 0, lumi);
@@ -220,15 +236,16 @@ int upcgpu_fill_lumi(upcgpu_ctx* c, double* lumi, double* lumi_s, double* lumi_p
 
 int upcgpu_lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* out, double* out_s, double* out_p)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!M || !Y) return UPCGPU_EINVAL;
   if (n == 0) return UPCGPU_OK;
   return lumi_cells(c, M, Y, n, out, out_s, out_p);
 }
 
-int upcgpu_get_fill_stats(const upcgpu_ctx* c, upcgpu_fill_stats* st)
+int upcgpu_get_fill_stats(upcgpu_ctx* c, upcgpu_fill_stats* st)
 {
-  if (!c || !st) return UPCGPU_EINVAL;
+  if (!st) return UPCGPU_EINVAL;
+  CHECK_CTX_SYNC(c);
   *st = c->stats;
   return UPCGPU_OK;
 }
@@ -277,13 +294,13 @@ int upcgpu_fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, c
 
 int upcgpu_sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   return sampler_build(c, cs, cszm, cszm_s, cszm_ps);
 }
 
 int upcgpu_sampler_get_cdf(upcgpu_ctx* c, double* sum2d, double* sumz, double* sumz_ps)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!c->sampler_ready) { c->err = "sampler_get_cdf: samplers not built"; return UPCGPU_EINVAL; }
   const size_t n = (size_t)c->p.nm * c->p.ny, nsz = (size_t)c->p.nm * (c->p.nz + 1);
   if (sum2d) UPC_CUDA(c, cudaMemcpy(sum2d, c->sum2d, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost));
@@ -294,7 +311,7 @@ int upcgpu_sampler_get_cdf(upcgpu_ctx* c, double* sum2d, double* sumz, double* s
 
 int upcgpu_sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int* ybin, int* mbin, double* y, double* m)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!u) return UPCGPU_EINVAL;
   if (n == 0) return UPCGPU_OK;
   return sample_ym(c, u, n, k, ybin, mbin, y, m);
@@ -302,7 +319,7 @@ int upcgpu_sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int
 
 int upcgpu_sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, double* z)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!u || !mbin || !z) return UPCGPU_EINVAL;
   if (n == 0) return UPCGPU_OK;
   return sample_z(c, mbin, u, n, ps, z);
@@ -310,7 +327,7 @@ int upcgpu_sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, i
 
 int upcgpu_hist_pdf_init(upcgpu_ctx* c, const double* bins, size_t n, double* sum)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!bins || !sum || n == 0) return UPCGPU_EINVAL;
   return hist_pdf_init(c, bins, n, sum);
 }
@@ -318,7 +335,7 @@ int upcgpu_hist_pdf_init(upcgpu_ctx* c, const double* bins, size_t n, double* su
 int upcgpu_hist_sample2d(upcgpu_ctx* c, const double* sum, int nx, int ny, const double* xe, const double* ye,
                          const double* u, size_t n, long long* k, double* x, double* y)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!sum || !xe || !ye || !u || !x || !y || nx < 1 || ny < 1) return UPCGPU_EINVAL;
   if (n == 0) return UPCGPU_OK;
   return hist_sample2d(c, sum, nx, ny, xe, ye, u, n, k, x, y);
@@ -327,7 +344,7 @@ int upcgpu_hist_sample2d(upcgpu_ctx* c, const double* sum, int nx, int ny, const
 int upcgpu_hist_sample1d(upcgpu_ctx* c, const double* sum, int n, const double* edges, const double* u, size_t nsamp,
                          double* x)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!sum || !edges || !u || !x || n < 1) return UPCGPU_EINVAL;
   if (nsamp == 0) return UPCGPU_OK;
   return hist_sample1d(c, sum, n, edges, u, nsamp, x);
@@ -336,14 +353,14 @@ int upcgpu_hist_sample1d(upcgpu_ctx* c, const double* sum, int n, const double* 
 int upcgpu_generate(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, int* npart, int* pdg,
                     int* status, int* mother, double* p4, double* aux, uint64_t* n_accepted)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
   return generate(c, seed, first_candidate, n_candidates, npart, pdg, status, mother, p4, aux, n_accepted, false);
 }
 
 int upcgpu_generate_device(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, uint64_t* n_accepted)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
   return generate(c, seed, first_candidate, n_candidates, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_accepted,
                   true);
@@ -351,7 +368,7 @@ int upcgpu_generate_device(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidat
 
 int upcgpu_photon_pt_cdf(upcgpu_ctx* c, double e_phot, double* cdf)
 {
-  CHECK_CTX(c);
+  CHECK_CTX_SYNC(c);
   if (!cdf) return UPCGPU_EINVAL;
   return photon_pt_cdf(c, e_phot, cdf);
 }

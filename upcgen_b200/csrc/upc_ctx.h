@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -50,6 +52,7 @@ struct upcgpu_ctx_impl {
                              // function-local statics, src/UpcCrossSection.cpp:853-969)
   SplineSeg *gaa_seg = nullptr, *ff_seg = nullptr, *bk_seg = nullptr;
   double* d_scal = nullptr;  // small device scratch for scalars
+  double* h_scal = nullptr;  // its pinned host mirror (one asynchronous read-back per table stage)
   DevTables tab{};
 
   // luminosity tables, full [nm][ny], index 0 unpol, 1 scalar, 2 pseudoscalar
@@ -73,6 +76,14 @@ struct upcgpu_ctx_impl {
   // flux-row scratch of the lumi fill (allocated once, reused by every fill)
   void* slab = nullptr;
   int slab_max_m = 0;
+  // A fill is queued on the stream and collected later (finish_fill): number of slabs whose reports are pending
+  int fill_pending = 0;
+  cudaEvent_t fill_ev[2] = {nullptr, nullptr};
+  // integral count of a (shard, nshards, first local row, rows) slab: a pure function of the parameter block, read back
+  // from the device the first time and reused to size the head kernel's grid afterwards
+  std::map<std::array<int, 4>, long long> n_items_cache;
+  bool func_attrs_set = false;   // cudaFuncSetAttribute done on this context's device
+  long long test_head_pool = 0;  // UPCGPU_TEST_HEAD_POOL: slots of the hand-over state pool (tests of the fallback path)
 };
 
 }  // namespace upc

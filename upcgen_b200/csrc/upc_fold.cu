@@ -103,9 +103,13 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
       cur = nblk;
     }
     UPC_CUDA(c, cudaMemcpyAsync(&total, outb, sizeof(double), cudaMemcpyDeviceToHost, st));
-    UPC_CUDA(c, cudaStreamSynchronize(st));
+    UPC_CUDA(c, cudaStreamSynchronize(st));  // the one host wait of a sharded step: a queued fill is collected here
   }
   UPC_CUDA(c, cudaGetLastError());
+  if (c->fill_pending) {
+    const int frc = finish_fill(c);
+    if (frc) return frc;
+  }
   if (totcs_mb) *totcs_mb = total * 1e-6;  // :696
   if (cs) UPC_CUDA(c, cudaMemcpy(cs, c->cs, n * sizeof(double), cudaMemcpyDeviceToHost));
   if (ratio && p.use_pol) UPC_CUDA(c, cudaMemcpy(ratio, c->ratio, n * sizeof(double), cudaMemcpyDeviceToHost));

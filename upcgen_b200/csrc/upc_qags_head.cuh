@@ -73,6 +73,7 @@ struct HeadState {
 };
 static_assert(sizeof(HeadState) % 8 == 0, "HeadState layout");
 enum { kHdPositive = 1, kHdExtrapolate = 2, kHdDisallow = 4 };
+constexpr unsigned kHdNoSlot = 0xffffffffu;  // state_slot[item]: no hand-over state (pool full)
 
 template <int CAP, int EPS>
 struct HdSharedT {
@@ -257,12 +258,13 @@ struct HeadCounters {
 // HeadState with the capacity of the reference-sized fallback (CAP = 16, two CTAs per SM).
 template <int CAP, int EPS, bool RESUME>
 __global__ void __launch_bounds__(kHdThreads, RESUME ? 2 : 3)
-k_flux_qags_head(long long n_items, const int* __restrict__ n_order, int n_m, int rows_per_m, int nb,
+k_flux_qags_head(const long long* __restrict__ n_items_dev, const int* __restrict__ n_order, int n_m, int rows_per_m, int nb,
                  const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
                  const unsigned* __restrict__ order, const double* __restrict__ hg, const double* __restrict__ j1h,
                  FluxConsts fc, double* __restrict__ W, int* __restrict__ neval_out, HeadCounters* __restrict__ ctr,
-                 HeadState* __restrict__ state, unsigned char* __restrict__ done_flag,
-                 unsigned char* __restrict__ left_flag)
+                 HeadState* __restrict__ state, unsigned* __restrict__ state_slot, unsigned* __restrict__ slot_ctr,
+                 unsigned state_cap, long long* __restrict__ overflow_items, unsigned long long* __restrict__ overflow_ctr,
+                 unsigned char* __restrict__ done_flag, unsigned char* __restrict__ left_flag)
 {
   using SH = HdSharedT<CAP, EPS>;
   extern __shared__ __align__(16) unsigned char hd_smem[];
@@ -270,17 +272,21 @@ k_flux_qags_head(long long n_items, const int* __restrict__ n_order, int n_m, in
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31;
 
-  const long long t = (long long)blockIdx.x * kHdThreads + tid;
-  const long long n_mine = RESUME ? (long long)*n_order : n_items;
+  // The first pass is launched with one thread per integral (the host sizes the grid from the integral count of
+  // the previous identical fill, the device count is authoritative); the second pass has a grid for a quarter of the
+  // integrals and strides over what the first left.
+  const long long n_mine = RESUME ? (long long)*n_order : *n_items_dev;
+  const long long stride = (long long)gridDim.x * kHdThreads;
   double my_evals = 0, my_made = 0, my_tab = 0;
   unsigned my_err = 0, my_left = 0;
-  if (t < n_mine) {
+#pragma unroll 1
+  for (long long t = (long long)blockIdx.x * kHdThreads + tid; t < n_mine; t += stride) {
     const unsigned q = order[t];
     const unsigned per_ir = (unsigned)nb * (unsigned)n_m;
     const unsigned ir = q / per_ir, rem = q - ir * per_ir;
     const int i = (int)(rem / (unsigned)n_m), iml = (int)(rem - (unsigned)i * (unsigned)n_m);
     const size_t row = (size_t)iml * rows_per_m + ir;
-    const long long item = item_off[row] + i;          // row-major index: done_flag, state (k_flux_qags_rows)
+    const long long item = item_off[row] + i;          // row-major index: done_flag, state_slot (k_flux_qags_rows)
     const RowInfo ri = rows[row];
     const double* g = hg + (size_t)ir * kHdG * n_m + iml;
     const size_t gs = (size_t)n_m;
@@ -312,8 +318,11 @@ k_flux_qags_head(long long n_items, const int* __restrict__ n_order, int n_m, in
     };
     bool go = true;
     int neval_in = 0;
-    if (RESUME) {
-      const HeadState& hs = state[item];
+    // hand-over states live in a pool of state_cap slots (8 % of the integrals of cfg2 need one): slot kHdNoSlot =
+    // the first pass found the pool full, the integral starts again from the first rule
+    unsigned sl = RESUME ? state_slot[item] : kHdNoSlot;
+    if (RESUME && sl != kHdNoSlot) {
+      const HeadState& hs = state[sl];
 #pragma unroll
       for (int k = 0; k < 11; ++k) sh.sc[k][tid] = hs.sc[k];
 #pragma unroll
@@ -350,37 +359,54 @@ k_flux_qags_head(long long n_items, const int* __restrict__ n_order, int n_m, in
       if (done) break;
       go = next_step();
     }
-    done_flag[item] = done ? 1 : 0;
     if (!RESUME) left_flag[t] = done ? 0 : 1;
-    my_made = S.neval - neval_in;
-    if (jt) my_tab = my_made;
+    const double made = S.neval - neval_in;
+    my_made += made;
+    if (jt) my_tab += made;
+    bool to_overflow = false;
     if (done) {
       const double Q = S.result / fc.A;                  // :214
       const double flux = fc.factor * Q * Q / ri.k;      // :215
       W[(size_t)row * nb + i] = flux * (b * w);
       if (neval_out) neval_out[(size_t)row * nb + i] = S.neval;
-      my_evals = S.neval;
+      my_evals += S.neval;
       if (S.ier != 0) my_err++;
     } else {
-      HeadState& hs = state[item];
-#pragma unroll
-      for (int k = 0; k < 11; ++k) hs.sc[k] = sh.sc[k][tid];
-#pragma unroll
-      for (int k = 0; k < EPS; ++k) hs.eps[k] = sh.ep[k][tid];
-#pragma unroll
-      for (int k = 0; k < CAP; ++k) {
-        hs.rl[k] = sh.rl[k][tid]; hs.el[k] = sh.el[k][tid];
-        hs.hp[k] = sh.hp[k][tid]; hs.od[k] = sh.od[k][tid];
+      if (sl == kHdNoSlot) {
+        sl = atomicAdd(slot_ctr, 1u);
+        if (sl >= state_cap) sl = kHdNoSlot;
+        state_slot[item] = sl;
       }
-      hs.size = S.size; hs.nrmax = S.nrmax; hs.i = S.i; hs.maximum_level = S.maximum_level; hs.ktmin = S.ktmin;
-      hs.roundoff_type1 = S.roundoff_type1; hs.roundoff_type2 = S.roundoff_type2; hs.roundoff_type3 = S.roundoff_type3;
-      hs.error_type = S.error_type; hs.error_type2 = S.error_type2; hs.iteration = S.iteration;
-      hs.tab_n = S.tab_n; hs.tab_nres = S.tab_nres;
-      hs.flags = (S.positive_integrand ? kHdPositive : 0) | (S.extrapolate ? kHdExtrapolate : 0) |
-                 (S.disallow_extrapolation ? kHdDisallow : 0);
-      hs.neval = S.neval;
-      my_left++;
+      if (sl != kHdNoSlot) {
+        HeadState& hs = state[sl];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) hs.sc[k] = sh.sc[k][tid];
+#pragma unroll
+        for (int k = 0; k < EPS; ++k) hs.eps[k] = sh.ep[k][tid];
+#pragma unroll
+        for (int k = 0; k < CAP; ++k) {
+          hs.rl[k] = sh.rl[k][tid]; hs.el[k] = sh.el[k][tid];
+          hs.hp[k] = sh.hp[k][tid]; hs.od[k] = sh.od[k][tid];
+        }
+        hs.size = S.size; hs.nrmax = S.nrmax; hs.i = S.i; hs.maximum_level = S.maximum_level; hs.ktmin = S.ktmin;
+        hs.roundoff_type1 = S.roundoff_type1; hs.roundoff_type2 = S.roundoff_type2; hs.roundoff_type3 = S.roundoff_type3;
+        hs.error_type = S.error_type; hs.error_type2 = S.error_type2; hs.iteration = S.iteration;
+        hs.tab_n = S.tab_n; hs.tab_nres = S.tab_nres;
+        hs.flags = (S.positive_integrand ? kHdPositive : 0) | (S.extrapolate ? kHdExtrapolate : 0) |
+                   (S.disallow_extrapolation ? kHdDisallow : 0);
+        hs.neval = S.neval;
+      } else if (RESUME) {
+        // no slot even now: the integral is redone from scratch by the large-workspace pass (k_flux_qags_overflow);
+        // its evaluations here are not counted twice
+        to_overflow = true;
+        overflow_items[atomicAdd(overflow_ctr, 1ull)] = item;
+        my_made -= made;
+        if (jt) my_tab -= made;
+      }
+      if (!to_overflow) my_left++;
     }
+    // done_flag = 0 sends the integral to k_flux_qags_rows, which needs its state
+    done_flag[item] = (done || to_overflow) ? 1 : 0;
   }
   const double ev = warp_sum(my_evals), evm = warp_sum(my_made), evt = warp_sum(my_tab);
   const unsigned er = __reduce_add_sync(0xffffffffu, my_err);

@@ -340,7 +340,8 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
                                          double* __restrict__ W, int* __restrict__ neval_out,
                                          QagsCounters* __restrict__ ctr, long long* __restrict__ overflow_items,
                                          double* __restrict__ gbuf, const HeadState* __restrict__ head_state,
-                                         const int* __restrict__ left_idx, const int* __restrict__ nq_left)
+                                         const unsigned* __restrict__ state_slot, const int* __restrict__ left_idx,
+                                         const int* __restrict__ nq_left)
 {
   const unsigned lane = ltid & 31, warp = ltid >> 5;
   const unsigned lt = (1u << lane) - 1;
@@ -398,7 +399,7 @@ __device__ __forceinline__ void rc_owner(RcGroup& sh, const double* node, const 
             sh.slot_ctx[ltid] = (unsigned char)my_ctx;
             if (pos == 0) sh.ctx_c0[my_ctx] = ri.k * ri.k / fc.g1 / fc.g1;  // w*w/g/g, :187
             // the QAGS state the head left (upc_qags_head.cuh)
-            const HeadState& hs = head_state[item0 + my_i];
+            const HeadState& hs = head_state[state_slot[item0 + my_i]];  // pool slot of this integral
 #pragma unroll
             for (int k = 0; k < 11; ++k) sh.sc[k][ltid] = hs.sc[k];
 #pragma unroll
@@ -556,8 +557,8 @@ __global__ void __launch_bounds__(kRcThreads, 1)
 k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const long long* __restrict__ item_off,
                  FluxConsts fc, DevTables tab, double* __restrict__ W, int* __restrict__ neval_out,
                  QagsCounters* __restrict__ ctr, long long* __restrict__ overflow_items, double* __restrict__ gbuf_all,
-                 const HeadState* __restrict__ head_state, const int* __restrict__ left_idx,
-                 const int* __restrict__ nq_left)
+                 const HeadState* __restrict__ head_state, const unsigned* __restrict__ state_slot,
+                 const int* __restrict__ left_idx, const int* __restrict__ nq_left)
 {
   extern __shared__ __align__(16) unsigned char rc_smem[];
   RcShared& sh = *reinterpret_cast<RcShared*>(rc_smem);
@@ -579,7 +580,7 @@ k_flux_qags_rows(int n_rows, int nb, const RowInfo* __restrict__ rows, const lon
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRcRegsOwner));
     const int grp = tid / kRcSlots;
     rc_owner(sh.g[grp], sh.node, sh.snode, sh.sid, grp, tid - grp * kRcSlots, n_rows, nb, rows, item_off, fc, tab.ff_seg, tab.ff_last, W,
-             neval_out, ctr, overflow_items, gbuf + (size_t)grp * (kRcG * 21), head_state, left_idx, nq_left);
+             neval_out, ctr, overflow_items, gbuf + (size_t)grp * (kRcG * 21), head_state, state_slot, left_idx, nq_left);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRcRegsEval));
     const int etid = tid - 256;

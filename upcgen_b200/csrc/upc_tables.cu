@@ -64,34 +64,47 @@ __global__ void k_ta(double R, double a, const double* rho0p, double* xb, double
   }
 }
 
-// GSL cspline_init for a small table, one thread (gsl_linalg_solve_symm_tridiag, LDL^T)
-__global__ void k_spline_small(const double* xa, const double* ya, int size, double* c)
+// GSL cspline_init for a small table (gsl_linalg_solve_symm_tridiag, LDL^T), one CTA.  The three recurrences are
+// sequential and walked by one thread in GSL's order -- but on shared memory, with the matrix entries and right-hand
+// sides formed in parallel beforehand (a single thread reading global memory at every step took 71 / 173 us for the
+// two 200-knot tables: the critical path of the table stage).
+__global__ void __launch_bounds__(256) k_spline_small(const double* xa, const double* ya, int size, double* c)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ double sx[kNB], sy[kNB], sdiag[kNB], soff[kNB], srhs[kNB], gamma[kNB], alpha[kNB], z[kNB], xs[kNB];
+  const int tid = threadIdx.x;
   const int max_index = size - 1;
   const int N = max_index - 1;
-  double gamma[kNB], z[kNB], alpha[kNB];
-  c[0] = 0.;
-  c[max_index] = 0.;
-  auto diag = [&](int i) { return 2.0 * ((xa[i + 2] - xa[i + 1]) + (xa[i + 1] - xa[i])); };
-  auto off = [&](int i) { return xa[i + 2] - xa[i + 1]; };
-  auto rhs = [&](int i) {
-    double h_i = xa[i + 1] - xa[i], h_ip1 = xa[i + 2] - xa[i + 1];
-    double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
-    return 3.0 * ((ya[i + 2] - ya[i + 1]) * g_ip1 - (ya[i + 1] - ya[i]) * g_i);
-  };
-  alpha[0] = diag(0);
-  gamma[0] = off(0) / alpha[0];
-  for (int i = 1; i < N - 1; i++) {
-    alpha[i] = diag(i) - off(i - 1) * gamma[i - 1];
-    gamma[i] = off(i) / alpha[i];
+  for (int i = tid; i < size; i += blockDim.x) { sx[i] = xa[i]; sy[i] = ya[i]; }
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) {
+    sdiag[i] = 2.0 * ((sx[i + 2] - sx[i + 1]) + (sx[i + 1] - sx[i]));
+    soff[i] = sx[i + 2] - sx[i + 1];
+    const double h_i = sx[i + 1] - sx[i], h_ip1 = sx[i + 2] - sx[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    srhs[i] = 3.0 * ((sy[i + 2] - sy[i + 1]) * g_ip1 - (sy[i + 1] - sy[i]) * g_i);
   }
-  if (N > 1) alpha[N - 1] = diag(N - 1) - off(N - 2) * gamma[N - 2];
-  z[0] = rhs(0);
-  for (int i = 1; i < N; i++) z[i] = rhs(i) - gamma[i - 1] * z[i - 1];
-  double* x = c + 1;
-  x[N - 1] = z[N - 1] / alpha[N - 1];
-  for (int i = N - 2; i >= 0; i--) x[i] = z[i] / alpha[i] - gamma[i] * x[i + 1];
+  __syncthreads();
+  if (tid == 0) {
+    alpha[0] = sdiag[0];
+    gamma[0] = soff[0] / alpha[0];
+    for (int i = 1; i < N - 1; i++) {
+      alpha[i] = sdiag[i] - soff[i - 1] * gamma[i - 1];
+      gamma[i] = soff[i] / alpha[i];
+    }
+    if (N > 1) alpha[N - 1] = sdiag[N - 1] - soff[N - 2] * gamma[N - 2];
+    z[0] = srhs[0];
+    for (int i = 1; i < N; i++) z[i] = srhs[i] - gamma[i - 1] * z[i - 1];
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) z[i] = z[i] / alpha[i];  // the quotients of the back substitution
+  __syncthreads();
+  if (tid == 0) {
+    xs[N - 1] = z[N - 1];
+    for (int i = N - 2; i >= 0; i--) xs[i] = z[i] - gamma[i] * xs[i + 1];
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) c[i + 1] = xs[i];
+  if (tid == 0) { c[0] = 0.; c[max_index] = 0.; }
 }
 
 // T2b: G_AA(b) = exp(-sigma_NN T_AA(b)), src/UpcCrossSection.cpp:389-406.  One block per b,
@@ -376,8 +389,12 @@ __global__ void k_bk_raw(const BkTable* T, const double* b, int mode, size_t n, 
   if (i < n) out[i] = calc_breakup(T, b[i], mode);
 }
 
-// scalar look-ups finishing the tables: ff_last = F(Q2max - dQ2), P20 = P(20)
-__global__ void k_table_scalars(const SplineSeg* ff_seg, const SplineSeg* bk_seg, int use_breakup, double* out)
+// scalars finishing the tables, one launch, so that the host needs one read-back:
+//   out[0] = ff_last = F(Q2max - dQ2), out[1] = P20 = P(20), out[2] = number of photo-nuclear energy knots,
+//   out[3] = number of leading G_AA segments bounded by 1e-20 (the inner cut of the cell quadrature);
+// and the clamp segment {P(20), 0, 0, 0} of the breakup table at index i20.
+__global__ void k_table_scalars(const SplineSeg* ff_seg, SplineSeg* bk_seg, int use_breakup, int i20, const BkTable* bk_table,
+                                const SplineSeg* gaa_seg, double* out)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   {
@@ -391,9 +408,26 @@ __global__ void k_table_scalars(const SplineSeg* ff_seg, const SplineSeg* bk_seg
     int i = (int)((x - kBkBmin) / kBkDb);
     while (knot(kBkBmin, kBkDb, i) > x) --i;
     while (knot(kBkBmin, kBkDb, i + 1) <= x) ++i;
-    out[1] = seg_eval(bk_seg[i], x - knot(kBkBmin, kBkDb, i));
+    const double p20 = seg_eval(bk_seg[i], x - knot(kBkBmin, kBkDb, i));
+    out[1] = p20;
+    out[2] = (double)bk_table->n;
+    bk_seg[i20] = SplineSeg{p20, 0., 0., 0.};  // b >= 20 (index clamp): P(20), :260
   } else {
     out[1] = 1.;
+    out[2] = 0.;
+  }
+  {
+    // inner cut: the leading G_AA segments whose magnitude is bounded by 1e-20 on the whole segment
+    // (|y| + |b| h + |c| h^2 + |d| h^3); see prepare_tables
+    const double hh = 20. / (kNB - 1);
+    int n_zero = 0;
+    while (n_zero < kNB - 1) {
+      const SplineSeg sg = gaa_seg[n_zero];
+      const double bound = fabs(sg.y) + hh * (fabs(sg.b) + hh * (fabs(sg.c) + hh * fabs(sg.d)));
+      if (!(bound <= 1e-20)) break;
+      ++n_zero;
+    }
+    out[3] = (double)n_zero;
   }
 }
 
@@ -485,9 +519,9 @@ int prepare_tables(upcgpu_ctx* c)
   cudaEventRecord(c->aux_ev[1], st);
   cudaStreamWaitEvent(st_ff, c->aux_ev[1], 0);
   UPC_K(c), k_ta<<<kNB, 256, 0, st>>>(p.R, p.a, c->d_scal, c->gaa_x, c->ta_y);
-  UPC_K(c), k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->ta_y, kNB, c->ta_c);
+  UPC_K(c), k_spline_small<<<1, 256, 0, st>>>(c->gaa_x, c->ta_y, kNB, c->ta_c);
   UPC_K(c), k_gaa<<<kNB, 256, 0, st>>>(c->gaa_x, c->ta_y, c->ta_c, csNN, gl, c->gaa_y);
-  UPC_K(c), k_spline_small<<<1, 1, 0, st>>>(c->gaa_x, c->gaa_y, kNB, c->gaa_c);
+  UPC_K(c), k_spline_small<<<1, 256, 0, st>>>(c->gaa_x, c->gaa_y, kNB, c->gaa_c);
   UPC_K(c), k_segs_from_arrays<<<1, 256, 0, st>>>(c->gaa_x, c->gaa_y, c->gaa_c, kNB, c->gaa_seg, 1.0);
 
   UPC_K(c), k_ff_y<<<(kNQ2 + 255) / 256, 256, 0, st_ff>>>(p.R, p.a, c->d_scal, c->ff_y);
@@ -522,9 +556,13 @@ int prepare_tables(upcgpu_ctx* c)
   cudaEventRecord(c->aux_ev[3], st_bk);
   cudaStreamWaitEvent(st, c->aux_ev[2], 0);
   cudaStreamWaitEvent(st, c->aux_ev[3], 0);
-  UPC_K(c), k_table_scalars<<<1, 1, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, c->d_scal + 1);
+  // segments 0..i20-1 of the breakup table cover [bmin, > 20); index i20 is the clamp segment
+  const int i20 = (int)((20. - kBkBmin) / kBkDb) + 1;
+  UPC_K(c), k_table_scalars<<<1, 1, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, i20, (const BkTable*)c->bk_table, c->gaa_seg, c->d_scal + 1);
   cudaEventRecord(e1, st);
-  UPC_CUDA(c, cudaStreamSynchronize(st));
+  if (!c->h_scal) UPC_CUDA(c, cudaMallocHost(&c->h_scal, 8 * sizeof(double)));
+  UPC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  UPC_CUDA(c, cudaStreamSynchronize(st));  // the one host wait of the table stage
   UPC_CUDA(c, cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
@@ -532,40 +570,18 @@ int prepare_tables(upcgpu_ctx* c)
   cudaEventDestroy(e1);
   c->stats.ms_tables = ms;
 
-  double h[3];
-  UPC_CUDA(c, cudaMemcpy(h, c->d_scal, sizeof(h), cudaMemcpyDeviceToHost));
+  const double* h = c->h_scal;  // rho0, ff_last, P20, energy knots, leading zero segments of G_AA
   c->info.rho0 = h[0];
   c->info.breakup_p20 = h[2];
-  if (use_bk) {
-    int nk = 0;
-    UPC_CUDA(c, cudaMemcpy(&nk, (const char*)c->bk_table + offsetof(BkTable, n), sizeof(int), cudaMemcpyDeviceToHost));
-    c->info.n_breakup_energy_knots = nk;
-    // the clamp segment used for b >= 20 (index bk_n): value P(20)
-    // number of real segments kept for lookups: those covering b < 20 -> index of b = 20
-    int i20 = (int)((20. - kBkBmin) / kBkDb) + 1;  // segments 0..i20-1 cover [bmin, >20)
-    SplineSeg tail{h[2], 0., 0., 0.};
-    UPC_CUDA(c, cudaMemcpy(c->bk_seg + i20, &tail, sizeof(tail), cudaMemcpyHostToDevice));
-    c->tab.bk_n = i20;
-  } else {
-    c->info.n_breakup_energy_knots = 0;
-    c->tab.bk_n = 0;
-  }
+  c->info.n_breakup_energy_knots = (int)h[3];
+  c->tab.bk_n = use_bk ? i20 : 0;
   {
     // inner cut of the cell quadrature: the leading G_AA segments whose magnitude is bounded by
     // 1e-20 on the whole segment (|y| + |b| h + |c| h^2 + |d| h^3); P(b) <= 1.  What is skipped adds less than
     // 1e-19 of a cell's sum (the far pairs alone, with G_AA = 1, are a fifth of the total weight): four orders below
     // one ulp.  (1e-30 put the cut at 10.6 fm for Pb-Pb 5.02 TeV, 1e-20 puts it at 12.4 fm: 20 % fewer look-ups.)
-    std::vector<SplineSeg> hseg(kNB);
-    UPC_CUDA(c, cudaMemcpy(hseg.data(), c->gaa_seg, kNB * sizeof(SplineSeg), cudaMemcpyDeviceToHost));
     const double hh = 20. / (kNB - 1);
-    int n_zero = 0;
-    while (n_zero < kNB - 1) {
-      const SplineSeg& sg = hseg[n_zero];
-      const double bound = fabs(sg.y) + hh * (fabs(sg.b) + hh * (fabs(sg.c) + hh * fabs(sg.d)));
-      if (!(bound <= 1e-20)) break;
-      ++n_zero;
-    }
-    const double b_in = n_zero * hh;
+    const double b_in = (int)h[4] * hh;
     c->tab.b_in2 = b_in * b_in;
     c->info.gaa_zero_below = b_in;
   }

@@ -81,27 +81,32 @@ def init_from_env(backend="nccl"):
 
 
 def fill_lumi_distributed(gpu, rank: int, world: int, device=None):
-    """Table stage on `world` GPUs: every rank fills its cyclic m rows (upcgpu_fill_lumi_shard),
-    the packed shards are all-gathered with NCCL straight between the library's device buffers, and
-    each rank un-permutes them into its full table.  Returns nothing; the table stays on device."""
+    """Table stage on `world` GPUs: every rank queues the fill of its m rows (upcgpu_fill_lumi_shard, asynchronous),
+    the packed shards are all-gathered with NCCL straight between the library's device buffers, and each rank
+    un-permutes them into its full table.  Everything is queued on the library's stream; nothing here waits for the
+    device (the fold that follows does, once).  Returns nothing; the table stays on device."""
     gpu.fill_lumi_shard(rank, world)
     if world == 1:
         return
     import torch
     import torch.distributed as dist
-    # the library's shard / gather buffers live as long as the context: the zero-copy views are made once
+    # Zero-copy views of the library's shard / gather buffers.  The library reallocates them when the shard count
+    # changes (an interleaved single-GPU fill does that), so the pointers are queried on every call and the views are
+    # rebuilt whenever one of them moved.
+    kinds = (1, 2) if gpu.P.use_pol else (0,)
+    ptrs = []
+    for which in kinds:
+        sptr, sn = gpu.lumi_shard_buffer(which)
+        gptr, gn = gpu.lumi_gather_buffer(which, world)
+        ptrs.append((sptr, sn, gptr, gn))
+    key = (world, tuple(ptrs), gpu.stream_handle())
     views = getattr(gpu, "_dist_views", None)
-    if views is None or views[0] != world:
-        kinds = (1, 2) if gpu.P.use_pol else (0,)
-        pairs = []
-        for which in kinds:
-            sptr, sn = gpu.lumi_shard_buffer(which)
-            gptr, gn = gpu.lumi_gather_buffer(which, world)
-            pairs.append((as_tensor(sptr, sn, device), as_tensor(gptr, gn, device)))
+    if views is None or views[0] != key:
+        pairs = [(as_tensor(sptr, sn, device), as_tensor(gptr, gn, device)) for sptr, sn, gptr, gn in ptrs]
         # the collective is issued on the library's own stream: the un-permute kernel that follows on that stream is
         # ordered behind it without a host synchronisation in between
         ext = torch.cuda.ExternalStream(gpu.stream_handle(), device=device)
-        views = (world, pairs, ext)
+        views = (key, pairs, ext)
         gpu._dist_views = views
     with torch.cuda.stream(views[2]):
         for src, dst in views[1]:
