@@ -12,7 +12,8 @@
  * Conventions
  *   - every function returns UPCGPU_OK (0) or a negative UPCGPU_E* code; the message of the
  *     last failure on a context is available from upcgpu_last_error().
- *   - one context = one CUDA device; a context is thread-compatible, not thread-safe.
+ *   - one context = one CUDA device (upcgpu_create) or several devices behind one handle (upcgpu_create_multi);
+ *     a context is thread-compatible, not thread-safe.
  *   - there is NO CPU fallback: without a usable CUDA device upcgpu_create fails.
  *   - tables are FP64.  lumi tables are [nm][ny] (im-major, as TH2D hD2LDMDY x=M, y=Y);
  *     sigma tables are [ny][nm] (transposed, as the reference's crossSectionYM).
@@ -96,6 +97,27 @@ typedef struct {
 /* ---- lifetime ------------------------------------------------------------------------ */
 /* replaces: new UpcCrossSection() + parameter assignment (src/UpcGenerator.cpp:30-40,183-305) */
 int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out);
+/* The same on n_gpus devices of this node, driven from this one process (devices: n_gpus ordinals, or NULL for
+ * 0 .. n_gpus-1).  Replaces the OpenMP team of the reference's grid driver (-nthreads; static m-slabs,
+ * src/UpcCrossSection.cpp:536-539): behind the returned handle stands one member context per device with its own host
+ * thread; an NCCL communicator over the devices (ncclCommInitAll; NCCL is loaded with dlopen) and peer access
+ * between them are set up here.  With such a handle
+ *   upcgpu_prepare_tables   builds the lookup tables on every device,
+ *   upcgpu_fill_lumi        deals the m rows to the devices (blocks of 32 rows round-robin), exchanges the shards
+ *                           (NCCL all-gather over NVLink, or -- upcgpu_group_set_exchange(ctx, 1) -- stores of every
+ *                           finished cell into all devices' tables from inside the cell kernel) and leaves the FULL
+ *                           table on every device; the host buffers are filled from device 0,
+ *   upcgpu_fold_sigma, upcgpu_sampler_build   run on every device (each samples events from its own copy),
+ *   upcgpu_generate[_device]   split the candidate range into contiguous ranges, one per device; Philox counters make
+ *                           the result independent of n_gpus,
+ * and every other entry point acts on device 0.  n_gpus = 1 is upcgpu_create. */
+int upcgpu_create_multi(const upcgpu_params* params, int n_gpus, const int* devices, upcgpu_ctx** out);
+/* number of devices behind a handle; the member context of `rank` (borrowed: do not destroy), e.g. to read a
+ * member's copy of a table; the exchange in use (0 NCCL all-gather, 1 peer stores) and a one-line description */
+int upcgpu_group_size(const upcgpu_ctx* ctx);
+int upcgpu_group_member(upcgpu_ctx* ctx, int rank, upcgpu_ctx** member);
+int upcgpu_group_set_exchange(upcgpu_ctx* ctx, int mode);
+int upcgpu_group_describe(const upcgpu_ctx* ctx, char* buf, size_t cap);
 void upcgpu_destroy(upcgpu_ctx* ctx);
 /* message of the last failure (ctx may be NULL for create failures) */
 const char* upcgpu_last_error(const upcgpu_ctx* ctx);
@@ -136,7 +158,10 @@ int upcgpu_flux_form(upcgpu_ctx* ctx, const double* b, const double* k, size_t n
  * whole grid, values already multiplied by dm*dy (:546-550).  Unpolarised: lumi[nm*ny];
  * polarised (use_pol): lumi_s, lumi_p.  Unused pointers may be NULL.  Host buffers. */
 int upcgpu_fill_lumi(upcgpu_ctx* ctx, double* lumi, double* lumi_s, double* lumi_p);
-/* Same, but computes only the m-rows of one shard -- blocks of B consecutive rows dealt round-robin: row im belongs
+/* Same, but QUEUES only the m-rows of one shard and returns without waiting for the device: the result is collected
+ * by the next entry point that reads results on the host (upcgpu_get_fill_stats, upcgpu_lumi_download,
+ * upcgpu_fold_sigma ...), which is also where a QAGS error state of the fill is reported.
+ * Computes only the m-rows of one shard -- blocks of B consecutive rows dealt round-robin: row im belongs
  * to shard (im / B) % nshards, B = 32 or, on small grids, the largest power of two with nm >= 2 B nshards -- keeps the result
  * on the device (see upcgpu_lumi_device) and copies nothing.  One rank per GPU calls this with
  * its rank; the exchange between ranks is the caller's (NCCL all-gather of the packed shard). */

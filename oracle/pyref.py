@@ -150,6 +150,11 @@ class RefGenerator:
         self.L.upcrefgen_photon_pt(float(e), n, pt.ctypes.data)
         return pt
 
+    def reseed_z(self, seed0):
+        """Decorrelates the z samplers (the reference seeds all of them alike, Q6): see upcrefgen_reseed_z."""
+        self.L.upcrefgen_reseed_z.argtypes = [C.c_ulong]
+        self.L.upcrefgen_reseed_z(int(seed0))
+
     def tape(self, on):
         self.L.upcrefgen_tape(int(on))
 

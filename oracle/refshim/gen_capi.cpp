@@ -129,6 +129,17 @@ long upcrefgen_generate(long n, int* npart, int* pdg, int* status, int* mother, 
   return acc;
 }
 
+// The reference seeds its 2-D sampler and all nm 1-D samplers with the SAME seed (src/UpcGenerator.cpp:688-700, Q6):
+// the k-th draw of EVERY mass bin's z sampler uses the same uniform, so the pooled cos(theta) sample of a run is not
+// i.i.d. (with 1001 bins, the first draw of each bin puts 1001 events on one quantile).  For two-sample tests the
+// streams are decorrelated by re-seeding sampler i with seed0 + 1 + i; the code that draws stays the reference's.
+void upcrefgen_reseed_z(unsigned long seed0)
+{
+  for (size_t i = 0; i < g_gen->samplersCsZ.size(); i++) gsl_rng_set(g_gen->samplersCsZ[i]->rng, seed0 + 1 + i);
+  for (size_t i = 0; i < g_gen->samplersCsSZ.size(); i++) gsl_rng_set(g_gen->samplersCsSZ[i]->rng, seed0 + 100001 + i);
+  for (size_t i = 0; i < g_gen->samplersCsPsZ.size(); i++) gsl_rng_set(g_gen->samplersCsPsZ[i]->rng, seed0 + 200001 + i);
+}
+
 // tape of the uniforms drawn by the reference's code (shim_tape.h): switch on / off (clears), read back
 void upcrefgen_tape(int on) { shim_tape().on = on != 0; shim_tape().v.clear(); shim_tape().tag.clear(); }
 long upcrefgen_tape_read(double* v, int* tag, long cap)

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libupcgpu.so")
-SOURCES = ["upc_capi.cu", "upc_tables.cu", "upc_lumi.cu", "upc_fold.cu", "upc_events.cu", "upc_elem_capi.cpp",
+SOURCES = ["upc_capi.cu", "upc_tables.cu", "upc_lumi.cu", "upc_fold.cu", "upc_events.cu", "upc_group.cu", "upc_elem_capi.cpp",
            "../host/UpcTwoPhotonDilep.cpp", "../host/UpcTwoPhotonALP.cpp", "../host/UpcTwoPhotonTabulated.cpp",
            "../host/UpcRootHist.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed, see upcgen_b200/build/nvcc.log")
-    subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", SO, *objs, "-lcudart", "-lz", "-ccbin", "/usr/bin/g++"])
+    subprocess.check_call([NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", SO, *objs, "-lcudart", "-lz", "-ldl", "-lpthread", "-ccbin", "/usr/bin/g++"])
     return SO
 
 

@@ -67,6 +67,8 @@ SYMBOLS = [
     "upcgpu_photon_pt_cdf", "upcgpu_philox", "upcgpu_invalidate_tables", "upcgpu_fp64_peak",
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
+    "upcgpu_create_multi", "upcgpu_group_size", "upcgpu_group_member", "upcgpu_group_set_exchange",
+    "upcgpu_group_describe",
 ]
 
 
@@ -119,6 +121,11 @@ def lib():
         L.upcgpu_launch_count.argtypes = [p]
         L.upcgpu_launch_count.restype = C.c_longlong
         L.upcgpu_fp64_peak.argtypes = [p, i, C.POINTER(d), C.POINTER(d)]
+        L.upcgpu_create_multi.argtypes = [C.POINTER(CParams), i, C.POINTER(i), C.POINTER(p)]
+        L.upcgpu_group_size.argtypes = [p]
+        L.upcgpu_group_member.argtypes = [p, i, C.POINTER(p)]
+        L.upcgpu_group_set_exchange.argtypes = [p, i]
+        L.upcgpu_group_describe.argtypes = [p, C.c_char_p, sz]
         _LIB = L
     return _LIB
 
@@ -157,20 +164,48 @@ def _f64(a):
 class UpcGpu:
     """One context = one GPU.  Thin, typed wrapper; methods map 1:1 onto include/upcgpu.h."""
 
-    def __init__(self, P: UpcParams, device: int = 0):
+    def __init__(self, P: UpcParams, device: int = 0, n_gpus: int = 1, devices=None, _borrowed=None):
+        """n_gpus > 1: several devices behind this one handle (upcgpu_create_multi), driven from this process."""
         self.L = lib()
         self.P = P
         self.cp = to_cparams(P)
+        self.nm, self.ny, self.nz = P.nm, P.ny, P.nz
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self.h = _borrowed
+            return
         h = C.c_void_p()
-        rc = self.L.upcgpu_create(C.byref(self.cp), device, C.byref(h))
+        if n_gpus > 1 or devices is not None:
+            devs = list(devices) if devices is not None else list(range(n_gpus))
+            arr = (C.c_int * len(devs))(*devs)
+            rc = self.L.upcgpu_create_multi(C.byref(self.cp), len(devs), arr, C.byref(h))
+        else:
+            rc = self.L.upcgpu_create(C.byref(self.cp), device, C.byref(h))
         if rc != OK:
             raise UpcGpuError(rc, self.L.upcgpu_last_error(None).decode())
         self.h = h
-        self.nm, self.ny, self.nz = P.nm, P.ny, P.nz
+
+    def group_size(self):
+        return self.L.upcgpu_group_size(self.h)
+
+    def group_member(self, rank):
+        """The member context of `rank` (borrowed: owned by this handle)."""
+        m = C.c_void_p()
+        self._chk(self.L.upcgpu_group_member(self.h, rank, C.byref(m)))
+        return UpcGpu(self.P, _borrowed=m)
+
+    def group_set_exchange(self, mode):
+        self._chk(self.L.upcgpu_group_set_exchange(self.h, mode))
+
+    def group_describe(self):
+        buf = C.create_string_buffer(256)
+        self._chk(self.L.upcgpu_group_describe(self.h, buf, 256))
+        return buf.value.decode()
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.upcgpu_destroy(self.h)
+            if getattr(self, "_owned", True):
+                self.L.upcgpu_destroy(self.h)
             self.h = None
 
     def __del__(self):

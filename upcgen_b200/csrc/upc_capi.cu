@@ -2,6 +2,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "upc_ctx.h"
 #include "upc_internal.h"
@@ -62,9 +63,65 @@ int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out)
   return UPCGPU_OK;
 }
 
+int upcgpu_create_multi(const upcgpu_params* params, int n_gpus, const int* devices, upcgpu_ctx** out)
+{
+  if (!params || !out) { g_create_err = "upcgpu_create_multi: null argument"; return UPCGPU_EINVAL; }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_err = "upcgpu_create_multi: no CUDA device; this library has no CPU fallback";
+    return UPCGPU_ENODEV;
+  }
+  if (n_gpus < 1 || n_gpus > kMaxPeers) { g_create_err = "upcgpu_create_multi: n_gpus must be 1.." + std::to_string(kMaxPeers); return UPCGPU_EINVAL; }
+  std::vector<int> devs(n_gpus);
+  for (int r = 0; r < n_gpus; ++r) {
+    devs[r] = devices ? devices[r] : r;
+    if (devs[r] < 0 || devs[r] >= ndev) {
+      g_create_err = "upcgpu_create_multi: device " + std::to_string(devs[r]) + " requested, " + std::to_string(ndev) + " present";
+      return UPCGPU_EINVAL;
+    }
+    for (int q = 0; q < r; ++q)
+      if (devs[q] == devs[r]) { g_create_err = "upcgpu_create_multi: a device is listed twice"; return UPCGPU_EINVAL; }
+  }
+  upcgpu_ctx* leader = nullptr;
+  int rc = upcgpu_create(params, devs[0], &leader);
+  if (rc) return rc;
+  if (n_gpus > 1) {
+    std::string err;
+    rc = group_create(leader, n_gpus, devs.data(), err);
+    if (rc) { g_create_err = "upcgpu_create_multi: " + err; upcgpu_destroy(leader); return rc; }
+  }
+  *out = leader;
+  return UPCGPU_OK;
+}
+
+int upcgpu_group_size(const upcgpu_ctx* c) { return c ? group_size(c) : 0; }
+
+int upcgpu_group_member(upcgpu_ctx* c, int rank, upcgpu_ctx** member)
+{
+  if (!c || !member) return UPCGPU_EINVAL;
+  *member = group_member(c, rank);
+  return *member ? UPCGPU_OK : UPCGPU_EINVAL;
+}
+
+int upcgpu_group_set_exchange(upcgpu_ctx* c, int mode)
+{
+  if (!c) return UPCGPU_EINVAL;
+  return group_set_exchange(c, mode);
+}
+
+int upcgpu_group_describe(const upcgpu_ctx* c, char* buf, size_t cap)
+{
+  if (!c || !buf || cap == 0) return UPCGPU_EINVAL;
+  if (!c->group) { std::snprintf(buf, cap, "1 device"); return UPCGPU_OK; }
+  group_describe(c, buf, cap);
+  return UPCGPU_OK;
+}
+
 void upcgpu_destroy(upcgpu_ctx* c)
 {
   if (!c) return;
+  if (c->group && c->group_rank == 0) group_destroy(c);  // the members, their threads, the NCCL communicators
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->gaa_x); cudaFree(c->gaa_y); cudaFree(c->gaa_c); cudaFree(c->ta_y); cudaFree(c->ta_c);
@@ -94,6 +151,7 @@ int upcgpu_device_name(const upcgpu_ctx* c, char* buf, size_t cap)
 int upcgpu_prepare_tables(upcgpu_ctx* c)
 {
   CHECK_CTX(c);
+  if (c->group && c->group_rank == 0) return group_prepare_tables(c);
   if (c->tables_ready) return UPCGPU_OK;
   return prepare_tables(c);
 }
@@ -111,6 +169,7 @@ int upcgpu_invalidate_tables(upcgpu_ctx* c)
 {
   if (!c) return UPCGPU_EINVAL;
   c->tables_ready = false;
+  if (c->group && c->group_rank == 0) group_invalidate_tables(c);
   return UPCGPU_OK;
 }
 
@@ -223,7 +282,8 @@ int upcgpu_fill_lumi(upcgpu_ctx* c, double* lumi, double* lumi_s, double* lumi_p
   CHECK_CTX_SYNC(c);
   int rc = upcgpu_prepare_tables(c);
   if (rc) return rc;
-  rc = fill_lumi_rows(c, 0, 1, /*wait=*/true);
+  // several GPUs behind this handle: the m rows are dealt to the devices, exchanged, and every device holds the table
+  rc = (c->group && c->group_rank == 0) ? group_fill_lumi(c) : fill_lumi_rows(c, 0, 1, /*wait=*/true);
   if (rc) return rc;
   if (!c->p.use_pol) {
     if (lumi) rc = upcgpu_lumi_download(c, 0, lumi);
@@ -246,7 +306,8 @@ int upcgpu_get_fill_stats(upcgpu_ctx* c, upcgpu_fill_stats* st)
 {
   if (!st) return UPCGPU_EINVAL;
   CHECK_CTX_SYNC(c);
-  *st = c->stats;
+  if (c->group && c->group_rank == 0) group_fill_stats(c, st);
+  else *st = c->stats;
   return UPCGPU_OK;
 }
 
@@ -262,20 +323,12 @@ int upcgpu_lumi_shard_buffer(upcgpu_ctx* c, int which, uint64_t* dev_ptr, size_t
 int upcgpu_lumi_gather_buffer(upcgpu_ctx* c, int which, int nshards, uint64_t* dev_ptr, size_t* n_doubles)
 {
   CHECK_CTX(c);
-  if (which < 0 || which > 2 || nshards < 1 || c->shard_n != nshards) {
-    c->err = "lumi_gather_buffer: call fill_lumi_shard with the same nshards first";
-    return UPCGPU_EINVAL;
-  }
-  size_t n = c->shard_rows * c->p.ny * nshards;
-  if (c->gather_n != nshards) {
-    for (int w = 0; w < 3; w++) { cudaFree(c->gather[w]); c->gather[w] = nullptr; }
-    const int w0 = c->p.use_pol ? 1 : 0, w1 = c->p.use_pol ? 2 : 0;
-    for (int w = w0; w <= w1; w++) UPC_CUDA(c, cudaMalloc(&c->gather[w], n * sizeof(double)));
-    c->gather_n = nshards;
-  }
+  if (which < 0 || which > 2) { c->err = "lumi_gather_buffer: bad table kind"; return UPCGPU_EINVAL; }
+  const int rc = ensure_gather_buffers(c, nshards);
+  if (rc) return rc;
   if (!c->gather[which]) { c->err = "lumi_gather_buffer: table kind does not match use_pol"; return UPCGPU_EINVAL; }
   if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)c->gather[which];
-  if (n_doubles) *n_doubles = n;
+  if (n_doubles) *n_doubles = c->shard_rows * c->p.ny * nshards;
   return UPCGPU_OK;
 }
 
@@ -289,12 +342,14 @@ int upcgpu_fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, c
                       double* ratio, double* totcs_mb)
 {
   CHECK_CTX(c);
+  if (c->group && c->group_rank == 0) return group_fold_sigma(c, sig_m, sig_s, sig_p, cs, ratio, totcs_mb);
   return fold_sigma(c, sig_m, sig_s, sig_p, cs, ratio, totcs_mb);
 }
 
 int upcgpu_sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps)
 {
   CHECK_CTX_SYNC(c);
+  if (c->group && c->group_rank == 0) return group_sampler_build(c, cs, cszm, cszm_s, cszm_ps);
   return sampler_build(c, cs, cszm, cszm_s, cszm_ps);
 }
 
@@ -355,6 +410,8 @@ int upcgpu_generate(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size
 {
   CHECK_CTX_SYNC(c);
   if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
+  if (c->group && c->group_rank == 0)
+    return group_generate(c, seed, first_candidate, n_candidates, npart, pdg, status, mother, p4, aux, n_accepted, false);
   return generate(c, seed, first_candidate, n_candidates, npart, pdg, status, mother, p4, aux, n_accepted, false);
 }
 
@@ -362,6 +419,9 @@ int upcgpu_generate_device(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidat
 {
   CHECK_CTX_SYNC(c);
   if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
+  if (c->group && c->group_rank == 0)
+    return group_generate(c, seed, first_candidate, n_candidates, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_accepted,
+                          true);
   return generate(c, seed, first_candidate, n_candidates, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_accepted,
                   true);
 }

@@ -12,6 +12,9 @@
 
 namespace upc {
 
+struct Group;  // upc_group.cu: the member contexts of a multi-GPU handle
+constexpr int kMaxPeers = 16;
+
 // device-resident lookup tables handed to the kernels by value
 struct DevTables {
   // G_AA: 200 knots on [0,20]; seg[i], i<199, plus seg[199] = {1,0,0,0} for b >= 20
@@ -82,7 +85,14 @@ struct upcgpu_ctx_impl {
   // integral count of a (shard, nshards, first local row, rows) slab: a pure function of the parameter block, read back
   // from the device the first time and reused to size the head kernel's grid afterwards
   std::map<std::array<int, 4>, long long> n_items_cache;
+  // several GPUs behind one handle (upcgpu_create_multi): set on every member; the leader (rank 0) owns the group
+  Group* group = nullptr;
+  int group_rank = 0;
+  // peer-store exchange: full lumi tables of every member, written by this member's cell kernel (set per fill)
+  double* peer_lumi[kMaxPeers][3] = {};
+  int n_peers = 0;
   bool func_attrs_set = false;   // cudaFuncSetAttribute done on this context's device
+  bool ev_attr_set = false;      // ... for the event kernels
   long long test_head_pool = 0;  // UPCGPU_TEST_HEAD_POOL: slots of the hand-over state pool (tests of the fallback path)
 };
 

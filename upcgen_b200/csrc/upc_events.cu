@@ -11,9 +11,13 @@
 // Slots are consumed by position, so results do not depend on batch size or GPU count.
 //
 // Photon pT: the reference caches one 5000-bin pdf per integer-MeV photon energy in a host map
-// (Q9).  Here a batch's photon energies are reduced to their distinct MeV keys on the device
-// (radix sort + unique), one CTA tabulates the cumulative pdf of each key, and the event kernel
-// inverts it; the pdf of a key is evaluated at the key's centre (key + 0.5) MeV.
+// (Q9).  Here the photons of a batch (two per candidate) are sorted by their MeV key on the device
+// (radix sort of (key, photon) pairs), and one CTA per DISTINCT key builds that key's cumulative pdf
+// in SHARED memory and serves all photons of the key from it -- the pdf of a key is evaluated at the
+// key's centre (key + 0.5) MeV.  Nothing but the photon pT (8 B per photon) reaches HBM: writing the
+// 5001-entry tables out and searching them from another kernel (round 1) moved 40 KB per key, ~300x
+// the bytes of the events themselves.  Batches are large (4 M candidates) because the cost of the
+// stage is the number of distinct keys per batch x 5000 form-factor evaluations.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -26,28 +30,50 @@
 namespace upc {
 
 constexpr int kPtBins = 5000;
+constexpr size_t kEvChunk = (size_t)1 << 22;  // candidates per batch (~300 B of scratch each)
+
+struct EvReport {  // pinned host mirror of the per-batch counters
+  unsigned long long n_acc;
+  int err;
+  int n_uniq;
+};
 
 struct EvScratch {
   size_t cap = 0;        // candidates
-  size_t cap_keys = 0;   // pT tables
   double *y = nullptr, *m = nullptr, *cost = nullptr;
-  int *keys = nullptr, *keys_sorted = nullptr, *uniq = nullptr, *n_uniq = nullptr;
-  double* cdf = nullptr;  // [cap_keys][kPtBins+1]
+  unsigned *keys = nullptr, *keys_sorted = nullptr, *pid = nullptr, *pid_sorted = nullptr;  // [2 cap] photons
+  unsigned* seg_off = nullptr;  // [2 cap]: first sorted photon of every distinct key
+  int* n_uniq = nullptr;
+  unsigned* next_tile = nullptr;  // work counter of k_pt_serve
+  double* pt = nullptr;         // [2 cap] photon pT, indexed by photon id 2 t + side
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
   int *npart = nullptr, *pdg = nullptr, *status = nullptr, *mother = nullptr;
   double *p4 = nullptr, *aux = nullptr;
   unsigned long long* n_acc = nullptr;
   int* err = nullptr;
+  EvReport* report = nullptr;
+  void release()
+  {
+    cudaFree(y); cudaFree(m); cudaFree(cost); cudaFree(keys); cudaFree(keys_sorted); cudaFree(pid); cudaFree(pid_sorted);
+    cudaFree(seg_off); cudaFree(pt); cudaFree(cub_tmp); cudaFree(npart); cudaFree(pdg); cudaFree(status); cudaFree(mother);
+    cudaFree(p4); cudaFree(aux);
+    y = m = cost = pt = p4 = aux = nullptr;
+    keys = keys_sorted = pid = pid_sorted = seg_off = nullptr;
+    cub_tmp = nullptr;
+    npart = pdg = status = mother = nullptr;
+    cap = 0;
+    cub_bytes = 0;
+  }
 };
 
 void free_event_scratch(upcgpu_ctx* c)
 {
   EvScratch* s = (EvScratch*)c->ev;
   if (!s) return;
-  cudaFree(s->y); cudaFree(s->m); cudaFree(s->cost); cudaFree(s->keys); cudaFree(s->keys_sorted); cudaFree(s->uniq);
-  cudaFree(s->n_uniq); cudaFree(s->cdf); cudaFree(s->cub_tmp); cudaFree(s->npart); cudaFree(s->pdg);
-  cudaFree(s->status); cudaFree(s->mother); cudaFree(s->p4); cudaFree(s->aux); cudaFree(s->n_acc); cudaFree(s->err);
+  s->release();
+  cudaFree(s->n_uniq); cudaFree(s->n_acc); cudaFree(s->err); cudaFree(s->next_tile);
+  if (s->report) cudaFreeHost(s->report);
   delete s;
   c->ev = nullptr;
 }
@@ -66,8 +92,8 @@ __device__ __forceinline__ int energy_key(double e) { return (int)(e * 1e3); }  
 
 // phase 1: (y, m), bins, cos(theta), photon-energy keys
 __global__ void k_ev_sample(EvParams P, uint64_t seed, uint64_t first, size_t n, double* __restrict__ y,
-                            double* __restrict__ m, double* __restrict__ cost, int* __restrict__ keys,
-                            int* __restrict__ err)
+                            double* __restrict__ m, double* __restrict__ cost, unsigned* __restrict__ keys,
+                            unsigned* __restrict__ pid, int* __restrict__ err)
 {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -77,6 +103,7 @@ __global__ void k_ev_sample(EvParams P, uint64_t seed, uint64_t first, size_t n,
   philox4x32_10(seed, cand, 1, u2, u3);
   long long k; double yy, mm;
   sample_ym_dev(P.sum2d, P.ny, P.nm, P.ye, P.me, r1, r2, k, yy, mm);  // UpcGenerator.cpp:737
+  if (keys) { pid[2 * t] = (unsigned)(2 * t); pid[2 * t + 1] = (unsigned)(2 * t + 1); }
   if (k < 0) {  // GSL: "cannot find r1 in cumulative pdf" -> abort in the reference
     atomicAdd(err, 1);
     y[t] = nan(""); m[t] = nan(""); cost[t] = 0;
@@ -98,12 +125,18 @@ __global__ void k_ev_sample(EvParams P, uint64_t seed, uint64_t first, size_t n,
   }
   y[t] = yy; m[t] = mm; cost[t] = cz;
   if (keys) {
-    keys[2 * t] = energy_key(mm / 2 * exp(yy));       // UpcCrossSection.cpp:1060-1061
-    keys[2 * t + 1] = energy_key(mm / 2 * exp(-yy));
+    keys[2 * t] = (unsigned)energy_key(mm / 2 * exp(yy));       // UpcCrossSection.cpp:1060-1061
+    keys[2 * t + 1] = (unsigned)energy_key(mm / 2 * exp(-yy));
   }
 }
 
-// phase 3: cumulative pT pdf of one photon-energy key per CTA (getPhotonPt, :1021-1038, and
+// first sorted photon of every distinct key
+struct KeyHead {
+  const unsigned* ks;
+  __device__ __forceinline__ bool operator()(unsigned i) const { return i == 0 || ks[i] != ks[i - 1]; }
+};
+
+// phase 3: cumulative pT pdf of one photon-energy key (getPhotonPt, :1021-1038, and
 // TH1::ComputeIntegral): cdf[0] = 0, cdf[i] = sum_{j<=i} p_j / total
 __device__ __forceinline__ double ff_lookup(const SplineSeg* __restrict__ ff, double t)
 {
@@ -113,33 +146,38 @@ __device__ __forceinline__ double ff_lookup(const SplineSeg* __restrict__ ff, do
   t = fmin(t, tmax);
   int idx = (int)((t - kQ2min) * (1. / kDQ2));
   idx = max(0, min(idx, kNQ2 - 2));
-  return seg_eval(ff[idx], t - fma((double)idx, kDQ2, kQ2min));
+  return seg_eval(ld_seg(ff + idx), t - fma((double)idx, kDQ2, kQ2min));
 }
 
-constexpr int kPtPerThread = (kPtBins + 255) / 256;  // 20 bins per thread
-constexpr int kPtRunPad = kPtPerThread + 1;          // runs padded to 21 doubles in shared memory (2-way conflicts)
+constexpr int kPtThreads = 256;
+constexpr int kPtPerThread = (kPtBins + kPtThreads - 1) / kPtThreads;  // 20 bins per thread
+constexpr int kPtRunPad = kPtPerThread + 1;  // runs padded to 21 doubles in shared memory (2-way conflicts)
 
-__global__ void __launch_bounds__(256) k_pt_tables(int n_keys, const int* __restrict__ keys, const double* e_direct,
-                                                   const SplineSeg* __restrict__ ff, double gtot, double R,
-                                                   double* __restrict__ cdf)
+struct PtShared {
+  typename cub::BlockScan<double, kPtThreads>::TempStorage scan;
+  double sp[kPtThreads * kPtRunPad];  // after pt_build: sp[(i / 20) * 21 + i % 20] = cdf[i + 1]
+};
+
+// cdf[i], i = 0 .. 5000, of the table pt_build left in shared memory
+__device__ __forceinline__ double pt_cdf_at(const double* sp, int i)
 {
-  // The pdf is evaluated and the cdf stored with bin = base + thread (neighbouring threads gather neighbouring
-  // form-factor segments and write neighbouring doubles); the prefix sum goes through shared memory: each thread
-  // sums a RUN of 20 consecutive bins serially and ONE block scan ranks the runs (a block scan per 256 bins -- 20
-  // of them, two barriers each -- was 60 % of this kernel's instructions).
-  typedef cub::BlockScan<double, 256> Scan;
-  __shared__ typename Scan::TempStorage tmp;
-  __shared__ double sp[256 * kPtRunPad];
-  const int kidx = blockIdx.x;
-  if (kidx >= n_keys) return;
+  if (i == 0) return 0.;
+  const int b = i - 1;
+  return sp[(b / kPtPerThread) * kPtRunPad + b % kPtPerThread];
+}
+
+// The pdf is evaluated with bin = base + thread (neighbouring threads gather neighbouring form-factor segments);
+// the prefix sum goes through shared memory: each thread sums a RUN of 20 consecutive bins serially and ONE block
+// scan ranks the runs; the thread then normalises its run in place.  Ends with a barrier.
+__device__ __forceinline__ void pt_build(PtShared& S, double e, const SplineSeg* __restrict__ ff, double gtot, double R)
+{
+  typedef cub::BlockScan<double, kPtThreads> Scan;
   const int tid = threadIdx.x;
-  const double e = e_direct ? e_direct[kidx] : (keys[kidx] + 0.5) * 1e-3;
   const double ereds = (e * e) / (gtot * gtot);
   const double pi2x4 = 4 * kPi * kPi;
-  double* out = cdf + (size_t)kidx * (kPtBins + 1);
 #pragma unroll 4
   for (int it = 0; it < kPtPerThread; ++it) {
-    const int b0 = it * 256 + tid;           // 0-based bin
+    const int b0 = it * kPtThreads + tid;           // 0-based bin
     double prob = 0;
     if (b0 < kPtBins) {
       const double pt = 6. * kHc / R / kPtBins * (b0 + 1);  // upper bin edge, :1033
@@ -147,45 +185,99 @@ __global__ void __launch_bounds__(256) k_pt_tables(int n_keys, const int* __rest
       const double f = ff_lookup(ff, arg);
       prob = (f * f) * pt * pt * pt / (pi2x4 * arg * arg);
     }
-    sp[(b0 / kPtPerThread) * kPtRunPad + b0 % kPtPerThread] = prob;
+    S.sp[(b0 / kPtPerThread) * kPtRunPad + b0 % kPtPerThread] = prob;
   }
   __syncthreads();
   double acc = 0;
-  double* run = sp + tid * kPtRunPad;
+  double* run = S.sp + tid * kPtRunPad;
 #pragma unroll
   for (int j = 0; j < kPtPerThread; ++j) {
     acc += run[j];
     run[j] = acc;
   }
   double before, tot;
-  Scan(tmp).ExclusiveSum(acc, before, tot);
-  run[kPtPerThread] = before;                // the pad slot carries the run's offset
+  Scan(S.scan).ExclusiveSum(acc, before, tot);
+#pragma unroll
+  for (int j = 0; j < kPtPerThread; ++j) {
+    const double v = before + run[j];
+    run[j] = tot != 0 ? v / tot : v;           // TH1::ComputeIntegral: integral[i] /= integral[n]
+  }
   __syncthreads();
-  if (tid == 0) out[0] = 0;
-#pragma unroll 4
-  for (int it = 0; it < kPtPerThread; ++it) {
-    const int b0 = it * 256 + tid;
-    if (b0 < kPtBins) {
-      const int r = b0 / kPtPerThread;
-      const double v = sp[r * kPtRunPad + kPtPerThread] + sp[r * kPtRunPad + b0 % kPtPerThread];
-      out[b0 + 1] = tot != 0 ? v / tot : v;
+}
+
+// TH1::GetRandom on the table in shared memory
+__device__ __forceinline__ double pt_sample(const double* sp, double r1, double R)
+{
+  if (pt_cdf_at(sp, kPtBins) == 0) return 0;
+  int lo = 0, hi = kPtBins;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (pt_cdf_at(sp, mid) <= r1) lo = mid; else hi = mid;
+  }
+  const double bw = (6. * kHc / R) / kPtBins;
+  double x = lo * bw;
+  const double c0 = pt_cdf_at(sp, lo);
+  if (r1 > c0) x += bw * (r1 - c0) / (pt_cdf_at(sp, lo + 1) - c0);
+  return x;
+}
+
+// Persistent grid over TILES of kPtThreads sorted photons, handed out by an atomic counter: a CTA walks the key runs
+// that intersect its tile, builds each key's table and serves the run's photons that lie in the tile (one photon per
+// thread).  Tiles, not keys, are the unit of work because the keys are very unequal: at low photon energies one
+// integer-MeV key holds 10^5-10^6 photons of a 4 M-candidate batch (one CTA per key left the whole stage waiting for
+// them), at high energies every photon has a key of its own.  A run that crosses a tile boundary is tabulated by
+// both tiles: at most one extra table per tile.
+// Photon id = 2 t + side; its uniform is slot `side` of Philox block 3 of candidate first + t (the slot map above),
+// recomputed here rather than stored.
+__global__ void __launch_bounds__(kPtThreads) k_pt_serve(const int* __restrict__ n_uniq_p, const unsigned* __restrict__ seg_off,
+                                                         unsigned n_photons, const unsigned* __restrict__ keys_sorted,
+                                                         const unsigned* __restrict__ pid_sorted, uint64_t seed,
+                                                         uint64_t first, const SplineSeg* __restrict__ ff, double gtot,
+                                                         double R, double* __restrict__ pt_out, unsigned* __restrict__ next_tile)
+{
+  extern __shared__ __align__(16) unsigned char pt_smem[];
+  PtShared& S = *reinterpret_cast<PtShared*>(pt_smem);
+  __shared__ unsigned s_tile;
+  const int n_uniq = *n_uniq_p;
+  const unsigned n_tiles = (n_photons + kPtThreads - 1) / kPtThreads;
+  for (;;) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(next_tile, 1u);
+    __syncthreads();
+    const unsigned tile = s_tile;
+    if (tile >= n_tiles) break;
+    const unsigned t0 = tile * kPtThreads, t1 = min(t0 + kPtThreads, n_photons);
+    // the run that holds photon t0: the last k with seg_off[k] <= t0
+    int lo = 0, hi = n_uniq;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_off[mid] <= t0) lo = mid; else hi = mid;
+    }
+    for (int k = lo; k < n_uniq; ++k) {
+      const unsigned q0 = seg_off[k];
+      if (q0 >= t1) break;
+      const unsigned q1 = (k + 1 < n_uniq) ? seg_off[k + 1] : n_photons;
+      const double e = (keys_sorted[q0] + 0.5) * 1e-3;
+      pt_build(S, e, ff, gtot, R);
+      const unsigned q = max(q0, t0) + threadIdx.x;
+      if (q < min(q1, t1)) {
+        const unsigned id = pid_sorted[q];
+        double u6, u7;
+        philox4x32_10(seed, first + (id >> 1), 3, u6, u7);
+        pt_out[id] = pt_sample(S.sp, (id & 1) ? u7 : u6, R);
+      }
+      __syncthreads();  // the table is rebuilt for the next run
     }
   }
 }
 
-// TH1::GetRandom on a tabulated integral
-__device__ __forceinline__ double pt_sample(const double* __restrict__ cdf, double r1, double R)
+// test hook: the table of one photon energy, written out
+__global__ void __launch_bounds__(kPtThreads) k_pt_table_one(const double* __restrict__ e_direct, const SplineSeg* __restrict__ ff,
+                                                             double gtot, double R, double* __restrict__ cdf)
 {
-  if (cdf[kPtBins] == 0) return 0;
-  int lo = 0, hi = kPtBins;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (cdf[mid] <= r1) lo = mid; else hi = mid;
-  }
-  const double bw = (6. * kHc / R) / kPtBins;
-  double x = lo * bw;
-  if (r1 > cdf[lo]) x += bw * (r1 - cdf[lo]) / (cdf[lo + 1] - cdf[lo]);
-  return x;
+  extern __shared__ __align__(16) unsigned char pt_smem[];
+  PtShared& S = *reinterpret_cast<PtShared*>(pt_smem);
+  pt_build(S, e_direct[0], ff, gtot, R);
+  for (int i = threadIdx.x; i <= kPtBins; i += kPtThreads) cdf[i] = pt_cdf_at(S.sp, i);
 }
 
 struct LV { double x, y, z, t; };
@@ -232,18 +324,18 @@ __device__ __forceinline__ double lv_eta(const LV& v)
 
 // phase 4: kinematics
 __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, const double* __restrict__ y,
-                         const double* __restrict__ m, const double* __restrict__ cost, const int* __restrict__ uniq,
-                         int n_uniq, const double* __restrict__ cdf, int* __restrict__ npart, int* __restrict__ pdg,
-                         int* __restrict__ status, int* __restrict__ mother, double* __restrict__ p4,
-                         double* __restrict__ aux, unsigned long long* __restrict__ n_acc)
+                         const double* __restrict__ m, const double* __restrict__ cost, const double* __restrict__ pt_ph,
+                         int* __restrict__ npart, int* __restrict__ pdg, int* __restrict__ status,
+                         int* __restrict__ mother, double* __restrict__ p4, double* __restrict__ aux,
+                         unsigned long long* __restrict__ n_acc)
 {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= n) return;
   const uint64_t cand = first + t;
   const double yPair = y[t], mPair = m[t], cz = cost[t];
   int np = 0;
-  LV parts[3];
-  int ppdg[3] = {0, 0, 0}, pst[3] = {0, 0, 0}, pmo[3] = {0, 0, 0};
+  LV parts[UPCGPU_MAX_PART];
+  int ppdg[UPCGPU_MAX_PART] = {0, 0, 0, 0}, pst[UPCGPU_MAX_PART] = {0, 0, 0, 0}, pmo[UPCGPU_MAX_PART] = {0, 0, 0, 0};
   double pt1 = 0, pt2 = 0;
   bool ok = !(mPair != mPair);
   if (ok) {
@@ -252,23 +344,11 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
     if (!P.nonzero_gam_pt) {
       pPair = LV{0., 0., mPair * sinh(yPair), mPair * cosh(yPair)};
     } else {
-      double a1, a2, u6, u7;
+      double a1, a2;
       philox4x32_10(seed, cand, 2, a1, a2);
-      philox4x32_10(seed, cand, 3, u6, u7);
-      const double k1 = mPair / 2 * exp(yPair), k2 = mPair / 2 * exp(-yPair);
       const double angle1 = 2 * kPi * a1, angle2 = 2 * kPi * a2;
-      const int keyv[2] = {energy_key(k1), energy_key(k2)};
-      double pts[2];
-#pragma unroll
-      for (int s = 0; s < 2; s++) {
-        int lo = 0, hi = n_uniq;  // position of the key among the distinct keys
-        while (hi - lo > 1) {
-          int mid = (lo + hi) >> 1;
-          if (uniq[mid] <= keyv[s]) lo = mid; else hi = mid;
-        }
-        pts[s] = pt_sample(cdf + (size_t)lo * (kPtBins + 1), s ? u7 : u6, P.R);
-      }
-      pt1 = pts[0]; pt2 = pts[1];
+      pt1 = pt_ph[2 * t];        // getPhotonPt(k1), getPhotonPt(k2): drawn by k_pt_serve from the keys' tables
+      pt2 = pt_ph[2 * t + 1];
       double s1, c1, s2, c2;
       sincos(angle1, &s1, &c1);
       sincos(angle2, &s2, &c2);
@@ -349,7 +429,7 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
   npart[t] = np;
   for (int i = 0; i < UPCGPU_MAX_PART; i++) {
     const size_t o = t * UPCGPU_MAX_PART + i;
-    const bool v = i < np && i < 3;
+    const bool v = i < np;
     pdg[o] = v ? ppdg[i] : 0;
     status[o] = v ? pst[i] : 0;
     mother[o] = v ? pmo[i] : 0;
@@ -364,20 +444,37 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
   if (np > 0) atomicAdd(n_acc, 1ull);
 }
 
-static int ensure_scratch(upcgpu_ctx* c, size_t n, size_t n_keys)
+// bits of the largest photon-energy key the grid can produce (radix-sort passes)
+static int key_bits(const upcgpu_params& p)
+{
+  const double kmax = p.mmax / 2. * exp(fmax(fabs(p.ymin), fabs(p.ymax))) * 1e3 + 2.;
+  int bits = 1;
+  while (bits < 32 && (double)(1ull << bits) <= kmax) ++bits;
+  return bits;
+}
+
+static int ensure_scratch(upcgpu_ctx* c, size_t n)
 {
   EvScratch* s = (EvScratch*)c->ev;
   if (!s) { s = new EvScratch(); c->ev = s; }
+  if (!s->n_uniq) {
+    UPC_CUDA(c, cudaMalloc(&s->n_uniq, sizeof(int)));
+    UPC_CUDA(c, cudaMalloc(&s->next_tile, sizeof(unsigned)));
+    UPC_CUDA(c, cudaMalloc(&s->n_acc, sizeof(unsigned long long)));
+    UPC_CUDA(c, cudaMalloc(&s->err, sizeof(int)));
+    UPC_CUDA(c, cudaMallocHost(&s->report, sizeof(EvReport)));
+  }
   if (n > s->cap) {
-    cudaFree(s->y); cudaFree(s->m); cudaFree(s->cost); cudaFree(s->keys); cudaFree(s->keys_sorted); cudaFree(s->uniq);
-    cudaFree(s->npart); cudaFree(s->pdg); cudaFree(s->status); cudaFree(s->mother); cudaFree(s->p4); cudaFree(s->aux);
-    cudaFree(s->cub_tmp);
+    s->release();  // frees and nulls: a failed allocation below leaves nothing dangling
     UPC_CUDA(c, cudaMalloc(&s->y, n * sizeof(double)));
     UPC_CUDA(c, cudaMalloc(&s->m, n * sizeof(double)));
     UPC_CUDA(c, cudaMalloc(&s->cost, n * sizeof(double)));
-    UPC_CUDA(c, cudaMalloc(&s->keys, 2 * n * sizeof(int)));
-    UPC_CUDA(c, cudaMalloc(&s->keys_sorted, 2 * n * sizeof(int)));
-    UPC_CUDA(c, cudaMalloc(&s->uniq, 2 * n * sizeof(int)));
+    UPC_CUDA(c, cudaMalloc(&s->keys, 2 * n * sizeof(unsigned)));
+    UPC_CUDA(c, cudaMalloc(&s->keys_sorted, 2 * n * sizeof(unsigned)));
+    UPC_CUDA(c, cudaMalloc(&s->pid, 2 * n * sizeof(unsigned)));
+    UPC_CUDA(c, cudaMalloc(&s->pid_sorted, 2 * n * sizeof(unsigned)));
+    UPC_CUDA(c, cudaMalloc(&s->seg_off, 2 * n * sizeof(unsigned)));
+    UPC_CUDA(c, cudaMalloc(&s->pt, 2 * n * sizeof(double)));
     UPC_CUDA(c, cudaMalloc(&s->npart, n * sizeof(int)));
     UPC_CUDA(c, cudaMalloc(&s->pdg, n * UPCGPU_MAX_PART * sizeof(int)));
     UPC_CUDA(c, cudaMalloc(&s->status, n * UPCGPU_MAX_PART * sizeof(int)));
@@ -385,22 +482,13 @@ static int ensure_scratch(upcgpu_ctx* c, size_t n, size_t n_keys)
     UPC_CUDA(c, cudaMalloc(&s->p4, n * UPCGPU_MAX_PART * 4 * sizeof(double)));
     UPC_CUDA(c, cudaMalloc(&s->aux, n * 5 * sizeof(double)));
     size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, b1, (int*)nullptr, (int*)nullptr, (int)(2 * n), 0, 32, c->stream);
-    cub::DeviceSelect::Unique(nullptr, b2, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int)(2 * n), c->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr, (unsigned*)nullptr,
+                                    (int)(2 * n), 0, 32, c->stream);
+    cub::CountingInputIterator<unsigned> first(0u);
+    cub::DeviceSelect::If(nullptr, b2, first, (unsigned*)nullptr, (int*)nullptr, (int)(2 * n), KeyHead{nullptr}, c->stream);
     s->cub_bytes = std::max(b1, b2);
     UPC_CUDA(c, cudaMalloc(&s->cub_tmp, s->cub_bytes + 16));
     s->cap = n;
-  }
-  if (!s->n_uniq) {
-    UPC_CUDA(c, cudaMalloc(&s->n_uniq, sizeof(int)));
-    UPC_CUDA(c, cudaMalloc(&s->n_acc, sizeof(unsigned long long)));
-    UPC_CUDA(c, cudaMalloc(&s->err, sizeof(int)));
-  }
-  if (n_keys > s->cap_keys) {
-    cudaFree(s->cdf);
-    s->cdf = nullptr;
-    UPC_CUDA(c, cudaMalloc(&s->cdf, n_keys * (size_t)(kPtBins + 1) * sizeof(double)));
-    s->cap_keys = n_keys;
   }
   return UPCGPU_OK;
 }
@@ -427,38 +515,42 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
   if (c->p.nonzero_gam_pt && !c->tables_ready) { c->err = "generate: form-factor table not prepared"; return UPCGPU_EINVAL; }
   if (!c->p.ignore_csz && !c->sumz) { c->err = "generate: z samplers missing"; return UPCGPU_EINVAL; }
   cudaStream_t st = c->stream;
-  const size_t kChunk = (size_t)1 << 18;  // bounds the pT-table scratch: <= 2*kChunk keys * 40 KB = 21 GB worst case
   const EvParams P = make_evp(c);
+  if (!c->ev_attr_set) {
+    cudaFuncSetAttribute(k_pt_serve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    cudaFuncSetAttribute(k_pt_table_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    c->ev_attr_set = true;
+  }
+  const int kbits = key_bits(c->p);
   uint64_t total_acc = 0;
-  for (size_t off = 0; off < n; off += kChunk) {
-    const size_t cn = std::min(kChunk, n - off);
-    int rc = ensure_scratch(c, std::min(kChunk, n), 0);
+  for (size_t off = 0; off < n; off += kEvChunk) {
+    const size_t cn = std::min(kEvChunk, n - off);
+    int rc = ensure_scratch(c, std::min(kEvChunk, n));
     if (rc) return rc;
     EvScratch* s = (EvScratch*)c->ev;
     UPC_CUDA(c, cudaMemsetAsync(s->n_acc, 0, sizeof(unsigned long long), st));
     UPC_CUDA(c, cudaMemsetAsync(s->err, 0, sizeof(int), st));
     const unsigned g = (unsigned)((cn + 127) / 128);
     UPC_K(c), k_ev_sample<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, P.nonzero_gam_pt ? s->keys : nullptr,
-                                   s->err);
-    int n_uniq = 0;
+                                   s->pid, s->err);
     if (P.nonzero_gam_pt) {
+      const int n_ph = (int)(2 * cn);
       size_t tb = s->cub_bytes;
-      cub::DeviceRadixSort::SortKeys(s->cub_tmp, tb, s->keys, s->keys_sorted, (int)(2 * cn), 0, 32, st);
+      cub::DeviceRadixSort::SortPairs(s->cub_tmp, tb, s->keys, s->keys_sorted, s->pid, s->pid_sorted, n_ph, 0, kbits, st);
       tb = s->cub_bytes;
-      cub::DeviceSelect::Unique(s->cub_tmp, tb, s->keys_sorted, s->uniq, s->n_uniq, (int)(2 * cn), st);
-      UPC_CUDA(c, cudaMemcpyAsync(&n_uniq, s->n_uniq, sizeof(int), cudaMemcpyDeviceToHost, st));
-      UPC_CUDA(c, cudaStreamSynchronize(st));
-      rc = ensure_scratch(c, 0, (size_t)n_uniq);
-      if (rc) return rc;
-      s = (EvScratch*)c->ev;
-      UPC_K(c), k_pt_tables<<<n_uniq, 256, 0, st>>>(n_uniq, s->uniq, nullptr, c->ff_seg, c->p.gtot, c->p.R, s->cdf);
+      cub::CountingInputIterator<unsigned> cnt0(0u);
+      cub::DeviceSelect::If(s->cub_tmp, tb, cnt0, s->seg_off, s->n_uniq, n_ph, KeyHead{s->keys_sorted}, st);
+      // persistent grid: the number of distinct keys stays on the device
+      const int n_tiles = (n_ph + kPtThreads - 1) / kPtThreads;
+      const int grid = std::min(n_tiles, c->prop.multiProcessorCount * 5);
+      UPC_CUDA(c, cudaMemsetAsync(s->next_tile, 0, sizeof(unsigned), st));
+      UPC_K(c), k_pt_serve<<<grid, kPtThreads, sizeof(PtShared), st>>>(s->n_uniq, s->seg_off, (unsigned)n_ph, s->keys_sorted, s->pid_sorted,
+                                                             seed, first + off, c->ff_seg, c->p.gtot, c->p.R, s->pt, s->next_tile);
     }
-    UPC_K(c), k_ev_kin<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, s->uniq, n_uniq, s->cdf, s->npart, s->pdg,
-                                s->status, s->mother, s->p4, s->aux, s->n_acc);
-    unsigned long long acc = 0;
-    int herr = 0;
-    UPC_CUDA(c, cudaMemcpyAsync(&acc, s->n_acc, sizeof(acc), cudaMemcpyDeviceToHost, st));
-    UPC_CUDA(c, cudaMemcpyAsync(&herr, s->err, sizeof(herr), cudaMemcpyDeviceToHost, st));
+    UPC_K(c), k_ev_kin<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, s->pt, s->npart, s->pdg, s->status, s->mother,
+                                s->p4, s->aux, s->n_acc);
+    UPC_CUDA(c, cudaMemcpyAsync(&s->report->n_acc, s->n_acc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    UPC_CUDA(c, cudaMemcpyAsync(&s->report->err, s->err, sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!device_only) {
       if (npart) UPC_CUDA(c, cudaMemcpyAsync(npart + off, s->npart, cn * sizeof(int), cudaMemcpyDeviceToHost, st));
       const size_t o4 = off * UPCGPU_MAX_PART;
@@ -470,11 +562,11 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
     }
     UPC_CUDA(c, cudaStreamSynchronize(st));
     UPC_CUDA(c, cudaGetLastError());
-    if (herr) {
-      c->err = "generate: " + std::to_string(herr) + " uniforms fell outside the cumulative pdf (GSL: cannot find r1)";
+    if (s->report->err) {
+      c->err = "generate: " + std::to_string(s->report->err) + " uniforms fell outside the cumulative pdf (GSL: cannot find r1)";
       return UPCGPU_ERANGE;
     }
-    total_acc += acc;
+    total_acc += s->report->n_acc;
   }
   if (n_acc_out) *n_acc_out = total_acc;
   return UPCGPU_OK;
@@ -483,16 +575,25 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
 int photon_pt_cdf(upcgpu_ctx* c, double e, double* cdf)
 {
   if (!c->tables_ready) { c->err = "photon_pt_cdf: tables not prepared"; return UPCGPU_EINVAL; }
+  if (!c->ev_attr_set) {
+    cudaFuncSetAttribute(k_pt_serve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    cudaFuncSetAttribute(k_pt_table_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    c->ev_attr_set = true;
+  }
   double *de = nullptr, *dc = nullptr;
   UPC_CUDA(c, cudaMalloc(&de, sizeof(double)));
-  UPC_CUDA(c, cudaMalloc(&dc, (kPtBins + 1) * sizeof(double)));
-  UPC_CUDA(c, cudaMemcpy(de, &e, sizeof(double), cudaMemcpyHostToDevice));
-  UPC_K(c), k_pt_tables<<<1, 256, 0, c->stream>>>(1, nullptr, de, c->ff_seg, c->p.gtot, c->p.R, dc);
-  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
-  UPC_CUDA(c, cudaGetLastError());
-  UPC_CUDA(c, cudaMemcpy(cdf, dc, (kPtBins + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cudaMalloc(&dc, (kPtBins + 1) * sizeof(double)) != cudaSuccess) { cudaFree(de); c->err = "photon_pt_cdf: out of memory"; return UPCGPU_ECUDA; }
+  int rc = UPCGPU_OK;
+  if (cudaMemcpy(de, &e, sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) rc = UPCGPU_ECUDA;
+  if (!rc) {
+    UPC_K(c), k_pt_table_one<<<1, kPtThreads, sizeof(PtShared), c->stream>>>(de, c->ff_seg, c->p.gtot, c->p.R, dc);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess ||
+        cudaMemcpy(cdf, dc, (kPtBins + 1) * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = UPCGPU_ECUDA;
+  }
   cudaFree(de); cudaFree(dc);
-  return UPCGPU_OK;
+  if (rc) c->err = "photon_pt_cdf: CUDA error";
+  return rc;
 }
 
 }  // namespace upc

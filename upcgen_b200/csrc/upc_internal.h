@@ -34,6 +34,7 @@ int finish_fill(upcgpu_ctx* c);
 int lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* out, double* out_s, double* out_p);
 int lumi_unpack(upcgpu_ctx* c, int nshards);
 int ensure_lumi_buffers(upcgpu_ctx* c, int nshards);
+int ensure_gather_buffers(upcgpu_ctx* c, int nshards);
 void free_lumi_scratch(upcgpu_ctx* c);
 int fp64_peak(upcgpu_ctx* c, int iters, double* tflops, double* ms);
 
@@ -53,5 +54,24 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
              double* p4, double* aux, uint64_t* n_acc, bool device_only);
 int photon_pt_cdf(upcgpu_ctx* c, double e, double* cdf);
 void free_event_scratch(upcgpu_ctx* c);
+
+
+// upc_group.cu: several GPUs behind one handle
+int group_create(upcgpu_ctx* leader, int n_gpus, const int* devices, std::string& err);
+void group_destroy(upcgpu_ctx* leader);
+int group_size(const upcgpu_ctx* c);
+upcgpu_ctx* group_member(upcgpu_ctx* c, int rank);
+int group_exchange(const upcgpu_ctx* c);
+int group_set_exchange(upcgpu_ctx* c, int mode);
+int group_prepare_tables(upcgpu_ctx* leader);
+void group_invalidate_tables(upcgpu_ctx* leader);
+int group_fill_lumi(upcgpu_ctx* leader);
+int group_fold_sigma(upcgpu_ctx* leader, const double* sig_m, const double* sig_s, const double* sig_p, double* cs, double* ratio,
+                     double* totcs_mb);
+int group_sampler_build(upcgpu_ctx* leader, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps);
+int group_generate(upcgpu_ctx* leader, uint64_t seed, uint64_t first, size_t n, int* npart, int* pdg, int* status, int* mother,
+                   double* p4, double* aux, uint64_t* n_acc, bool device_only);
+void group_fill_stats(const upcgpu_ctx* leader, upcgpu_fill_stats* out);
+const char* group_describe(const upcgpu_ctx* leader, char* buf, size_t cap);
 
 }  // namespace upc

@@ -175,9 +175,18 @@ __global__ void k_ff_y(double R, double a, const double* rho0p, double* y)
 // the same LDL^T recurrences GSL uses and keeps the chunk.
 constexpr int kSpChunk = 48;   // short chunks: the kernel is a latency chain per thread (192: 0.33 ms for the 10^6-knot table)
 constexpr int kSpHalo = 64;
-__global__ void k_spline_windowed(double x0, double dx, const double* ya, int size, double* c)
+constexpr int kSpThreads = 64;
+__global__ void __launch_bounds__(kSpThreads) k_spline_windowed(double x0, double dx, const double* ya, int size, double* c)
 {
+  // The knot values of the block's window are staged in shared memory by coalesced loads: each of the 176 steps of a
+  // thread's recurrence needs three of them, and with the loads going to global memory (~700 cycles each, not
+  // overlapped by the compiler) the 20 200-knot breakup table took 104 us on 7 CTAs -- the critical path of the table stage.
+  __shared__ double sy[kSpThreads * kSpChunk + 2 * kSpHalo + 2];
   const int N = size - 2;  // unknowns u = 0..N-1  <->  c[u+1]
+  const int sb = blockIdx.x * kSpThreads * kSpChunk;
+  const int wsb = max(0, sb - kSpHalo), web = min(N, sb + kSpThreads * kSpChunk + kSpHalo);
+  for (int i = threadIdx.x; i < web - wsb + 2; i += kSpThreads) sy[i] = ya[wsb + i];
+  __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = t * kSpChunk;
   if (t == 0) {
@@ -189,14 +198,16 @@ __global__ void k_spline_windowed(double x0, double dx, const double* ya, int si
   const int ws = max(0, s - kSpHalo), we = min(N, e + kSpHalo);
   const int W = we - ws;
   double gamma[kSpChunk + 2 * kSpHalo], z[kSpChunk + 2 * kSpHalo];
+  const double* y = sy - wsb;  // y[i] = ya[i] for the indices of this block's window
   auto h = [&](int i) { return __dsub_rn(knot(x0, dx, i + 1), knot(x0, dx, i)); };
   auto rhs = [&](int i) {
     double h_i = h(i), h_ip1 = h(i + 1);
     double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
-    return 3.0 * ((ya[i + 2] - ya[i + 1]) * g_ip1 - (ya[i + 1] - ya[i]) * g_i);
+    return 3.0 * ((y[i + 2] - y[i + 1]) * g_ip1 - (y[i + 1] - y[i]) * g_i);
   };
   // forward: alpha_i = diag_i - off_{i-1} gamma_{i-1}; gamma_i = off_i/alpha_i; z_i = b_i - gamma_{i-1} z_{i-1}
   double alpha_prev = 0, gamma_prev = 0, z_prev = 0;
+#pragma unroll 4
   for (int j = 0; j < W; j++) {
     const int i = ws + j;
     double diag = 2.0 * (h(i + 1) + h(i));
@@ -373,6 +384,7 @@ __global__ void __launch_bounds__(32 * kBkWarps) k_bk_prob(const BkTable* __rest
   __syncwarp();
   if (lane == 0) {
     double pxn = 0.;
+#pragma unroll 8
     for (int k = 2; k < K; ++k) pxn = __dadd_rn(pxn, g[k]);
     double prob = 0.;
     if (mode == 1) prob = 1.;
@@ -527,7 +539,7 @@ int prepare_tables(upcgpu_ctx* c)
   UPC_K(c), k_ff_y<<<(kNQ2 + 255) / 256, 256, 0, st_ff>>>(p.R, p.a, c->d_scal, c->ff_y);
   {
     int nthr = (kNQ2 - 2 + kSpChunk - 1) / kSpChunk;
-    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st_ff>>>(kQ2min, kDQ2, c->ff_y, kNQ2, c->ff_c);
+    UPC_K(c), k_spline_windowed<<<(nthr + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st_ff>>>(kQ2min, kDQ2, c->ff_y, kNQ2, c->ff_c);
   }
   UPC_K(c), k_segs_uniform<<<(kNQ2 + 255) / 256, 256, 0, st_ff>>>(kQ2min, kDQ2, c->ff_y, c->ff_c, kNQ2, c->ff_seg, kNQ2 - 1);
   cudaEventRecord(c->aux_ev[2], st_ff);
@@ -549,7 +561,7 @@ int prepare_tables(upcgpu_ctx* c)
     UPC_K(c), k_bk_prob<<<(c->bk_nknots + kBkWarps - 1) / kBkWarps, 32 * kBkWarps, 0, st_bk>>>((const BkTable*)c->bk_table, p.breakup_mode, c->bk_nknots,
                                                           c->bk_y);
     int nthr = (c->bk_nknots - 2 + kSpChunk - 1) / kSpChunk;
-    UPC_K(c), k_spline_windowed<<<(nthr + 63) / 64, 64, 0, st_bk>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
+    UPC_K(c), k_spline_windowed<<<(nthr + kSpThreads - 1) / kSpThreads, kSpThreads, 0, st_bk>>>(kBkBmin, kBkDb, c->bk_y, c->bk_nknots, c->bk_c);
     UPC_K(c), k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st_bk>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
                                                               c->bk_seg, c->bk_nknots - 1);
   }

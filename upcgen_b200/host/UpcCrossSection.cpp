@@ -101,7 +101,21 @@ void UpcCrossSection::ensureContext()
 {
   if (ctx) return;
   upcgpu_params p = makeParams();
-  int rc = upcgpu_create(&p, device, &ctx);
+  int rc;
+  if (numGpus > 1) {
+    // the reference's -nthreads OpenMP team becomes -ngpus devices behind one handle: m rows dealt to the devices,
+    // NCCL all-gather of the table, events split by candidate ranges (include/upcgpu.h: upcgpu_create_multi)
+    std::vector<int> devs(numGpus);
+    for (int i = 0; i < numGpus; ++i) devs[i] = device + i;
+    rc = upcgpu_create_multi(&p, numGpus, devs.data(), &ctx);
+    if (rc == UPCGPU_OK) {
+      char buf[256];
+      upcgpu_group_describe(ctx, buf, sizeof(buf));
+      PLOG_INFO << "GPU group: " << buf;
+    }
+  } else {
+    rc = upcgpu_create(&p, device, &ctx);
+  }
   if (rc != UPCGPU_OK) {
     PLOG_FATAL << "upcgpu_create failed (" << rc << "): " << upcgpu_last_error(nullptr);
     std::_Exit(-1);

@@ -107,7 +107,8 @@ class UpcCrossSection
   void prepareTwoPhotonLumi();
 
   // ---- additions of the GPU build (not in the reference) ----
-  int device{0};                 // CUDA device of this instance
+  int device{0};                 // CUDA device of this instance (first device when numGpus > 1)
+  int numGpus{1};                // devices used for the table stage and the event stage (-ngpus; devices device .. device+numGpus-1)
   upcgpu_ctx* gpu() { return ctx; }
   const std::vector<double>& lumiTable() const { return lumi; }     // [nm][ny], x dm dy
   const std::vector<double>& lumiTableS() const { return lumiS; }

@@ -56,6 +56,7 @@ class UpcGenerator
 
   // additions of the GPU build
   void setDevice(int dev) { nucProcessCS->device = dev; }
+  void setNumGpus(int n) { nucProcessCS->numGpus = n < 1 ? 1 : n; }
   UpcCrossSection* crossSection() { return nucProcessCS; }
 
  private:

@@ -134,6 +134,11 @@ bool UpcRootHist::Read(const std::string& path, const std::string& objName, std:
       pos += (uint64_t)nbytes;
     }
     if (best.cycle < 0) throw std::runtime_error("no TH1D/TH2D named " + objName);
+    // these files are external input: the key must lie inside the file and hold its own header
+    if (best.keylen <= 0 || best.keylen > best.nbytes || best.pos + (uint64_t)best.nbytes > file.size())
+      throw std::runtime_error("truncated key of " + objName);
+    if (best.objlen < 0 || (uint64_t)best.objlen > ((uint64_t)1 << 31))
+      throw std::runtime_error("implausible object length of " + objName);
     // the object buffer, inflated if the key says so
     const unsigned char* raw = file.data() + best.pos + best.keylen;
     const size_t rawlen = (size_t)best.nbytes - best.keylen;
