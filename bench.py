@@ -335,7 +335,7 @@ class Bench:
         ms_sampler = (time.perf_counter() - t0) * 1e3
         n_ev = max(n_total // world, 1 << 14)
         first = rank * n_ev
-        gpu.generate_device(12345, first, min(n_ev, 1 << 20))  # warm-up: the scratch buffers grow on demand
+        gpu.generate_device(12345, first, n_ev)  # warm-up at full size: the scratch buffers grow on demand
         self.barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(self.ext_stream)

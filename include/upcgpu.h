@@ -213,6 +213,18 @@ int upcgpu_elem_fill_cs_zm(int proc_id, double a_lep, double alp_mass, double al
 int upcgpu_root_hist_read(const char* path, const char* name, int* dim, int* nx, double* xlo, double* xhi, int* ny,
                           double* ylo, double* yhi, double* cells, size_t cap, size_t* n_cells);
 
+/* The writer side (upcgen_b200/host/UpcRootFile.cpp), also without ROOT and without a GPU.
+ * upcgpu_root_write_th2d: a file with n_hist TH2D objects of common uniform axes -- the luminosity cache
+ * twoPhotonLumi[Pol].root as the reference writes it (src/UpcCrossSection.cpp:493-507, :578-585): names[i],
+ * cells[i] = (nx + 2) x (ny + 2) doubles, x fastest, under-/overflow cells included.
+ * upcgpu_root_write_tree: a file with one TTree of flat branches -- events.root with the tree "particles"
+ * (src/UpcGenerator.cpp:842-857): n_cols columns of n_rows values, types[i] = 'I' (Int_t) or 'D' (Double_t); integer
+ * columns are passed as doubles holding integral values. */
+int upcgpu_root_write_th2d(const char* path, int n_hist, const char* const* names, int nx, double xlo, double xhi, int ny,
+                           double ylo, double yhi, const double* const* cells);
+int upcgpu_root_write_tree(const char* path, const char* tree, const char* title, int n_cols, const char* const* names,
+                           const char* types, const double* const* columns, size_t n_rows);
+
 /* ---- samplers S1-S3 ------------------------------------------------------------------ */
 /* replaces the UpcSampler2D / UpcSampler1D constructors (include/UpcSampler.h:40-59, :81-109,
  * i.e. gsl_histogram[2d]_pdf_init) built in UpcGenerator::computeNuclXsection

@@ -49,7 +49,7 @@ def test_facade_classes_match_oracle(tmp_path, oracle_mod):
     assert d["s1sum"] == list(oracle_mod.pdf_init(np.array([1., 2., 0., 4., 3.])))
     assert all(0 <= v < 5 and not (2 <= v < 3) for v in d["s1"])
     # the cache file written by prepareTwoPhotonLumi is picked up by a second run
-    assert os.path.exists(tmp_path / "twoPhotonLumi.bin")
+    assert os.path.exists(tmp_path / "twoPhotonLumi.root")
     out2 = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert "Found pre-calculated" in out2.stderr
     assert json.loads(out2.stdout.strip().splitlines()[-1])["totCS"] == d["totCS"]
@@ -96,3 +96,56 @@ USE_HEPMC_OUTPUT 1
     pair = p[0::2, :4] + p[1::2, :4]
     minv = np.sqrt(pair[:, 3] ** 2 - pair[:, 0] ** 2 - pair[:, 1] ** 2 - pair[:, 2] ** 2)
     assert minv.min() >= 4 - 1e-6 and minv.max() <= 30 + 1e-6
+
+
+def test_upcgen_cli_reads_a_reference_style_lumi_cache_and_writes_events_root(tmp_path, oracle_mod):
+    """(f2) twoPhotonLumi.root -- here written by the ROOT-less writer from the ORACLE's table, i.e. the file a run of
+    the reference would have left behind -- is picked up instead of recomputing (src/UpcCrossSection.cpp:481-491), and
+    the cross section is the oracle's.  (f3) USE_ROOT_OUTPUT 1 writes events.root with the tree "particles" and its nine
+    branches (src/UpcGenerator.cpp:842-857), consistent with events.hepmc written by the same run."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_root_file import read_tree
+    from upcgen_b200 import capi
+    from upcgen_b200.config import UpcParams
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    par = """NUCLEUS_Z 82
+NUCLEUS_A 208
+SQRTS 5020
+PROC_ID 13
+NEVENTS 2000
+MMIN 4
+MMAX 30
+BINS_M 20
+BINS_Y 10
+BINS_Z 50
+FLUX_POINT 1
+BREAKUP_MODE 1
+NON_ZERO_GAM_PT 0
+SEED 7
+USE_ROOT_OUTPUT 1
+USE_HEPMC_OUTPUT 1
+"""
+    (tmp_path / "my.in").write_text(par)
+    P = UpcParams.from_text(par).init()
+    o = oracle_mod.Oracle(P)
+    lumi = o.fill_lumi()
+    _, _, tot = o.fold(lumi)
+    capi.root_write_th2d(str(tmp_path / "twoPhotonLumi.root"), {"hD2LDMDY": lumi}, P.nm, P.mmin, P.mmax, P.ny, P.ymin, P.ymax)
+    r = subprocess.run([os.path.join(HOST, "upcgen"), "-parfile", "my.in"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Found pre-calculated unpolarized 2D luminosity" in r.stderr
+    line = [l for l in r.stdout.splitlines() if "total cross section" in l][0]
+    assert float(line.split()[4]) == pytest.approx(tot, rel=1e-5)     # printed with 6 digits
+    t = read_tree((tmp_path / "events.root").read_bytes(), "particles")
+    assert t["entries"] == 4000 and list(t["cols"]) == ["eventNumber", "pdgCode", "particleID", "statusID", "motherID",
+                                                        "px", "py", "pz", "e"]
+    c = {k: v[1] for k, v in t["cols"].items()}
+    assert c["eventNumber"].tolist() == np.repeat(np.arange(2000), 2).tolist()
+    assert c["particleID"].tolist() == [1, 2] * 2000 and set(c["statusID"]) == {23} and set(c["motherID"]) == {0}
+    hep = [l.split() for l in (tmp_path / "events.hepmc").read_text().splitlines() if l.startswith("P ")]
+    assert len(hep) == 4000
+    assert [int(q[3]) for q in hep] == c["pdgCode"].tolist()
+    for j, name in enumerate(("px", "py", "pz", "e")):
+        assert np.allclose([float(q[4 + j]) for q in hep], c[name], rtol=2e-8, atol=1e-12)   # HepMC prints 9 digits

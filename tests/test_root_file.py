@@ -1,0 +1,353 @@
+"""The ROOT-less WRITER (upcgen_b200/host/UpcRootFile.cpp, through upcgpu_root_write_th2d / upcgpu_root_write_tree):
+the luminosity cache twoPhotonLumi[Pol].root and events.root as the reference writes them
+(src/UpcCrossSection.cpp:493-507, :578-585; src/UpcGenerator.cpp:842-857).  No GPU involved.
+
+ROOT is not available here to read the files back.  What pins the writer instead:
+  * the TH2D object it streams is BYTE-IDENTICAL to the one ROOT 6.22/09 wrote into the reference's own
+    cross_sections/lbyl/cross_section_zm.root when given the same name, axes and cells (runs where /root/reference is
+    mounted): class versions, member order, default attributes, byte counts -- everything ROOT's own streamer put there;
+  * the file-level records (header, directory, key list, streamer-info list, free segments) are walked by an
+    independent parser written here from the format description, every byte accounted for;
+  * the TTree is read back by an independent Python parser (below) that follows ROOT's streaming rules -- byte counts,
+    class tags and back references, the branches' basket tables, the basket keys -- and returns the columns.
+"""
+import os
+import struct
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT_DIR)
+REF = "/root/reference/cross_sections"
+
+
+class Buf:
+    def __init__(self, b, base=0):
+        self.b, self.p, self.base = b, 0, base   # base: offset of b[0] inside its key buffer (fKeylen)
+
+    def rd(self, fmt):
+        n = struct.calcsize(">" + fmt)
+        v = struct.unpack(">" + fmt, self.b[self.p:self.p + n])
+        self.p += n
+        return v[0] if len(v) == 1 else v
+
+    def tstring(self):
+        n = self.rd("B")
+        if n == 255:
+            n = self.rd("I")
+        s = self.b[self.p:self.p + n].decode("latin1")
+        self.p += n
+        return s
+
+    def cstring(self):
+        e = self.b.index(b"\0", self.p)
+        s = self.b[self.p:e].decode("latin1")
+        self.p = e + 1
+        return s
+
+    def obj(self):
+        v = self.rd("I")
+        assert v & 0x40000000, hex(v)
+        end = self.p + (v & 0x3FFFFFFF)
+        return end, self.rd("H")
+
+
+def read_keys(f):
+    """TFile header + the chain of keys; returns (header dict, [key dict])."""
+    assert f[:4] == b"root"
+    ver, begin, end, seekfree, nbfree, nfree, nbname, units, compress, seekinfo, nbinfo = struct.unpack(">iiiiiiibiii", f[4:45])
+    hdr = dict(ver=ver, begin=begin, end=end, seekfree=seekfree, nbfree=nbfree, nfree=nfree, nbname=nbname, units=units,
+               compress=compress, seekinfo=seekinfo, nbinfo=nbinfo)
+    keys, pos = [], begin
+    while pos < end:
+        nbytes, version, objlen, dt, keylen, cycle, seekkey, seekpdir = struct.unpack(">ihiIhhii", f[pos:pos + 26])
+        assert nbytes > 0 and version == 4
+        b = Buf(f[pos + 26:pos + keylen])
+        cls, name, title = b.tstring(), b.tstring(), b.tstring()
+        keys.append(dict(pos=pos, nbytes=nbytes, objlen=objlen, keylen=keylen, cycle=cycle, seekkey=seekkey,
+                         seekpdir=seekpdir, cls=cls, name=name, title=title, hdrlen=26 + b.p))
+        pos += nbytes
+    assert pos == end
+    return hdr, keys
+
+
+def key_data(f, k):
+    raw = f[k["pos"] + k["keylen"]:k["pos"] + k["nbytes"]]
+    if len(raw) == k["objlen"]:
+        return raw
+    out, q = b"", 0
+    while len(out) < k["objlen"]:
+        assert raw[q:q + 2] == b"ZL"
+        csz = raw[q + 3] | raw[q + 4] << 8 | raw[q + 5] << 16
+        out += zlib.decompress(raw[q + 9:q + 9 + csz])
+        q += 9 + csz
+    return out
+
+
+def check_file_records(f):
+    """header / directory / key list / streamer info / free segments are consistent with each other."""
+    hdr, keys = read_keys(f)
+    assert hdr["end"] == len(f) and hdr["begin"] == 100 and hdr["units"] == 4
+    d = keys[0]
+    assert d["cls"] == "TFile" and d["pos"] == 100 and d["seekkey"] == 100 and d["seekpdir"] == 0
+    b = Buf(key_data(f, d))
+    name, title = b.tstring(), b.tstring()
+    assert name == d["name"] and title == ""
+    assert hdr["nbname"] == d["keylen"] + b.p
+    ver, dc, dm, nbkeys, nbname, seekdir, seekparent, seekkeys = b.rd("hIIiiiii")
+    assert ver == 5 and seekdir == 100 and seekparent == 0 and nbname == hdr["nbname"]
+    uuid = b.b[b.p:b.p + 18]
+    assert uuid == f[45:63] and len(b.b) - b.p - 18 == 12
+    # key list
+    kl = [k for k in keys if k["pos"] == seekkeys]
+    assert len(kl) == 1 and kl[0]["nbytes"] == nbkeys and kl[0]["cls"] == "TFile"
+    kb = Buf(key_data(f, kl[0]))
+    listed = []
+    for _ in range(kb.rd("i")):
+        nbytes, version, objlen, dt, keylen, cycle, seekkey, seekpdir = kb.rd("ihiIhhii")
+        cls, nm, ti = kb.tstring(), kb.tstring(), kb.tstring()
+        listed.append((seekkey, cls, nm))
+        real = [k for k in keys if k["pos"] == seekkey][0]
+        assert (real["nbytes"], real["objlen"], real["keylen"], real["cls"], real["name"]) == (nbytes, objlen, keylen, cls, nm)
+        assert seekpdir == 100
+    assert kb.p == len(kb.b)
+    # streamer info: a TList
+    si = [k for k in keys if k["pos"] == hdr["seekinfo"]][0]
+    assert si["cls"] == "TList" and si["name"] == "StreamerInfo" and si["nbytes"] == hdr["nbinfo"]
+    # free segments: one, from the end of the file
+    fr = [k for k in keys if k["pos"] == hdr["seekfree"]][0]
+    assert fr["nbytes"] == hdr["nbfree"] and hdr["nfree"] == 1
+    v, first, last = struct.unpack(">hii", key_data(f, fr))
+    assert v == 1 and first == hdr["end"] and last == 2000000000
+    return hdr, keys, listed
+
+
+def test_th2d_roundtrip_and_records(tmp_path):
+    from upcgen_b200 import capi
+    rng = np.random.default_rng(1)
+    nm, ny = 37, 11
+    t0, t1 = rng.random((nm, ny)) * 1e3, rng.random((nm, ny))
+    path = str(tmp_path / "twoPhotonLumiPol.root")
+    capi.root_write_th2d(path, {"hD2LDMDY_s": t0, "hD2LDMDY_p": t1}, nm, 3.56, 50.0, ny, -6.0, 6.0)
+    f = open(path, "rb").read()
+    hdr, keys, listed = check_file_records(f)
+    assert [(c, n) for _, c, n in listed] == [("TH2D", "hD2LDMDY_s"), ("TH2D", "hD2LDMDY_p")]
+    # read back with the product's reader (the one the light-by-light plug-in uses on the reference's files)
+    for name, t in (("hD2LDMDY_s", t0), ("hD2LDMDY_p", t1)):
+        h = capi.root_hist_read(path, name)
+        assert (h["dim"], h["nx"], h["ny"]) == (2, nm, ny)
+        assert (h["xlo"], h["xhi"], h["ylo"], h["yhi"]) == (3.56, 50.0, -6.0, 6.0)
+        assert np.array_equal(h["cells"][1:-1, 1:-1].T, t)       # bin (im + 1, iy + 1) = table[im][iy]
+        assert np.all(h["cells"][0] == 0) and np.all(h["cells"][:, 0] == 0)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's cross_sections directory is not mounted")
+def test_th2d_bytes_equal_what_root_wrote(tmp_path):
+    """Same name, axes and cells as the TH2D in the reference's cross_section_zm.root -> the same streamed object,
+    byte for byte, as ROOT 6.22/09 produced."""
+    from upcgen_b200 import capi
+    src = os.path.join(REF, "lbyl", "cross_section_zm.root")
+    f = open(src, "rb").read()
+    _, keys = read_keys(f)
+    k = [k for k in keys if k["cls"] == "TH2D"][0]
+    real = key_data(f, k)
+    h = capi.root_hist_read(src, k["name"])
+    nx, ny = h["nx"], h["ny"]
+    path = str(tmp_path / "copy.root")
+    # all (nx + 2) x (ny + 2) cells, the overflow row included (this histogram has entries there)
+    import ctypes as C
+    L = capi.lib()
+    cells = np.ascontiguousarray(h["cells"], dtype=np.float64)
+    names = (C.c_char_p * 1)(k["name"].encode())
+    ptrs = (C.c_void_p * 1)(cells.ctypes.data)
+    L.upcgpu_root_write_th2d.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                         C.c_double, C.c_double, C.c_void_p]
+    assert L.upcgpu_root_write_th2d(path.encode(), 1, names, nx, h["xlo"], h["xhi"], ny, h["ylo"], h["yhi"], ptrs) == 0
+    g = open(path, "rb").read()
+    _, keys2 = read_keys(g)
+    mine = key_data(g, [q for q in keys2 if q["cls"] == "TH2D"][0])
+    assert len(mine) == len(real)
+    diff = [i for i in range(len(real)) if real[i] != mine[i]]
+    assert not diff, (len(diff), diff[:20])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's cross_sections directory is not mounted")
+def test_record_checker_accepts_files_root_wrote():
+    """check_file_records -- the statement of how header, directory, key list, streamer info and free segments hang
+    together that the writer's output is held to -- holds for the four files ROOT itself wrote for the reference."""
+    for p in ("lbyl/cross_section_zm.root", "lbyl/cross_section_m.root", "pi0pi0/cross_section_m.root", "pi0pi0/cross_section_zm.root"):
+        hdr, keys, listed = check_file_records(open(os.path.join(REF, p), "rb").read())
+        assert len(listed) == 1 and listed[0][1] in ("TH1D", "TH2D")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# an independent reader of flat TTrees (TTree v20, TBranch v13, TLeaf{I,D}, TBasket) following ROOT's streaming rules
+def read_tree(f, name):
+    hdr, keys, listed = check_file_records(f)
+    k = [k for k in keys if k["cls"] == "TTree" and k["name"] == name][0]
+    b = Buf(key_data(f, k), base=k["keylen"])
+    classes = {}   # tag position -> class name
+    objects = {}   # tag position -> leaf dict
+
+    def tnamed():
+        end, v = b.obj()
+        assert v == 1
+        assert b.rd("H") == 1
+        b.rd("I"); b.rd("I")
+        n, t = b.tstring(), b.tstring()
+        assert b.p == end
+        return n, t
+
+    def skip_obj(version):
+        end, v = b.obj()
+        assert v == version
+        b.p = end
+
+    def tobjarray():
+        end, v = b.obj()
+        assert v == 3
+        assert b.rd("H") == 1
+        b.rd("I"); b.rd("I")
+        assert b.tstring() == ""
+        n, low = b.rd("i"), b.rd("i")
+        assert low == 0
+        return end, n
+
+    def object_any():
+        """WriteObjectAny: byte count, class tag (new: 0xFFFFFFFF + name; known: position | 0x80000000), object."""
+        start = b.p
+        first = b.rd("I")
+        if first == 0:
+            return None, None, start
+        if not (first & 0x40000000):          # reference to an object already streamed
+            return "ref", first, start
+        end = b.p + (first & 0x3FFFFFFF)
+        tagpos = b.p
+        tag = b.rd("I")
+        if tag == 0xFFFFFFFF:
+            cls = b.cstring()
+            classes[b.base + tagpos + 2] = cls
+        else:
+            assert tag & 0x80000000
+            cls = classes[tag & 0x7FFFFFFF]
+        return cls, end, start
+
+    def tio_features():
+        end, v = b.obj()
+        b.p = end
+
+    end_tree, v = b.obj()
+    assert v == 20
+    tname, ttitle = tnamed()
+    skip_obj(2); skip_obj(2); skip_obj(2)
+    entries, totbytes, zipbytes, saved, flushed = b.rd("qqqqq")
+    weight = b.rd("d")
+    timer, scan, update, deflen, ncluster = b.rd("iiiii")
+    maxentries, maxloop, maxvirt, autosave, autoflush, estimate = b.rd("qqqqqq")
+    assert ncluster == 0 and b.rd("B") == 0 and b.rd("B") == 0
+    tio_features()
+    end_br, nbr = tobjarray()
+    branches = []
+    for _ in range(nbr):
+        cls, end, start = object_any()
+        assert cls == "TBranch"
+        e2, v = b.obj()
+        assert v == 13
+        bname, btitle = tnamed()
+        skip_obj(2)
+        compress, basketsize, entryoffsetlen, writebasket = b.rd("iiii")
+        entrynumber = b.rd("q")
+        tio_features()
+        offset, maxbaskets, splitlevel = b.rd("iii")
+        bentries, firstentry, btot, bzip = b.rd("qqqq")
+        e3, n3 = tobjarray(); assert n3 == 0 and b.p == e3
+        e4, nleaves = tobjarray()
+        assert nleaves == 1
+        lcls, lend, lstart = object_any()
+        assert lcls in ("TLeafI", "TLeafD")
+        e5, v5 = b.obj(); assert v5 == 1
+        e6, v6 = b.obj(); assert v6 == 2
+        lname, ltitle = tnamed()
+        flen, lentype, loffset, isrange, isunsigned, leafcount = b.rd("iiiBBI")
+        assert b.p == e6 and flen == 1 and leafcount == 0
+        b.rd("ii" if lcls == "TLeafI" else "dd")
+        assert b.p == e5 == lend and b.p == e4
+        objects[b.base + lstart + 2] = dict(name=lname, cls=lcls)
+        e7, n7 = tobjarray(); assert n7 == 0 and b.p == e7
+        assert b.rd("B") == 1
+        bbytes = [b.rd("i") for _ in range(maxbaskets)]
+        assert b.rd("B") == 1
+        bentry = [b.rd("q") for _ in range(maxbaskets)]
+        assert b.rd("B") == 1
+        bseek = [b.rd("q") for _ in range(maxbaskets)]
+        assert b.tstring() == ""
+        assert b.p == e2 == end
+        assert entrynumber == bentries == entries and compress == 0
+        branches.append(dict(name=bname, title=btitle, leaf=lcls, lentype=lentype, nbaskets=writebasket, bytes=bbytes,
+                             entry=bentry, seek=bseek, tot=btot))
+    assert b.p == end_br
+    end_lv, nlv = tobjarray()
+    assert nlv == nbr
+    for i in range(nlv):
+        kind, ref, _ = object_any()
+        assert kind == "ref" and objects[ref]["name"] == branches[i]["name"]
+    assert b.p == end_lv
+    assert b.rd("I") == 0 and b.rd("i") == 0 and b.rd("i") == 0
+    assert b.rd("IIII") == (0, 0, 0, 0)
+    assert b.p == end_tree == len(b.b)
+    # baskets
+    cols = {}
+    by_pos = {k["pos"]: k for k in keys}
+    total = 0
+    for br in branches:
+        vals = []
+        for i in range(br["nbaskets"]):
+            k = by_pos[br["seek"][i]]
+            assert k["cls"] == "TBasket" and k["name"] == br["name"] and k["title"] == name and k["nbytes"] == br["bytes"][i]
+            hb = Buf(f[k["pos"] + k["hdrlen"]:k["pos"] + k["keylen"]])
+            ver, bufsize, nevsize, nev, last, flag = hb.rd("hiiiiB")
+            assert hb.p == len(hb.b) and ver == 3 and flag == 0
+            assert nevsize == br["lentype"] and last == k["keylen"] + k["objlen"] and k["objlen"] == nev * nevsize
+            nxt = br["entry"][i + 1]
+            assert br["entry"][i] + nev == nxt
+            dt = ">i4" if br["leaf"] == "TLeafI" else ">f8"
+            vals.append(np.frombuffer(f, dtype=dt, count=nev, offset=k["pos"] + k["keylen"]))
+            total += k["nbytes"]
+        assert br["entry"][br["nbaskets"]] == entries
+        cols[br["name"]] = (br["title"], np.concatenate(vals) if vals else np.zeros(0))
+    assert total == totbytes == zipbytes
+    assert all(k[1] != "TBasket" for k in listed)       # baskets are not in the directory's key list
+    return dict(name=tname, title=ttitle, entries=entries, autosave=autosave, cols=cols)
+
+
+def test_tree_roundtrip(tmp_path):
+    """events.root as src/UpcGenerator.cpp:842-857 declares it: tree "particles", nine branches."""
+    from upcgen_b200 import capi
+    rng = np.random.default_rng(2)
+    n = 2_300_001    # more than one basket per branch (2^20 entries each)
+    cols = {"eventNumber": ("I", np.repeat(np.arange(n // 3 + 1), 3)[:n]), "pdgCode": ("I", rng.choice([13, -13, 22], n)),
+            "particleID": ("I", np.tile([1, 2, 3], n // 3 + 1)[:n]), "statusID": ("I", np.full(n, 23)),
+            "motherID": ("I", rng.integers(0, 3, n)), "px": ("D", rng.normal(size=n)), "py": ("D", rng.normal(size=n)),
+            "pz": ("D", rng.normal(size=n) * 50), "e": ("D", rng.random(n) * 100)}
+    path = str(tmp_path / "events.root")
+    capi.root_write_tree(path, "particles", "Generated particles", cols)
+    t = read_tree(open(path, "rb").read(), "particles")
+    assert t["name"] == "particles" and t["title"] == "Generated particles" and t["entries"] == n and t["autosave"] == 0
+    assert list(t["cols"]) == list(cols)
+    for name, (typ, vals) in cols.items():
+        title, got = t["cols"][name]
+        assert title == f"{name}/{typ}"
+        assert np.array_equal(got, np.asarray(vals, dtype=got.dtype.newbyteorder("=")))
+
+
+def test_tree_empty_and_small(tmp_path):
+    from upcgen_b200 import capi
+    for n in (0, 1, 5):
+        path = str(tmp_path / f"e{n}.root")
+        capi.root_write_tree(path, "particles", "Generated particles", {"pdgCode": ("I", np.arange(n)), "e": ("D", np.arange(n) * 0.5)})
+        t = read_tree(open(path, "rb").read(), "particles")
+        assert t["entries"] == n
+        assert np.array_equal(t["cols"]["e"][1], np.arange(n) * 0.5)

@@ -68,7 +68,7 @@ SYMBOLS = [
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
     "upcgpu_create_multi", "upcgpu_group_size", "upcgpu_group_member", "upcgpu_group_set_exchange",
-    "upcgpu_group_describe",
+    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_tree",
 ]
 
 
@@ -459,6 +459,43 @@ def root_hist_read(path: str, name: str):
     out = dict(dim=dim.value, nx=nx.value, xlo=xlo.value, xhi=xhi.value, ny=ny.value, ylo=ylo.value, yhi=yhi.value)
     out["cells"] = cells.reshape(ny.value + 2, nx.value + 2) if dim.value == 2 else cells
     return out
+
+
+def root_write_th2d(path: str, hists: dict, nx, xlo, xhi, ny, ylo, yhi):
+    """Writes TH2D objects {name: table[nx][ny]} (bin (ix + 1, iy + 1) = table[ix][iy], as the reference fills
+    hD2LDMDY: src/UpcCrossSection.cpp:564-571) into a ROOT file, without ROOT."""
+    L = lib()
+    names = list(hists)
+    cells = []
+    for nme in names:
+        t = _f64(hists[nme])
+        assert t.shape == (nx, ny)
+        c = np.zeros((ny + 2, nx + 2))
+        c[1:-1, 1:-1] = t.T
+        cells.append(np.ascontiguousarray(c))
+    arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    arr_c = (C.c_void_p * len(names))(*[c.ctypes.data for c in cells])
+    L.upcgpu_root_write_th2d.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                         C.c_double, C.c_double, C.c_void_p]
+    rc = L.upcgpu_root_write_th2d(path.encode(), len(names), arr_n, nx, xlo, xhi, ny, ylo, yhi, arr_c)
+    if rc != OK:
+        raise UpcGpuError(rc, f"root_write_th2d: cannot write {path}")
+
+
+def root_write_tree(path: str, tree: str, title: str, columns: dict):
+    """Writes a TTree of flat branches {name: (type 'I' | 'D', values)} into a ROOT file, without ROOT."""
+    L = lib()
+    names = list(columns)
+    vals = [_f64(columns[n][1]) for n in names]
+    types = "".join(columns[n][0] for n in names).encode()
+    arr_n = (C.c_char_p * len(names))(*[n.encode() for n in names])
+    arr_c = (C.c_void_p * len(names))(*[v.ctypes.data for v in vals])
+    L.upcgpu_root_write_tree.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_void_p, C.c_char_p, C.c_void_p,
+                                         C.c_size_t]
+    rc = L.upcgpu_root_write_tree(path.encode(), tree.encode(), title.encode(), len(names), arr_n, types, arr_c,
+                                  vals[0].size)
+    if rc != OK:
+        raise UpcGpuError(rc, f"root_write_tree: cannot write {path}")
 
 
 def philox(seed, ctr0, block, n):

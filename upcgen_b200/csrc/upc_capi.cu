@@ -133,6 +133,7 @@ void upcgpu_destroy(upcgpu_ctx* c)
   cudaFree(c->edges_y); cudaFree(c->edges_m); cudaFree(c->edges_z);
   free_event_scratch(c);
   free_lumi_scratch(c);
+  cudaFree(c->cell_counter);
   for (int i = 0; i < 2; ++i) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   for (int i = 0; i < 4; ++i) if (c->aux_ev[i]) cudaEventDestroy(c->aux_ev[i]);
   for (int i = 0; i < 2; ++i) if (c->fill_ev[i]) cudaEventDestroy(c->fill_ev[i]);

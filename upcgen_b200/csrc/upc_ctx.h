@@ -21,6 +21,7 @@ struct DevTables {
   const SplineSeg* gaa_seg;
   double gaa_inv_db;  // 199/20
   double gaa_db;
+  int gaa_i0;         // first segment of the live window kept in shared memory by the cell kernel (segments below are cut)
   double b_in2;       // G_AA's spline is <= 1e-30 in magnitude on [0, sqrt(b_in2)]: (b1, b2) pairs that stay below contribute nothing
   // breakup: knots b_i = 1e-6 + db*i, i < nbk (covers [0, 20.2]); seg[nbk-1] = {P20,0,0,0}
   const SplineSeg* bk_seg;
@@ -79,6 +80,7 @@ struct upcgpu_ctx_impl {
   // flux-row scratch of the lumi fill (allocated once, reused by every fill)
   void* slab = nullptr;
   int slab_max_m = 0;
+  unsigned* cell_counter = nullptr;  // work counter of the persistent cell kernel
   // A fill is queued on the stream and collected later (finish_fill): number of slabs whose reports are pending
   int fill_pending = 0;
   cudaEvent_t fill_ev[2] = {nullptr, nullptr};

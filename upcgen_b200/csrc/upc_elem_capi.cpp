@@ -2,9 +2,13 @@
 // (upcgen_b200/host/UpcTwoPhoton*.cpp), for callers that cannot instantiate the C++ classes
 // (the Python tests/bench).  The C++ facade calls the classes directly.
 #include <memory>
+#include <string>
+#include <vector>
 
 #include "../../include/upcgpu.h"
 #include "../host/UpcPhysConstants.h"
+#include "../host/UpcRootFile.h"
+#include "../host/UpcRootHist.h"
 #include "../host/UpcTwoPhotonALP.h"
 #include "../host/UpcTwoPhotonDilep.h"
 #include "../host/UpcTwoPhotonTabulated.h"
@@ -86,6 +90,50 @@ int upcgpu_root_hist_read(const char* path, const char* name, int* dim, int* nx,
     for (size_t i = 0; i < h.fArray.size(); ++i) cells[i] = h.fArray[i];
   }
   return UPCGPU_OK;
+}
+
+// The writer side (upcgen_b200/host/UpcRootFile.cpp): the luminosity cache twoPhotonLumi[Pol].root as the reference
+// writes it (n_hist TH2D objects: names[i], cells[i] = (nx + 2) * (ny + 2) doubles, x fastest) ...
+int upcgpu_root_write_th2d(const char* path, int n_hist, const char* const* names, int nx, double xlo, double xhi, int ny,
+                           double ylo, double yhi, const double* const* cells)
+{
+  if (!path || n_hist < 1 || !names || !cells || nx < 1 || ny < 1) return UPCGPU_EINVAL;
+  try {
+    UpcRootFileWriter w;
+    const size_t nc = (size_t)(nx + 2) * (ny + 2);
+    for (int i = 0; i < n_hist; ++i) {
+      if (!names[i] || !cells[i]) return UPCGPU_EINVAL;
+      std::vector<double> c(cells[i], cells[i] + nc);
+      w.AddTH2D(names[i], "", nx, xlo, xhi, ny, ylo, yhi, c, (double)nx * ny);
+    }
+    std::string err;
+    return w.Write(path, err) ? UPCGPU_OK : UPCGPU_EINVAL;
+  } catch (...) {
+    return UPCGPU_EINVAL;
+  }
+}
+
+// ... and a TTree of flat branches (events.root: tree "particles", src/UpcGenerator.cpp:842-857): n_cols columns of
+// n_rows values each, types[i] = 'I' (Int_t) or 'D' (Double_t), integer columns passed as doubles
+int upcgpu_root_write_tree(const char* path, const char* tree, const char* title, int n_cols, const char* const* names,
+                           const char* types, const double* const* columns, size_t n_rows)
+{
+  if (!path || !tree || n_cols < 1 || !names || !types || !columns) return UPCGPU_EINVAL;
+  try {
+    UpcRootFileWriter w;
+    std::vector<UpcRootFileWriter::Column> cols(n_cols);
+    for (int i = 0; i < n_cols; ++i) {
+      if (!names[i] || !columns[i]) return UPCGPU_EINVAL;
+      cols[i].name = names[i];
+      cols[i].type = types[i];
+      cols[i].values.assign(columns[i], columns[i] + n_rows);
+    }
+    w.AddTree(tree, title ? title : "", cols);
+    std::string err;
+    return w.Write(path, err) ? UPCGPU_OK : UPCGPU_EINVAL;
+  } catch (...) {
+    return UPCGPU_EINVAL;
+  }
 }
 
 } // extern "C"

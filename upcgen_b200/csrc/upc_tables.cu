@@ -175,17 +175,28 @@ __global__ void k_ff_y(double R, double a, const double* rho0p, double* y)
 // the same LDL^T recurrences GSL uses and keeps the chunk.
 constexpr int kSpChunk = 48;   // short chunks: the kernel is a latency chain per thread (192: 0.33 ms for the 10^6-knot table)
 constexpr int kSpHalo = 64;
-constexpr int kSpThreads = 64;
+constexpr int kSpThreads = 32;
+constexpr int kSpWin = kSpThreads * kSpChunk + 2 * kSpHalo + 2;
 __global__ void __launch_bounds__(kSpThreads) k_spline_windowed(double x0, double dx, const double* ya, int size, double* c)
 {
-  // The knot values of the block's window are staged in shared memory by coalesced loads: each of the 176 steps of a
-  // thread's recurrence needs three of them, and with the loads going to global memory (~700 cycles each, not
-  // overlapped by the compiler) the 20 200-knot breakup table took 104 us on 7 CTAs -- the critical path of the table stage.
-  __shared__ double sy[kSpThreads * kSpChunk + 2 * kSpHalo + 2];
+  // Everything a step of the recurrence needs except the recurrence itself -- the knot spacings h_i and the right-hand
+  // sides (two divisions each) -- is formed beforehand, in parallel, into shared memory; a step of a thread's chain is
+  // then one FMA and one division (alpha -> gamma) with the second division (z / alpha) beside it.  With the spacings,
+  // right-hand sides and their three loads inside the chain a step took ~1100 cycles: 100 us for the 20 200-knot
+  // breakup table on 7 CTAs, the critical path of the table stage.
+  __shared__ double sy[kSpWin], sh[kSpWin], srhs[kSpWin];
   const int N = size - 2;  // unknowns u = 0..N-1  <->  c[u+1]
   const int sb = blockIdx.x * kSpThreads * kSpChunk;
   const int wsb = max(0, sb - kSpHalo), web = min(N, sb + kSpThreads * kSpChunk + kSpHalo);
-  for (int i = threadIdx.x; i < web - wsb + 2; i += kSpThreads) sy[i] = ya[wsb + i];
+  const int nwin = web - wsb;  // unknowns of the block's window; knots wsb .. web + 1
+  for (int i = threadIdx.x; i < nwin + 2; i += kSpThreads) sy[i] = ya[wsb + i];
+  for (int i = threadIdx.x; i < nwin + 1; i += kSpThreads) sh[i] = __dsub_rn(knot(x0, dx, wsb + i + 1), knot(x0, dx, wsb + i));
+  __syncthreads();
+  for (int i = threadIdx.x; i < nwin; i += kSpThreads) {
+    const double h_i = sh[i], h_ip1 = sh[i + 1];
+    const double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
+    srhs[i] = 3.0 * ((sy[i + 2] - sy[i + 1]) * g_ip1 - (sy[i + 1] - sy[i]) * g_i);
+  }
   __syncthreads();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int s = t * kSpChunk;
@@ -198,28 +209,22 @@ __global__ void __launch_bounds__(kSpThreads) k_spline_windowed(double x0, doubl
   const int ws = max(0, s - kSpHalo), we = min(N, e + kSpHalo);
   const int W = we - ws;
   double gamma[kSpChunk + 2 * kSpHalo], z[kSpChunk + 2 * kSpHalo];
-  const double* y = sy - wsb;  // y[i] = ya[i] for the indices of this block's window
-  auto h = [&](int i) { return __dsub_rn(knot(x0, dx, i + 1), knot(x0, dx, i)); };
-  auto rhs = [&](int i) {
-    double h_i = h(i), h_ip1 = h(i + 1);
-    double g_i = (h_i != 0.0) ? 1.0 / h_i : 0.0, g_ip1 = (h_ip1 != 0.0) ? 1.0 / h_ip1 : 0.0;
-    return 3.0 * ((y[i + 2] - y[i + 1]) * g_ip1 - (y[i + 1] - y[i]) * g_i);
-  };
+  const double* h = sh - wsb;      // h[i] = x_{i+1} - x_i
+  const double* rhs = srhs - wsb;  // right-hand side of unknown i
   // forward: alpha_i = diag_i - off_{i-1} gamma_{i-1}; gamma_i = off_i/alpha_i; z_i = b_i - gamma_{i-1} z_{i-1}
-  double alpha_prev = 0, gamma_prev = 0, z_prev = 0;
+  double gamma_prev = 0, z_prev = 0;
 #pragma unroll 4
   for (int j = 0; j < W; j++) {
     const int i = ws + j;
-    double diag = 2.0 * (h(i + 1) + h(i));
-    double off = h(i + 1);
-    double alpha = (j == 0) ? diag : diag - h(i) * gamma_prev;  // off_{i-1} = h(i)
-    double g = off / alpha;
-    double zz = (j == 0) ? rhs(i) : rhs(i) - gamma_prev * z_prev;
+    const double diag = 2.0 * (h[i + 1] + h[i]);
+    const double off = h[i + 1];
+    const double alpha = (j == 0) ? diag : diag - h[i] * gamma_prev;  // off_{i-1} = h(i)
+    const double g = off / alpha;
+    const double zz = (j == 0) ? rhs[i] : rhs[i] - gamma_prev * z_prev;
     gamma[j] = g;
     z[j] = zz / alpha;  // store c_i = z_i/alpha_i
-    alpha_prev = alpha; gamma_prev = g; z_prev = zz;
+    gamma_prev = g; z_prev = zz;
   }
-  (void)alpha_prev;
   // back substitution x_i = c_i - gamma_i x_{i+1}
   double xn = z[W - 1];
   if (we - 1 >= s && we - 1 < e) c[we - 1 + 1] = xn;
@@ -405,10 +410,26 @@ __global__ void k_bk_raw(const BkTable* T, const double* b, int mode, size_t n, 
 //   out[0] = ff_last = F(Q2max - dQ2), out[1] = P20 = P(20), out[2] = number of photo-nuclear energy knots,
 //   out[3] = number of leading G_AA segments bounded by 1e-20 (the inner cut of the cell quadrature);
 // and the clamp segment {P(20), 0, 0, 0} of the breakup table at index i20.
-__global__ void k_table_scalars(const SplineSeg* ff_seg, SplineSeg* bk_seg, int use_breakup, int i20, const BkTable* bk_table,
-                                const SplineSeg* gaa_seg, double* out)
+__global__ void __launch_bounds__(256) k_table_scalars(const SplineSeg* ff_seg, SplineSeg* bk_seg, int use_breakup, int i20,
+                                                       const BkTable* bk_table, const SplineSeg* gaa_seg, double* out)
 {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ int s_first;
+  if (threadIdx.x == 0) s_first = kNB - 1;
+  __syncthreads();
+  {
+    // inner cut: the leading G_AA segments whose magnitude is bounded by 1e-20 on the whole segment
+    // (|y| + |b| h + |c| h^2 + |d| h^3); see prepare_tables.  One thread per segment; the first that fails.
+    const double hh = 20. / (kNB - 1);
+    const int i = threadIdx.x;
+    if (i < kNB - 1) {
+      const SplineSeg sg = gaa_seg[i];
+      const double bound = fabs(sg.y) + hh * (fabs(sg.b) + hh * (fabs(sg.c) + hh * fabs(sg.d)));
+      if (!(bound <= 1e-20)) atomicMin(&s_first, i);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  out[3] = (double)s_first;
   {
     // src/UpcCrossSection.cpp:188: gsl_spline_eval(.., Q2max - dQ2): the last knot exactly
     double x = kQ2max - kDQ2;
@@ -427,19 +448,6 @@ __global__ void k_table_scalars(const SplineSeg* ff_seg, SplineSeg* bk_seg, int 
   } else {
     out[1] = 1.;
     out[2] = 0.;
-  }
-  {
-    // inner cut: the leading G_AA segments whose magnitude is bounded by 1e-20 on the whole segment
-    // (|y| + |b| h + |c| h^2 + |d| h^3); see prepare_tables
-    const double hh = 20. / (kNB - 1);
-    int n_zero = 0;
-    while (n_zero < kNB - 1) {
-      const SplineSeg sg = gaa_seg[n_zero];
-      const double bound = fabs(sg.y) + hh * (fabs(sg.b) + hh * (fabs(sg.c) + hh * fabs(sg.d)));
-      if (!(bound <= 1e-20)) break;
-      ++n_zero;
-    }
-    out[3] = (double)n_zero;
   }
 }
 
@@ -570,7 +578,7 @@ int prepare_tables(upcgpu_ctx* c)
   cudaStreamWaitEvent(st, c->aux_ev[3], 0);
   // segments 0..i20-1 of the breakup table cover [bmin, > 20); index i20 is the clamp segment
   const int i20 = (int)((20. - kBkBmin) / kBkDb) + 1;
-  UPC_K(c), k_table_scalars<<<1, 1, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, i20, (const BkTable*)c->bk_table, c->gaa_seg, c->d_scal + 1);
+  UPC_K(c), k_table_scalars<<<1, 256, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, i20, (const BkTable*)c->bk_table, c->gaa_seg, c->d_scal + 1);
   cudaEventRecord(e1, st);
   if (!c->h_scal) UPC_CUDA(c, cudaMallocHost(&c->h_scal, 8 * sizeof(double)));
   UPC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -595,6 +603,7 @@ int prepare_tables(upcgpu_ctx* c)
     const double hh = 20. / (kNB - 1);
     const double b_in = (int)h[4] * hh;
     c->tab.b_in2 = b_in * b_in;
+    c->tab.gaa_i0 = std::max(0, (int)h[4] - 1);  // one segment of margin below the cut (b is compared with b_in * (1 - 1e-12))
     c->info.gaa_zero_below = b_in;
   }
   c->tab.gaa_seg = c->gaa_seg;

@@ -1,6 +1,8 @@
 // UpcCrossSection over the CUDA C-ABI.  Method-by-method counterpart of the reference's
 // src/UpcCrossSection.cpp; every numeric kernel of that file runs on the GPU here.
 #include "UpcCrossSection.h"
+#include "UpcRootFile.h"
+#include "UpcRootHist.h"
 #include "UpcTwoPhotonTabulated.h"
 
 #include <cmath>
@@ -18,12 +20,6 @@ std::mt19937_64& hostRng()
   return rng;
 }
 double uniform(double a, double b) { return a + (b - a) * std::generate_canonical<double, 53>(hostRng()); }
-
-struct LumiCacheHeader {
-  char magic[8];
-  int32_t nm, ny, pol, isPoint, breakupMode, Z, A, pad;
-  double R, a, sqrts, mmin, mmax, ymin, ymax;
-};
 } // namespace
 
 UpcCrossSection::UpcCrossSection()
@@ -232,32 +228,44 @@ void UpcCrossSection::prepareTwoPhotonLumi()
 {
   ensureTables();
   const size_t n = (size_t)nm * ny;
-  // cache file: the reference keeps twoPhotonLumi[Pol].root and reuses it whenever it exists; here a
-  // raw binary with a parameter header, reused only when the header matches
-  std::string fname = std::string(lumiFileDirectory) + "/twoPhotonLumi" + (usePolarizedCS ? "Pol.bin" : ".bin");
-  LumiCacheHeader want{};
-  std::memcpy(want.magic, "UPCLUMI1", 8);
-  want.nm = nm; want.ny = ny; want.pol = usePolarizedCS; want.isPoint = isPoint; want.breakupMode = breakupMode;
-  want.Z = Z; want.A = A; want.R = R; want.a = a; want.sqrts = sqrts;
-  want.mmin = mmin; want.mmax = mmax; want.ymin = ymin; want.ymax = ymax;
+  // The cache file, as in the reference (src/UpcCrossSection.cpp:481-491, :578-585): twoPhotonLumi[Pol].root with the
+  // TH2D hD2LDMDY (or hD2LDMDY_s / hD2LDMDY_p), bin (im + 1, iy + 1) = table[im][iy].  A file the REFERENCE wrote is
+  // picked up here, and one written here is picked up by the reference (UpcRootHist / UpcRootFile: no ROOT needed).
+  // Like the reference, an existing file is used without looking at the parameters it was made with -- except that a
+  // file whose grid has other dimensions cannot be used and is recomputed.
+  const std::string fname = std::string(lumiFileDirectory) + "/twoPhotonLumi" + (usePolarizedCS ? "Pol.root" : ".root");
   {
-    std::ifstream in(fname, std::ios::binary);
-    LumiCacheHeader got{};
-    if (in && in.read(reinterpret_cast<char*>(&got), sizeof(got)) && std::memcmp(&got, &want, sizeof(got)) == 0) {
-      std::vector<double>& t0 = usePolarizedCS ? lumiS : lumi;
-      t0.resize(n);
-      in.read(reinterpret_cast<char*>(t0.data()), n * sizeof(double));
-      if (usePolarizedCS) {
-        lumiPs.resize(n);
-        in.read(reinterpret_cast<char*>(lumiPs.data()), n * sizeof(double));
+    std::ifstream probe(fname, std::ios::binary);
+    if (probe.good()) {
+      probe.close();
+      const char* names[2] = {usePolarizedCS ? "hD2LDMDY_s" : "hD2LDMDY", "hD2LDMDY_p"};
+      std::vector<double>* tabs[2] = {usePolarizedCS ? &lumiS : &lumi, &lumiPs};
+      bool ok = true;
+      std::string why;
+      for (int t = 0; t < (usePolarizedCS ? 2 : 1) && ok; ++t) {
+        UpcRootHist h;
+        std::string err;
+        if (!h.Read(fname, names[t], err)) { ok = false; why = err; break; }
+        if (h.dim != 2 || h.GetNbinsX() != nm || h.GetNbinsY() != ny) {
+          ok = false;
+          why = "its grid is " + std::to_string(h.GetNbinsX()) + " x " + std::to_string(h.GetNbinsY()) + ", not " +
+                std::to_string(nm) + " x " + std::to_string(ny);
+          break;
+        }
+        if (h.fXaxis.fXmin != mmin || h.fXaxis.fXmax != mmax || h.fYaxis.fXmin != ymin || h.fYaxis.fXmax != ymax)
+          PLOG_WARNING << fname << ": axis ranges differ from the current MMIN/MMAX/YMIN/YMAX (used as it is, like the reference does)";
+        tabs[t]->resize(n);
+        for (int im = 0; im < nm; ++im)
+          for (int iy = 0; iy < ny; ++iy) (*tabs[t])[(size_t)im * ny + iy] = h.GetBinContent(im + 1, iy + 1);
       }
-      if (in) {
+      if (ok) {
         PLOG_INFO << "Found pre-calculated " << (usePolarizedCS ? "polarized" : "unpolarized") << " 2D luminosity";
         int rc = usePolarizedCS ? upcgpu_lumi_upload(ctx, 1, lumiS.data()) : upcgpu_lumi_upload(ctx, 0, lumi.data());
         if (!rc && usePolarizedCS) rc = upcgpu_lumi_upload(ctx, 2, lumiPs.data());
         if (rc) fail("upcgpu_lumi_upload", rc);
         return;
       }
+      PLOG_WARNING << "Cannot use " << fname << " (" << why << "): computing the luminosity again";
     }
   }
   PLOG_INFO << "Precalculated 2D luminosity is not found. Starting all over...";
@@ -272,14 +280,24 @@ void UpcCrossSection::prepareTwoPhotonLumi()
   if (rc) fail("upcgpu_fill_lumi", rc);
   upcgpu_fill_stats st;
   upcgpu_get_fill_stats(ctx, &st);
-  PLOG_INFO << "Two-photon luminosity: " << n << " cells in " << st.ms_total << " ms on the GPU";
-  std::ofstream out(fname, std::ios::binary);
-  if (out) {
-    out.write(reinterpret_cast<const char*>(&want), sizeof(want));
-    const std::vector<double>& t0 = usePolarizedCS ? lumiS : lumi;
-    out.write(reinterpret_cast<const char*>(t0.data()), n * sizeof(double));
-    if (usePolarizedCS) out.write(reinterpret_cast<const char*>(lumiPs.data()), n * sizeof(double));
-    PLOG_INFO << "Two-photon luminosity was written to " << fname;
+  PLOG_INFO << "Two-photon luminosity: " << n << " cells in " << st.ms_total << " ms on " << upcgpu_group_size(ctx) << " GPU(s)";
+  {
+    UpcRootFileWriter w;
+    auto cells_of = [&](const std::vector<double>& t) {
+      std::vector<double> c((size_t)(nm + 2) * (ny + 2), 0.);
+      for (int im = 0; im < nm; ++im)
+        for (int iy = 0; iy < ny; ++iy) c[(size_t)(iy + 1) * (nm + 2) + (im + 1)] = t[(size_t)im * ny + iy];
+      return c;
+    };
+    if (usePolarizedCS) {
+      w.AddTH2D("hD2LDMDY_s", "", nm, mmin, mmax, ny, ymin, ymax, cells_of(lumiS), (double)n);
+      w.AddTH2D("hD2LDMDY_p", "", nm, mmin, mmax, ny, ymin, ymax, cells_of(lumiPs), (double)n);
+    } else {
+      w.AddTH2D("hD2LDMDY", "", nm, mmin, mmax, ny, ymin, ymax, cells_of(lumi), (double)n);
+    }
+    std::string err;
+    if (w.Write(fname, err)) PLOG_INFO << "Two-photon luminosity was written to " << fname;
+    else PLOG_WARNING << "Two-photon luminosity was NOT cached: " << err;
   }
 }
 

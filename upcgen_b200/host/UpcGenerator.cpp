@@ -1,6 +1,7 @@
 // UpcGenerator over the GPU path.  Counterpart of the reference's src/UpcGenerator.cpp for the
 // two-photon processes with closed-form elementary cross sections (dileptons, ALP).
 #include "UpcGenerator.h"
+#include "UpcRootFile.h"
 
 #include <algorithm>
 #include <cstdlib>
@@ -318,6 +319,20 @@ long int UpcGenerator::generateEvent(std::vector<int>& pdgs, std::vector<int>& s
 void UpcGenerator::writeEvent(long int evt, const std::vector<int>& pdgs, const std::vector<int>& statuses,
                               const std::vector<int>& mothers, const std::vector<TLorentzVector>& particles)
 {
+  if (useROOTOut) {
+    // the rows of the tree "particles" (src/UpcGenerator.cpp:595-608); written by generateEvents when the loop ends
+    for (size_t i = 0; i < particles.size(); i++) {
+      treeCols[0].push_back((double)(int)evt);  // eventNumber/I: the low 32 bits of the long it is bound to (Q10)
+      treeCols[1].push_back(pdgs[i]);
+      treeCols[2].push_back((double)(i + 1));
+      treeCols[3].push_back(statuses[i]);
+      treeCols[4].push_back(mothers[i]);
+      treeCols[5].push_back(particles[i].Px());
+      treeCols[6].push_back(particles[i].Py());
+      treeCols[7].push_back(particles[i].Pz());
+      treeCols[8].push_back(particles[i].E());
+    }
+  }
   if (!writerHepMC) return;
   int nVertices = -1;
   int lastMotherId = -1;
@@ -337,9 +352,12 @@ void UpcGenerator::generateEvents()
 {
   std::vector<int> pdgs, statuses, mothers;
   std::vector<TLorentzVector> particles;
-  if (useROOTOut && !useHepMCOut) {
-    PLOG_WARNING << "events.root needs ROOT, which is not part of this build: writing events.hepmc instead";
-    useHepMCOut = true;
+  if (useROOTOut) {
+    // events.root, tree "particles" with the reference's nine branches (src/UpcGenerator.cpp:842-857), written without
+    // ROOT by UpcRootFile.cpp when the loop ends (uncompressed; the reference asks for LZ4 level 9)
+    PLOG_WARNING << "Using ROOT tree for output!";
+    PLOG_INFO << "Events will be written to events.root";
+    treeCols.assign(9, std::vector<double>());
   }
   if (useHepMCOut) writerHepMC = new WriterHepMC("events.hepmc");
   PLOG_INFO << "Generating " << nEvents << " events...";
@@ -360,6 +378,22 @@ void UpcGenerator::generateEvents()
     PLOG_INFO << "Kinematic cuts were used";
     PLOG_INFO << "Number of rejected events = " << rejected;
     PLOG_INFO << std::fixed << std::setprecision(6) << "Cross section with cuts = " << fidCS << " mb";
+  }
+  if (useROOTOut) {
+    static const char* names[9] = {"eventNumber", "pdgCode", "particleID", "statusID", "motherID", "px", "py", "pz", "e"};
+    std::vector<UpcRootFileWriter::Column> cols(9);
+    for (int i = 0; i < 9; i++) {
+      cols[i].name = names[i];
+      cols[i].type = i < 5 ? 'I' : 'D';
+      cols[i].values.swap(treeCols[i]);
+    }
+    UpcRootFileWriter w;
+    std::string err;
+    w.AddTree("particles", "Generated particles", cols);
+    if (!w.Write("events.root", err)) {
+      PLOG_FATAL << "cannot write events.root: " << err;
+      std::_Exit(-1);
+    }
   }
   delete writerHepMC;
   writerHepMC = nullptr;

@@ -108,6 +108,7 @@ class UpcGenerator
     }
   };
   WriterHepMC* writerHepMC{nullptr};
+  std::vector<std::vector<double>> treeCols;  // the nine branches of the tree "particles" (events.root)
   void writeEvent(long int evt, const std::vector<int>& pdgs, const std::vector<int>& statuses,
                   const std::vector<int>& mothers, const std::vector<TLorentzVector>& particles);
 

@@ -1,0 +1,52 @@
+// UpcRootFile.h -- a ROOT-less WRITER of the two kinds of .root files the reference produces on this path:
+//   * the two-photon-luminosity cache twoPhotonLumi[Pol].root with the TH2D hD2LDMDY[_s,_p]
+//     (src/UpcCrossSection.cpp:493-507, :564-585), so that a table filled on the GPU is picked up by the reference
+//     (and by this build) exactly like one the reference computed itself;
+//   * events.root with the TTree "particles" and its nine branches (src/UpcGenerator.cpp:842-857, fill :595-608).
+//
+// The byte layout follows ROOT's file format (TFile header, TKey records, the directory / key-list / free-segment /
+// streamer-info records, TBuffer streaming with byte counts and class versions) as ROOT 6.22-6.3x writes it; the
+// TH1/TH2/TAxis member sequence was checked byte by byte against the histograms in the reference's own
+// cross_sections/*.root files (written by ROOT 6.22/09).  Objects are written uncompressed.  ROOT itself is not
+// available in this build environment: what reads these files back here is upcgen_b200/host/UpcRootHist.cpp and an
+// independent Python parser (tests/test_root_file.py).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+class UpcRootFileWriter
+{
+ public:
+  // a TH2D with uniform axes; cells: (nx + 2) * (ny + 2) doubles, x fastest, under-/overflow cells included
+  void AddTH2D(const std::string& name, const std::string& title, int nx, double xlo, double xhi, int ny, double ylo,
+               double yhi, const std::vector<double>& cells, double entries);
+
+  // a TTree of flat branches, one leaf each: type 'I' (Int_t) or 'D' (Double_t); all columns the same length.
+  // Integer columns are given as doubles holding integral values.
+  struct Column {
+    std::string name;
+    char type;  // 'I' or 'D'
+    std::vector<double> values;
+  };
+  void AddTree(const std::string& name, const std::string& title, const std::vector<Column>& columns);
+
+  // writes the file; returns false and sets err on failure
+  bool Write(const std::string& path, std::string& err);
+
+ private:
+  struct Record {
+    std::string cls, name, title;
+    std::vector<unsigned char> data;  // streamed object
+    bool listed;                      // appears in the directory's key list (baskets do not)
+    uint32_t seek = 0;
+  };
+  std::vector<Record> records_;
+  // baskets of the trees are written before the tree's own record; the tree streamer needs their positions, which
+  // are fixed once the layout is known: trees are therefore streamed inside Write()
+  struct Tree {
+    std::string name, title;
+    std::vector<Column> columns;
+  };
+  std::vector<Tree> trees_;
+};
