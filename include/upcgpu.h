@@ -171,6 +171,10 @@ int upcgpu_fill_lumi_shard(upcgpu_ctx* ctx, int shard, int nshards);
 int upcgpu_lumi_cells(upcgpu_ctx* ctx, const double* M, const double* Y, size_t n, double* out,
                       double* out_s, double* out_p);
 int upcgpu_get_fill_stats(upcgpu_ctx* ctx, upcgpu_fill_stats* st);
+/* replaces UpcCrossSection::calcPhotonFlux (src/UpcCrossSection.cpp:700-722), the b-integrated photon flux of the
+ * vector-meson path: flux_pos[i] = calcPhotonFlux(M[i], +Y[i]), flux_neg[i] = calcPhotonFlux(M[i], -Y[i]) -- the two
+ * values calcNucCrossSectionY (:724-748) needs per rapidity.  Either output may be NULL. */
+int upcgpu_photon_flux(upcgpu_ctx* ctx, const double* M, const double* Y, size_t n, double* flux_pos, double* flux_neg);
 
 /* Device-resident buffers for the multi-GPU exchange (device pointers as integers so that no
  * CUDA type appears here).  packed shard: [rows_per_shard][ny] per table, the shard's rows in ascending

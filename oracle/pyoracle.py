@@ -93,6 +93,7 @@ def lib():
         L.upco_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, dp, dp]
         L.upco_generate_event.restype = i
         L.upco_generate_event.argtypes = [p, C.c_uint64, C.c_uint64, p, p, p, p, ip, p, p, p, p, p]
+        L.upco_photon_flux.restype = d; L.upco_photon_flux.argtypes = [p, d, d]
         L.upco_generate_event_u.restype = i
         L.upco_generate_event_u.argtypes = [p, p, p, p, p, p, ip, p, p, p, p, p]
         _LIB = L
@@ -187,6 +188,10 @@ class Oracle:
         err = C.c_double(); ne = C.c_int(); last = C.c_int(); ier = C.c_int()
         r = self.L.upco_qags_fluxform(self.h, b, k, C.byref(err), C.byref(ne), C.byref(last), C.byref(ier))
         return r, err.value, ne.value, last.value, ier.value
+
+    def photon_flux(self, M, Y):
+        """calcPhotonFlux (src/UpcCrossSection.cpp:700-722)."""
+        return self.L.upco_photon_flux(self.h, float(M), float(Y))
 
     # lumi
     def lumi(self, M, Y):

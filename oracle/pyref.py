@@ -31,6 +31,7 @@ class Reference:
         for name, args in [("upcref_rho0", []), ("upcref_gtot", []), ("upcref_factor", []), ("upcref_formfac", [d]),
                            ("upcref_formfac_knot", [C.c_int]), ("upcref_flux_point", [d, d]), ("upcref_flux_form", [d, d]),
                            ("upcref_breakup_raw", [d, C.c_int]), ("upcref_breakup_spline", [d]), ("upcref_lumi", [d, d]),
+                           ("upcref_photon_flux", [d, d]),
                            ("upcref_sigma_m", [d]), ("upcref_sigma_zm", [d, d]), ("upcref_sigma_m_pol", [d, C.c_int]),
                            ("upcref_sigma_zm_pol", [d, d, C.c_int])]:
             getattr(L, name).restype = d

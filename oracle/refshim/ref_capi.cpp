@@ -83,6 +83,7 @@ double upcref_breakup_raw(double b, int mode) { return g_cs->calcBreakupProb(b, 
 double upcref_breakup_spline(double b) { return gsl_spline_eval(gslSplineBreakP, b, nullptr); }
 double upcref_breakup_knot(int i, double* c) { if (c) *c = gslSplineBreakP->c[i]; return gslSplineBreakP->y[i]; }
 double upcref_lumi(double M, double Y) { return g_cs->calcTwoPhotonLumi(M, Y); }
+double upcref_photon_flux(double M, double Y) { return g_cs->calcPhotonFlux(M, Y); }
 void upcref_lumi_pol(double M, double Y, double* s, double* p) { g_cs->calcTwoPhotonLumiPol(*s, *p, M, Y); }
 double upcref_sigma_m(double m) { return g_cs->elemProcess->calcCrossSectionM(m); }
 double upcref_sigma_zm(double z, double m) { return g_cs->elemProcess->calcCrossSectionZM(z, m); }

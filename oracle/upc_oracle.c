@@ -1287,6 +1287,28 @@ static double calcTwoPhotonLumi(upco_ctx* c, double M, double Y, int* neval)
   return 2 * M_PI * M_PI * M * sum;
 }
 
+/* calcPhotonFlux, src/UpcCrossSection.cpp:700-722: the b-integrated photon flux of the vector-meson path */
+double upco_photon_flux(upco_ctx* c, double M, double Y)
+{
+  const upco_params* p = &c->p;
+  const double R = p->R;
+  double k = M / 2. * exp(Y);
+  double bmin = p->is_point ? 1 * R : 0.05 * R;
+  double bmax = fmax(5. * p->g1 * kHc / k, 5 * R);
+  double log_delta_b = (log(bmax) - log(bmin)) / p->nb1;
+  double sum = 0;
+  for (int i = 0; i < p->nb1; i++) {
+    double bl = bmin * exp(i * log_delta_b);
+    double bh = bmin * exp((i + 1) * log_delta_b);
+    double b = (bh + bl) / 2.;
+    double breakup = 1.;
+    if (p->breakup_mode != 1) breakup = bk_spline(c, b < 20. ? b : 20.);
+    double gaa = b < 20. ? upco_cspline_eval(c->vB, c->vGAA, c->cGAA, NB, b) : 1.;
+    sum += breakup * gaa * fluxForm_n(c, b, k, NULL) * b * (bh - bl);
+  }
+  return 2. * M_PI * k * sum;
+}
+
 /* src/UpcCrossSection.cpp:274-335 */
 static void calcTwoPhotonLumiPol(upco_ctx* c, double* ns, double* np, double M, double Y, int* neval)
 {

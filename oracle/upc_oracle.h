@@ -141,6 +141,7 @@ void upco_philox(uint64_t seed, uint64_t ctr, uint32_t block, double* u0, double
 /* --- event generation with the product's uniform slot map (E1-E5) ---
    cs_sum: 2-D CDF (ny*nm+1); z_sum: nm CDFs of nz+1 (or pol: s then ps); ratio [ny][nm].
    Output arrays sized 4 particles/event (ALP: 3 used; pairs: 2).  returns 1 accepted/0. */
+double upco_photon_flux(upco_ctx* c, double M, double Y);
 int upco_generate_event_u(upco_ctx* c, const double* u, const double* cs_sum, const double* z_sum,
                           const double* z_sum_ps, const double* ratio, int* npart, int* pdg, int* status, int* mother,
                           double* p4, double* aux);

@@ -68,7 +68,7 @@ SYMBOLS = [
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
     "upcgpu_create_multi", "upcgpu_group_size", "upcgpu_group_member", "upcgpu_group_set_exchange",
-    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_tree",
+    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_tree", "upcgpu_photon_flux",
 ]
 
 
@@ -308,6 +308,15 @@ class UpcGpu:
         out = np.zeros(mm.size)
         self._chk(self.L.upcgpu_lumi_cells(self.h, _p(mm), _p(yy), mm.size, _p(out), None, None))
         return out.reshape(M.shape)
+
+    def photon_flux(self, M, Y):
+        """calcPhotonFlux(M, +Y) and calcPhotonFlux(M, -Y) (src/UpcCrossSection.cpp:700-722)."""
+        M, Y = np.broadcast_arrays(_f64(M), _f64(Y))
+        mm, yy = _f64(M.ravel()), _f64(Y.ravel())
+        fp, fn = np.zeros(mm.size), np.zeros(mm.size)
+        self.L.upcgpu_photon_flux.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        self._chk(self.L.upcgpu_photon_flux(self.h, _p(mm), _p(yy), mm.size, _p(fp), _p(fn)))
+        return fp.reshape(M.shape), fn.reshape(M.shape)
 
     def fill_stats(self):
         st = CFillStats()

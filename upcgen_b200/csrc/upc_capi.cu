@@ -303,6 +303,14 @@ int upcgpu_lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n,
   return lumi_cells(c, M, Y, n, out, out_s, out_p);
 }
 
+int upcgpu_photon_flux(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* flux_pos, double* flux_neg)
+{
+  CHECK_CTX_SYNC(c);
+  if (!M || !Y || (!flux_pos && !flux_neg)) return UPCGPU_EINVAL;
+  if (n == 0) return UPCGPU_OK;
+  return lumi_cells(c, M, Y, n, nullptr, nullptr, nullptr, flux_pos, flux_neg);
+}
+
 int upcgpu_get_fill_stats(upcgpu_ctx* c, upcgpu_fill_stats* st)
 {
   if (!st) return UPCGPU_EINVAL;

@@ -31,7 +31,8 @@ int breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out)
 int flux_points(upcgpu_ctx* c, const double* b, const double* k, size_t n, int force_point, double* out, int* neval);
 int fill_lumi_rows(upcgpu_ctx* c, int shard, int nshards, bool wait);
 int finish_fill(upcgpu_ctx* c);
-int lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* out, double* out_s, double* out_p);
+int lumi_cells(upcgpu_ctx* c, const double* M, const double* Y, size_t n, double* out, double* out_s, double* out_p,
+               double* flux_pos = nullptr, double* flux_neg = nullptr);
 int lumi_unpack(upcgpu_ctx* c, int nshards);
 int ensure_lumi_buffers(upcgpu_ctx* c, int nshards);
 int ensure_gather_buffers(upcgpu_ctx* c, int nshards);

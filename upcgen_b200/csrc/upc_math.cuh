@@ -102,6 +102,9 @@ __device__ __forceinline__ double tmath_bessel_k1(double x)
   return (exp(-x) / sqrt(x)) * (q1 + y * (q2 + y * (q3 + y * (q4 + y * (q5 + y * (q6 + y * q7))))));
 }
 
+// knot of a uniform table exactly as the reference forms it: x0 + i*dx (two roundings)
+__device__ __forceinline__ double knot(double x0, double dx, int i) { return __dadd_rn(x0, __dmul_rn((double)i, dx)); }
+
 // One spline interval in evaluation form: S(x) = y + d*(b + d*(c + d*dd)), d = x - x_i, with
 // b, dd computed exactly as GSL's cspline coeff_calc does from (y_i, y_i+1, c_i, c_i+1, dx).
 struct __align__(32) SplineSeg {

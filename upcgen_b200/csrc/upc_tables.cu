@@ -139,8 +139,7 @@ __global__ void k_segs_from_arrays(const double* xa, const double* ya, const dou
   if (i == n - 1) seg[i] = SplineSeg{tail_value, 0., 0., 0.};
 }
 
-// knot of a uniform table exactly as the reference forms it: x0 + i*dx (two roundings)
-__device__ __forceinline__ double knot(double x0, double dx, int i) { return __dadd_rn(x0, __dmul_rn((double)i, dx)); }
+// (knot(x0, dx, i): a knot of a uniform table exactly as the reference forms it, upc_math.cuh)
 // ... except the breakup table, which is written `bmin + db * i` (same thing)
 
 __global__ void k_segs_uniform(double x0, double dx, const double* ya, const double* ca, int n, SplineSeg* seg,

@@ -3,6 +3,7 @@
 #include "UpcCrossSection.h"
 #include "UpcRootFile.h"
 #include "UpcRootHist.h"
+#include "UpcPhotoNuclearVM.h"
 #include "UpcTwoPhotonTabulated.h"
 
 #include <cmath>
@@ -67,10 +68,21 @@ void UpcCrossSection::setElemProcess(int procID)
     }
     case 443:
     case 100443:
-    case 553:
-      PLOG_FATAL << "Process " << procID << " needs the vector-meson path, which is outside the GPU build (see DESIGN.md, "
-                 << "out of scope). Exiting...";
-      std::_Exit(-1);
+    case 553: {
+      UpcPhotoNuclearVM* vm = nullptr;
+      try {
+        vm = new UpcPhotoNuclearVM(procID, shadowingOption, dghtPDG);
+      } catch (const std::exception& e) {
+        PLOG_FATAL << "Vector-meson process " << procID << ": " << e.what() << " (DECAY_PDG " << dghtPDG << "). Exiting...";
+        std::_Exit(-1);
+      }
+      if (!vm->ok) {
+        PLOG_FATAL << vm->error << ". Exiting...";
+        std::_Exit(-1);
+      }
+      elemProcess = vm;
+      break;
+    }
     default:
       PLOG_FATAL << "Unknown process ID! Check manual and enter a correct ID! Exiting...";
       std::_Exit(-1);
@@ -139,7 +151,8 @@ void UpcCrossSection::init()
   prepareGAA();
   prepareFormFac();
   if (breakupMode > 1) prepareBreakupProb();
-  prepareTwoPhotonLumi();
+  if (elemProcess->partPDG != 443 && elemProcess->partPDG != 100443 && elemProcess->partPDG != 553)
+    prepareTwoPhotonLumi(); // two-photon luminosity (the vector-meson path needs the photon flux only, :127-131)
 }
 
 template <typename ArrayType>
@@ -395,19 +408,63 @@ void UpcCrossSection::getPairMomentum(double mPair, double yPair, TLorentzVector
   pPair.SetPxPyPzE(px, py, mtPair * std::sinh(yPair), mtPair * std::cosh(yPair));
 }
 
-// ---- vector-meson photoproduction path: out of scope of the GPU build ----
-double UpcCrossSection::calcPhotonFlux(double, double)
+// ---- vector-meson photoproduction path (src/UpcCrossSection.cpp:700-748, :1076-1104) ----
+// the b-integrated photon flux, on the GPU (flux rows of the luminosity stage + one thread per photon energy)
+double UpcCrossSection::calcPhotonFlux(double M, double Y)
 {
-  PLOG_FATAL << "calcPhotonFlux: the 1-D vector-meson path is not part of the GPU build";
-  std::_Exit(-1);
+  ensureTables();
+  double out = 0;
+  int rc = upcgpu_photon_flux(ctx, &M, &Y, 1, &out, nullptr);
+  if (rc) fail("upcgpu_photon_flux", rc);
+  return out;
 }
-void UpcCrossSection::calcNucCrossSectionY(std::vector<std::vector<double>>&, std::vector<std::vector<double>>&, double&)
+
+// :724-748.  All 2 ny fluxes come from one GPU call; the fold with the plug-in's sigma(+-y) is the reference's loop.
+void UpcCrossSection::calcNucCrossSectionY(std::vector<std::vector<double>>& crossSectionY,
+                                           std::vector<std::vector<double>>& csYRatio, double& totCS)
 {
-  PLOG_FATAL << "calcNucCrossSectionY: the 1-D vector-meson path is not part of the GPU build";
-  std::_Exit(-1);
+  PLOG_INFO << "Calculating nuclear cross section...";
+  ensureTables();
+  const double dy = (ymax - ymin) / ny;
+  std::vector<double> mm(ny, elemProcess->mPart), yy(ny), f1(ny), f2(ny);
+  for (int iy = 0; iy < ny; iy++) yy[iy] = ymin + dy * iy;
+  int rc = upcgpu_photon_flux(ctx, mm.data(), yy.data(), ny, f1.data(), f2.data());
+  if (rc) fail("upcgpu_photon_flux", rc);
+  for (int iy = 0; iy < ny; iy++) {
+    const double y = yy[iy];
+    const double cs1 = elemProcess->calcCrossSectionY(y);
+    const double cs2 = elemProcess->calcCrossSectionY(-y);
+    const double upcCs1 = f1[iy] * cs1;
+    const double upcCs2 = f2[iy] * cs2;
+    crossSectionY[iy][0] = upcCs1 + upcCs2;
+    totCS += upcCs1 + upcCs2;
+    csYRatio[iy][0] = upcCs1 / upcCs2;
+  }
+  totCS *= dy; // already in [mb] for VM
+  PLOG_INFO << "Total nuclear cross section = " << std::fixed << totCS << " mb";
 }
-void UpcCrossSection::getMomentumVM(double, double, int, TLorentzVector&)
+
+// :1076-1104: photon pT from the tabulated pdf, pomeron pT by rejection from the squared form factor
+void UpcCrossSection::getMomentumVM(double m, double y, int target, TLorentzVector& p)
 {
-  PLOG_FATAL << "getMomentumVM: the 1-D vector-meson path is not part of the GPU build";
-  std::_Exit(-1);
+  double sign = target ? 1 : -1;
+  double ePhot = m / 2 * std::exp(sign * y);
+  double ePom = m / 2 * std::exp(-sign * y);
+  double ptPhot = getPhotonPt(ePhot);
+  double phi1 = uniform(0, 2 * M_PI);
+  double phi2 = uniform(0, 2 * M_PI);
+  double tmin = (ePom * ePom) / (g1 * g1);
+  double ptPom;
+  while (true) {
+    ptPom = 32. * uniform(0., 1.) * phys_consts::hc * R;
+    double t2 = tmin + ptPom * ptPom;
+    double ff = calcFormFac(t2) / A;
+    double test = uniform(0., 1.);
+    if (test < ff * ff * ptPom) break;
+  }
+  double px = ptPhot * std::cos(phi1) + ptPom * std::cos(phi2);
+  double py = ptPhot * std::sin(phi1) + ptPom * std::sin(phi2);
+  double pt = std::sqrt(px * px + py * py);
+  double mtPair = std::sqrt(m * m + pt * pt);
+  p.SetPxPyPzE(px, py, mtPair * std::sinh(y), mtPair * std::cosh(y));
 }

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <ctime>
+#include <random>
 #include <sstream>
 
 int UpcGenerator::debug = 0;
@@ -29,6 +30,14 @@ upcgpu_ctx* samplerContext()
   }
   return g_ownCtx;
 }
+// gRandom stand-in of the host-side event code (vector mesons): std::mt19937_64, as TRandomMT64
+static std::mt19937_64& genRng()
+{
+  static std::mt19937_64 rng(0x5eedULL);
+  return rng;
+}
+void seedHost(uint64_t s) { genRng().seed(s); }
+double hostUniform(double a, double b) { return a + (b - a) * std::generate_canonical<double, 53>(genRng()); }
 } // namespace upc_host
 
 UpcGenerator::UpcGenerator()
@@ -41,6 +50,7 @@ UpcGenerator::UpcGenerator()
 
 UpcGenerator::~UpcGenerator()
 {
+  delete samplerCsYM;
   upc_host::registerSamplerContext(nullptr);
   delete nucProcessCS; // (the reference leaks it)
 }
@@ -193,6 +203,15 @@ void UpcGenerator::init()
     PLOG_WARNING << "For ALP production angular distribution is ignored!";
   }
   cs->setElemProcess(procID);
+  if (procID == 443 || procID == 100443 || procID == 553) {  // :120-130
+    isSingleProduction = true; // one particle
+    isPairProductionVM = true; // two-part decay
+    ignoreCSZ = true;
+    double mPart = cs->elemProcess->mPart;
+    cs->mmin = mPart - 1e-6;
+    cs->mmax = mPart + 1e-6;
+    cs->nm = 1;
+  }
   if (procID >= 11 && procID <= 15) {
     isPairProduction = true;
     auto* proc = (UpcTwoPhotonDilep*)cs->elemProcess;
@@ -215,6 +234,7 @@ void UpcGenerator::init()
   cs->init(); // tables + two-photon luminosity on the GPU
   upc_host::registerSamplerContext(cs->gpu());
   if (seed == 0) seed = time(nullptr); // the reference seeds gRandom with the wall clock for SEED 0
+  upc_host::seedHost((uint64_t)seed);
   if ((doFSR || doDecays) && pythiaVersion > 0)
     PLOG_WARNING << "Decays with Pythia are not used! (Pythia is not part of the GPU build)";
   computeNuclXsection();
@@ -225,6 +245,21 @@ void UpcGenerator::computeNuclXsection()
   auto* cs = nucProcessCS;
   const int nm = cs->nm, nz = cs->nz, ny = cs->ny;
   const double dm = (cs->mmax - cs->mmin) / nm, dz = (cs->zmax - cs->zmin) / nz, dy = (cs->ymax - cs->ymin) / ny;
+  if (procID == 443 || procID == 100443 || procID == 553) {
+    // vector mesons: a 1-D table in y (src/UpcGenerator.cpp:701-712)
+    nucCSYM.assign(ny, std::vector<double>(1, 0.));
+    nucTargRatioCSYM.assign(ny, std::vector<double>(1, 0.));
+    totCS = 0;
+    cs->calcNucCrossSectionY(nucCSYM, nucTargRatioCSYM, totCS);
+    binEdgesM.assign(2, 0.);
+    binEdgesM[0] = cs->mmin;
+    binEdgesM[1] = cs->mmax;
+    binEdgesY.resize(ny + 1);
+    for (int i = 0; i < ny + 1; ++i) binEdgesY[i] = cs->ymin + dy * i;
+    delete samplerCsYM;
+    samplerCsYM = new UpcSampler2D(nucCSYM, binEdgesY, binEdgesM, seed);
+    return;
+  }
   std::vector<std::vector<double>> csZM, csZMS, csZMPS;
   if (usePolarizedCS) {
     csZMS.resize(nm, std::vector<double>(nz, 0.));
@@ -291,6 +326,109 @@ void UpcGenerator::refillBlock()
 }
 
 // one candidate per call; returns 1 when it passes the kinematic cuts, else 0 with empty vectors
+// vector-meson event, host code following src/UpcGenerator.cpp:715-832 for isVM
+long int UpcGenerator::generateEventVM(std::vector<int>& pdgs, std::vector<int>& statuses, std::vector<int>& mothers,
+                                       std::vector<TLorentzVector>& particles)
+{
+  auto* cs = nucProcessCS;
+  double mPair, yPair;
+  (*samplerCsYM)(yPair, mPair);
+  int yPairBin = samplerCsYM->getBinX(yPair);
+  int mPairBin = samplerCsYM->getBinY(mPair);
+  if (yPairBin < 0) yPairBin = 0;
+  if (yPairBin >= (int)nucTargRatioCSYM.size()) yPairBin = (int)nucTargRatioCSYM.size() - 1;
+  if (mPairBin != 0) mPairBin = 0;  // one mass bin (the reference's getBinY can leave it through its integer arithmetic)
+  (void)upc_host::hostUniform(-1., 1.);  // cos(theta) of ignoreCSZ processes: drawn, then unused (:756)
+  TLorentzVector pPair;
+  double ratio = nucTargRatioCSYM[yPairBin][mPairBin];
+  bool target = upc_host::hostUniform(0, 1) < ratio;
+  cs->getMomentumVM(mPair, yPair, target, pPair);
+  // singleProduction :474-485
+  particles.emplace_back(pPair);
+  pdgs.emplace_back(cs->elemProcess->partPDG);
+  mothers.emplace_back(0);
+  statuses.emplace_back(23);
+  if (!checkKinCuts(particles)) {
+    pdgs.clear(); statuses.clear(); mothers.clear(); particles.clear();
+    return 0;
+  }
+  if (isPairProductionVM) twoPartDecayVM(pdgs, statuses, mothers, particles, 1);
+  genParticles.clear();
+  for (size_t ii = 0; ii < particles.size(); ++ii)
+    genParticles.emplace_back(pdgs[ii], statuses[ii], mothers[ii], mothers[ii], -1, -1, particles[ii].Px(), particles[ii].Py(),
+                              particles[ii].Pz(), particles[ii].E(), 0.0, 0.0, 0.0, 0.0);
+  return 1;
+}
+
+// :563-587
+bool UpcGenerator::checkKinCuts(std::vector<TLorentzVector>& particles)
+{
+  for (const auto& tlvec : particles) {
+    if (doPtCut && tlvec.Pt() < minPt) return false;
+    if (doEtaCut) {
+      double eta = tlvec.Eta();
+      if (eta < minEta || eta > maxEta) return false;
+    }
+  }
+  return true;
+}
+
+// :425-472: decay angle by rejection from 1 + cos^2 (leptons) or 1 + 0.605 cos^2 (protons), J. Breitweg et al.
+void UpcGenerator::twoPartDecayVM(std::vector<int>& pdgs, std::vector<int>& statuses, std::vector<int>& mothers,
+                                  std::vector<TLorentzVector>& particles, int id)
+{
+  auto* cs = nucProcessCS;
+  int decayProdPDG = cs->elemProcess->dghtPDG;
+  double theta, dndtheta = 0;
+  while (true) {
+    theta = M_PI * upc_host::hostUniform(0., 1.);
+    double test = upc_host::hostUniform(0., 1.);
+    if (decayProdPDG == 11 || decayProdPDG == 13) dndtheta = std::sin(theta) * (1. + (std::cos(theta) * std::cos(theta)));
+    else if (decayProdPDG == 2212) dndtheta = std::sin(theta) * (1. + (0.605 * std::cos(theta) * std::cos(theta)));
+    if (test < dndtheta) break;
+  }
+  int sign1 = upc_host::hostUniform(-1, 1) > 0 ? 1 : -1;
+  int sign2 = -sign1;
+  const int status = 33;
+  const TLorentzVector particle = particles[id - 1];
+  double mDecay = cs->elemProcess->mDght;
+  double pMag = std::sqrt(particle.Mag2() / 4. - mDecay * mDecay);
+  double phi = upc_host::hostUniform(0., 2. * M_PI);
+  const double amag = std::fabs(pMag);
+  double v[3] = {amag * std::sin(theta) * std::cos(phi), amag * std::sin(theta) * std::sin(phi), amag * std::cos(theta)};
+  const double bx = particle.Px() / particle.E(), by = particle.Py() / particle.E(), bz = particle.Pz() / particle.E();
+  const double pm = particle.P();
+  const double tot = pm > 0 ? 1.0 / pm : 1.0;
+  const double u1 = particle.Px() * tot, u2 = particle.Py() * tot, u3 = particle.Pz() * tot;
+  for (int k = 0; k < 2; ++k) {
+    const double sgn = k == 0 ? -1. : 1.;
+    double x = sgn * v[0], y = sgn * v[1], z = sgn * v[2];
+    const double e0 = std::sqrt(x * x + y * y + z * z + mDecay * mDecay);
+    // TVector3::RotateUz
+    double up = u1 * u1 + u2 * u2;
+    if (up) {
+      up = std::sqrt(up);
+      const double px = x, py = y, pz = z;
+      x = (u1 * u3 * px - u2 * py + u1 * up * pz) / up;
+      y = (u2 * u3 * px + u1 * py + u2 * up * pz) / up;
+      z = (u3 * u3 * px - px + u3 * up * pz) / up;
+    } else if (u3 < 0.) {
+      x = -x; z = -z;
+    }
+    // TLorentzVector::Boost
+    const double b2 = bx * bx + by * by + bz * bz;
+    const double gamma = 1.0 / std::sqrt(1.0 - b2);
+    const double bp = bx * x + by * y + bz * z;
+    const double gamma2 = b2 > 0 ? (gamma - 1.0) / b2 : 0.0;
+    TLorentzVector d(x + gamma2 * bp * bx + gamma * bx * e0, y + gamma2 * bp * by + gamma * by * e0,
+                     z + gamma2 * bp * bz + gamma * bz * e0, gamma * (e0 + bp));
+    pdgs.emplace_back((k == 0 ? sign1 : sign2) * decayProdPDG);
+    statuses.emplace_back(status);
+    mothers.emplace_back(id);
+    particles.emplace_back(d);
+  }
+}
+
 long int UpcGenerator::generateEvent(std::vector<int>& pdgs, std::vector<int>& statuses, std::vector<int>& mothers,
                                      std::vector<TLorentzVector>& particles)
 {
@@ -298,6 +436,7 @@ long int UpcGenerator::generateEvent(std::vector<int>& pdgs, std::vector<int>& s
   statuses.clear();
   mothers.clear();
   particles.clear();
+  if (procID == 443 || procID == 100443 || procID == 553) return generateEventVM(pdgs, statuses, mothers, particles);
   if (block.pos == block.n) refillBlock();
   const size_t i = block.pos++;
   const int np = block.npart[i];

@@ -69,6 +69,7 @@ class UpcGenerator
   bool ignoreCSZ;
   std::vector<TParticle> genParticles;
   std::vector<std::vector<double>> nucCSYM;
+  std::vector<std::vector<double>> nucTargRatioCSYM; // for VM production
   std::vector<std::vector<double>> polCSRatio;
   std::vector<double> binEdgesM, binEdgesZ, binEdgesY;
 
@@ -79,6 +80,15 @@ class UpcGenerator
   int numThreads{1};
   bool isPairProduction{false};
   bool isSingleProduction{false};
+  bool isPairProductionVM{false};
+  // vector-meson events are generated on the host (one (y) draw, rejection sampling of the pomeron pT and of the decay
+  // angle: src/UpcGenerator.cpp:425-472, src/UpcCrossSection.cpp:1076-1104)
+  UpcSampler2D* samplerCsYM{nullptr};
+  long int generateEventVM(std::vector<int>& pdgs, std::vector<int>& statuses, std::vector<int>& mothers,
+                           std::vector<TLorentzVector>& particles);
+  void twoPartDecayVM(std::vector<int>& pdgs, std::vector<int>& statuses, std::vector<int>& mothers,
+                      std::vector<TLorentzVector>& particles, int id);
+  bool checkKinCuts(std::vector<TLorentzVector>& particles);
 
   // a very simple HepMC writer: particles only, no vertex information (as the reference's)
   class WriterHepMC

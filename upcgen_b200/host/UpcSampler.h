@@ -19,6 +19,9 @@ namespace upc_host
 // default-parameter context created on first use
 upcgpu_ctx* samplerContext();
 void registerSamplerContext(upcgpu_ctx* ctx);
+// gRandom stand-in of the host-side event code (std::mt19937_64, as TRandomMT64)
+void seedHost(uint64_t s);
+double hostUniform(double a, double b);
 } // namespace upc_host
 
 class UpcSampler1D
