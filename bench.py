@@ -51,12 +51,14 @@ FLOP_PER_QAGS_EVAL = 100.0          # one integrand evaluation of fluxFormIntegr
 FLOP_CELL = {(0, 0): 1.19e6, (0, 1): 1.91e6, (1, 0): 1.30e6, (1, 1): 2.05e6}  # (pol, breakup) per cell
 
 
-def make_config(workload, P, world):
+def make_config(workload, P, world, peer=None):
     """The `config` object of the JSON line (the same for both arms)."""
+    how = ("the cell kernel stores every finished cell into the table of every rank over NVLink (CUDA IPC peer memory); "
+           "a one-element NCCL all-reduce orders the fold behind it" if peer else "NCCL all-gather of the table")
     return {"workload": WORKLOAD_TEXT[workload], "cells": P.nm * P.ny, "grid": [P.nm, P.ny],
             "l2": "flushed between timed steps (256 MiB device write)",
             "reflection": "columns iy > ny/2 of a y grid symmetric about 0 are written from their mirror images",
-            "parallelism": f"m rows in blocks of 32 dealt round-robin over {world} GPU(s); NCCL all-gather of the table"
+            "parallelism": f"m rows in blocks of 32 dealt in a snake over {world} GPU(s); {how}"
             if world > 1 else "single GPU"}
 
 
@@ -199,6 +201,19 @@ class Bench:
             self.sig = dict(sig_s=capi.elem_sigma_m(P, 1), sig_p=capi.elem_sigma_m(P, 2))
         else:
             self.sig = dict(sig_m=capi.elem_sigma_m(P, 0))
+        # N > 1: the exchange is folded into the cell kernel (stores into every rank's table through CUDA IPC
+        # mappings) unless the devices cannot map each other or UPCGPU_EXCHANGE=nccl asks for the all-gather
+        self.peer = False
+        if world > 1 and os.environ.get("UPCGPU_EXCHANGE", "peer") != "nccl":
+            from upcgen_b200 import dist as udist
+            self.peer = udist.setup_peer_exchange(self.gpu, rank, world)
+
+    def fill(self):
+        from upcgen_b200 import dist as udist
+        if self.peer:
+            udist.fill_lumi_peers(self.gpu, self.rank, self.world, self.dev)
+        else:
+            udist.fill_lumi_distributed(self.gpu, self.rank, self.world, self.dev)
 
     def close(self):
         self.gpu.close()
@@ -222,7 +237,7 @@ class Bench:
         gpu = self.gpu
         gpu.invalidate_tables()
         gpu.prepare_tables()
-        udist.fill_lumi_distributed(gpu, self.rank, self.world, self.dev)
+        self.fill()
         if self.fold:
             gpu.fold_sigma(download=False, **self.sig)   # the step's one host wait
         else:
@@ -302,11 +317,13 @@ class Bench:
             def step():
                 gpu.invalidate_tables()
                 gpu.prepare_tables()
-                udist.fill_lumi_distributed(gpu, self.rank, world, self.dev)
+                self.fill()
                 for which in kinds:
                     gpu.lumi_download(which)
                 return gpu.fold_sigma(download=True, **sig)[2] if fold else 0.0
-            api = ("per rank: upcgpu_fill_lumi_shard + NCCL all-gather + upcgpu_lumi_unpack + upcgpu_lumi_download"
+            api = (("per rank: upcgpu_fill_lumi_shard_peers (cell kernel stores into every rank's table) + upcgpu_lumi_download"
+                    if self.peer else
+                    "per rank: upcgpu_fill_lumi_shard + NCCL all-gather + upcgpu_lumi_unpack + upcgpu_lumi_download")
                    + (" + upcgpu_fold_sigma" if fold else "") + " (host buffers; bytes are per rank; max over ranks)")
         tot_mb = step()
         dts = []
@@ -475,6 +492,7 @@ def main():
         events = B.time_events(args.events or min(P.n_events, 1 << 20))
     roofline = B.roofline(stage, st, peak_tf)
     device_name = gpu.device_name()
+    peer_exchange = B.peer
     work = {"qags_integrals": st["qags_integrals"], "qags_evals": st["qags_evals"],
             "band_pairs": st["band_pairs"], "flux_rows": st["flux_rows"]}
     B.close()
@@ -519,7 +537,7 @@ def main():
             "metric": "lumi_cells_per_s", "value": B.n_cells / (ms * 1e-3), "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": make_config(args.workload, P, world),
+            "config": make_config(args.workload, P, world, peer_exchange),
             "sigma_table_ms": ms,
             "stage_ms": stage, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "events": events,

@@ -184,6 +184,16 @@ int upcgpu_lumi_shard_buffer(upcgpu_ctx* ctx, int which, uint64_t* dev_ptr, size
  * un-permuted into the full [nm][ny] device table by upcgpu_lumi_unpack */
 int upcgpu_lumi_gather_buffer(upcgpu_ctx* ctx, int which, int nshards, uint64_t* dev_ptr, size_t* n_doubles);
 int upcgpu_lumi_unpack(upcgpu_ctx* ctx, int nshards);
+/* The exchange folded into the cell kernel, between PROCESSES (one rank per GPU on one node): every rank exports the
+ * CUDA IPC handles of its full tables (3 x 64 bytes: unpolarised, scalar, pseudoscalar; unused ones zero), the ranks
+ * swap them with whatever they communicate with, every rank imports all of them (handles of rank d at
+ * handles + d * 3 * 64), and upcgpu_fill_lumi_shard_peers fills this rank's m rows with a cell kernel that stores
+ * every finished cell straight into the table of EVERY rank over NVLink -- no gather buffer, no un-permute.  Queued
+ * like upcgpu_fill_lumi_shard; before the fold the caller orders the ranks behind it with any collective on
+ * upcgpu_stream_handle (a one-element all-reduce).  Inside one process upcgpu_create_multi + exchange 1 does the same. */
+int upcgpu_lumi_ipc_export(upcgpu_ctx* ctx, void* handles);
+int upcgpu_lumi_ipc_import(upcgpu_ctx* ctx, int nshards, int rank, const void* handles);
+int upcgpu_fill_lumi_shard_peers(upcgpu_ctx* ctx);
 /* copy the full device table to / from the host (which as above) */
 int upcgpu_lumi_download(upcgpu_ctx* ctx, int which, double* host);
 int upcgpu_lumi_upload(upcgpu_ctx* ctx, int which, const double* host);

@@ -222,14 +222,21 @@ def test_cyclic_rows_cover_grid():
         seen = sorted(sum((udist.cyclic_rows(nm, r, w) for r in range(w)), []))
         assert seen == list(range(nm))
         assert max(len(udist.cyclic_rows(nm, r, w)) for r in range(w)) == udist.rows_per_shard(nm, w)
-        assert len(udist.cyclic_rows(nm, 0, w)) == udist.rows_per_shard(nm, w)      # shard 0 is the largest
         blk = udist.shard_block(nm, w)
         for r in range(w):                                                          # local index -> m row, as the kernels do
             rows = udist.cyclic_rows(nm, r, w)
-            assert rows == [(li // blk) * blk * w + r * blk + li % blk for li in range(len(rows))]
+
+            def to_im(li):
+                cyc = li // blk
+                pos = w - 1 - r if cyc & 1 else r
+                return (cyc * w + pos) * blk + li % blk
+            assert rows == [to_im(li) for li in range(len(rows))]
     # the bench grid on 8 GPUs: whole warps of neighbouring rows, shards within 3 % of the mean (the last one is short)
     sizes = [len(udist.cyclic_rows(1001, r, 8)) for r in range(8)]
     assert udist.shard_block(1001, 8) == 32 and max(sizes) == 128 and sorted(sizes)[1] >= 96
+    # the snake: rank 0 holds the first block of even cycles and the last block of odd ones
+    r0 = udist.cyclic_rows(1001, 0, 8)
+    assert r0[:32] == list(range(32)) and r0[32:64] == list(range(15 * 32, 16 * 32)) and r0[64:96] == list(range(16 * 32, 17 * 32))
 
 
 def test_head_interval_table_covers_the_oracles_bisections(get_oracle):

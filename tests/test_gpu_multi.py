@@ -158,6 +158,57 @@ def test_upcgen_cli_ngpus_equals_one_gpu(tmp_path):
     assert xa == xb
 
 
+_PEER_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from upcgen_b200 import capi, dist as udist
+from upcgen_b200.config import named_config
+rank, local, world = udist.init_from_env("nccl")
+dev = torch.device("cuda", local)
+for cfg, extra in (("cfg2", "BINS_M 150\nBINS_Y 20\n"), ("cfg1", "PROC_ID 11\nUSE_POLARIZED_CS 1\nBINS_M 70\nBINS_Y 11\nMMIN 1\nMMAX 20\n")):
+    P = named_config(cfg, extra)
+    g = capi.UpcGpu(P, local)
+    g.prepare_tables()
+    ref = g.fill_lumi()                                  # the whole grid on this rank's GPU
+    assert udist.setup_peer_exchange(g, rank, world)     # CUDA IPC mappings of every rank's tables
+    for w in ((1, 2) if P.use_pol else (0,)):
+        g.lumi_upload(w, np.zeros((P.nm, P.ny)))         # wipe: what is read back below was written by the peers
+    dist.barrier()
+    udist.fill_lumi_peers(g, rank, world, dev)
+    got = [g.lumi_download(w) for w in ((1, 2) if P.use_pol else (0,))]
+    exp = list(ref) if P.use_pol else [ref]
+    assert all(np.array_equal(a, b) for a, b in zip(got, exp)), (cfg, rank)
+    # ... and the NCCL all-gather path gives the same table
+    for w in ((1, 2) if P.use_pol else (0,)):
+        g.lumi_upload(w, np.zeros((P.nm, P.ny)))
+    dist.barrier()
+    udist.fill_lumi_distributed(g, rank, world, dev)
+    got = [g.lumi_download(w) for w in ((1, 2) if P.use_pol else (0,))]
+    assert all(np.array_equal(a, b) for a, b in zip(got, exp)), (cfg, rank, "nccl")
+    dist.barrier()
+    g.close()
+if rank == 0:
+    print("PEER_OK")
+dist.destroy_process_group()
+"""
+
+
+@two
+def test_torchrun_peer_store_exchange(tmp_path):
+    """One process per GPU (the bench's launch mode): the cell kernel stores every finished cell into every rank's
+    table through CUDA IPC mappings (upcgpu_lumi_ipc_export / _import, upcgpu_fill_lumi_shard_peers); every rank ends
+    up with the single-GPU table, bit for bit, as it does through the NCCL all-gather."""
+    script = tmp_path / "peer_worker.py"
+    script.write_text(_PEER_WORKER.format(root=ROOT))
+    n = min(NDEV, 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29577", str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "PEER_OK" in r.stdout
+
+
 def test_head_state_pool_fallback():
     """The pool of QAGS hand-over states is a quarter of the integrals; when it runs dry the integral restarts in the
     second head pass and, if there is still no slot, in the large-workspace pass.  Forced here with a 3-slot pool

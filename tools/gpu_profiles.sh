@@ -1,14 +1,16 @@
 #!/bin/bash
-# launch list + ncu --set full captures of the three main kernels of a cfg2 step (profiles/ are summarised from these)
+# launch lists + ncu --set full captures of the main kernels (profiles/ are summarised from these with tools/ncu_summary.py)
 mkdir -p gpurun_out
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    python tools/profile_step.py cfg2 1 1 > gpurun_out/launches.log 2>&1
-for K in "k_flux_qags_head<11" "k_flux_qags_head<16" k_flux_qags_rows k_cells; do
-  timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$K" -s 1 -c 1 -f -o "gpurun_out/prof_${K//[<]/_}" \
-      python tools/profile_step.py cfg2 1 1 > "gpurun_out/prof_${K//[<]/_}.log" 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_cfg2.csv \
+    python tools/profile_step.py cfg2 1 1 1000000 > gpurun_out/launches_cfg2.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_cfg5.csv \
+    python tools/profile_step.py cfg5 0 1 8000000 > gpurun_out/launches_cfg5.log 2>&1
+for K in "k_flux_qags_head<11" k_cells; do
+  timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$K" -s 1 -c 1 -f -o "gpurun_out/prof_${K//[<]/_}_cfg2" \
+      python tools/profile_step.py cfg2 1 1 > "gpurun_out/prof_${K//[<]/_}_cfg2.log" 2>&1
 done
-timeout 300 python bench.py --workload cfg1 --no-cpu-baseline > gpurun_out/bench_cfg1.json 2> gpurun_out/bench_cfg1.err
-timeout 300 python bench.py --workload cfg4 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg4.json 2> gpurun_out/bench_cfg4.err
-timeout 300 python bench.py --workload cfg5 --no-cpu-baseline > gpurun_out/bench_cfg5.json 2> gpurun_out/bench_cfg5.err
-timeout 300 python bench.py --workload cfg3 --no-cpu-baseline > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err
+timeout 400 ncu --set full --clock-control none --import-source on -k "regex:k_cells" -s 1 -c 1 -f -o gpurun_out/prof_k_cells_cfg1 \
+    python tools/profile_step.py cfg1 1 1 > gpurun_out/prof_k_cells_cfg1.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k "regex:k_pt_serve_keys" -c 1 -f -o gpurun_out/prof_k_pt_serve_keys_cfg2 \
+    python tools/profile_step.py cfg2 0 1 1000000 > gpurun_out/prof_k_pt_serve_keys_cfg2.log 2>&1
 ls -la gpurun_out | tail -20

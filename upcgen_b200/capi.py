@@ -69,6 +69,7 @@ SYMBOLS = [
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
     "upcgpu_create_multi", "upcgpu_group_size", "upcgpu_group_member", "upcgpu_group_set_exchange",
     "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_tree", "upcgpu_photon_flux",
+    "upcgpu_lumi_ipc_export", "upcgpu_lumi_ipc_import", "upcgpu_fill_lumi_shard_peers",
 ]
 
 
@@ -332,6 +333,22 @@ class UpcGpu:
         ptr, n = C.c_uint64(), C.c_size_t()
         self._chk(self.L.upcgpu_lumi_gather_buffer(self.h, which, nshards, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
+
+    def lumi_ipc_export(self) -> bytes:
+        """CUDA IPC handles of this context's full tables (3 x 64 bytes)."""
+        buf = C.create_string_buffer(192)
+        self.L.upcgpu_lumi_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+        self._chk(self.L.upcgpu_lumi_ipc_export(self.h, buf))
+        return buf.raw
+
+    def lumi_ipc_import(self, nshards, rank, handles: bytes):
+        assert len(handles) == nshards * 192
+        self.L.upcgpu_lumi_ipc_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        self._chk(self.L.upcgpu_lumi_ipc_import(self.h, nshards, rank, handles))
+
+    def fill_lumi_shard_peers(self):
+        self.L.upcgpu_fill_lumi_shard_peers.argtypes = [C.c_void_p]
+        self._chk(self.L.upcgpu_fill_lumi_shard_peers(self.h))
 
     def lumi_unpack(self, nshards):
         self._chk(self.L.upcgpu_lumi_unpack(self.h, nshards))

@@ -123,6 +123,9 @@ void upcgpu_destroy(upcgpu_ctx* c)
   if (!c) return;
   if (c->group && c->group_rank == 0) group_destroy(c);  // the members, their threads, the NCCL communicators
   cudaSetDevice(c->device);
+  for (int d = 0; d < c->ipc_n; ++d)
+    for (int w = 0; w < 3; ++w)
+      if (d != c->ipc_rank && c->ipc_lumi[d][w]) cudaIpcCloseMemHandle(c->ipc_lumi[d][w]);
   if (c->stream) cudaStreamSynchronize(c->stream);
   cudaFree(c->gaa_x); cudaFree(c->gaa_y); cudaFree(c->gaa_c); cudaFree(c->ta_y); cudaFree(c->ta_c);
   cudaFree(c->ff_y); cudaFree(c->ff_c); cudaFree(c->bk_y); cudaFree(c->bk_c);
@@ -339,6 +342,59 @@ int upcgpu_lumi_gather_buffer(upcgpu_ctx* c, int which, int nshards, uint64_t* d
   if (dev_ptr) *dev_ptr = (uint64_t)(uintptr_t)c->gather[which];
   if (n_doubles) *n_doubles = c->shard_rows * c->p.ny * nshards;
   return UPCGPU_OK;
+}
+
+// ---- peer stores between processes (one rank per GPU): CUDA IPC handles of the full tables ----
+int upcgpu_lumi_ipc_export(upcgpu_ctx* c, void* handles /* 3 x 64 bytes */)
+{
+  CHECK_CTX_SYNC(c);
+  if (!handles) return UPCGPU_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  const int rc = ensure_lumi_buffers(c, 0);
+  if (rc) return rc;
+  std::memset(handles, 0, 3 * sizeof(cudaIpcMemHandle_t));
+  for (int w = 0; w < 3; ++w)
+    if (c->lumi[w]) UPC_CUDA(c, cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handles + w, c->lumi[w]));
+  return UPCGPU_OK;
+}
+
+int upcgpu_lumi_ipc_import(upcgpu_ctx* c, int nshards, int rank, const void* handles /* nshards x 3 x 64 bytes */)
+{
+  CHECK_CTX_SYNC(c);
+  if (!handles || nshards < 1 || nshards > kMaxPeers || rank < 0 || rank >= nshards) { c->err = "lumi_ipc_import: bad argument"; return UPCGPU_EINVAL; }
+  int rc = ensure_lumi_buffers(c, 0);
+  if (rc) return rc;
+  for (int d = 0; d < c->ipc_n; ++d)
+    for (int w = 0; w < 3; ++w)
+      if (d != c->ipc_rank && c->ipc_lumi[d][w]) { cudaIpcCloseMemHandle(c->ipc_lumi[d][w]); c->ipc_lumi[d][w] = nullptr; }
+  c->ipc_n = 0;
+  const int w0 = c->p.use_pol ? 1 : 0, w1 = c->p.use_pol ? 2 : 0;
+  for (int d = 0; d < nshards; ++d)
+    for (int w = w0; w <= w1; ++w) {
+      if (d == rank) { c->ipc_lumi[d][w] = c->lumi[w]; continue; }
+      void* ptr = nullptr;
+      UPC_CUDA(c, cudaIpcOpenMemHandle(&ptr, ((const cudaIpcMemHandle_t*)handles)[d * 3 + w], cudaIpcMemLazyEnablePeerAccess));
+      c->ipc_lumi[d][w] = (double*)ptr;
+    }
+  c->ipc_n = nshards;
+  c->ipc_rank = rank;
+  return UPCGPU_OK;
+}
+
+// Sharded fill whose cell kernel stores every finished cell into the full table of EVERY rank (the tables imported
+// with upcgpu_lumi_ipc_import): no gather buffer, no un-permute.  Queued like upcgpu_fill_lumi_shard; the caller
+// orders the ranks behind it (any collective on upcgpu_stream_handle, e.g. a one-element all-reduce) before the fold.
+int upcgpu_fill_lumi_shard_peers(upcgpu_ctx* c)
+{
+  CHECK_CTX(c);
+  if (c->ipc_n < 1) { c->err = "fill_lumi_shard_peers: call upcgpu_lumi_ipc_import first"; return UPCGPU_EINVAL; }
+  for (int d = 0; d < c->ipc_n; ++d)
+    for (int w = 0; w < 3; ++w) c->peer_lumi[d][w] = c->ipc_lumi[d][w];
+  c->n_peers = c->ipc_n;
+  const int rc = fill_lumi_rows(c, c->ipc_rank, c->ipc_n, /*wait=*/false);
+  c->n_peers = 0;
+  c->lumi_ready = true;  // ... once the caller's collective has passed on this stream
+  return rc;
 }
 
 int upcgpu_lumi_unpack(upcgpu_ctx* c, int nshards)

@@ -93,6 +93,10 @@ struct upcgpu_ctx_impl {
   // peer-store exchange: full lumi tables of every member, written by this member's cell kernel (set per fill)
   double* peer_lumi[kMaxPeers][3] = {};
   int n_peers = 0;
+  // ... the same between PROCESSES (one rank per GPU): the other ranks' tables mapped through CUDA IPC
+  // (upcgpu_lumi_ipc_export / _import); ipc_n = number of ranks, ipc_rank = this one
+  double* ipc_lumi[kMaxPeers][3] = {};
+  int ipc_n = 0, ipc_rank = -1;
   bool func_attrs_set = false;   // cudaFuncSetAttribute done on this context's device
   bool ev_attr_set = false;      // ... for the event kernels
   long long test_head_pool = 0;  // UPCGPU_TEST_HEAD_POOL: slots of the hand-over state pool (tests of the fallback path)

@@ -16,7 +16,7 @@
 // in SHARED memory and serves all photons of the key from it -- the pdf of a key is evaluated at the
 // key's centre (key + 0.5) MeV.  Nothing but the photon pT (8 B per photon) reaches HBM: writing the
 // 5001-entry tables out and searching them from another kernel (round 1) moved 40 KB per key, ~300x
-// the bytes of the events themselves.  Batches are large (4 M candidates) because the cost of the
+// the bytes of the events themselves.  Batches are large (8 M candidates) because the cost of the
 // stage is the number of distinct keys per batch x 5000 form-factor evaluations.
 #include <cub/cub.cuh>
 
@@ -30,7 +30,7 @@
 namespace upc {
 
 constexpr int kPtBins = 5000;
-constexpr size_t kEvChunk = (size_t)1 << 22;  // candidates per batch (~300 B of scratch each)
+constexpr size_t kEvChunk = (size_t)1 << 23;  // candidates per batch (~300 B of scratch each: 2.5 GB)
 
 struct EvReport {  // pinned host mirror of the per-batch counters
   unsigned long long n_acc;
@@ -183,7 +183,9 @@ __device__ __forceinline__ void pt_build(PtShared& S, double e, const SplineSeg*
       const double pt = 6. * kHc / R / kPtBins * (b0 + 1);  // upper bin edge, :1033
       const double arg = pt * pt + ereds;
       const double f = ff_lookup(ff, arg);
-      prob = (f * f) * pt * pt * pt / (pi2x4 * arg * arg);
+      // (the division of :1036 as a multiplication by a Newton-refined reciprocal: ~1e-16 relative on a pdf whose
+      // draws are compared statistically; the table is the FP64-bound part of the event stage)
+      prob = (f * f) * pt * pt * pt * rcp_fast(pi2x4 * arg * arg);
     }
     S.sp[(b0 / kPtPerThread) * kPtRunPad + b0 % kPtPerThread] = prob;
   }
@@ -221,19 +223,51 @@ __device__ __forceinline__ double pt_sample(const double* sp, double r1, double 
   return x;
 }
 
-// Persistent grid over TILES of kPtThreads sorted photons, handed out by an atomic counter: a CTA walks the key runs
-// that intersect its tile, builds each key's table and serves the run's photons that lie in the tile (one photon per
-// thread).  Tiles, not keys, are the unit of work because the keys are very unequal: at low photon energies one
-// integer-MeV key holds 10^5-10^6 photons of a 4 M-candidate batch (one CTA per key left the whole stage waiting for
-// them), at high energies every photon has a key of its own.  A run that crosses a tile boundary is tabulated by
-// both tiles: at most one extra table per tile.
+// Two kernels serve the photons of a batch from per-key tables in shared memory; the keys are very unequal -- at low
+// photon energies one integer-MeV key holds 10^5-10^6 photons of a 4 M-candidate batch, at high energies every photon
+// has a key of its own -- and each regime gets the work decomposition that suits it:
+//   k_pt_serve_keys   one table per DISTINCT key, keys dealt to a persistent grid round-robin (neighbouring CTAs work
+//                     on neighbouring keys, i.e. on the same part of the form-factor table at the same time); the CTA
+//                     serves the first kPtHead photons of the key;
+//   k_pt_serve_tiles  the photons beyond the first kPtHead of their key, in tiles of kPtThreads sorted photons handed
+//                     out by an atomic counter: a heavy key is shared by many CTAs (each rebuilds its table: one
+//                     extra table per 256 photons), a tile without such photons costs one look at its run lengths.
 // Photon id = 2 t + side; its uniform is slot `side` of Philox block 3 of candidate first + t (the slot map above),
 // recomputed here rather than stored.
-__global__ void __launch_bounds__(kPtThreads) k_pt_serve(const int* __restrict__ n_uniq_p, const unsigned* __restrict__ seg_off,
-                                                         unsigned n_photons, const unsigned* __restrict__ keys_sorted,
-                                                         const unsigned* __restrict__ pid_sorted, uint64_t seed,
-                                                         uint64_t first, const SplineSeg* __restrict__ ff, double gtot,
-                                                         double R, double* __restrict__ pt_out, unsigned* __restrict__ next_tile)
+constexpr unsigned kPtHead = 2048;
+
+__device__ __forceinline__ void pt_serve_one(const PtShared& S, unsigned q, const unsigned* __restrict__ pid_sorted, uint64_t seed,
+                                             uint64_t first, double R, double* __restrict__ pt_out)
+{
+  const unsigned id = pid_sorted[q];
+  double u6, u7;
+  philox4x32_10(seed, first + (id >> 1), 3, u6, u7);
+  pt_out[id] = pt_sample(S.sp, (id & 1) ? u7 : u6, R);
+}
+
+__global__ void __launch_bounds__(kPtThreads) k_pt_serve_keys(const int* __restrict__ n_uniq_p, const unsigned* __restrict__ seg_off,
+                                                              unsigned n_photons, const unsigned* __restrict__ keys_sorted,
+                                                              const unsigned* __restrict__ pid_sorted, uint64_t seed,
+                                                              uint64_t first, const SplineSeg* __restrict__ ff, double gtot,
+                                                              double R, double* __restrict__ pt_out)
+{
+  extern __shared__ __align__(16) unsigned char pt_smem[];
+  PtShared& S = *reinterpret_cast<PtShared*>(pt_smem);
+  const int n_uniq = *n_uniq_p;
+  for (int k = blockIdx.x; k < n_uniq; k += gridDim.x) {
+    const unsigned q0 = seg_off[k], q1 = (k + 1 < n_uniq) ? seg_off[k + 1] : n_photons;
+    pt_build(S, (keys_sorted[q0] + 0.5) * 1e-3, ff, gtot, R);
+    const unsigned qe = min(q1, q0 + kPtHead);
+    for (unsigned q = q0 + threadIdx.x; q < qe; q += kPtThreads) pt_serve_one(S, q, pid_sorted, seed, first, R, pt_out);
+    __syncthreads();  // the table is rebuilt for the next key
+  }
+}
+
+__global__ void __launch_bounds__(kPtThreads) k_pt_serve_tiles(const int* __restrict__ n_uniq_p, const unsigned* __restrict__ seg_off,
+                                                               unsigned n_photons, const unsigned* __restrict__ keys_sorted,
+                                                               const unsigned* __restrict__ pid_sorted, uint64_t seed,
+                                                               uint64_t first, const SplineSeg* __restrict__ ff, double gtot,
+                                                               double R, double* __restrict__ pt_out, unsigned* __restrict__ next_tile)
 {
   extern __shared__ __align__(16) unsigned char pt_smem[];
   PtShared& S = *reinterpret_cast<PtShared*>(pt_smem);
@@ -252,21 +286,17 @@ __global__ void __launch_bounds__(kPtThreads) k_pt_serve(const int* __restrict__
       const int mid = (lo + hi) >> 1;
       if (seg_off[mid] <= t0) lo = mid; else hi = mid;
     }
-    for (int k = lo; k < n_uniq; ++k) {
-      const unsigned q0 = seg_off[k];
-      if (q0 >= t1) break;
-      const unsigned q1 = (k + 1 < n_uniq) ? seg_off[k + 1] : n_photons;
-      const double e = (keys_sorted[q0] + 0.5) * 1e-3;
-      pt_build(S, e, ff, gtot, R);
-      const unsigned q = max(q0, t0) + threadIdx.x;
-      if (q < min(q1, t1)) {
-        const unsigned id = pid_sorted[q];
-        double u6, u7;
-        philox4x32_10(seed, first + (id >> 1), 3, u6, u7);
-        pt_out[id] = pt_sample(S.sp, (id & 1) ? u7 : u6, R);
-      }
-      __syncthreads();  // the table is rebuilt for the next run
+    // Only the run that holds t0 can have photons of rank >= kPtHead inside this tile beyond its start ... and any
+    // later run that starts inside the tile has ranks < kPtThreads <= kPtHead there: at most ONE run needs serving.
+    const unsigned q0 = seg_off[lo];
+    const unsigned q1 = (lo + 1 < n_uniq) ? seg_off[lo + 1] : n_photons;
+    const unsigned from = max(t0, q0 + kPtHead), to = min(q1, t1);
+    if (from < to) {  // uniform over the CTA
+      pt_build(S, (keys_sorted[q0] + 0.5) * 1e-3, ff, gtot, R);
+      const unsigned q = from + threadIdx.x;
+      if (q < to) pt_serve_one(S, q, pid_sorted, seed, first, R, pt_out);
     }
+    __syncthreads();  // s_tile and the table are reused
   }
 }
 
@@ -517,7 +547,8 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
   cudaStream_t st = c->stream;
   const EvParams P = make_evp(c);
   if (!c->ev_attr_set) {
-    cudaFuncSetAttribute(k_pt_serve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    cudaFuncSetAttribute(k_pt_serve_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    cudaFuncSetAttribute(k_pt_serve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
     cudaFuncSetAttribute(k_pt_table_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
     c->ev_attr_set = true;
   }
@@ -540,12 +571,15 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
       tb = s->cub_bytes;
       cub::CountingInputIterator<unsigned> cnt0(0u);
       cub::DeviceSelect::If(s->cub_tmp, tb, cnt0, s->seg_off, s->n_uniq, n_ph, KeyHead{s->keys_sorted}, st);
-      // persistent grid: the number of distinct keys stays on the device
+      // persistent grids: the number of distinct keys stays on the device
       const int n_tiles = (n_ph + kPtThreads - 1) / kPtThreads;
-      const int grid = std::min(n_tiles, c->prop.multiProcessorCount * 5);
+      const int grid = std::min(n_ph, c->prop.multiProcessorCount * 5);
+      UPC_K(c), k_pt_serve_keys<<<grid, kPtThreads, sizeof(PtShared), st>>>(s->n_uniq, s->seg_off, (unsigned)n_ph, s->keys_sorted,
+                                                                  s->pid_sorted, seed, first + off, c->ff_seg, c->p.gtot, c->p.R, s->pt);
       UPC_CUDA(c, cudaMemsetAsync(s->next_tile, 0, sizeof(unsigned), st));
-      UPC_K(c), k_pt_serve<<<grid, kPtThreads, sizeof(PtShared), st>>>(s->n_uniq, s->seg_off, (unsigned)n_ph, s->keys_sorted, s->pid_sorted,
-                                                             seed, first + off, c->ff_seg, c->p.gtot, c->p.R, s->pt, s->next_tile);
+      UPC_K(c), k_pt_serve_tiles<<<std::min(n_tiles, grid), kPtThreads, sizeof(PtShared), st>>>(
+          s->n_uniq, s->seg_off, (unsigned)n_ph, s->keys_sorted, s->pid_sorted, seed, first + off, c->ff_seg, c->p.gtot, c->p.R, s->pt,
+          s->next_tile);
     }
     UPC_K(c), k_ev_kin<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, s->pt, s->npart, s->pdg, s->status, s->mother,
                                 s->p4, s->aux, s->n_acc);
@@ -576,7 +610,8 @@ int photon_pt_cdf(upcgpu_ctx* c, double e, double* cdf)
 {
   if (!c->tables_ready) { c->err = "photon_pt_cdf: tables not prepared"; return UPCGPU_EINVAL; }
   if (!c->ev_attr_set) {
-    cudaFuncSetAttribute(k_pt_serve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    cudaFuncSetAttribute(k_pt_serve_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
+    cudaFuncSetAttribute(k_pt_serve_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
     cudaFuncSetAttribute(k_pt_table_one, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PtShared));
     c->ev_attr_set = true;
   }

@@ -154,9 +154,18 @@ __global__ void __launch_bounds__(32) k_running_mean(const double* __restrict__ 
       const int m = (int)min((size_t)kSeqChunk, n - i0);
       const double* b = sb[buf];
       const double* r = sr[buf];
-#pragma unroll 4
-      for (int j = 0; j < m; ++j)   // mean += (bin[i] - mean) / (i + 1)
-        mean = __dadd_rn(mean, div_by_known(__dsub_rn(b[j], mean), (double)(i0 + j + 1), r[j]));
+      // mean += (bin[i] - mean) / (i + 1): eight elements' operands are fetched into registers ahead of the chain, so
+      // that the chain is the seven dependent FP64 operations per element and nothing else
+      int j = 0;
+      for (; j + 8 <= m; j += 8) {
+        double bv[8], rv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { bv[k] = b[j + k]; rv[k] = r[j + k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          mean = __dadd_rn(mean, div_by_known(__dsub_rn(bv[k], mean), (double)(i0 + j + k + 1), rv[k]));
+      }
+      for (; j < m; ++j) mean = __dadd_rn(mean, div_by_known(__dsub_rn(b[j], mean), (double)(i0 + j + 1), r[j]));
     } else {
       // lanes 1..31 stage the next chunk meanwhile
       for (size_t j = nxt + (lane - 1); j < nxt + kSeqChunk && j < n; j += 31) {
@@ -190,8 +199,18 @@ __global__ void __launch_bounds__(32) k_seq_cumsum(const double* __restrict__ te
     const int m = (int)min((size_t)kSeqChunk, n - i0);
     if (lane == 0) {
       const double* t = st[buf];
-#pragma unroll 8
-      for (int j = 0; j < m; ++j) {
+      // sum[k + 1] = sum[k] + term[k]: sixteen terms into registers, sixteen chained additions, sixteen stores
+      int j = 0;
+      for (; j + 16 <= m; j += 16) {
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = t[j + k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { s = __dadd_rn(s, v[k]); v[k] = s; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) so[j + k] = v[k];
+      }
+      for (; j < m; ++j) {
         s = __dadd_rn(s, t[j]);
         so[j] = s;
       }

@@ -172,6 +172,7 @@ __global__ void k_ff_y(double R, double a, const double* rho0p, double* y)
 // strictly diagonally dominant, so the influence of a far knot decays as (2-sqrt 3)^distance
 // (1e-37 after 64 knots): each thread solves the system on its chunk plus a 64-knot halo with
 // the same LDL^T recurrences GSL uses and keeps the chunk.
+// (rcp_fast: upc_math.cuh)
 constexpr int kSpChunk = 48;   // short chunks: the kernel is a latency chain per thread (192: 0.33 ms for the 10^6-knot table)
 constexpr int kSpHalo = 64;
 constexpr int kSpThreads = 32;
@@ -218,10 +219,11 @@ __global__ void __launch_bounds__(kSpThreads) k_spline_windowed(double x0, doubl
     const double diag = 2.0 * (h[i + 1] + h[i]);
     const double off = h[i + 1];
     const double alpha = (j == 0) ? diag : diag - h[i] * gamma_prev;  // off_{i-1} = h(i)
-    const double g = off / alpha;
+    const double ra = rcp_fast(alpha);
+    const double g = off * ra;
     const double zz = (j == 0) ? rhs[i] : rhs[i] - gamma_prev * z_prev;
     gamma[j] = g;
-    z[j] = zz / alpha;  // store c_i = z_i/alpha_i
+    z[j] = zz * ra;  // store c_i = z_i/alpha_i
     gamma_prev = g; z_prev = zz;
   }
   // back substitution x_i = c_i - gamma_i x_{i+1}

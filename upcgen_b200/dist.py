@@ -1,6 +1,6 @@
 """Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch).
 
-The (y, m) grid shards by m rows, block-cyclically (blocks of 32 consecutive rows dealt round-robin).
+The (y, m) grid shards by m rows: blocks of 32 consecutive rows dealt to the ranks in a snake.
 Cells are independent, so the only exchange on the table path is one all-gather of the packed
 shards, after which every rank un-permutes the rows into its full device table and folds it
 locally.  Event sampling shards by Philox counter ranges and needs no collective at all.
@@ -35,15 +35,23 @@ def shard_block(nm: int, world: int) -> int:
     return b
 
 
+def shard_of_row(im: int, world: int, blk: int) -> int:
+    """shard_of_row() of csrc/upc_lumi.cu: blocks dealt in a snake (cycle 0: shards 0..G-1, cycle 1: G-1..0, ...)."""
+    jb = im // blk
+    cyc, pos = divmod(jb, world)
+    return world - 1 - pos if cyc & 1 else pos
+
+
 def cyclic_rows(nm: int, rank: int, world: int):
     """m rows owned by `rank` (host-side logic shared with the CPU tests): blocks of shard_block() consecutive rows
-    dealt round-robin, row im belongs to shard (im // block) % world; ascending."""
+    dealt in a snake over the ranks (the cost of a row falls with m; the snake pairs dear blocks with cheap ones);
+    ascending."""
     blk = shard_block(nm, world)
-    return [im for im in range(nm) if (im // blk) % world == rank]
+    return [im for im in range(nm) if shard_of_row(im, world, blk) == rank]
 
 
 def rows_per_shard(nm: int, world: int) -> int:
-    """Rows of the packed shard buffer = the row count of shard 0, the largest."""
+    """Rows of the packed shard buffer = the row count of the largest shard."""
     blk = shard_block(nm, world)
     cyc = blk * world
     return (nm // cyc) * blk + min(nm % cyc, blk)
@@ -78,6 +86,39 @@ def init_from_env(backend="nccl"):
         else:
             dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, local, world
+
+
+def setup_peer_exchange(gpu, rank: int, world: int) -> bool:
+    """One-time set-up of the peer-store exchange between the ranks of one node: every rank's full lumi tables are
+    mapped into every other rank through CUDA IPC (handles swapped with all_gather_object).  Returns False when a rank
+    cannot map its peers (no peer access between the devices): the caller then stays on the NCCL all-gather."""
+    import torch.distributed as dist
+    mine = gpu.lumi_ipc_export()
+    allh = [None] * world
+    dist.all_gather_object(allh, mine)
+    ok = True
+    try:
+        gpu.lumi_ipc_import(world, rank, b"".join(allh))
+    except Exception:
+        ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    return all(flags)
+
+
+def fill_lumi_peers(gpu, rank: int, world: int, device=None):
+    """Table stage with the exchange folded into the cell kernel: every rank fills its m rows and its kernel stores
+    each finished cell into the table of every rank (set up by setup_peer_exchange).  A one-element all-reduce on the
+    library's stream orders every rank's fold behind every rank's kernel; nothing here waits for the device."""
+    import torch
+    import torch.distributed as dist
+    gpu.fill_lumi_shard_peers()
+    tok = getattr(gpu, "_peer_token", None)
+    if tok is None:
+        tok = (torch.zeros(1, device=device), torch.cuda.ExternalStream(gpu.stream_handle(), device=device))
+        gpu._peer_token = tok
+    with torch.cuda.stream(tok[1]):
+        dist.all_reduce(tok[0])
 
 
 def fill_lumi_distributed(gpu, rank: int, world: int, device=None):

@@ -1,3 +1,8 @@
+// Interface compatibility notice: the class, member and method names declared in this file reproduce the public
+// interface of Upcgen (https://github.com/nburmaso/upcgen), Copyright (C) 2021-2025 Nazar Burmasov, Evgeny Kryshen,
+// distributed under the GNU General Public License, version 3 or later (see LICENSE-UPCGEN-NOTICE.md at the
+// repository root).  They are kept identical so that code written against the reference compiles against this
+// drop-in; the implementation behind them is this project's own.
 // Elementary-process plug-in interface: the reference's only "plugin API"
 // (include/UpcElemProcess.h:26-62).  Same member names, same virtuals, so that a process class
 // written against the reference compiles against this header unchanged.  The plug-ins stay host

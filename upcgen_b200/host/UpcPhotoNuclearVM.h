@@ -1,3 +1,8 @@
+// Interface compatibility notice: the class, member and method names declared in this file reproduce the public
+// interface of Upcgen (https://github.com/nburmaso/upcgen), Copyright (C) 2021-2025 Nazar Burmasov, Evgeny Kryshen,
+// distributed under the GNU General Public License, version 3 or later (see LICENSE-UPCGEN-NOTICE.md at the
+// repository root).  They are kept identical so that code written against the reference compiles against this
+// drop-in; the implementation behind them is this project's own.
 // UpcPhotoNuclearVM -- elementary process of the vector-meson path: coherent photoproduction of J/psi, psi(2S) and
 // Upsilon(1S) off a nucleus (reference: include/UpcPhotoNuclearVM.h, src/UpcPhotoNuclearVM.cpp).  Same class name,
 // constructor and virtuals.  Host code, like every elementary-process plug-in; the b-integrated photon flux it is

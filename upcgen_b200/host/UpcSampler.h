@@ -1,3 +1,8 @@
+// Interface compatibility notice: the class, member and method names declared in this file reproduce the public
+// interface of Upcgen (https://github.com/nburmaso/upcgen), Copyright (C) 2021-2025 Nazar Burmasov, Evgeny Kryshen,
+// distributed under the GNU General Public License, version 3 or later (see LICENSE-UPCGEN-NOTICE.md at the
+// repository root).  They are kept identical so that code written against the reference compiles against this
+// drop-in; the implementation behind them is this project's own.
 // UpcSampler1D / UpcSampler2D -- the reference's inverse-CDF samplers (include/UpcSampler.h) with the
 // same constructors, operator() and getBinX/getBinY.  The cumulative table is built on the GPU in
 // GSL's sequential order (upcgpu_hist_pdf_init) and draws are produced there in blocks from a

@@ -1,3 +1,8 @@
+// Interface compatibility notice: the class, member and method names declared in this file reproduce the public
+// interface of Upcgen (https://github.com/nburmaso/upcgen), Copyright (C) 2021-2025 Nazar Burmasov, Evgeny Kryshen,
+// distributed under the GNU General Public License, version 3 or later (see LICENSE-UPCGEN-NOTICE.md at the
+// repository root).  They are kept identical so that code written against the reference compiles against this
+// drop-in; the implementation behind them is this project's own.
 // Closed-form gamma gamma -> l+ l- cross sections, incl. the anomalous-moment terms.
 // Formulas as evaluated by the reference (src/UpcTwoPhotonDilep.cpp:46-134); the operation order
 // inside each expression is kept so that sigma(m) is bit-identical to a reference build, which

@@ -1,3 +1,8 @@
+// Interface compatibility notice: the class, member and method names declared in this file reproduce the public
+// interface of Upcgen (https://github.com/nburmaso/upcgen), Copyright (C) 2021-2025 Nazar Burmasov, Evgeny Kryshen,
+// distributed under the GNU General Public License, version 3 or later (see LICENSE-UPCGEN-NOTICE.md at the
+// repository root).  They are kept identical so that code written against the reference compiles against this
+// drop-in; the implementation behind them is this project's own.
 // Elementary processes whose cross sections the reference ships as histograms in ROOT files:
 //   UpcTwoPhotonLbyL    gamma gamma -> gamma gamma   (include/UpcTwoPhotonLbyL.h, src/UpcTwoPhotonLbyL.cpp)
 //   UpcTwoPhotonDipion  gamma gamma -> pi0 pi0       (include/UpcTwoPhotonDipion.h, src/UpcTwoPhotonDipion.cpp)
