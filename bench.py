@@ -346,10 +346,13 @@ class Bench:
         cszm = None if P.ignore_csz else capi.elem_cs_zm(P, 0)
         gpu.sampler_build(cszm=cszm)          # warm-up (allocations)
         torch.cuda.synchronize(self.dev)
-        t0 = time.perf_counter()
-        gpu.sampler_build(cszm=cszm)          # S1: the CDFs of the (y, m) table and of the nm z tables
-        torch.cuda.synchronize(self.dev)
-        ms_sampler = (time.perf_counter() - t0) * 1e3
+        ms_sampler = None
+        for _ in range(3):                    # wall clock around a host call: the best of three
+            t0 = time.perf_counter()
+            gpu.sampler_build(cszm=cszm)      # S1: the CDFs of the (y, m) table and of the nm z tables
+            torch.cuda.synchronize(self.dev)
+            dt = (time.perf_counter() - t0) * 1e3
+            ms_sampler = dt if ms_sampler is None else min(ms_sampler, dt)
         n_ev = max(n_total // world, 1 << 14)
         first = rank * n_ev
         gpu.generate_device(12345, first, n_ev)  # warm-up at full size: the scratch buffers grow on demand

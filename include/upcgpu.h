@@ -103,10 +103,11 @@ int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out);
  * thread; an NCCL communicator over the devices (ncclCommInitAll; NCCL is loaded with dlopen) and peer access
  * between them are set up here.  With such a handle
  *   upcgpu_prepare_tables   builds the lookup tables on every device,
- *   upcgpu_fill_lumi        deals the m rows to the devices (blocks of 32 rows round-robin), exchanges the shards
- *                           (NCCL all-gather over NVLink, or -- upcgpu_group_set_exchange(ctx, 1) -- stores of every
- *                           finished cell into all devices' tables from inside the cell kernel) and leaves the FULL
- *                           table on every device; the host buffers are filled from device 0,
+ *   upcgpu_fill_lumi        deals the m rows to the devices (blocks of 32 rows, in a snake), exchanges the shards
+ *                           (stores of every finished cell into all devices' tables from inside the cell kernel where
+ *                           the devices have peer access -- the default --, or an NCCL all-gather over NVLink:
+ *                           upcgpu_group_set_exchange(ctx, 0)) and leaves the FULL table on every device; the host
+ *                           buffers are filled from device 0,
  *   upcgpu_fold_sigma, upcgpu_sampler_build   run on every device (each samples events from its own copy),
  *   upcgpu_generate[_device]   split the candidate range into contiguous ranges, one per device; Philox counters make
  *                           the result independent of n_gpus,

@@ -158,6 +158,30 @@ def test_upcgen_cli_ngpus_equals_one_gpu(tmp_path):
     assert xa == xb
 
 
+@two
+def test_cfg4_sharded_over_the_group_reproduces_the_golden_subgrid(capi):
+    """BASELINE config 4 at its full size (10001 x 1201 cells) filled by every device of the box through one handle:
+    the oracle's golden sub-grid is reproduced, every member holds the same table bit for bit, and the work counters
+    are those of the grid (one integral per (y row, b index, m row) of the form-factor flux)."""
+    from upcgen_b200.config import named_config
+    P = named_config("cfg4")
+    g = capi.UpcGpu(P, n_gpus=min(NDEV, 8))
+    g.prepare_tables()
+    table = g.fill_lumi()
+    st = g.fill_stats()
+    assert st["qags_errors"] == 0 and st["qags_overflow"] == 0
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "cfg4_subgrid.npz"))
+    im, iy = gold["im"], gold["iy"]
+    ref = gold["lumi"] * float(gold["dm"]) * float(gold["dy"])
+    sel = ref > 1e-250
+    eg = np.max(np.abs(table[np.ix_(im, iy)][sel] - ref[sel]) / ref[sel])
+    print("cfg4 on", g.group_size(), "GPUs: golden sub-grid max rel", eg, "integrals", st["qags_integrals"])
+    assert eg < 1e-7
+    for r in range(1, g.group_size()):
+        assert np.array_equal(g.group_member(r).lumi_download(0), table), r
+    g.close()
+
+
 _PEER_WORKER = r"""
 import os, sys
 sys.path.insert(0, {root!r})

@@ -134,6 +134,7 @@ void upcgpu_destroy(upcgpu_ctx* c)
   for (int w = 0; w < 3; w++) { cudaFree(c->lumi[w]); cudaFree(c->shard[w]); cudaFree(c->gather[w]); }
   cudaFree(c->cs); cudaFree(c->ratio); cudaFree(c->sum2d); cudaFree(c->sumz); cudaFree(c->sumz_ps);
   cudaFree(c->edges_y); cudaFree(c->edges_m); cudaFree(c->edges_z);
+  cudaFree(c->samp_term); cudaFree(c->samp_mean); cudaFree(c->samp_dz);
   free_event_scratch(c);
   free_lumi_scratch(c);
   cudaFree(c->cell_counter);

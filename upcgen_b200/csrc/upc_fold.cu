@@ -268,23 +268,22 @@ int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const dou
   UPC_K(c), k_edges<<<(p.ny + 128) / 128, 128, 0, st>>>(p.ymin, dy, p.ny, c->edges_y);
   UPC_K(c), k_edges<<<(p.nm + 128) / 128, 128, 0, st>>>(p.mmin, dm, p.nm, c->edges_m);
   UPC_K(c), k_edges<<<(p.nz + 128) / 128, 128, 0, st>>>(p.zmin, dz, p.nz, c->edges_z);
-  double *term = nullptr, *mean = nullptr;
-  UPC_CUDA(c, cudaMalloc(&term, n * sizeof(double)));
-  UPC_CUDA(c, cudaMalloc(&mean, sizeof(double)));
+  if (!c->samp_term) UPC_CUDA(c, cudaMalloc(&c->samp_term, n * sizeof(double)));
+  if (!c->samp_mean) UPC_CUDA(c, cudaMalloc(&c->samp_mean, sizeof(double)));
+  double *term = c->samp_term, *mean = c->samp_mean;
   UPC_K(c), k_running_mean<<<1, 32, 0, st>>>(c->cs, n, mean);
   UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->cs, n, mean, term);
   UPC_K(c), k_seq_cumsum<<<1, 32, 0, st>>>(term, n, c->sum2d);
   // z samplers
   const size_t nzm = (size_t)p.nm * p.nz, nsz = (size_t)p.nm * (p.nz + 1);
-  double* dz_in = nullptr;
   const double* first = p.use_pol ? cszm_s : cszm;
   if (!p.ignore_csz) {
     if (!first || (p.use_pol && !cszm_ps)) {
-      cudaFree(term); cudaFree(mean);
       c->err = "sampler_build: missing z cross-section table";
       return UPCGPU_EINVAL;
     }
-    UPC_CUDA(c, cudaMalloc(&dz_in, nzm * sizeof(double)));
+    if (!c->samp_dz) UPC_CUDA(c, cudaMalloc(&c->samp_dz, nzm * sizeof(double)));
+    double* dz_in = c->samp_dz;
     if (!c->sumz) UPC_CUDA(c, cudaMalloc(&c->sumz, nsz * sizeof(double)));
     UPC_CUDA(c, cudaMemcpyAsync(dz_in, first, nzm * sizeof(double), cudaMemcpyHostToDevice, st));
     UPC_K(c), k_pdf_init_rows<<<(p.nm + 63) / 64, 64, 0, st>>>(dz_in, p.nm, p.nz, c->sumz);
@@ -297,7 +296,6 @@ int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const dou
   }
   UPC_CUDA(c, cudaStreamSynchronize(st));
   UPC_CUDA(c, cudaGetLastError());
-  cudaFree(term); cudaFree(mean); cudaFree(dz_in);
   c->sampler_ready = true;
   return UPCGPU_OK;
 }

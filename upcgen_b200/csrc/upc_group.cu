@@ -3,12 +3,13 @@
 // upcgpu_create_multi gives the caller a context like upcgpu_create does; behind it stands one member
 // context per device, each driven by its own host thread.  The reference's grid driver
 // (UpcCrossSection::prepareTwoPhotonLumi, src/UpcCrossSection.cpp:463-592) slabs the m rows over OpenMP
-// threads; here the rows are dealt to the devices (blocks of 32 rows round-robin, see shard_block) and every
+// threads; here the rows are dealt to the devices (blocks of 32 rows in a snake, see shard_of_row) and every
 // device ends up with the full table, because every device samples events from it afterwards:
 //
-//   exchange 0 (default): NCCL.  ncclCommInitAll over the devices; each member all-gathers its packed
-//     shard (ncclAllGather on the member's stream) and un-permutes the gathered buffer (k_unpack).
-//   exchange 1: peer stores.  With peer access enabled the cell kernel itself writes every finished cell into
+//   exchange 0: NCCL (the fallback where the devices cannot map each other).  ncclCommInitAll over the devices;
+//     each member all-gathers its packed shard (ncclAllGather on the member's stream) and un-permutes the
+//     gathered buffer (k_unpack).
+//   exchange 1 (default with peer access): peer stores.  The cell kernel itself writes every finished cell into
 //     the full table of EVERY device (8-byte stores over NVLink while the quadrature of the other cells goes
 //     on); no gather buffer, no un-permute kernel -- the collective is folded into the kernel's epilogue.
 //     The members then wait for each other's "cells done" events (cudaStreamWaitEvent across devices).
@@ -242,7 +243,7 @@ int group_create(upcgpu_ctx* leader, int n_gpus, const int* devices, std::string
     group_destroy(leader);
     return UPCGPU_ECUDA;
   }
-  g->exchange = g->have_nccl ? 0 : 1;
+  g->exchange = g->have_peer ? 1 : 0;  // peer stores where the devices can map each other, else the all-gather
   if (const char* e = std::getenv("UPCGPU_EXCHANGE")) {
     if (!std::strcmp(e, "peer") && g->have_peer) g->exchange = 1;
     if (!std::strcmp(e, "nccl") && g->have_nccl) g->exchange = 0;
