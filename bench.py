@@ -284,29 +284,32 @@ class Bench:
         n_tab = 2 if pol else 1
         d2h = int(n_tab * n_cells * 8 + (n_cells * 8 * (2 if pol else 1) + 8 if fold else 0))
         h2d = int(sum(np.asarray(v).size * 8 for v in sig.values()))
+        host_lumi = [torch.empty((P.nm, P.ny), dtype=torch.float64).pin_memory() for _ in range(n_tab)]
+        host_cs = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory()
+        host_ratio = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory() if pol else None
+        host_sig = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in sig.items()}
+        tot = C.c_double()
+
+        def vp(t):
+            return None if t is None else C.c_void_p(t.data_ptr())
+
+        def fold_host():
+            if pol:
+                gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, None, vp(host_sig["sig_s"]), vp(host_sig["sig_p"]),
+                                                 vp(host_cs), vp(host_ratio), C.byref(tot)))
+            else:
+                gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, vp(host_sig["sig_m"]), None, None, vp(host_cs), None,
+                                                 C.byref(tot)))
+            return tot.value
+
         if world == 1:
-            host_lumi = [torch.empty((P.nm, P.ny), dtype=torch.float64).pin_memory() for _ in range(n_tab)]
-            host_cs = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory()
-            host_ratio = torch.empty((P.ny, P.nm), dtype=torch.float64).pin_memory() if pol else None
-            host_sig = {k: torch.from_numpy(v.copy()).pin_memory() for k, v in sig.items()}
-            tot = C.c_double()
-
-            def vp(t):
-                return None if t is None else C.c_void_p(t.data_ptr())
-
             def step():
                 gpu.invalidate_tables()
-                if not fold:
+                if pol:
                     gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
-                elif pol:
-                    gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, None, vp(host_lumi[0]), vp(host_lumi[1])))
-                    gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, None, vp(host_sig["sig_s"]), vp(host_sig["sig_p"]),
-                                                     vp(host_cs), vp(host_ratio), C.byref(tot)))
                 else:
                     gpu._chk(gpu.L.upcgpu_fill_lumi(gpu.h, vp(host_lumi[0]), None, None))
-                    gpu._chk(gpu.L.upcgpu_fold_sigma(gpu.h, vp(host_sig["sig_m"]), None, None, vp(host_cs), None,
-                                                     C.byref(tot)))
-                return tot.value
+                return fold_host() if fold else 0.0
             api = ("upcgpu_fill_lumi" + (" + upcgpu_fold_sigma" if fold else "")
                    + " (include/upcgpu.h), pinned host buffers")
         else:
@@ -318,13 +321,13 @@ class Bench:
                 gpu.invalidate_tables()
                 gpu.prepare_tables()
                 self.fill()
-                for which in kinds:
-                    gpu.lumi_download(which)
-                return gpu.fold_sigma(download=True, **sig)[2] if fold else 0.0
+                for j, which in enumerate(kinds):
+                    gpu._chk(gpu.L.upcgpu_lumi_download(gpu.h, which, vp(host_lumi[j])))
+                return fold_host() if fold else 0.0
             api = (("per rank: upcgpu_fill_lumi_shard_peers (cell kernel stores into every rank's table) + upcgpu_lumi_download"
                     if self.peer else
                     "per rank: upcgpu_fill_lumi_shard + NCCL all-gather + upcgpu_lumi_unpack + upcgpu_lumi_download")
-                   + (" + upcgpu_fold_sigma" if fold else "") + " (host buffers; bytes are per rank; max over ranks)")
+                   + (" + upcgpu_fold_sigma" if fold else "") + " (pinned host buffers; bytes are per rank; max over ranks)")
         tot_mb = step()
         dts = []
         for _ in range(steps):

@@ -336,6 +336,28 @@ def test_sampler_cdf_and_indices_bit_exact(get_gpu, get_oracle, oracle_mod):
         assert z[i] == oracle_mod.sample1d(sz[mbin[i]], ze, uz[i])
 
 
+def test_sampler_cdf_bit_exact_on_a_large_wild_table(capi, oracle_mod):
+    """S1 on 3 * 10^6 bins whose contents span 600 orders of magnitude, with zeros, a subnormal start and exact ties:
+    the device's running mean (a three-operation division by the known bin count, upc_fold.cu) and cumulative sum
+    must reproduce gsl_histogram2d_pdf_init's sequential arithmetic bit for bit."""
+    from upcgen_b200.config import named_config
+    P = named_config("cfg1", "BINS_M 2000\nBINS_Y 1500\n")
+    rng = np.random.default_rng(5)
+    n = P.nm * P.ny
+    cs = np.exp(rng.uniform(-700, 700, n)) * (rng.uniform(0, 1, n) > 0.1)
+    cs[:40] = np.array([3, 5, 1, 7, 2, 9, 6, 4] * 5) * 5e-324      # subnormal quotients and ties at the start
+    cs[40:64] = np.exp(rng.uniform(-740, -690, 24))
+    cs[1000:1100] = 0.0
+    cs[2_000_000:2_000_010] = 2.0 ** rng.integers(-900, 900, 10)
+    cs = cs.reshape(P.ny, P.nm)
+    g = capi.UpcGpu(P, 0)
+    g.sampler_build(cs=cs, cszm=np.ones((P.nm, P.nz)))
+    s2, _, _ = g.sampler_cdf()
+    g.close()
+    ref = oracle_mod.pdf_init(cs)
+    assert np.array_equal(s2, ref)
+
+
 def test_philox_matches_oracle(capi, oracle_mod):
     got = capi.philox(12345, 7, 3, 5)
     for i in range(5):

@@ -124,28 +124,43 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
 // loads and the reciprocals 1/(i+1) formed in parallel.  (The per-bin divisions bin/mean/n have no
 // dependency and run in parallel.)
 //
-// x / d with d = i + 1 and y = RN(1/d) given: q0 = RN(x y); one residual correction makes it faithful, the second
-// (Markstein: q faithful, r = x - d q exact by FMA, y correctly rounded => RN(q + r y) = RN(x / d)) makes it the
-// correctly rounded quotient -- the value __ddiv_rn returns, on a dependent chain half as long.
+// x / d for an INTEGER d = i + 1 < 2^40 with y = RN(1/d) given: q0 = RN(x y) is within 2 ulp of x/d; r = x - d q0 is
+// exact in the FMA (a multiple of ulp(q0)/2 below 2^42 ulp); q1 = RN(q0 + r y) = RN(x/d + e) with |e| <= 2 ulp 2^-53.
+// x/d cannot lie that close to a rounding boundary m = (k + 1/2) ulp: x - d m is a non-zero multiple of ulp(q)/2
+// (non-zero because d (2k+1) spans 54 bits or more and x has 53), so |x/d - m| >= ulp/(2 d) >= 2^-41 ulp >> |e|.
+// Hence q1 is the correctly rounded quotient -- the value __ddiv_rn returns -- on a chain of three operations.  (Normal
+// range only: among subnormals exact ties exist.  The caller takes the library division while the running mean is
+// below kMeanSafe: with bins >= 0 and mean >= kMeanSafe, x - mean is 0 or at least one ulp of the mean in size,
+// far above the subnormals, and step i lowers the mean by the factor 1 - 1/(i + 1) at most.)
 __device__ __forceinline__ double div_by_known(double x, double d, double y)
 {
-  double q = __dmul_rn(x, y);
-  q = __fma_rn(__fma_rn(-q, d, x), y, q);
-  q = __fma_rn(__fma_rn(-q, d, x), y, q);
-  return q;
+  const double q = __dmul_rn(x, y);
+  return __fma_rn(__fma_rn(-q, d, x), y, q);
 }
 
 constexpr int kSeqChunk = 1024;
+constexpr double kMeanSafe = 0x1p-900;
 
+// tools/micro/seq_chain.cu measures the pieces on B200: a dependent DFMA is 8.2 cycles, this five-operation recurrence
+// (sub, mul, fma, fma, add) runs at 53 cycles per bin, with __ddiv_rn in it at 137.
 __global__ void __launch_bounds__(32) k_running_mean(const double* __restrict__ bin, size_t n, double* __restrict__ mean_out)
 {
   __shared__ double sb[2][kSeqChunk], sr[2][kSeqChunk];
+  __shared__ int sneg[2];  // a negative bin in the chunk (GSL refuses such a histogram): library division throughout
   const int lane = threadIdx.x;
   double mean = 0;
   int buf = 0;
-  for (int j = lane; j < kSeqChunk && (size_t)j < n; j += 32) {
-    sb[0][j] = bin[j];
-    sr[0][j] = __drcp_rn((double)(j + 1));
+  if (lane < 2) sneg[lane] = 0;
+  __syncwarp();
+  {
+    bool neg = false;
+    for (int j = lane; j < kSeqChunk && (size_t)j < n; j += 32) {
+      const double v = bin[j];
+      neg |= v < 0.;
+      sb[0][j] = v;
+      sr[0][j] = __drcp_rn((double)(j + 1));
+    }
+    if (neg) sneg[0] = 1;
   }
   __syncwarp();
   for (size_t i0 = 0; i0 < n; i0 += kSeqChunk, buf ^= 1) {
@@ -154,24 +169,35 @@ __global__ void __launch_bounds__(32) k_running_mean(const double* __restrict__ 
       const int m = (int)min((size_t)kSeqChunk, n - i0);
       const double* b = sb[buf];
       const double* r = sr[buf];
-      // mean += (bin[i] - mean) / (i + 1): eight elements' operands are fetched into registers ahead of the chain, so
-      // that the chain is the seven dependent FP64 operations per element and nothing else
-      int j = 0;
-      for (; j + 8 <= m; j += 8) {
-        double bv[8], rv[8];
+      // mean += (bin[i] - mean) / (i + 1).  The fast division needs mean >= kMeanSafe throughout: decided once per
+      // chunk (from the second chunk on a chunk lowers the mean by a factor 2 at most; the first one starts at 0)
+      if (sneg[buf] != 0 || !(mean >= 2. * kMeanSafe) || i0 == 0) {
+#pragma unroll 1
+        for (int j = 0; j < m; ++j) mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn(b[j], mean), (double)(i0 + j + 1)));
+      } else {
+        int j = 0;
+        for (; j + 8 <= m; j += 8) {  // eight bins per trip
+          double bv[8], rv[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { bv[k] = b[j + k]; rv[k] = r[j + k]; }
+          for (int k = 0; k < 8; ++k) { bv[k] = b[j + k]; rv[k] = r[j + k]; }
+          const double base = (double)(i0 + j);  // one conversion per trip; base + k is exact
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          mean = __dadd_rn(mean, div_by_known(__dsub_rn(bv[k], mean), (double)(i0 + j + k + 1), rv[k]));
+          for (int k = 0; k < 8; ++k)
+            mean = __dadd_rn(mean, div_by_known(__dsub_rn(bv[k], mean), base + (double)(k + 1), rv[k]));
+        }
+        for (; j < m; ++j) mean = __dadd_rn(mean, __ddiv_rn(__dsub_rn(b[j], mean), (double)(i0 + j + 1)));
       }
-      for (; j < m; ++j) mean = __dadd_rn(mean, div_by_known(__dsub_rn(b[j], mean), (double)(i0 + j + 1), r[j]));
+      sneg[buf] = 0;
     } else {
       // lanes 1..31 stage the next chunk meanwhile
+      bool neg = false;
       for (size_t j = nxt + (lane - 1); j < nxt + kSeqChunk && j < n; j += 31) {
-        sb[buf ^ 1][j - nxt] = bin[j];
+        const double v = bin[j];
+        neg |= v < 0.;
+        sb[buf ^ 1][j - nxt] = v;
         sr[buf ^ 1][j - nxt] = __drcp_rn((double)(j + 1));
       }
+      if (neg) sneg[buf ^ 1] = 1;
     }
     __syncwarp();
   }
