@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- the hot path of upcgen on B200: luminosity/sigma table fill (cells/s) + events/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2] [--no-legs]
 
 One STEP = one pass of the table path over the whole (y, m) grid of the workload:
-    prepare the lookup tables (T1-T4)  ->  fill the two-photon luminosity table (F1-F3, L1-L3)
-    [-> NCCL all-gather of the m-row shards when N > 1]  ->  fold with sigma(m) (X1).
-`value` is cells/s with everything resident in HBM, timed with CUDA events on the library's
-stream (max over ranks); `e2e` is the same step through the host-buffer C-ABI calls
-(upcgpu_fill_lumi / upcgpu_fold_sigma) with pinned host buffers and the copies inside the timed
-region.  The event stage (S1-S3, E1-E5) is timed separately and reported under "events".
+    prepare the lookup tables (T1-T4)  ->  fill the two-photon luminosity table (F1-F3, L1-L3); with N > 1 the m rows
+    are dealt to the ranks and the cell kernel stores every finished cell into every rank's table over NVLink (CUDA
+    IPC peer memory; UPCGPU_EXCHANGE=nccl: an all-gather instead)  ->  fold with sigma(m) (X1).
+`value` is cells/s with everything resident in HBM, timed with CUDA events on the library's stream (max over ranks);
+`e2e` is the same step through the host-buffer C-ABI calls (upcgpu_fill_lumi / upcgpu_fold_sigma; per rank for N > 1:
+upcgpu_fill_lumi_shard_peers + upcgpu_lumi_download + upcgpu_fold_sigma) with pinned host buffers and the copies inside
+the timed region.  The event stage (S1-S3, E1-E5) is timed separately and reported under "events".
 
---impl reference times the CPU path (oracle/libupcoracle.so: our OpenMP restatement of the
-reference's algorithm -- the reference binary itself cannot be built here, it needs ROOT + GSL)
-on all host threads, on a bounded sample of the same grid.
+The headline workload is cfg2 (BASELINE configs[1]).  The same JSON line carries the north-star target as two more
+objects, measured by the same code at the same N: "cfg4" (10001 x 1201 cells, table step and e2e) and "events_cfg5"
+(10^7 candidates of the Xe-Xe ALP config); --no-legs skips them.
+
+--impl reference times the reference's own CPU implementation of the path on all host threads, on a bounded sample of
+the same grid: oracle/_ref (the reference's sources compiled against the GSL/ROOT shim; kind "reference") when it was
+built, else the oracle port (kind "port").  The reference binary itself needs ROOT + GSL and cannot be built here.
 """
 import argparse
 import json
@@ -37,14 +42,16 @@ WORKLOAD_TEXT = {
 }
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, and its FP64-pipe activity, from
-# the committed `ncu --set full` captures (profiles/r01_v15_ncu_qags_head_pass1_cfg2.txt, r01_v13_ncu_qags_rows_cfg2.txt, r01_v15_ncu_cells_cfg2.txt)
+# the committed `ncu --set full` captures (profiles/r02_ncu_qags_head_pass1_cfg2.txt, r01_v13_ncu_qags_rows_cfg2.txt, r02_ncu_k_cells_cfg{1,2}.txt)
 NCU_QUOTED = {
-    ("cfg2", "k_flux_qags_head"): {"traffic": 670.9e6 + 495.1e6, "fp64_pipe_pct": 60.5,
-                                   "source": "profiles/r01_v15_ncu_qags_head_pass1_cfg2.txt"},
+    ("cfg2", "k_flux_qags_head"): {"traffic": 672.9e6 + 496.7e6, "fp64_pipe_pct": 59.3,
+                                   "source": "profiles/r02_ncu_qags_head_pass1_cfg2.txt"},
     ("cfg2", "k_flux_qags_rows"): {"traffic": 28.9e6 + 0.06e6, "fp64_pipe_pct": 3.8,
                                    "source": "profiles/r01_v13_ncu_qags_rows_cfg2.txt"},
-    ("cfg2", "k_cells"): {"traffic": 234.8e6 + 4.9e6, "fp64_pipe_pct": 52.3,
-                          "source": "profiles/r01_v15_ncu_cells_cfg2.txt"},
+    ("cfg2", "k_cells"): {"traffic": 234.8e6 + 6.6e6, "fp64_pipe_pct": 44.4,
+                          "source": "profiles/r02_ncu_k_cells_cfg2.txt"},
+    ("cfg1", "k_cells"): {"traffic": 234.5e6 + 4.4e6, "fp64_pipe_pct": 50.3,
+                          "source": "profiles/r02_ncu_k_cells_cfg1.txt"},
 }
 
 # algorithmic work per unit
