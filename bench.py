@@ -154,7 +154,8 @@ def make_cpu_leg(workload, cores):
 
 
 def reference_arm(args):
-    """CPU arm: the oracle (kind 'port') on all host threads, bounded sample of the workload."""
+    """CPU arm: the reference's own sources from oracle/_ref (kind 'reference'; else the oracle port, kind 'port') on
+    all host threads, bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -174,7 +175,8 @@ def reference_arm(args):
         "impl": "reference", "metric": "lumi_cells_per_s", "value": val, "unit": "cells/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": make_config(args.workload, P, args.gpus),
+        "config": make_config(args.workload, P, args.gpus,
+                              args.gpus > 1 and os.environ.get("UPCGPU_EXCHANGE", "") != "nccl"),  # = the GPU arm's
         "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference binary needs ROOT+GSL and cannot be built in this image; kind=reference runs the "

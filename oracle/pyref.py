@@ -47,6 +47,17 @@ class Reference:
         self.P = P
         assert L.upcref_init(C.byref(rp)) == 0
 
+    def vm_sigma_y(self, pdg, shadowing, dght_pdg, ys):
+        """sigma(y) of the reference's own UpcPhotoNuclearVM::calcCrossSectionY (src/UpcPhotoNuclearVM.cpp:340-381)."""
+        ys = np.ascontiguousarray(ys, dtype=np.float64)
+        out = np.zeros(ys.size)
+        mp = C.c_double()
+        self.L.upcref_vm_sigma_y.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+        rc = self.L.upcref_vm_sigma_y(pdg, shadowing, dght_pdg, ys.ctypes.data, ys.size, out.ctypes.data, C.byref(mp))
+        if rc:
+            raise RuntimeError(f"upcref_vm_sigma_y: {rc}")
+        return out, mp.value
+
     def gaa(self):
         y, c = np.zeros(200), np.zeros(200)
         self.L.upcref_gaa(y.ctypes.data, c.ctypes.data)

@@ -3,23 +3,21 @@
 #include <pthread.h>
 
 #include <cstring>
+#include <stdexcept>
 
 #include "UpcCrossSection.h"
 
 TRandom* gRandom = new TRandomMT64();
 TSystem* gSystem = new TSystem();
 
-// elementary processes that need ROOT files / the VM path: constructors exist only so that
-// setElemProcess links; they are never instantiated here
+// elementary processes that need ROOT histogram files: constructors exist only so that setElemProcess links; they are
+// never instantiated here (the vector-meson plug-in IS the reference's: src/UpcPhotoNuclearVM.cpp)
 UpcTwoPhotonLbyL::UpcTwoPhotonLbyL(bool, double, double) {}
 double UpcTwoPhotonLbyL::calcCrossSectionM(double) { return 0; }
 double UpcTwoPhotonLbyL::calcCrossSectionZM(double, double) { return 0; }
 UpcTwoPhotonDipion::UpcTwoPhotonDipion(bool, double, double) {}
 double UpcTwoPhotonDipion::calcCrossSectionM(double) { return 0; }
 double UpcTwoPhotonDipion::calcCrossSectionZM(double, double) { return 0; }
-UpcPhotoNuclearVM::UpcPhotoNuclearVM(int, int, int) {}
-UpcPhotoNuclearVM::~UpcPhotoNuclearVM() {}
-double UpcPhotoNuclearVM::calcCrossSectionY(double) { return 0; }
 
 extern gsl_spline* gslSplineGAA;
 extern gsl_spline* gslSplineFormFac;
@@ -89,6 +87,21 @@ double upcref_sigma_m(double m) { return g_cs->elemProcess->calcCrossSectionM(m)
 double upcref_sigma_zm(double z, double m) { return g_cs->elemProcess->calcCrossSectionZM(z, m); }
 double upcref_sigma_m_pol(double m, int ps) { return ps ? g_cs->elemProcess->calcCrossSectionMPolPS(m) : g_cs->elemProcess->calcCrossSectionMPolS(m); }
 double upcref_sigma_zm_pol(double z, double m, int ps) { return ps ? g_cs->elemProcess->calcCrossSectionZMPolPS(z, m) : g_cs->elemProcess->calcCrossSectionZMPolS(z, m); }
+// the reference's vector-meson plug-in (src/UpcPhotoNuclearVM.cpp, compiled unmodified): sigma(y) of
+// calcCrossSectionY for n rapidities; needs upcref_init (calcFormFac and the statics sqrts, mNucl, R, a, rho0).
+// getRgLtaVG keeps its table in function-local statics: one (PDG, SHADOWING 4) combination per process.
+int upcref_vm_sigma_y(int pdg, int shadowing, int dght_pdg, const double* y, int n, double* out, double* m_part)
+{
+  if (!g_cs) return -1;
+  try {
+    UpcPhotoNuclearVM vm(pdg, shadowing, dght_pdg);
+    for (int i = 0; i < n; ++i) out[i] = vm.calcCrossSectionY(y[i]);
+    if (m_part) *m_part = vm.mPart;
+  } catch (const std::exception&) {
+    return -2;
+  }
+  return 0;
+}
 // the reference's grid driver + fold on its own small grid: prepareTwoPhotonLumi (OpenMP region, TH2D,
 // "file") followed by calcNucCrossSectionYM; cs [ny][nm]
 double upcref_grid_and_fold(int nthreads, const char* dir, double* cs, double* ratio)

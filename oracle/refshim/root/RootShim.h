@@ -302,10 +302,141 @@ class TLorentzVector
   TVector3 fP;
   double fE{0};
 };
-class TF1 {};
-class TGraph {};
+// ---- what src/UpcPhotoNuclearVM.cpp uses of TF1 / TGraph / TSpline3 (restated from ROOT's documented behaviour) ----
+extern "C" int upco_qags(double (*f)(double, void*), void* par, double a, double b, double epsabs, double epsrel,
+                         size_t limit, double* result, double* abserr);
+// TF1 over a C function f(x[], par[]): Eval, and Integral(a, b, epsrel = 1e-12) = TF1::IntegralOneDim, which hands the
+// function to ROOT::Math::IntegratorOneDim with epsabs = epsrel: the adaptive-singular integrator (GSL QAGS) of a ROOT
+// with MathMore.  (A ROOT without MathMore falls back to its Gauss-Legendre integrator; on these smooth integrands the
+// two agree to the 1e-12 they are asked for.)
+class TF1
+{
+ public:
+  typedef double (*Fn)(double*, double*);
+  TF1(const char*, Fn f, double, double, int npar) : fFn(f), fPar(npar > 0 ? npar : 1, 0.) {}
+  void FixParameter(int i, double v) { fPar[i] = v; }
+  void SetParameter(int i, double v) { fPar[i] = v; }
+  double Eval(double x)
+  {
+    double xx[1] = {x};
+    return fFn(xx, fPar.data());
+  }
+  double Integral(double a, double b, double epsrel = 1e-12)
+  {
+    double res = 0, err = 0;
+    upco_qags(&TF1::Thunk, this, a, b, epsrel, epsrel, 1000, &res, &err);
+    return res;
+  }
+
+ private:
+  static double Thunk(double x, void* self) { return ((TF1*)self)->Eval(x); }
+  Fn fFn;
+  std::vector<double> fPar;
+};
+
+class TSpline3;
+// TGraph: points, and Eval(x, spline, option): through the spline when one is given, else the straight line through
+// the two points around x (beyond the ends: through the two end points), TGraph::Eval
+class TGraph : public TObject
+{
+ public:
+  enum { kIsSortedX = 1 << 19 };
+  void SetPoint(int i, double x, double y)
+  {
+    if ((int)fX.size() <= i) { fX.resize(i + 1, 0.); fY.resize(i + 1, 0.); }
+    fX[i] = x; fY[i] = y;
+  }
+  void SetBit(unsigned) {}
+  int GetN() const { return (int)fX.size(); }
+  const double* GetX() const { return fX.data(); }
+  const double* GetY() const { return fY.data(); }
+  inline double Eval(double x, TSpline3* spline = nullptr, const char* = "") const;
+  std::vector<double> fX, fY;
+};
+
+// TSpline3(title, graph) with its default end conditions: ROOT's BuildCoeff is de Boor's CUBSPL with ibcbeg = ibcend =
+// 0, the not-a-knot spline (the first two and the last two cubic pieces coincide); Eval picks the piece that holds x
+// (the first or last piece beyond the ends) and returns y + d (b + d (c + d D)).
+class TSpline3 : public TObject
+{
+ public:
+  TSpline3(const char*, const TGraph* g, const char* = nullptr, double = 0, double = 0)
+  {
+    const int n = g->GetN();
+    fX.assign(g->GetX(), g->GetX() + n);
+    fY.assign(g->GetY(), g->GetY() + n);
+    fB.assign(n, 0.); fC.assign(n, 0.); fD.assign(n, 0.);
+    Build();
+  }
+  void SetBit(unsigned) {}
+  double Eval(double x) const
+  {
+    const int n = (int)fX.size();
+    int k = int(std::upper_bound(fX.begin(), fX.end(), x) - fX.begin()) - 1;
+    if (k < 0) k = 0;
+    if (k > n - 2) k = n - 2;
+    const double d = x - fX[k];
+    return fY[k] + d * (fB[k] + d * (fC[k] + d * fD[k]));
+  }
+
+ private:
+  // second derivatives M_i from the interior continuity equations plus the two not-a-knot rows, solved by Gaussian
+  // elimination with partial pivoting on the (n x n) system (n = 37 here); then the piecewise coefficients
+  void Build()
+  {
+    const int n = (int)fX.size();
+    std::vector<double> h(n - 1);
+    for (int i = 0; i + 1 < n; ++i) h[i] = fX[i + 1] - fX[i];
+    std::vector<std::vector<long double>> a(n, std::vector<long double>(n + 1, 0.L));
+    for (int i = 1; i + 1 < n; ++i) {
+      a[i][i - 1] = h[i - 1];
+      a[i][i] = 2.L * ((long double)h[i - 1] + h[i]);
+      a[i][i + 1] = h[i];
+      a[i][n] = 6.L * (((long double)fY[i + 1] - fY[i]) / h[i] - ((long double)fY[i] - fY[i - 1]) / h[i - 1]);
+    }
+    // not-a-knot: the third derivative (M_{i+1} - M_i) / h_i is continuous across x_1 and across x_{n-2}
+    a[0][0] = h[1]; a[0][1] = -((long double)h[0] + h[1]); a[0][2] = h[0];
+    a[n - 1][n - 3] = h[n - 2]; a[n - 1][n - 2] = -((long double)h[n - 3] + h[n - 2]); a[n - 1][n - 1] = h[n - 3];
+    for (int c = 0; c < n; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < n; ++r)
+        if (fabsl(a[r][c]) > fabsl(a[piv][c])) piv = r;
+      std::swap(a[c], a[piv]);
+      for (int r = c + 1; r < n; ++r) {
+        const long double f = a[r][c] / a[c][c];
+        if (f == 0.L) continue;
+        for (int k = c; k <= n; ++k) a[r][k] -= f * a[c][k];
+      }
+    }
+    std::vector<long double> M(n);
+    for (int r = n - 1; r >= 0; --r) {
+      long double sacc = a[r][n];
+      for (int k = r + 1; k < n; ++k) sacc -= a[r][k] * M[k];
+      M[r] = sacc / a[r][r];
+    }
+    for (int i = 0; i + 1 < n; ++i) {
+      fC[i] = double(M[i] / 2.L);
+      fD[i] = double((M[i + 1] - M[i]) / (6.L * h[i]));
+      fB[i] = double(((long double)fY[i + 1] - fY[i]) / h[i] - h[i] * (2.L * M[i] + M[i + 1]) / 6.L);
+    }
+  }
+  std::vector<double> fX, fY, fB, fC, fD;
+};
+
+inline double TGraph::Eval(double x, TSpline3* spline, const char*) const
+{
+  if (spline) return spline->Eval(x);
+  const int n = GetN();
+  if (n == 0) return 0;
+  if (n == 1) return fY[0];
+  int low = int(std::upper_bound(fX.begin(), fX.end(), x) - fX.begin()) - 1, up;
+  if (low < 0) { low = 0; up = 1; }
+  else if (low >= n - 1) { up = n - 1; low = n - 2; }
+  else up = low + 1;
+  if (fX[low] == fX[up]) return fY[low];
+  return fY[up] + (x - fX[up]) * (fY[low] - fY[up]) / (fX[low] - fX[up]);
+}
 class TGraph2D {};
-class TSpline3 {};
 // the output tree of generateEvents (src/UpcGenerator.cpp:842-857): branch addresses are recorded and every Fill()
 // appends the current values, so that tests can read back what the reference would have written to events.root
 class TTree

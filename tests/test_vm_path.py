@@ -133,6 +133,48 @@ def test_vm_plugin_lta_shadowing(get_oracle):
     assert np.max(np.abs(mine[sel] / ref[sel] - 1)) < 1e-8
 
 
+_VM_REF_CASE = r"""
+import json, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+from oracle import pyref
+from upcgen_b200.config import named_config
+P = named_config("cfg1")
+ref = pyref.Reference(P)
+ys = -6 + 0.5 * np.arange(25)
+out = {{}}
+for pdg, shad, dght in {cases!r}:
+    sig, mpart = ref.vm_sigma_y(pdg, shad, dght, ys)
+    out[f"{{pdg}}_{{shad}}_{{dght}}"] = dict(sigma=sig.tolist(), mPart=mpart)
+print("RESULT " + json.dumps(out))
+"""
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("cases", [[(443, 4, 13), (553, 0, 11)], [(100443, 4, 13), (443, 0, 11)]])
+def test_vm_plugin_equals_the_references_own(cases, get_oracle):
+    """The host plug-in against the REFERENCE's src/UpcPhotoNuclearVM.cpp, compiled unmodified into oracle/_ref (TF1 /
+    TGraph / TSpline3 behind it are shim restatements: QAGS at 1e-12, not-a-knot spline, linear TGraph::Eval): sigma(y)
+    on 25 rapidities for the impulse approximation and the LTA shadowing (SHADOWING 4), J/psi, psi(2S), Upsilon.  The
+    two sides integrate the squared form factor with different adaptive rules: agreement is 3e-15, the bar 1e-12."""
+    r = subprocess.run([sys.executable, "-c", _VM_REF_CASE.format(root=ROOT, cases=cases)], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    P, o = get_oracle("cfg1")
+    for pdg, shad, dght in cases:
+        d = _vm_check(pdg, shad, dght, P, o.rho0(), env={"UPCGEN_CROSS_SEC_DIR": REF})
+        want = ref[f"{pdg}_{shad}_{dght}"]
+        assert d["mPart"] == want["mPart"]
+        mine, theirs = np.array(d["sigma"]), np.array(want["sigma"])
+        assert np.array_equal(mine == 0, theirs == 0), (pdg, shad)
+        sel = theirs > 0
+        assert sel.sum() > 10
+        e = np.max(np.abs(mine[sel] / theirs[sel] - 1))
+        print(pdg, shad, "max rel", e)
+        assert e < 1e-12, (pdg, shad, e)
+
+
 # ---- GPU ------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("extra,tol", [("FLUX_POINT 1\nBREAKUP_MODE 1\n", 1e-9), ("FLUX_POINT 0\nBREAKUP_MODE 1\n", 1e-7),
@@ -209,3 +251,61 @@ USE_HEPMC_OUTPUT 1
     rap = 0.5 * np.log((p[:, 0, 3] + p[:, 0, 2]) / (p[:, 0, 3] - p[:, 0, 2]))
     assert rap.min() >= -4 - 1e-9 and rap.max() <= 4 + 1e-9 and abs(rap.mean()) < 0.3
     assert np.all(np.hypot(p[:, 0, 0], p[:, 0, 1]) < 1.5)                   # photon + pomeron pT: a few hundred MeV at most
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("flux_point", [1, 0])
+def test_upcgen_cli_jpsi_vs_the_references_generator(tmp_path, flux_point):
+    """PROC_ID 443 through the C++ drop-in (photon flux on the GPU) against the REFERENCE's own UpcGenerator run on the
+    CPU in the same configuration (src/UpcGenerator.cpp: init, computeNuclXsection's VM branch, generateEvent with
+    getMomentumVM and twoPartDecayVM; src/UpcPhotoNuclearVM.cpp): the total cross section agrees to the printed digits
+    and 8000 events of each are compatible in the J/psi's rapidity and pT and the muons' pT and eta (two-sample KS)."""
+    from scipy import stats
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    n = 8000
+    par = f"""NUCLEUS_Z 82
+NUCLEUS_A 208
+WS_R 6.68
+WS_A 0.447
+SQRTS 5020
+PROC_ID 443
+SHADOWING 0
+DECAY_PDG 13
+NEVENTS {n}
+YMIN -4
+YMAX 4
+BINS_Y 40
+FLUX_POINT {flux_point}
+BREAKUP_MODE 1
+NON_ZERO_GAM_PT 1
+SEED 31
+USE_ROOT_OUTPUT 0
+USE_HEPMC_OUTPUT 1
+"""
+    (tmp_path / "vm.in").write_text(par)
+    r = subprocess.run([os.path.join(HOST, "upcgen"), "-parfile", "vm.in"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    mine_tot = float([l for l in r.stdout.splitlines() if "total cross section" in l][0].split()[4])
+    parts = [l.split() for l in (tmp_path / "events.hepmc").read_text().splitlines() if l.startswith("P ")]
+    mine = np.array([[float(x) for x in q[4:8]] for q in parts]).reshape(n, 3, 4)
+
+    mp = 3.0969
+    ref = pyref.RefGenerator(par, str(tmp_path / "ref"), lumi=np.zeros((1, 40)), grid=(1, 40, mp - 1e-6, mp + 1e-6, -4., 4.))
+    assert mine_tot == pytest.approx(ref.totcs(), rel=1e-5)      # six printed digits
+    ev = ref.generate(n)
+    assert ev["n_accepted"] == n
+    theirs = ev["p4"][:, :3, :]
+
+    def obs(p):
+        jp, mu = p[:, 0], p[:, 1:3].reshape(-1, 4)
+        rap = 0.5 * np.log((jp[:, 3] + jp[:, 2]) / (jp[:, 3] - jp[:, 2]))
+        pt_mu = np.hypot(mu[:, 0], mu[:, 1])
+        eta = np.arcsinh(mu[:, 2] / pt_mu)
+        return {"y": rap, "pt": np.hypot(jp[:, 0], jp[:, 1]), "pt_mu": pt_mu, "eta_mu": eta}
+    a, b = obs(mine), obs(theirs)
+    for k in a:
+        pv = stats.ks_2samp(a[k], b[k]).pvalue
+        print("FLUX_POINT", flux_point, k, "KS p =", pv)
+        assert pv > 1e-3, (k, pv)
