@@ -18,6 +18,6 @@ g = capi.UpcGpu(P, 0)
 for i in range(steps):
     g.invalidate_tables()
     g.prepare_tables()
-    g.fill_lumi_shard(0, n)
+    g.fill_lumi_shard(int(os.environ.get("SHARD", "0")), n)
     print("step", i, g.fill_stats())
 g.close()
