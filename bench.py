@@ -397,7 +397,7 @@ class Bench:
               "ms": ms_ev, "sharding": "Philox counter ranges, no collective", "sampler_build_ms": ms_sampler}
         # the same through upcgpu_generate with pinned host buffers for every output array (per rank; max over ranks)
         n_small = min(n_ev, e2e_cap)
-        mp = capi.MAX_PART
+        mp = gpu.particles_per_event()     # particle slots per candidate: upcgpu_generate_packed (2 pairs, 3 ALP + decay)
         hb = {"npart": torch.empty(n_small, dtype=torch.int32).pin_memory(),
               "pdg": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
               "status": torch.empty((n_small, mp), dtype=torch.int32).pin_memory(),
@@ -406,10 +406,10 @@ class Bench:
         nacc = C.c_uint64()
 
         def gen_e2e():
-            gpu._chk(gpu.L.upcgpu_generate(gpu.h, 12345, first, n_small, C.c_void_p(hb["npart"].data_ptr()),
-                                           C.c_void_p(hb["pdg"].data_ptr()), C.c_void_p(hb["status"].data_ptr()),
-                                           C.c_void_p(hb["mother"].data_ptr()), C.c_void_p(hb["p4"].data_ptr()), None,
-                                           C.byref(nacc)))
+            gpu._chk(gpu.L.upcgpu_generate_packed(gpu.h, 12345, first, n_small, mp, C.c_void_p(hb["npart"].data_ptr()),
+                                                  C.c_void_p(hb["pdg"].data_ptr()), C.c_void_p(hb["status"].data_ptr()),
+                                                  C.c_void_p(hb["mother"].data_ptr()), C.c_void_p(hb["p4"].data_ptr()),
+                                                  None, C.byref(nacc)))
 
         gen_e2e()
         self.barrier()
@@ -421,6 +421,8 @@ class Bench:
         ev["e2e_events_per_s"] = world * n_small / dt
         ev["e2e_candidates_per_rank"] = n_small
         ev["e2e_d2h_bytes"] = int(sum(t.numel() * t.element_size() for t in hb.values()))
+        ev["e2e_api"] = (f"upcgpu_generate_packed, {mp} particle slots per candidate, pinned host buffers; chunks of 2^21 "
+                         "candidates, the copies of one chunk beside the kernels of the next")
         return ev
 
     def roofline(self, stage, st, peak_tf):
@@ -555,7 +557,7 @@ def main():
         B4.close()
         B5 = Bench("cfg5", rank, local, world, dev)
         B5.step_device()                      # tables, lumi table, fold: the sigma table the samplers are built from
-        ev5 = B5.time_events(10_000_000, e2e_cap=1 << 21)
+        ev5 = B5.time_events(10_000_000, e2e_cap=1 << 23)
         ev5["workload"] = WORKLOAD_TEXT["cfg5"]
         B5.close()
 

@@ -279,6 +279,16 @@ int upcgpu_hist_sample1d(upcgpu_ctx* ctx, const double* sum, int n, const double
 int upcgpu_generate(upcgpu_ctx* ctx, uint64_t seed, uint64_t first_candidate, size_t n_candidates,
                     int* npart, int* pdg, int* status, int* mother, double* p4, double* aux,
                     uint64_t* n_accepted);
+/* The same with the particle arrays packed to part_stride slots per candidate instead of UPCGPU_MAX_PART:
+ * pdg/status/mother[i*part_stride+j], p4[(i*part_stride+j)*4+..]; part_stride must be at least
+ * upcgpu_particles_per_event() -- 2 for pair production, 1 for single production, + 2 with the uniform two-body decay
+ * (ALP -> gamma gamma) -- so an accepted event always fits.  Fewer bytes cross PCIe: 92 B per candidate for lepton
+ * pairs instead of 180.  With PINNED host buffers the copies of one chunk of candidates overlap the kernels of the
+ * next (pageable buffers work, without the overlap). */
+int upcgpu_particles_per_event(const upcgpu_ctx* ctx);
+int upcgpu_generate_packed(upcgpu_ctx* ctx, uint64_t seed, uint64_t first_candidate, size_t n_candidates, int part_stride,
+                           int* npart, int* pdg, int* status, int* mother, double* p4, double* aux,
+                           uint64_t* n_accepted);
 /* device-only variant for throughput measurement: generates and keeps results on the device,
  * returns the accepted count */
 int upcgpu_generate_device(upcgpu_ctx* ctx, uint64_t seed, uint64_t first_candidate, size_t n_candidates,

@@ -473,6 +473,36 @@ def test_events_distributions_independent_of_batching(get_gpu, get_oracle):
     assert np.max(np.abs(minv - a["aux"][:, 1]) / a["aux"][:, 1]) < 1e-9
 
 
+def test_packed_event_output_and_pipelined_chunks(get_gpu, get_oracle, capi):
+    """upcgpu_generate_packed: the same events with the particle arrays packed to the process's particle count per
+    candidate; a request below that count is refused; a run of more than one host chunk (2^21 candidates, copies on a
+    second stream beside the next chunk's kernels) equals the same candidates generated in two separate calls."""
+    P, g = get_gpu("cfg1")
+    _, o = get_oracle("cfg1")
+    _built_sampler(g, o, P)
+    assert g.particles_per_event() == 2
+    a = g.generate(7, 0, 5000)
+    b = g.generate_packed(7, 0, 5000)
+    assert b["p4"].shape == (5000, 2, 4)
+    for k in ("pdg", "status", "mother", "p4"):
+        assert np.array_equal(a[k][:, :2], b[k]), k
+    assert np.array_equal(a["npart"], b["npart"]) and np.array_equal(a["aux"], b["aux"]) and a["n_accepted"] == b["n_accepted"]
+    with pytest.raises(capi.UpcGpuError):
+        g.generate_packed(7, 0, 100, part_stride=1)
+    with pytest.raises(capi.UpcGpuError):
+        g.generate_packed(7, 0, 100, part_stride=5)
+    n = (1 << 21) + 70001
+    whole = g.generate_packed(11, 1000, n, with_aux=False)
+    h1 = g.generate_packed(11, 1000, 1 << 21, with_aux=False)
+    h2 = g.generate_packed(11, 1000 + (1 << 21), 70001, with_aux=False)
+    for k in ("npart", "pdg", "p4"):
+        assert np.array_equal(whole[k][:1 << 21], h1[k]) and np.array_equal(whole[k][1 << 21:], h2[k]), k
+    assert whole["n_accepted"] == h1["n_accepted"] + h2["n_accepted"] == int((whole["npart"] > 0).sum())
+    # the ALP config: single production + two decay photons = 3 slots
+    P5, g5 = get_gpu("cfg5")
+    assert g5.particles_per_event() == 3
+
+
 # ---- committed golden fixtures (tests/golden, generated by tools/gen_golden.py) -----------------
 import json as _json
 import os as _os

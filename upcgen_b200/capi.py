@@ -63,7 +63,8 @@ SYMBOLS = [
     "upcgpu_flux_point", "upcgpu_flux_form", "upcgpu_fill_lumi", "upcgpu_fill_lumi_shard", "upcgpu_lumi_cells",
     "upcgpu_get_fill_stats", "upcgpu_lumi_shard_buffer", "upcgpu_lumi_gather_buffer", "upcgpu_lumi_unpack",
     "upcgpu_lumi_download", "upcgpu_lumi_upload", "upcgpu_fold_sigma", "upcgpu_sampler_build",
-    "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_device",
+    "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_packed", "upcgpu_particles_per_event",
+    "upcgpu_generate_device",
     "upcgpu_photon_pt_cdf", "upcgpu_philox", "upcgpu_invalidate_tables", "upcgpu_fp64_peak",
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
@@ -110,6 +111,8 @@ def lib():
         L.upcgpu_sample_z.argtypes = [p, p, p, sz, i, p]
         L.upcgpu_generate.argtypes = [p, C.c_uint64, C.c_uint64, sz, p, p, p, p, p, p, C.POINTER(C.c_uint64)]
         L.upcgpu_generate_device.argtypes = [p, C.c_uint64, C.c_uint64, sz, C.POINTER(C.c_uint64)]
+        L.upcgpu_generate_packed.argtypes = [p, C.c_uint64, C.c_uint64, sz, C.c_int, p, p, p, p, p, p, C.POINTER(C.c_uint64)]
+        L.upcgpu_particles_per_event.argtypes = [p]
         L.upcgpu_photon_pt_cdf.argtypes = [p, d, p]
         L.upcgpu_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, sz, p]
         L.upcgpu_invalidate_tables.argtypes = [p]
@@ -431,6 +434,21 @@ class UpcGpu:
         nacc = C.c_uint64()
         self._chk(self.L.upcgpu_generate(self.h, seed, first, n, _p(npart), _p(pdg), _p(st), _p(mo), _p(p4), _p(aux),
                                          C.byref(nacc)))
+        return dict(npart=npart, pdg=pdg, status=st, mother=mo, p4=p4, aux=aux, n_accepted=nacc.value)
+
+    def particles_per_event(self):
+        return int(self.L.upcgpu_particles_per_event(self.h))
+
+    def generate_packed(self, seed, first, n, part_stride=None, with_aux=True):
+        """upcgpu_generate_packed: the particle arrays hold part_stride slots per candidate (default: the number of
+        particles an event of this process has) instead of MAX_PART."""
+        ps = self.particles_per_event() if part_stride is None else int(part_stride)
+        npart = np.zeros(n, np.int32)
+        pdg = np.zeros((n, ps), np.int32); st = np.zeros((n, ps), np.int32); mo = np.zeros((n, ps), np.int32)
+        p4 = np.zeros((n, ps, 4)); aux = np.zeros((n, 5)) if with_aux else None
+        nacc = C.c_uint64()
+        self._chk(self.L.upcgpu_generate_packed(self.h, seed, first, n, ps, _p(npart), _p(pdg), _p(st), _p(mo), _p(p4),
+                                                _p(aux), C.byref(nacc)))
         return dict(npart=npart, pdg=pdg, status=st, mother=mo, p4=p4, aux=aux, n_accepted=nacc.value)
 
     def generate_device(self, seed, first, n):

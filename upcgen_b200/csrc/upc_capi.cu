@@ -471,14 +471,31 @@ int upcgpu_hist_sample1d(upcgpu_ctx* c, const double* sum, int n, const double* 
   return hist_sample1d(c, sum, n, edges, u, nsamp, x);
 }
 
+int upcgpu_particles_per_event(const upcgpu_ctx* c)
+{
+  if (!c) return UPCGPU_EINVAL;
+  return particles_per_event(c);
+}
+
+int upcgpu_generate_packed(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, int part_stride, int* npart,
+                           int* pdg, int* status, int* mother, double* p4, double* aux, uint64_t* n_accepted)
+{
+  CHECK_CTX_SYNC(c);
+  if (part_stride < particles_per_event(c) || part_stride > UPCGPU_MAX_PART) {
+    c->err = "generate: part_stride must be between upcgpu_particles_per_event() and UPCGPU_MAX_PART";
+    return UPCGPU_EINVAL;
+  }
+  if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
+  if (c->group && c->group_rank == 0)
+    return group_generate(c, seed, first_candidate, n_candidates, part_stride, npart, pdg, status, mother, p4, aux, n_accepted, false);
+  return generate(c, seed, first_candidate, n_candidates, part_stride, npart, pdg, status, mother, p4, aux, n_accepted, false);
+}
+
 int upcgpu_generate(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, int* npart, int* pdg,
                     int* status, int* mother, double* p4, double* aux, uint64_t* n_accepted)
 {
-  CHECK_CTX_SYNC(c);
-  if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
-  if (c->group && c->group_rank == 0)
-    return group_generate(c, seed, first_candidate, n_candidates, npart, pdg, status, mother, p4, aux, n_accepted, false);
-  return generate(c, seed, first_candidate, n_candidates, npart, pdg, status, mother, p4, aux, n_accepted, false);
+  return upcgpu_generate_packed(c, seed, first_candidate, n_candidates, UPCGPU_MAX_PART, npart, pdg, status, mother, p4, aux,
+                                n_accepted);
 }
 
 int upcgpu_generate_device(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidate, size_t n_candidates, uint64_t* n_accepted)
@@ -486,10 +503,10 @@ int upcgpu_generate_device(upcgpu_ctx* c, uint64_t seed, uint64_t first_candidat
   CHECK_CTX_SYNC(c);
   if (n_candidates == 0) { if (n_accepted) *n_accepted = 0; return UPCGPU_OK; }
   if (c->group && c->group_rank == 0)
-    return group_generate(c, seed, first_candidate, n_candidates, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_accepted,
-                          true);
-  return generate(c, seed, first_candidate, n_candidates, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_accepted,
-                  true);
+    return group_generate(c, seed, first_candidate, n_candidates, UPCGPU_MAX_PART, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, n_accepted, true);
+  return generate(c, seed, first_candidate, n_candidates, UPCGPU_MAX_PART, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                  n_accepted, true);
 }
 
 int upcgpu_photon_pt_cdf(upcgpu_ctx* c, double e_phot, double* cdf)

@@ -53,6 +53,8 @@ struct EvScratch {
   unsigned long long* n_acc = nullptr;
   int* err = nullptr;
   EvReport* report = nullptr;
+  cudaStream_t copy_stream = nullptr;          // device -> host copies of a chunk's events, beside the next chunk's kernels
+  cudaEvent_t kin_done = nullptr, copy_done = nullptr;
   void release()
   {
     cudaFree(y); cudaFree(m); cudaFree(cost); cudaFree(keys); cudaFree(keys_sorted); cudaFree(pid); cudaFree(pid_sorted);
@@ -74,6 +76,9 @@ void free_event_scratch(upcgpu_ctx* c)
   s->release();
   cudaFree(s->n_uniq); cudaFree(s->n_acc); cudaFree(s->err); cudaFree(s->next_tile);
   if (s->report) cudaFreeHost(s->report);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  if (s->kin_done) cudaEventDestroy(s->kin_done);
+  if (s->copy_done) cudaEventDestroy(s->copy_done);
   delete s;
   c->ev = nullptr;
 }
@@ -357,7 +362,7 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
                          const double* __restrict__ m, const double* __restrict__ cost, const double* __restrict__ pt_ph,
                          int* __restrict__ npart, int* __restrict__ pdg, int* __restrict__ status,
                          int* __restrict__ mother, double* __restrict__ p4, double* __restrict__ aux,
-                         unsigned long long* __restrict__ n_acc)
+                         unsigned long long* __restrict__ n_acc, int part_stride)
 {
   size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -457,8 +462,8 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
   }
   if (!ok) np = 0;
   npart[t] = np;
-  for (int i = 0; i < UPCGPU_MAX_PART; i++) {
-    const size_t o = t * UPCGPU_MAX_PART + i;
+  for (int i = 0; i < part_stride; i++) {  // part_stride >= the particles an event of this process can have
+    const size_t o = t * part_stride + i;
     const bool v = i < np;
     pdg[o] = v ? ppdg[i] : 0;
     status[o] = v ? pst[i] : 0;
@@ -538,7 +543,20 @@ static EvParams make_evp(const upcgpu_ctx* c)
   return P;
 }
 
-int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart, int* pdg, int* status, int* mother,
+// particles an accepted event of this context's process has: the pair or the single particle, plus two decay products
+int particles_per_event(const upcgpu_ctx* c)
+{
+  const EvParams P = make_evp(c);
+  return (P.is_pair ? 2 : 1) + (P.decay_pdg != 0 ? 2 : 0);
+}
+
+// Candidates are processed in chunks.  Device-resident runs take chunks of kEvChunk (the photon-pT stage costs one table
+// per DISTINCT key of a chunk, so chunks are large).  Runs that deliver to host buffers take chunks of kEvChunkHost and
+// pipeline them: the copies of chunk i run on a second stream while the kernels of chunk i + 1 sample, sort and serve;
+// only that chunk's kinematics kernel, which overwrites the output arrays, waits for the copies.  One host wait at the end.
+constexpr size_t kEvChunkHost = (size_t)1 << 21;
+
+int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int part_stride, int* npart, int* pdg, int* status, int* mother,
              double* p4, double* aux, uint64_t* n_acc_out, bool device_only)
 {
   if (!c->sampler_ready) { c->err = "generate: samplers not built"; return UPCGPU_EINVAL; }
@@ -553,14 +571,22 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
     c->ev_attr_set = true;
   }
   const int kbits = key_bits(c->p);
-  uint64_t total_acc = 0;
-  for (size_t off = 0; off < n; off += kEvChunk) {
-    const size_t cn = std::min(kEvChunk, n - off);
-    int rc = ensure_scratch(c, std::min(kEvChunk, n));
-    if (rc) return rc;
-    EvScratch* s = (EvScratch*)c->ev;
-    UPC_CUDA(c, cudaMemsetAsync(s->n_acc, 0, sizeof(unsigned long long), st));
-    UPC_CUDA(c, cudaMemsetAsync(s->err, 0, sizeof(int), st));
+  const size_t chunk = device_only ? kEvChunk : kEvChunkHost;
+  int rc = ensure_scratch(c, std::min(chunk, n));
+  if (rc) return rc;
+  EvScratch* s = (EvScratch*)c->ev;
+  if (!device_only && !s->copy_stream) {
+    UPC_CUDA(c, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    UPC_CUDA(c, cudaEventCreateWithFlags(&s->kin_done, cudaEventDisableTiming));
+    UPC_CUDA(c, cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+  }
+  cudaStream_t cs = s->copy_stream;
+  // the accepted count and the error flag accumulate over the chunks on the device
+  UPC_CUDA(c, cudaMemsetAsync(s->n_acc, 0, sizeof(unsigned long long), st));
+  UPC_CUDA(c, cudaMemsetAsync(s->err, 0, sizeof(int), st));
+  bool copies_in_flight = false;
+  for (size_t off = 0; off < n; off += chunk) {
+    const size_t cn = std::min(chunk, n - off);
     const unsigned g = (unsigned)((cn + 127) / 128);
     UPC_K(c), k_ev_sample<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, P.nonzero_gam_pt ? s->keys : nullptr,
                                    s->pid, s->err);
@@ -581,28 +607,33 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart,
           s->n_uniq, s->seg_off, (unsigned)n_ph, s->keys_sorted, s->pid_sorted, seed, first + off, c->ff_seg, c->p.gtot, c->p.R, s->pt,
           s->next_tile);
     }
+    if (copies_in_flight) UPC_CUDA(c, cudaStreamWaitEvent(st, s->copy_done, 0));  // the previous chunk's events have left
     UPC_K(c), k_ev_kin<<<g, 128, 0, st>>>(P, seed, first + off, cn, s->y, s->m, s->cost, s->pt, s->npart, s->pdg, s->status, s->mother,
-                                s->p4, s->aux, s->n_acc);
-    UPC_CUDA(c, cudaMemcpyAsync(&s->report->n_acc, s->n_acc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    UPC_CUDA(c, cudaMemcpyAsync(&s->report->err, s->err, sizeof(int), cudaMemcpyDeviceToHost, st));
+                                s->p4, s->aux, s->n_acc, part_stride);
     if (!device_only) {
-      if (npart) UPC_CUDA(c, cudaMemcpyAsync(npart + off, s->npart, cn * sizeof(int), cudaMemcpyDeviceToHost, st));
-      const size_t o4 = off * UPCGPU_MAX_PART;
-      if (pdg) UPC_CUDA(c, cudaMemcpyAsync(pdg + o4, s->pdg, cn * UPCGPU_MAX_PART * sizeof(int), cudaMemcpyDeviceToHost, st));
-      if (status) UPC_CUDA(c, cudaMemcpyAsync(status + o4, s->status, cn * UPCGPU_MAX_PART * sizeof(int), cudaMemcpyDeviceToHost, st));
-      if (mother) UPC_CUDA(c, cudaMemcpyAsync(mother + o4, s->mother, cn * UPCGPU_MAX_PART * sizeof(int), cudaMemcpyDeviceToHost, st));
-      if (p4) UPC_CUDA(c, cudaMemcpyAsync(p4 + o4 * 4, s->p4, cn * UPCGPU_MAX_PART * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      if (aux) UPC_CUDA(c, cudaMemcpyAsync(aux + off * 5, s->aux, cn * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      UPC_CUDA(c, cudaEventRecord(s->kin_done, st));
+      UPC_CUDA(c, cudaStreamWaitEvent(cs, s->kin_done, 0));
+      const size_t os = off * (size_t)part_stride, ns = cn * (size_t)part_stride;
+      if (npart) UPC_CUDA(c, cudaMemcpyAsync(npart + off, s->npart, cn * sizeof(int), cudaMemcpyDeviceToHost, cs));
+      if (pdg) UPC_CUDA(c, cudaMemcpyAsync(pdg + os, s->pdg, ns * sizeof(int), cudaMemcpyDeviceToHost, cs));
+      if (status) UPC_CUDA(c, cudaMemcpyAsync(status + os, s->status, ns * sizeof(int), cudaMemcpyDeviceToHost, cs));
+      if (mother) UPC_CUDA(c, cudaMemcpyAsync(mother + os, s->mother, ns * sizeof(int), cudaMemcpyDeviceToHost, cs));
+      if (p4) UPC_CUDA(c, cudaMemcpyAsync(p4 + os * 4, s->p4, ns * 4 * sizeof(double), cudaMemcpyDeviceToHost, cs));
+      if (aux) UPC_CUDA(c, cudaMemcpyAsync(aux + off * 5, s->aux, cn * 5 * sizeof(double), cudaMemcpyDeviceToHost, cs));
+      UPC_CUDA(c, cudaEventRecord(s->copy_done, cs));
+      copies_in_flight = true;
     }
-    UPC_CUDA(c, cudaStreamSynchronize(st));
-    UPC_CUDA(c, cudaGetLastError());
-    if (s->report->err) {
-      c->err = "generate: " + std::to_string(s->report->err) + " uniforms fell outside the cumulative pdf (GSL: cannot find r1)";
-      return UPCGPU_ERANGE;
-    }
-    total_acc += s->report->n_acc;
   }
-  if (n_acc_out) *n_acc_out = total_acc;
+  UPC_CUDA(c, cudaMemcpyAsync(&s->report->n_acc, s->n_acc, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  UPC_CUDA(c, cudaMemcpyAsync(&s->report->err, s->err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  UPC_CUDA(c, cudaStreamSynchronize(st));
+  if (copies_in_flight) UPC_CUDA(c, cudaStreamSynchronize(cs));
+  UPC_CUDA(c, cudaGetLastError());
+  if (s->report->err) {
+    c->err = "generate: " + std::to_string(s->report->err) + " uniforms fell outside the cumulative pdf (GSL: cannot find r1)";
+    return UPCGPU_ERANGE;
+  }
+  if (n_acc_out) *n_acc_out = s->report->n_acc;
   return UPCGPU_OK;
 }
 

@@ -360,8 +360,8 @@ int group_sampler_build(upcgpu_ctx* leader, const double* cs, const double* cszm
 }
 
 // candidates [first, first + n) in contiguous ranges, one per device; host arrays are filled in place
-int group_generate(upcgpu_ctx* leader, uint64_t seed, uint64_t first, size_t n, int* npart, int* pdg, int* status, int* mother,
-                   double* p4, double* aux, uint64_t* n_acc, bool device_only)
+int group_generate(upcgpu_ctx* leader, uint64_t seed, uint64_t first, size_t n, int part_stride, int* npart, int* pdg, int* status,
+                   int* mother, double* p4, double* aux, uint64_t* n_acc, bool device_only)
 {
   Group* g = leader->group;
   const int G = g->n;
@@ -372,9 +372,10 @@ int group_generate(upcgpu_ctx* leader, uint64_t seed, uint64_t first, size_t n, 
     cudaSetDevice(c->device);
     const size_t o = std::min(n, per * (size_t)r), cn = std::min(per, n - o);
     if (cn == 0) return (int)UPCGPU_OK;
-    return generate(c, seed, first + o, cn, npart ? npart + o : nullptr, pdg ? pdg + o * UPCGPU_MAX_PART : nullptr,
-                    status ? status + o * UPCGPU_MAX_PART : nullptr, mother ? mother + o * UPCGPU_MAX_PART : nullptr,
-                    p4 ? p4 + o * UPCGPU_MAX_PART * 4 : nullptr, aux ? aux + o * 5 : nullptr, &acc[r], device_only);
+    const size_t os = o * (size_t)part_stride;
+    return generate(c, seed, first + o, cn, part_stride, npart ? npart + o : nullptr, pdg ? pdg + os : nullptr,
+                    status ? status + os : nullptr, mother ? mother + os : nullptr, p4 ? p4 + os * 4 : nullptr,
+                    aux ? aux + o * 5 : nullptr, &acc[r], device_only);
   });
   uint64_t tot = 0;
   for (uint64_t a : acc) tot += a;

@@ -51,7 +51,8 @@ int hist_sample2d(upcgpu_ctx* c, const double* sum, int nx, int ny, const double
 int hist_sample1d(upcgpu_ctx* c, const double* sum, int nb, const double* edges, const double* u, size_t n, double* x);
 
 // upc_events.cu
-int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int* npart, int* pdg, int* status, int* mother,
+int particles_per_event(const upcgpu_ctx* c);
+int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int part_stride, int* npart, int* pdg, int* status, int* mother,
              double* p4, double* aux, uint64_t* n_acc, bool device_only);
 int photon_pt_cdf(upcgpu_ctx* c, double e, double* cdf);
 void free_event_scratch(upcgpu_ctx* c);
@@ -70,7 +71,7 @@ int group_fill_lumi(upcgpu_ctx* leader);
 int group_fold_sigma(upcgpu_ctx* leader, const double* sig_m, const double* sig_s, const double* sig_p, double* cs, double* ratio,
                      double* totcs_mb);
 int group_sampler_build(upcgpu_ctx* leader, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps);
-int group_generate(upcgpu_ctx* leader, uint64_t seed, uint64_t first, size_t n, int* npart, int* pdg, int* status, int* mother,
+int group_generate(upcgpu_ctx* leader, uint64_t seed, uint64_t first, size_t n, int part_stride, int* npart, int* pdg, int* status, int* mother,
                    double* p4, double* aux, uint64_t* n_acc, bool device_only);
 void group_fill_stats(const upcgpu_ctx* leader, upcgpu_fill_stats* out);
 const char* group_describe(const upcgpu_ctx* leader, char* buf, size_t cap);

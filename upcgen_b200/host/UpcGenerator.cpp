@@ -308,16 +308,19 @@ void UpcGenerator::computeNuclXsection()
 void UpcGenerator::refillBlock()
 {
   const size_t n = 1 << 16;
+  // the particle arrays carry as many slots per candidate as an event of this process has particles
+  const int ps = upcgpu_particles_per_event(nucProcessCS->gpu());
+  block.stride = ps;
   block.npart.resize(n);
-  block.pdg.resize(n * UPCGPU_MAX_PART);
-  block.status.resize(n * UPCGPU_MAX_PART);
-  block.mother.resize(n * UPCGPU_MAX_PART);
-  block.p4.resize(n * UPCGPU_MAX_PART * 4);
+  block.pdg.resize(n * ps);
+  block.status.resize(n * ps);
+  block.mother.resize(n * ps);
+  block.p4.resize(n * ps * 4);
   uint64_t nacc = 0;
-  int rc = upcgpu_generate(nucProcessCS->gpu(), (uint64_t)seed, nextCandidate, n, block.npart.data(), block.pdg.data(),
-                           block.status.data(), block.mother.data(), block.p4.data(), nullptr, &nacc);
+  int rc = upcgpu_generate_packed(nucProcessCS->gpu(), (uint64_t)seed, nextCandidate, n, ps, block.npart.data(),
+                                  block.pdg.data(), block.status.data(), block.mother.data(), block.p4.data(), nullptr, &nacc);
   if (rc) {
-    PLOG_FATAL << "upcgpu_generate failed: " << upcgpu_last_error(nucProcessCS->gpu());
+    PLOG_FATAL << "upcgpu_generate_packed failed: " << upcgpu_last_error(nucProcessCS->gpu());
     std::_Exit(-1);
   }
   nextCandidate += n;
@@ -443,7 +446,7 @@ long int UpcGenerator::generateEvent(std::vector<int>& pdgs, std::vector<int>& s
   if (np == 0) return 0;
   genParticles.clear();
   for (int j = 0; j < np; ++j) {
-    const size_t o = i * UPCGPU_MAX_PART + j;
+    const size_t o = i * block.stride + j;
     pdgs.emplace_back(block.pdg[o]);
     statuses.emplace_back(block.status[o]);
     mothers.emplace_back(block.mother[o]);

@@ -132,6 +132,7 @@ class UpcGenerator
     std::vector<int> npart, pdg, status, mother;
     std::vector<double> p4;
     size_t pos{0}, n{0};
+    int stride{4};  // particle slots per candidate in pdg/status/mother/p4 (upcgpu_generate_packed)
   } block;
   uint64_t nextCandidate{0};
   void refillBlock();
