@@ -79,8 +79,14 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (arrival time, csv line)
         self.proc = None
+        self.t_begin = 0.0
+
+    def mark_begin(self):
+        """Start of the timed region: only samples that arrive after this moment are used.  (The sampler itself is
+        started BEFORE the warm-up steps, so that spawning nvidia-smi does not fall into a timed step.)"""
+        self.t_begin = time.perf_counter()
 
     def start(self):
         try:
@@ -91,16 +97,22 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def count(self):
+        """samples that have arrived since mark_begin"""
+        return sum(1 for t_arr, _ in list(self.rows) if t_arr >= self.t_begin)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for t_arr, r in self.rows:
+            if t_arr < self.t_begin:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -257,6 +269,8 @@ class Bench:
         """Device-resident step: CUDA events on the library's stream, L2 flushed between steps, max over ranks."""
         import numpy as np
         torch, gpu = self.torch, self.gpu
+        if clocks:
+            clocks.start()
         for _ in range(warmup):
             self.step_device()
         stage = {"ms_tables": 0.0, "ms_flux": 0.0, "ms_qags": 0.0, "ms_cells": 0.0}
@@ -264,7 +278,7 @@ class Bench:
         launches0 = gpu.launch_count()
         self.barrier()
         if clocks:
-            clocks.start()
+            clocks.mark_begin()
         for _ in range(steps):
             l2_flush.fill_(1)                 # flush L2 between timed iterations (126 MB L2 < 256 MiB)
             self.barrier()
@@ -279,15 +293,22 @@ class Bench:
                 stage[k] += st[k] / steps
         launches = gpu.launch_count() - launches0
         ms = self.max_over_ranks(float(np.mean(ms_steps)))
+        self.ms_steps = [round(x, 4) for x in ms_steps]   # this rank's timed steps, one by one
         stats = gpu.fill_stats()
         clk = None
         if clocks:
-            # nvidia-smi needs ~100 ms to start and samples every 100 ms: when the timed steps are shorter than that
-            # (cfg2 on 8 GPUs: 5 x 2.7 ms) the same step is repeated, untimed, until 350 ms of load have been seen.
-            # The count derives from the max-over-ranks time, so every rank runs the same number (the fill is collective)
-            n_extra = int(max(0, math.ceil((350.0 - ms * steps) / max(ms, 1e-3))))
-            for _ in range(n_extra):
-                self.step_device()
+            # nvidia-smi needs a few hundred ms to deliver its first line (longer with eight of them starting at once)
+            # and samples every 100 ms: when the timed steps are over before two samples have arrived (cfg2 on 8 GPUs:
+            # 5 x 2.7 ms) the same step is repeated, untimed, until they have (at most 4 s).  Every rank takes the same
+            # decision -- the fill is collective --, so the "still waiting" flag is reduced over the ranks.
+            n_extra, t_wait = 0, time.perf_counter()
+            while True:
+                waiting = clocks.count() < 2 and time.perf_counter() - t_wait < 4.0
+                if self.max_over_ranks(1.0 if waiting else 0.0) == 0.0:
+                    break
+                for _ in range(10):
+                    self.step_device()
+                n_extra += 10
             clk = clocks.stop()
             clk["window"] = ("the timed steps" if n_extra == 0 else
                              f"the timed steps + {n_extra} untimed repetitions of the same step")
@@ -567,7 +588,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": make_config(args.workload, P, world, peer_exchange),
-            "sigma_table_ms": ms,
+            "sigma_table_ms": ms, "ms_steps_rank0": B.ms_steps,
             "stage_ms": stage, "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "events": events,
             "work": work, "cfg4": cfg4, "events_cfg5": ev5,

@@ -21,6 +21,10 @@ static thread_local std::string g_create_err;
   if ((c)->fill_pending) {                        \
     int _rc = finish_fill(c);                     \
     if (_rc) return _rc;                          \
+  }                                               \
+  if ((c)->tables_pending) {                      \
+    int _rc = finish_tables(c);                   \
+    if (_rc) return _rc;                          \
   }
 
 extern "C" {
@@ -140,6 +144,7 @@ void upcgpu_destroy(upcgpu_ctx* c)
   cudaFree(c->cell_counter);
   for (int i = 0; i < 2; ++i) if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
   for (int i = 0; i < 4; ++i) if (c->aux_ev[i]) cudaEventDestroy(c->aux_ev[i]);
+  for (int i = 0; i < 2; ++i) if (c->tab_ev[i]) cudaEventDestroy(c->tab_ev[i]);
   for (int i = 0; i < 2; ++i) if (c->fill_ev[i]) cudaEventDestroy(c->fill_ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -57,6 +57,12 @@ struct upcgpu_ctx_impl {
   SplineSeg *gaa_seg = nullptr, *ff_seg = nullptr, *bk_seg = nullptr;
   double* d_scal = nullptr;  // small device scratch for scalars
   double* h_scal = nullptr;  // its pinned host mirror (one asynchronous read-back per table stage)
+  // The scalars are a pure function of the (immutable) parameter block: the first table stage waits for them, later
+  // ones take them from this cache and leave the comparison with what the device produced to the next host wait
+  bool scal_cached = false;
+  double scal_cache[5] = {0, 0, 0, 0, 0};
+  bool tables_pending = false;  // a table stage is queued whose scalars (and stage time) have not been collected
+  cudaEvent_t tab_ev[2] = {nullptr, nullptr};
   DevTables tab{};
 
   // luminosity tables, full [nm][ny], index 0 unpol, 1 scalar, 2 pseudoscalar

@@ -110,6 +110,10 @@ int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const do
     const int frc = finish_fill(c);
     if (frc) return frc;
   }
+  if (c->tables_pending) {  // a table stage queued without a fill behind it
+    const int trc = finish_tables(c);
+    if (trc) return trc;
+  }
   if (totcs_mb) *totcs_mb = total * 1e-6;  // :696
   if (cs) UPC_CUDA(c, cudaMemcpy(cs, c->cs, n * sizeof(double), cudaMemcpyDeviceToHost));
   if (ratio && p.use_pol) UPC_CUDA(c, cudaMemcpy(ratio, c->ratio, n * sizeof(double), cudaMemcpyDeviceToHost));

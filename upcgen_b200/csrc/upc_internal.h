@@ -24,6 +24,7 @@ namespace upc {
 
 // upc_tables.cu
 int prepare_tables(upcgpu_ctx* c);
+int finish_tables(upcgpu_ctx* c);  // collects a queued table stage: waits, checks the scalars against the cache
 int eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, double* out);
 int breakup_raw(upcgpu_ctx* c, const double* b, int mode, size_t n, double* out);
 

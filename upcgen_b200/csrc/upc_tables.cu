@@ -3,6 +3,7 @@
 //   (prepareFormFac) and the breakup-probability spline (prepareBreakupProb/calcBreakupProb),
 // reference src/UpcCrossSection.cpp:152-163, :364-461, :752-1019.
 // All of it runs once per context in ~1 ms; nothing here is on the CPU.
+#include <cstring>
 #include <cstddef>
 #include <cstdio>
 
@@ -501,10 +502,15 @@ int prepare_tables(upcgpu_ctx* c)
 {
   const upcgpu_params& p = c->p;
   cudaStream_t st = c->stream;
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
-  cudaEventRecord(e0, st);
+  if (c->tables_pending) {  // an earlier, uncollected table stage: collect it before its events are reused
+    const int frc = finish_tables(c);
+    if (frc) return frc;
+  }
+  if (!c->tab_ev[0]) {
+    UPC_CUDA(c, cudaEventCreate(&c->tab_ev[0]));
+    UPC_CUDA(c, cudaEventCreate(&c->tab_ev[1]));
+  }
+  cudaEventRecord(c->tab_ev[0], st);
 
   if (!c->d_scal) {
   UPC_CUDA(c, cudaMalloc(&c->d_scal, 64 * sizeof(double)));
@@ -580,18 +586,19 @@ int prepare_tables(upcgpu_ctx* c)
   // segments 0..i20-1 of the breakup table cover [bmin, > 20); index i20 is the clamp segment
   const int i20 = (int)((20. - kBkBmin) / kBkDb) + 1;
   UPC_K(c), k_table_scalars<<<1, 256, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, i20, (const BkTable*)c->bk_table, c->gaa_seg, c->d_scal + 1);
-  cudaEventRecord(e1, st);
+  cudaEventRecord(c->tab_ev[1], st);
   if (!c->h_scal) UPC_CUDA(c, cudaMallocHost(&c->h_scal, 8 * sizeof(double)));
   UPC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  UPC_CUDA(c, cudaStreamSynchronize(st));  // the one host wait of the table stage
-  UPC_CUDA(c, cudaGetLastError());
-  float ms = 0;
-  cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  c->stats.ms_tables = ms;
+  c->tables_pending = true;
+  if (!c->scal_cached) {
+    // first table stage of this context: the one host wait; the scalars go into the cache
+    const int frc = finish_tables(c);
+    if (frc) return frc;
+  }
+  // later stages: nothing waits here -- the kernels that follow are queued behind the tables with the cached scalars as
+  // launch parameters, and finish_tables (at the step's host wait) checks them against what the device produced
 
-  const double* h = c->h_scal;  // rho0, ff_last, P20, energy knots, leading zero segments of G_AA
+  const double* h = c->scal_cache;  // rho0, ff_last, P20, energy knots, leading zero segments of G_AA
   c->info.rho0 = h[0];
   c->info.breakup_p20 = h[2];
   c->info.n_breakup_energy_knots = (int)h[3];
@@ -616,6 +623,27 @@ int prepare_tables(upcgpu_ctx* c)
   c->tab.ff_seg = c->ff_seg;
   c->tab.ff_last = h[1];
   c->tables_ready = true;
+  return UPCGPU_OK;
+}
+
+int finish_tables(upcgpu_ctx* c)
+{
+  if (!c->tables_pending) return UPCGPU_OK;
+  c->tables_pending = false;
+  cudaSetDevice(c->device);
+  UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  UPC_CUDA(c, cudaGetLastError());
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->tab_ev[0], c->tab_ev[1]);
+  c->stats.ms_tables = ms;
+  if (!c->scal_cached) {
+    std::memcpy(c->scal_cache, c->h_scal, sizeof(c->scal_cache));
+    c->scal_cached = true;
+  } else if (std::memcmp(c->scal_cache, c->h_scal, sizeof(c->scal_cache)) != 0) {
+    c->tables_ready = false;
+    c->err = "prepare_tables: the table scalars differ from the ones of this context's first table stage";
+    return UPCGPU_ECUDA;
+  }
   return UPCGPU_OK;
 }
 
