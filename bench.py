@@ -77,8 +77,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index = index
+    def __init__(self, indices):
+        self.index = ",".join(str(i) for i in indices)   # the GPUs of the job (one node, ranks = device ordinals)
+        self.n_gpus = len(indices)
         self.rows = []          # (arrival time, csv line)
         self.proc = None
         self.t_begin = 0.0
@@ -99,7 +100,7 @@ class ClockSampler:
 
     def count(self):
         """samples that have arrived since mark_begin"""
-        return sum(1 for t_arr, _ in list(self.rows) if t_arr >= self.t_begin)
+        return sum(1 for t_arr, _ in list(self.rows) if t_arr >= self.t_begin) // self.n_gpus
 
     def _read(self):
         for line in self.proc.stdout:
@@ -125,7 +126,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "gpus": self.index}
 
 
 def make_cpu_leg(workload, cores):
@@ -265,7 +266,7 @@ class Bench:
         else:
             gpu.fill_stats()                             # no fold: collect the queued fill
 
-    def time_device(self, steps, warmup, l2_flush, clocks=None):
+    def time_device(self, steps, warmup, l2_flush, clocks=None, want_clocks=False):
         """Device-resident step: CUDA events on the library's stream, L2 flushed between steps, max over ranks."""
         import numpy as np
         torch, gpu = self.torch, self.gpu
@@ -296,22 +297,24 @@ class Bench:
         self.ms_steps = [round(x, 4) for x in ms_steps]   # this rank's timed steps, one by one
         stats = gpu.fill_stats()
         clk = None
-        if clocks:
-            # nvidia-smi needs a few hundred ms to deliver its first line (longer with eight of them starting at once)
-            # and samples every 100 ms: when the timed steps are over before two samples have arrived (cfg2 on 8 GPUs:
-            # 5 x 2.7 ms) the same step is repeated, untimed, until they have (at most 4 s).  Every rank takes the same
-            # decision -- the fill is collective --, so the "still waiting" flag is reduced over the ranks.
+        if want_clocks:
+            # nvidia-smi needs a few hundred ms to deliver its first line and samples every 100 ms: when the timed steps
+            # are over before two samples have arrived (cfg2 on 8 GPUs: 5 x 2.7 ms) the same step is repeated, untimed,
+            # until they have (at most 4 s).  ONE sampler per job (rank 0, all GPUs of the job in one nvidia-smi
+            # process: eight pollers beside eight ranks perturbed the steps they were watching); every rank takes the
+            # same decision -- the fill is collective --, so the "still waiting" flag is reduced over the ranks.
             n_extra, t_wait = 0, time.perf_counter()
             while True:
-                waiting = clocks.count() < 2 and time.perf_counter() - t_wait < 4.0
+                waiting = clocks is not None and clocks.count() < 2 and time.perf_counter() - t_wait < 4.0
                 if self.max_over_ranks(1.0 if waiting else 0.0) == 0.0:
                     break
                 for _ in range(10):
                     self.step_device()
                 n_extra += 10
-            clk = clocks.stop()
-            clk["window"] = ("the timed steps" if n_extra == 0 else
-                             f"the timed steps + {n_extra} untimed repetitions of the same step")
+            if clocks is not None:
+                clk = clocks.stop()
+                clk["window"] = ("the timed steps" if n_extra == 0 else
+                                 f"the timed steps + {n_extra} untimed repetitions of the same step")
         return ms, stage, clk, launches, stats
 
     def time_e2e(self, steps, l2_flush):
@@ -535,7 +538,8 @@ def main():
     for _ in range(2):
         B.step_device()                       # first touch: allocations, the integral-count cache
     peak_tf, _ = gpu.fp64_peak(400000)
-    ms, stage, clk, launches, st = B.time_device(args.steps, args.warmup, l2_flush, ClockSampler(local))
+    ms, stage, clk, launches, st = B.time_device(args.steps, args.warmup, l2_flush,
+                                                  ClockSampler(list(range(world))) if rank == 0 else None, want_clocks=True)
     e2e = B.time_e2e(args.steps, l2_flush)
     events = None
     if args.workload in ("cfg1", "cfg2", "cfg5"):
