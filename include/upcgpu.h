@@ -247,6 +247,10 @@ int upcgpu_root_write_tree(const char* path, const char* tree, const char* title
  * cszm [nm][nz] (unpol) or cszm_s/cszm_ps (pol); NULL when ignore_csz. */
 int upcgpu_sampler_build(upcgpu_ctx* ctx, const double* cs, const double* cszm, const double* cszm_s,
                          const double* cszm_ps);
+/* diagnostics of the CDF build (S1): blocks of bins done by the speculate-and-verify recurrences, blocks that needed a
+ * sequential run, verification rounds -- out6[0..2] for the running mean, out6[3..5] for the cumulative sum; summed over
+ * this context's builds */
+int upcgpu_sampler_spec_stats(upcgpu_ctx* ctx, unsigned long long* out6);
 /* copy the cumulative tables back (test hook: hpdf->sum of the reference's samplers) */
 int upcgpu_sampler_get_cdf(upcgpu_ctx* ctx, double* sum2d /*ny*nm+1*/, double* sumz /*nm*(nz+1)*/,
                            double* sumz_ps);

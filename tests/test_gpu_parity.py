@@ -358,6 +358,47 @@ def test_sampler_cdf_bit_exact_on_a_large_wild_table(capi, oracle_mod):
     assert np.array_equal(s2, ref)
 
 
+def test_pdf_init_speculate_and_verify_is_bit_exact(capi, oracle_mod):
+    """gsl_histogram2d_pdf_init beyond its first 4096 bins runs as blocks of speculated, then verified steps
+    (k_seq_spec, upc_fold.cu).  Whatever the table, the cumulative table must be the sequential one bit for bit; on
+    smooth tables the blocks must verify (the fast path is the one that runs), on hostile ones they fall back."""
+    from upcgen_b200.config import named_config
+    P = named_config("cfg1", "BINS_M 16\nBINS_Y 8\n")
+    g = capi.UpcGpu(P, 0)
+    rng = np.random.default_rng(17)
+    n = (1 << 20) + 4099
+    i = np.arange(n)
+    tables = {
+        "smooth": np.exp(-30 * (i / n - 0.45) ** 2) * (1 + 0.1 * np.sin(i / 777.0)) * 3.7e-4,
+        "ones": np.ones(1 << 20),
+        "tenths": np.full(300007, 0.1),
+        "uniform": rng.uniform(0, 1, n),
+        "lognormal": np.exp(rng.normal(0, 12, n)),
+        "ramp up": (i + 1.0) * 1e-3,
+        "ramp down": (n - i) * 7.0,
+        "zero runs": np.where((i // 5000) % 3 == 1, 0.0, rng.uniform(1, 2, n)),
+        "rows of a sigma table": np.outer(np.exp(-np.linspace(-6, 6, 1201) ** 2 / 4), 1.0 / np.linspace(1, 100, 1001) ** 3).ravel(),
+        "short": rng.uniform(0, 1, 4097),
+        "shorter": rng.uniform(0, 1, 100),
+    }
+    for name, t in tables.items():
+        s0 = g.sampler_spec_stats()
+        got = g.hist_pdf_init(t)
+        s1 = g.sampler_spec_stats()
+        ref = oracle_mod.pdf_init(t)
+        blocks, fb = s1["blocks"] - s0["blocks"], s1["fallback_blocks"] - s0["fallback_blocks"]
+        rounds = s1["rounds"] - s0["rounds"]
+        print(f"{name:24s} n = {t.size:8d}: blocks {blocks:4d}, sequential {fb:4d}, rounds per block {rounds / max(blocks, 1):.2f}",
+              {k: {q: s1[k][q] - s0[k][q] for q in s1[k]} for k in ("mean", "cumsum")})
+        assert np.array_equal(got, ref), name
+        # (an exactly linear ramp is the hostile case for the running mean: every step's real increment is the same
+        # non-integer number of ulps, the rounded sequence tunes itself onto the rounding boundary and each decision
+        # hangs on the last ulp of its predecessor -- it is walked sequentially, still exactly)
+        if name in ("smooth", "ones", "tenths", "uniform", "rows of a sigma table"):
+            assert fb <= 0.1 * blocks + 2, (name, blocks, fb)
+    g.close()
+
+
 def test_philox_matches_oracle(capi, oracle_mod):
     got = capi.philox(12345, 7, 3, 5)
     for i in range(5):

@@ -47,3 +47,13 @@ if what in ("all", "cells", "alp"):
     ev = g.generate(9, 0, 20000)
     print("alp:", float(t.sum()), tot, ev["n_accepted"])
     g.close()
+if what in ("all", "pdf"):
+    # the speculate-and-verify CDF build (tables beyond 4096 bins): a smooth table, one with a sign change of regime
+    P = named_config("cfg1", "BINS_M 16\nBINS_Y 8\n")
+    g = capi.UpcGpu(P, 0)
+    rng = np.random.default_rng(3)
+    i = np.arange(40000)
+    for t in (np.exp(-((i / 40000.0 - 0.4) ** 2) * 20) * 1e-3, np.exp(rng.normal(0, 9, 23000)), (i[:9000] + 1.0) * 1e-3):
+        s2 = g.hist_pdf_init(t)
+        print("pdf:", t.size, float(s2[-1]), g.sampler_spec_stats()["blocks"])
+    g.close()

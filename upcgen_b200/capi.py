@@ -63,7 +63,7 @@ SYMBOLS = [
     "upcgpu_flux_point", "upcgpu_flux_form", "upcgpu_fill_lumi", "upcgpu_fill_lumi_shard", "upcgpu_lumi_cells",
     "upcgpu_get_fill_stats", "upcgpu_lumi_shard_buffer", "upcgpu_lumi_gather_buffer", "upcgpu_lumi_unpack",
     "upcgpu_lumi_download", "upcgpu_lumi_upload", "upcgpu_fold_sigma", "upcgpu_sampler_build",
-    "upcgpu_sampler_get_cdf", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_packed", "upcgpu_particles_per_event",
+    "upcgpu_sampler_get_cdf", "upcgpu_sampler_spec_stats", "upcgpu_sample_ym", "upcgpu_sample_z", "upcgpu_generate", "upcgpu_generate_packed", "upcgpu_particles_per_event",
     "upcgpu_generate_device",
     "upcgpu_photon_pt_cdf", "upcgpu_philox", "upcgpu_invalidate_tables", "upcgpu_fp64_peak",
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
@@ -380,6 +380,14 @@ class UpcGpu:
     def sampler_build(self, cs=None, cszm=None, cszm_s=None, cszm_ps=None):
         arrs = [None if a is None else _f64(a) for a in (cs, cszm, cszm_s, cszm_ps)]
         self._chk(self.L.upcgpu_sampler_build(self.h, *[_p(a) for a in arrs]))
+
+    def sampler_spec_stats(self):
+        out = (C.c_ulonglong * 6)()
+        self.L.upcgpu_sampler_spec_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._chk(self.L.upcgpu_sampler_spec_stats(self.h, out))
+        return dict(blocks=int(out[0] + out[3]), fallback_blocks=int(out[1] + out[4]), rounds=int(out[2] + out[5]),
+                    mean=dict(blocks=int(out[0]), fallback_blocks=int(out[1]), rounds=int(out[2])),
+                    cumsum=dict(blocks=int(out[3]), fallback_blocks=int(out[4]), rounds=int(out[5])))
 
     def sampler_cdf(self):
         n = self.nm * self.ny

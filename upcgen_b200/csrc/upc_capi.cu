@@ -138,7 +138,7 @@ void upcgpu_destroy(upcgpu_ctx* c)
   for (int w = 0; w < 3; w++) { cudaFree(c->lumi[w]); cudaFree(c->shard[w]); cudaFree(c->gather[w]); }
   cudaFree(c->cs); cudaFree(c->ratio); cudaFree(c->sum2d); cudaFree(c->sumz); cudaFree(c->sumz_ps);
   cudaFree(c->edges_y); cudaFree(c->edges_m); cudaFree(c->edges_z);
-  cudaFree(c->samp_term); cudaFree(c->samp_mean); cudaFree(c->samp_dz);
+  cudaFree(c->samp_term); cudaFree(c->samp_mean); cudaFree(c->samp_dz); cudaFree(c->spec_stats);
   free_event_scratch(c);
   free_lumi_scratch(c);
   cudaFree(c->cell_counter);
@@ -422,6 +422,13 @@ int upcgpu_sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, co
   CHECK_CTX_SYNC(c);
   if (c->group && c->group_rank == 0) return group_sampler_build(c, cs, cszm, cszm_s, cszm_ps);
   return sampler_build(c, cs, cszm, cszm_s, cszm_ps);
+}
+
+int upcgpu_sampler_spec_stats(upcgpu_ctx* c, unsigned long long* out6)
+{
+  CHECK_CTX_SYNC(c);
+  if (!out6) return UPCGPU_EINVAL;
+  return sampler_spec_stats(c, out6);
 }
 
 int upcgpu_sampler_get_cdf(upcgpu_ctx* c, double* sum2d, double* sumz, double* sumz_ps)

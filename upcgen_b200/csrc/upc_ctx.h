@@ -77,6 +77,8 @@ struct upcgpu_ctx_impl {
   double *cs = nullptr, *ratio = nullptr;
   double *sum2d = nullptr, *sumz = nullptr, *sumz_ps = nullptr;
   double *edges_y = nullptr, *edges_m = nullptr, *edges_z = nullptr;
+  bool spec_attr_set = false;          // dynamic shared memory opt-in of k_seq_spec on this context's device
+  struct SpecStats* spec_stats = nullptr;  // device counters of the speculate-and-verify recurrences (may stay null)
   double *samp_term = nullptr, *samp_mean = nullptr, *samp_dz = nullptr;  // sampler_build's scratch (kept: no malloc/free per build)
   bool fold_ready = false, sampler_ready = false;
   double* fold_ws = nullptr;  // scratch of fold_sigma: 3 x nm sigma values + the block sums of the total (kept: a

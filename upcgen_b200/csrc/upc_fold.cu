@@ -7,6 +7,8 @@
 // tables and the selected bins are bit-identical to a generic x86-64 build of the reference.
 #include <cstdio>
 
+#include <cub/cub.cuh>
+
 #include "upc_ctx.h"
 #include "upc_internal.h"
 #include "upc_sampler.cuh"
@@ -253,6 +255,252 @@ __global__ void __launch_bounds__(32) k_seq_cumsum(const double* __restrict__ te
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The two recurrences of gsl_histogram2d_pdf_init beyond their first kSeqHead elements: speculate and verify.
+//
+// v[k] = step(v[k-1], x[k]) must be reproduced bit for bit, and it is a dependent chain.  But deep into a long table the
+// INCREMENT of a step hardly depends on v: for the running mean it is rint((x - v) / (n ulp)) ulps, which changes by one
+// when v moves by n ulps; for the cumulative sum it is rint(t / ulp) ulps whatever v is (ties and a change of binade
+// aside).  So a block of B elements is done like this:
+//   candidates c[j] (all v_start to begin with);
+//   round: every element takes the TRUE step from its predecessor's candidate, nxt[j] = step(c[j-1], x[j]), in parallel;
+//          if nxt[j] == c[j] for every j the candidates ARE the sequence (induction over j: c[-1] = v_start is exact, and
+//          each c[j] is the exact step from an exact predecessor) -- done;
+//          otherwise the steps' increments, as integers in ulps of v_start, are prefix-summed and give new candidates.
+// Nothing is assumed about how good the candidates are: exactness rests on the verification alone, which uses the very
+// operations of the sequential code.  When a block does not verify within kSpecRounds rounds (a change of binade, increments
+// that are not whole ulps, values near zero) its verified PREFIX is kept -- everything before the first mismatch is exact by
+// the same induction --, one thread walks kSpecSeqRun elements sequentially, and speculation resumes behind them with a
+// short block.  On smooth tables two or three rounds verify; the block length grows with the element index (the running mean's increments are insensitive to v only when
+// B << n).  cfg4's 12 M bins: 0.43 s of chain -> see DESIGN.md.
+constexpr int kSpecThreads = 1024;
+constexpr int kSpecItemsMax = 8;
+constexpr int kSpecRounds = 8;
+constexpr int kSpecSeqRun = 128;  // elements walked sequentially past a spot where the candidates did not verify
+constexpr size_t kSeqHead = 4096;
+// a thread walks `items` consecutive elements of the block, so neighbouring lanes are `items` (up to 8) doubles apart in shared
+// memory: one padding double per eight keeps them on different banks
+#define SPX(j) ((j) + ((j) >> 3))
+constexpr int kSpecPadded = kSpecThreads * kSpecItemsMax + kSpecThreads * kSpecItemsMax / 8 + 8;  // elements left to the sequential kernels (k_running_mean, k_seq_cumsum)
+
+struct StepMean {  // mean += (bin - mean) / (i + 1)
+  static __device__ __forceinline__ double step(double v, double x, double n) { return __dadd_rn(v, __ddiv_rn(__dsub_rn(x, v), n)); }
+  // first candidates: the recurrence in real arithmetic, v_j = (i0 v_start + x_0 + .. + x_j) / (i0 + j + 1).  (A step moves
+  // the mean by ~(x - v) / (n ulp) ulps -- 1e10 on a typical table -- so "all v_start" would be 1e14 ulps off at the end of
+  // a block and the rounds, which contract an error by ~B / n each, would need nine of them; from this guess, two.)
+  static constexpr bool kLinearGuess = true;
+  // the step with the division by the known count done on its reciprocal (div_by_known): equal to step() when v >= kMeanSafe
+  // and x >= 0 -- the caller's "bad" flag covers both
+  static __device__ __forceinline__ double step_fast(double v, double x, double n, double rn) { return __dadd_rn(v, div_by_known(__dsub_rn(x, v), n, rn)); }
+  static constexpr bool kHasFast = true;
+  // a sequential run by one thread; fast_ok: v >= 2 kMeanSafe and no negative bin in the run (see div_by_known)
+  static __device__ __forceinline__ double run(double v, const double* sx, double* cand, int j0, int j1, size_t i0, bool fast_ok)
+  {
+    if (fast_ok) {
+      for (int j = j0; j < j1; ++j) {
+        const double nn = (double)(i0 + j + 1);
+        v = __dadd_rn(v, div_by_known(__dsub_rn(sx[SPX(j)], v), nn, __drcp_rn(nn)));
+        cand[SPX(j)] = v;
+      }
+    } else {
+      for (int j = j0; j < j1; ++j) { v = step(v, sx[SPX(j)], (double)(i0 + j + 1)); cand[SPX(j)] = v; }
+    }
+    return v;
+  }
+};
+struct StepSum {  // sum += term
+  static __device__ __forceinline__ double step(double v, double x, double) { return __dadd_rn(v, x); }
+  static constexpr bool kLinearGuess = false;  // the increment of a step does not depend on v: "all v_start" is one round off
+  static __device__ __forceinline__ double step_fast(double v, double x, double, double) { return __dadd_rn(v, x); }
+  static constexpr bool kHasFast = false;
+  static __device__ __forceinline__ double run(double v, const double* sx, double* cand, int j0, int j1, size_t, bool)
+  {
+    for (int j = j0; j < j1; ++j) { v = __dadd_rn(v, sx[SPX(j)]); cand[SPX(j)] = v; }
+    return v;
+  }
+};
+
+struct SpecStats {
+  unsigned long long blocks, fallback_blocks, rounds;
+};
+
+template <class STEP, bool WRITE_ALL>
+__global__ void __launch_bounds__(kSpecThreads) k_seq_spec(const double* __restrict__ x, size_t n, size_t start, double* __restrict__ out,
+                                                          SpecStats* __restrict__ stats)
+{
+  // out: WRITE_ALL ? out[k + 1] = v after element k (out[start] holds v_start) : out[0] = v, read and written
+  extern __shared__ __align__(16) unsigned char spec_smem[];
+  double* sx = reinterpret_cast<double*>(spec_smem);            // [B]
+  double* cand = sx + kSpecPadded;                               // [B]
+  typedef cub::BlockScan<long long, kSpecThreads> Scan;
+  typedef cub::BlockScan<double, kSpecThreads> ScanD;
+  __shared__ union {
+    typename Scan::TempStorage i;
+    typename ScanD::TempStorage d;
+  } scan_tmp;
+  __shared__ double s_cur;
+  __shared__ int s_first_bad;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_cur = WRITE_ALL ? out[start] : out[0];
+  __syncthreads();
+  unsigned long long n_blocks = 0, n_fallback = 0, n_rounds = 0;
+  size_t i0 = start;
+  int items_now = kSpecItemsMax;  // shrinks to 1 after a block that did not verify, doubles after one that did
+  int fail_streak = 0;
+  while (i0 < n) {
+    const double cur = s_cur;
+    size_t it = (i0 + 1) / (4 * (size_t)kSpecThreads);
+    const int items = (int)min((size_t)items_now, it < 1 ? (size_t)1 : it);
+    const int B = (int)min((size_t)kSpecThreads * items, n - i0);
+    bool neg = false;
+    for (int j = tid; j < B; j += kSpecThreads) {
+      const double v = x[i0 + j];
+      neg |= v < 0.;
+      sx[SPX(j)] = v;
+      cand[SPX(j)] = cur;
+    }
+    const bool any_neg = __syncthreads_or(neg);
+    // ulp grid of the block: that of cur's binade
+    const int e = (int)((__double2hiint(cur) >> 20) & 0x7ff);
+    int accepted = 0;  // candidates [0, accepted) are known to be the exact sequence
+    if (e > 60 && e < 2040 && cur > 0.) {
+      const int j0 = tid * items;
+      if (STEP::kLinearGuess) {
+        double loc[kSpecItemsMax], tsum = 0;
+#pragma unroll
+        for (int k = 0; k < kSpecItemsMax; ++k) {
+          const int j = j0 + k;
+          if (k < items && j < B) tsum += sx[SPX(j)];
+          loc[k] = tsum;
+        }
+        double before;
+        ScanD(scan_tmp.d).ExclusiveSum(tsum, before);
+        const double base = (double)i0 * cur;
+#pragma unroll
+        for (int k = 0; k < kSpecItemsMax; ++k) {
+          const int j = j0 + k;
+          if (k < items && j < B) cand[SPX(j)] = (base + (before + loc[k])) / (double)(i0 + j + 1);
+        }
+        __syncthreads();
+      }
+      const double inv_u = __hiloint2double((2098 - e) << 20, 0);  // 2^(52 - (e - 1023)) = 1 / ulp(cur)
+      const double u = __hiloint2double((e - 52) << 20, 0);
+      // the counts and their reciprocals once per block (the rounds reuse them)
+      const bool fast_step = STEP::kHasFast && !any_neg;
+      double nn[kSpecItemsMax], rn[kSpecItemsMax];
+#pragma unroll
+      for (int k = 0; k < kSpecItemsMax; ++k) {
+        nn[k] = (double)(i0 + j0 + k + 1);
+        rn[k] = fast_step ? __drcp_rn(nn[k]) : 0.;
+      }
+      for (int r = 0; r < kSpecRounds; ++r) {
+        ++n_rounds;
+        if (tid == 0) s_first_bad = B;
+        __syncthreads();
+        long long d[kSpecItemsMax];
+        bool bad = false;
+        int my_first = B;
+        long long tot = 0;
+#pragma unroll
+        for (int k = 0; k < kSpecItemsMax; ++k) {
+          d[k] = 0;
+          const int j = j0 + k;
+          if (k < items && j < B) {
+            const double pred = j == 0 ? cur : cand[SPX(j - 1)];
+            const double nxt = fast_step ? STEP::step_fast(pred, sx[SPX(j)], nn[k], rn[k]) : STEP::step(pred, sx[SPX(j)], nn[k]);
+            if (fast_step) bad |= !(pred >= kMeanSafe);  // (a candidate outside the range where step_fast is the exact step)
+            if (nxt != cand[SPX(j)] && j < my_first) my_first = j;
+            const double q = (nxt - pred) * inv_u;  // the step's increment in ulps of cur: whole, and small, or this path is not for it
+            const long long qi = __double2ll_rn(q);
+            bad |= !(fabs(q) < 1e15) || (double)qi != q;
+            d[k] = qi;
+            tot += qi;
+          }
+        }
+        if (my_first < B) atomicMin(&s_first_bad, my_first);
+        const bool any_bad = __syncthreads_or(bad);  // (also the barrier behind the atomicMin)
+        accepted = s_first_bad;  // every candidate before the first mismatch is the exact step from an exact predecessor
+        if (accepted == B || any_bad || r == kSpecRounds - 1) break;
+        long long before;
+        Scan(scan_tmp.i).ExclusiveSum(tot, before);
+        long long acc = before;
+#pragma unroll
+        for (int k = 0; k < kSpecItemsMax; ++k) {
+          const int j = j0 + k;
+          if (k < items && j < B) {
+            acc += d[k];
+            cand[SPX(j)] = __dadd_rn(cur, __dmul_rn((double)acc, u));
+          }
+        }
+        __syncthreads();
+      }
+    }
+    int done = B;
+    if (accepted < B) {  // uniform over the block: keep the verified prefix, walk a short run sequentially, speculate again
+      // ... with runs that double while the failures follow each other (a table whose rounding decisions all hang on the
+      // last ulp -- an exactly linear ramp is one -- is then walked at the sequential kernels' pace)
+      ++n_fallback;
+      const int seq = min(B - accepted, kSpecSeqRun << min(fail_streak, 6));
+      if (tid == 0) {
+        const double v0 = accepted ? cand[SPX(accepted - 1)] : cur;
+        STEP::run(v0, sx, cand, accepted, accepted + seq, i0, !any_neg && v0 >= 2. * kMeanSafe && (size_t)seq <= i0);
+      }
+      __syncthreads();
+      done = accepted + seq;
+      ++fail_streak;
+      items_now = fail_streak > 2 ? kSpecItemsMax : 1;  // (long runs need long blocks to be loaded)
+    } else {
+      fail_streak = 0;
+      items_now = min(2 * items_now, kSpecItemsMax);
+    }
+    ++n_blocks;
+    if (WRITE_ALL)
+      for (int j = tid; j < done; j += kSpecThreads) out[i0 + j + 1] = cand[SPX(j)];
+    if (tid == 0) s_cur = cand[SPX(done - 1)];
+    __syncthreads();
+    i0 += done;
+  }
+  if (tid == 0) {
+    if (!WRITE_ALL) out[0] = s_cur;
+    if (stats) { stats->blocks += n_blocks; stats->fallback_blocks += n_fallback; stats->rounds += n_rounds; }
+  }
+}
+
+// blocks done, blocks that needed a sequential run, verification rounds -- for the running mean, then for the cumulative
+// sum; summed over the builds of this context (diagnostics)
+int sampler_spec_stats(upcgpu_ctx* c, unsigned long long out[6])
+{
+  for (int i = 0; i < 6; ++i) out[i] = 0;
+  if (!c->spec_stats) return UPCGPU_OK;
+  SpecStats h[2];
+  UPC_CUDA(c, cudaMemcpy(h, c->spec_stats, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 2; ++k) { out[3 * k] = h[k].blocks; out[3 * k + 1] = h[k].fallback_blocks; out[3 * k + 2] = h[k].rounds; }
+  return UPCGPU_OK;
+}
+
+constexpr size_t kSpecSmem = 2 * (size_t)kSpecPadded * sizeof(double);
+
+// gsl_histogram2d_pdf_init on the device: mean (1 double), term [n] scratch, sum [n + 1]
+static int pdf_init_device(upcgpu_ctx* c, const double* bin, size_t n, double* mean, double* term, double* sum, cudaStream_t st)
+{
+  if (!c->spec_attr_set) {
+    cudaFuncSetAttribute(k_seq_spec<StepMean, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem);
+    cudaFuncSetAttribute(k_seq_spec<StepSum, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSpecSmem);
+    c->spec_attr_set = true;
+  }
+  if (!c->spec_stats) {
+    UPC_CUDA(c, cudaMalloc(&c->spec_stats, 2 * sizeof(SpecStats)));  // [0] running mean, [1] cumulative sum
+    UPC_CUDA(c, cudaMemsetAsync(c->spec_stats, 0, 2 * sizeof(SpecStats), st));
+  }
+  const size_t head = std::min(n, kSeqHead);
+  UPC_K(c), k_running_mean<<<1, 32, 0, st>>>(bin, head, mean);
+  if (n > head) UPC_K(c), k_seq_spec<StepMean, false><<<1, kSpecThreads, kSpecSmem, st>>>(bin, n, head, mean, c->spec_stats);
+  UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(bin, n, mean, term);
+  UPC_K(c), k_seq_cumsum<<<1, 32, 0, st>>>(term, head, sum);
+  if (n > head) UPC_K(c), k_seq_spec<StepSum, true><<<1, kSpecThreads, kSpecSmem, st>>>(term, n, head, sum, c->spec_stats + 1);
+  return UPCGPU_OK;
+}
+
 // gsl_histogram_pdf_init for the nm z-samplers: one thread per sampler
 __global__ void k_pdf_init_rows(const double* __restrict__ bin, int nrows, int n, double* __restrict__ sum)
 {
@@ -301,9 +549,10 @@ int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const dou
   if (!c->samp_term) UPC_CUDA(c, cudaMalloc(&c->samp_term, n * sizeof(double)));
   if (!c->samp_mean) UPC_CUDA(c, cudaMalloc(&c->samp_mean, sizeof(double)));
   double *term = c->samp_term, *mean = c->samp_mean;
-  UPC_K(c), k_running_mean<<<1, 32, 0, st>>>(c->cs, n, mean);
-  UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->cs, n, mean, term);
-  UPC_K(c), k_seq_cumsum<<<1, 32, 0, st>>>(term, n, c->sum2d);
+  {
+    const int prc = pdf_init_device(c, c->cs, n, mean, term, c->sum2d, st);
+    if (prc) return prc;
+  }
   // z samplers
   const size_t nzm = (size_t)p.nm * p.nz, nsz = (size_t)p.nm * (p.nz + 1);
   const double* first = p.use_pol ? cszm_s : cszm;
@@ -412,9 +661,10 @@ int hist_pdf_init(upcgpu_ctx* c, const double* bins, size_t n, double* sum)
   UPC_CUDA(c, cudaMalloc(&dm, sizeof(double)));
   UPC_CUDA(c, cudaMalloc(&ds, (n + 1) * sizeof(double)));
   UPC_CUDA(c, cudaMemcpyAsync(db, bins, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  UPC_K(c), k_running_mean<<<1, 32, 0, c->stream>>>(db, n, dm);
-  UPC_K(c), k_pdf_terms<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(db, n, dm, dt);
-  UPC_K(c), k_seq_cumsum<<<1, 32, 0, c->stream>>>(dt, n, ds);
+  {
+    const int prc = pdf_init_device(c, db, n, dm, dt, ds, c->stream);
+    if (prc) { cudaFree(db); cudaFree(dm); cudaFree(dt); cudaFree(ds); return prc; }
+  }
   UPC_CUDA(c, cudaMemcpyAsync(sum, ds, (n + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
   UPC_CUDA(c, cudaGetLastError());

@@ -43,6 +43,7 @@ int fp64_peak(upcgpu_ctx* c, int iters, double* tflops, double* ms);
 // upc_fold.cu
 int fold_sigma(upcgpu_ctx* c, const double* sig_m, const double* sig_s, const double* sig_p, double* cs, double* ratio,
                double* totcs_mb);
+int sampler_spec_stats(upcgpu_ctx* c, unsigned long long out[6]);
 int sampler_build(upcgpu_ctx* c, const double* cs, const double* cszm, const double* cszm_s, const double* cszm_ps);
 int sample_ym(upcgpu_ctx* c, const double* u, size_t n, long long* k, int* ybin, int* mbin, double* y, double* m);
 int sample_z(upcgpu_ctx* c, const int* mbin, const double* u, size_t n, int ps, double* z);
