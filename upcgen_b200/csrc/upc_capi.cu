@@ -27,6 +27,16 @@ static thread_local std::string g_create_err;
     if (_rc) return _rc;                          \
   }
 
+// The context's main stream (and the form-factor side stream) get the highest priority the device offers; the breakup
+// table's side stream keeps the default, lowest one: its chain runs beside the flux stage and must not take SM slots
+// from it (pending blocks of a higher-priority stream are placed first).
+cudaError_t upc::create_stream(cudaStream_t* st, bool high_priority)
+{
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  return cudaStreamCreateWithPriority(st, cudaStreamNonBlocking, high_priority ? greatest : least);
+}
+
 extern "C" {
 
 int upcgpu_abi_version(void) { return 1; }
@@ -58,7 +68,7 @@ int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out)
   c->device = device;
   if (const char* e = std::getenv("UPCGPU_TEST_HEAD_POOL")) c->test_head_pool = std::atoll(e);
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      create_stream(&c->stream, /*high_priority=*/true) != cudaSuccess) {
     g_create_err = std::string("upcgpu_create: ") + cudaGetErrorString(cudaGetLastError());
     delete c;
     return UPCGPU_ECUDA;

@@ -61,6 +61,7 @@ struct upcgpu_ctx_impl {
   // ones take them from this cache and leave the comparison with what the device produced to the next host wait
   bool scal_cached = false;
   double scal_cache[5] = {0, 0, 0, 0, 0};
+  bool bk_deferred = false;     // the breakup chain of the queued table stage runs beside the flux stage: cells wait for aux_ev[3]
   bool tables_pending = false;  // a table stage is queued whose scalars (and stage time) have not been collected
   cudaEvent_t tab_ev[2] = {nullptr, nullptr};
   DevTables tab{};

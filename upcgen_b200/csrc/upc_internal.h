@@ -23,6 +23,7 @@
 namespace upc {
 
 // upc_tables.cu
+cudaError_t create_stream(cudaStream_t* st, bool high_priority);
 int prepare_tables(upcgpu_ctx* c);
 int finish_tables(upcgpu_ctx* c);  // collects a queued table stage: waits, checks the scalars against the cache
 int eval_table(upcgpu_ctx* c, int which, const double* x, size_t n, double* out);

@@ -412,8 +412,7 @@ __global__ void k_bk_raw(const BkTable* T, const double* b, int mode, size_t n, 
 //   out[0] = ff_last = F(Q2max - dQ2), out[1] = P20 = P(20), out[2] = number of photo-nuclear energy knots,
 //   out[3] = number of leading G_AA segments bounded by 1e-20 (the inner cut of the cell quadrature);
 // and the clamp segment {P(20), 0, 0, 0} of the breakup table at index i20.
-__global__ void __launch_bounds__(256) k_table_scalars(const SplineSeg* ff_seg, SplineSeg* bk_seg, int use_breakup, int i20,
-                                                       const BkTable* bk_table, const SplineSeg* gaa_seg, double* out)
+__global__ void __launch_bounds__(256) k_table_scalars(const SplineSeg* ff_seg, const SplineSeg* gaa_seg, double* out)
 {
   __shared__ int s_first;
   if (threadIdx.x == 0) s_first = kNB - 1;
@@ -438,6 +437,12 @@ __global__ void __launch_bounds__(256) k_table_scalars(const SplineSeg* ff_seg, 
     int i = kNQ2 - 2;
     out[0] = seg_eval(ff_seg[i], x - knot(kQ2min, kDQ2, i));
   }
+}
+
+// the breakup table's part, at the end of ITS chain (which runs beside the flux stage, see prepare_tables):
+// out[1] = P(20), out[2] = energy knots, and the clamp segment {P(20), 0, 0, 0} at index i20
+__global__ void k_bk_scalars(SplineSeg* bk_seg, int use_breakup, int i20, const BkTable* bk_table, double* out)
+{
   if (use_breakup) {
     double x = 20.;
     int i = (int)((x - kBkBmin) / kBkDb);
@@ -534,7 +539,8 @@ int prepare_tables(upcgpu_ctx* c)
   // T2 (G_AA), T3 (form factor) and T4 (breakup) are independent chains of small, latency-bound kernels:
   // G_AA stays on the main stream, the other two run beside it on side streams (T3 needs rho0 only)
   if (!c->aux[0]) {
-    for (int i = 0; i < 2; ++i) UPC_CUDA(c, cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    UPC_CUDA(c, create_stream(&c->aux[0], /*high_priority=*/true));   // form factor: the flux stage waits for it
+    UPC_CUDA(c, create_stream(&c->aux[1], /*high_priority=*/false));  // breakup: runs beside the flux stage
     for (int i = 0; i < 4; ++i) UPC_CUDA(c, cudaEventCreateWithFlags(&c->aux_ev[i], cudaEventDisableTiming));
   }
   cudaStream_t st_ff = c->aux[0], st_bk = c->aux[1];
@@ -580,15 +586,26 @@ int prepare_tables(upcgpu_ctx* c)
     UPC_K(c), k_segs_uniform<<<(c->bk_nknots + 255) / 256, 256, 0, st_bk>>>(kBkBmin, kBkDb, c->bk_y, c->bk_c, c->bk_nknots,
                                                               c->bk_seg, c->bk_nknots - 1);
   }
-  cudaEventRecord(c->aux_ev[3], st_bk);
-  cudaStreamWaitEvent(st, c->aux_ev[2], 0);
-  cudaStreamWaitEvent(st, c->aux_ev[3], 0);
   // segments 0..i20-1 of the breakup table cover [bmin, > 20); index i20 is the clamp segment
   const int i20 = (int)((20. - kBkBmin) / kBkDb) + 1;
-  UPC_K(c), k_table_scalars<<<1, 256, 0, st>>>(c->ff_seg, c->bk_seg, use_bk, i20, (const BkTable*)c->bk_table, c->gaa_seg, c->d_scal + 1);
-  cudaEventRecord(c->tab_ev[1], st);
   if (!c->h_scal) UPC_CUDA(c, cudaMallocHost(&c->h_scal, 8 * sizeof(double)));
-  UPC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  // the breakup chain ends with its scalars and their copy; its event is what the cell stage waits for
+  UPC_K(c), k_bk_scalars<<<1, 1, 0, st_bk>>>(c->bk_seg, use_bk, i20, (const BkTable*)c->bk_table, c->d_scal + 1);
+  UPC_CUDA(c, cudaMemcpyAsync(c->h_scal + 2, c->d_scal + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_bk));
+  cudaEventRecord(c->aux_ev[3], st_bk);
+  cudaStreamWaitEvent(st, c->aux_ev[2], 0);
+  UPC_K(c), k_table_scalars<<<1, 256, 0, st>>>(c->ff_seg, c->gaa_seg, c->d_scal + 1);
+  UPC_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  UPC_CUDA(c, cudaMemcpyAsync(c->h_scal + 4, c->d_scal + 4, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (c->scal_cached) {
+    // Not the first table stage of this context: the flux stage needs G_AA's inner cut and the form factor only, so the
+    // main stream does NOT wait for the breakup chain (0.21 ms, two thirds of the table stage) -- it runs beside the
+    // flux rows, and the cell stage waits for its event (run_slab; finish_tables when no fill follows).
+    c->bk_deferred = true;
+  } else {
+    cudaStreamWaitEvent(st, c->aux_ev[3], 0);
+  }
+  cudaEventRecord(c->tab_ev[1], st);
   c->tables_pending = true;
   if (!c->scal_cached) {
     // first table stage of this context: the one host wait; the scalars go into the cache
@@ -632,6 +649,10 @@ int finish_tables(upcgpu_ctx* c)
   c->tables_pending = false;
   cudaSetDevice(c->device);
   UPC_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->bk_deferred) {  // no cell stage took the breakup chain's event: wait for the chain here
+    UPC_CUDA(c, cudaStreamSynchronize(c->aux[1]));
+    c->bk_deferred = false;
+  }
   UPC_CUDA(c, cudaGetLastError());
   float ms = 0;
   cudaEventElapsedTime(&ms, c->tab_ev[0], c->tab_ev[1]);
