@@ -212,12 +212,13 @@ __device__ __forceinline__ DV<N> j1_smallN(const DV<N>& x, const H& h)
 // J1 for three arbitrary positive arguments: each branch is evaluated for all three when any of them needs
 // it, then selected per argument.  An argument outside a branch's domain gives a meaningless (possibly
 // non-finite) value in that branch, which the selection drops: no clamping.  The class test is an integer
-// comparison of the bit patterns (x > 8 for positive x), off the FP64 pipe.
+// comparison of the bit patterns (x >= 8 for positive x), off the FP64 pipe.
 __device__ __forceinline__ bool j1_is_large(double x)
 {
-  // x > 8 for positive x, on the two 32-bit halves (a 64-bit comparison makes ptxas form integer min/max chains)
-  const unsigned hi = (unsigned)__double2hiint(x), lo = (unsigned)__double2loint(x);
-  return hi > 0x40200000u || (hi == 0x40200000u && lo != 0u);
+  // x >= 8 for positive x, on the high word alone (both branches of J1 are valid AT 8: the large-argument fit covers
+  // u = 128 / x^2 - 1 in [-1, 1], closed).  One integer comparison; a 64-bit one makes ptxas form min/max chains, and
+  // the strict "x > 8" needed a second comparison of the low word per argument.
+  return (unsigned)__double2hiint(x) >= 0x40200000u;
 }
 
 __device__ __forceinline__ D3 j1_3(const D3& x)
