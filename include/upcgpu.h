@@ -59,7 +59,8 @@ typedef struct {
   int is_pair;         /* UpcGenerator::isPairProduction */
   int is_single;       /* UpcGenerator::isSingleProduction */
   int ignore_csz;      /* UpcGenerator::ignoreCSZ */
-  int decay_uniform_pdg; /* !=0: twoPartDecayUniform of particle 1 into two of this pdg (ALP: 22) */
+  int decay_uniform_pdg; /* !=0: twoPartDecayUniform into two of this pdg (22) of the single particle (ALP, :806-808) or of
+                          * BOTH particles of a pair (pi0 pi0, src/UpcGenerator.cpp:799-803) */
   int do_pt_cut, do_eta_cut;
   double pt_min, eta_min, eta_max;
 } upcgpu_params;
@@ -228,6 +229,10 @@ int upcgpu_elem_fill_cs_zm(int proc_id, double a_lep, double alp_mass, double al
 int upcgpu_root_hist_read(const char* path, const char* name, int* dim, int* nx, double* xlo, double* xhi, int* ny,
                           double* ylo, double* yhi, double* cells, size_t cap, size_t* n_cells);
 
+/* a TH1D with a uniform axis (the form of cross_sections/<process>/cross_section_m.root, which UpcTwoPhotonLbyL /
+ * UpcTwoPhotonDipion read): cells[nx + 2] with under- and overflow */
+int upcgpu_root_write_th1d(const char* path, const char* name, int nx, double xlo, double xhi, const double* cells,
+                           double entries);
 /* The writer side (upcgen_b200/host/UpcRootFile.cpp), also without ROOT and without a GPU.
  * upcgpu_root_write_th2d: a file with n_hist TH2D objects of common uniform axes -- the luminosity cache
  * twoPhotonLumi[Pol].root as the reference writes it (src/UpcCrossSection.cpp:493-507, :578-585): names[i],
@@ -272,21 +277,21 @@ int upcgpu_hist_sample1d(upcgpu_ctx* ctx, const double* sum, int n, const double
                          size_t nsamp, double* x);
 
 /* ---- events E1-E5 -------------------------------------------------------------------- */
-#define UPCGPU_MAX_PART 4
+#define UPCGPU_MAX_PART 6
 /* replaces the body of UpcGenerator::generateEvent (src/UpcGenerator.cpp:715-832) incl.
  * getPairMomentum/getPhotonPt (src/UpcCrossSection.cpp:1021-1074), pairProduction,
  * singleProduction, twoPartDecayUniform and checkKinCuts, for candidates
  * [first_candidate, first_candidate + n_candidates) of the Philox4x32-10 stream keyed by seed.
  * Output (host, SoA, sized n_candidates): npart[i] (0 = rejected by the cuts),
- * pdg/status/mother[i*4+j], p4[(i*4+j)*4 + {px,py,pz,E}].  aux (may be NULL) [i*5+..] =
+ * pdg/status/mother[i*UPCGPU_MAX_PART+j], p4[(i*UPCGPU_MAX_PART+j)*4 + {px,py,pz,E}].  aux (may be NULL) [i*5+..] =
  * yPair, mPair, cos(theta), pT(gamma1), pT(gamma2). */
 int upcgpu_generate(upcgpu_ctx* ctx, uint64_t seed, uint64_t first_candidate, size_t n_candidates,
                     int* npart, int* pdg, int* status, int* mother, double* p4, double* aux,
                     uint64_t* n_accepted);
 /* The same with the particle arrays packed to part_stride slots per candidate instead of UPCGPU_MAX_PART:
  * pdg/status/mother[i*part_stride+j], p4[(i*part_stride+j)*4+..]; part_stride must be at least
- * upcgpu_particles_per_event() -- 2 for pair production, 1 for single production, + 2 with the uniform two-body decay
- * (ALP -> gamma gamma) -- so an accepted event always fits.  Fewer bytes cross PCIe: 92 B per candidate for lepton
+ * upcgpu_particles_per_event() -- 2 for pair production, 1 for single production, + 2 per uniform two-body decay
+ * (ALP -> gamma gamma: 3; pi0 pi0 -> 4 gamma: 6) -- so an accepted event always fits.  Fewer bytes cross PCIe: 92 B per candidate for lepton
  * pairs instead of 180.  With PINNED host buffers the copies of one chunk of candidates overlap the kernels of the
  * next (pageable buffers work, without the overlap). */
 int upcgpu_particles_per_event(const upcgpu_ctx* ctx);

@@ -249,8 +249,8 @@ class Oracle:
 
     def generate_event(self, seed, cand, cs_sum, z_sum, z_sum_ps=None, ratio=None):
         npart = C.c_int()
-        pdg = np.zeros(4, np.int32); st = np.zeros(4, np.int32); mo = np.zeros(4, np.int32)
-        p4 = np.zeros((4, 4)); aux = np.zeros(5)
+        pdg = np.zeros(6, np.int32); st = np.zeros(6, np.int32); mo = np.zeros(6, np.int32)
+        p4 = np.zeros((6, 4)); aux = np.zeros(5)
         acc = self.L.upco_generate_event(self.h, seed, cand, _ptr(cs_sum), _ptr(z_sum), _ptr(z_sum_ps),
                                          _ptr(ratio), C.byref(npart), _ptr(pdg), _ptr(st), _ptr(mo),
                                          _ptr(p4), _ptr(aux))
@@ -261,10 +261,11 @@ class Oracle:
     def generate_event_u(self, u, cs_sum, z_sum, z_sum_ps=None, ratio=None):
         """generateEvent with the twelve uniforms of the slot map injected (see upco_generate_event_u)."""
         u = np.ascontiguousarray(u, float)
-        assert u.size == 12
+        assert u.size in (12, 14)
+        u = np.concatenate([u, np.zeros(14 - u.size)])
         npart = C.c_int()
-        pdg = np.zeros(4, np.int32); st = np.zeros(4, np.int32); mo = np.zeros(4, np.int32)
-        p4 = np.zeros((4, 4)); aux = np.zeros(5)
+        pdg = np.zeros(6, np.int32); st = np.zeros(6, np.int32); mo = np.zeros(6, np.int32)
+        p4 = np.zeros((6, 4)); aux = np.zeros(5)
         acc = self.L.upco_generate_event_u(self.h, _ptr(u), _ptr(cs_sum), _ptr(z_sum), _ptr(z_sum_ps), _ptr(ratio),
                                            C.byref(npart), _ptr(pdg), _ptr(st), _ptr(mo), _ptr(p4), _ptr(aux))
         n = npart.value

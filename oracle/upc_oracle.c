@@ -1100,6 +1100,7 @@ upco_ctx* upco_create(const upco_params* p, int nbc_used)
     case 15: c->mPart = kMTau; c->partPDG = 15; c->isCharged = 1; c->isPair = 1; break;
     case 51: c->mPart = p->alp_mass; c->partPDG = 51; c->isCharged = 0; c->isSingle = 1;
              c->ignoreCSZ = 1; break;
+    case 111: c->mPart = 0.1349770; c->partPDG = 111; c->isCharged = 0; c->isPair = 1; break;  /* src/UpcTwoPhotonDipion.cpp:37-39 */
     default: c->mPart = 0; c->partPDG = p->proc_id; c->isPair = 1; break;
   }
   /* UpcCrossSection::init, src/UpcCrossSection.cpp:116-137 */
@@ -1658,7 +1659,8 @@ static double lv_eta(const lv* v)
    dependent); the product uses the key's lower edge + 0.5 MeV. */
 static double key_energy(int key) { return (key + 0.5) * 1e-3; }
 
-/* generateEvent with the twelve uniforms of the slot map injected (u[2 j], u[2 j + 1] = block j of SURVEY.md appendix
+/* generateEvent with the uniforms of the slot map injected (twelve; fourteen for the pi0 pi0 process, whose second decay
+ * reads u[12], u[13]) (u[2 j], u[2 j + 1] = block j of SURVEY.md appendix
    B): the form the tests use to replay an event of the reference's own generateEvent (oracle/refshim/gen_capi.cpp
    records the uniforms it drew) */
 int upco_generate_event_u(upco_ctx* c, const double* u, const double* cs_sum,
@@ -1675,7 +1677,7 @@ int upco_generate_event_u(upco_ctx* c, const double* u, const double* cs_sum,
   for (int i = 0; i <= nz; i++) ze[i] = p->zmin + dz * i;
   for (int i = 0; i <= ny; i++) ye[i] = p->ymin + dy * i;
   int n = 0, accepted = 1;
-  lv parts[4];
+  lv parts[6];
 
   /* UpcGenerator.cpp:735-739 */
   long long k;
@@ -1749,14 +1751,16 @@ int upco_generate_event_u(upco_ctx* c, const double* u, const double* cs_sum,
       if (eta < p->eta_min || eta > p->eta_max) { accepted = 0; break; }
     }
   }
-  /* ALP decay: twoPartDecayUniform(..., id=1, 0., 22) :526-561 */
-  if (accepted && p->proc_id == 51) {
-    const lv* part = &parts[0];
+  /* uniform two-body decays into photons, twoPartDecayUniform(..., id, 0., 22) :526-561: the ALP (id = 1, :806-808) or
+   * both pi0 of a pair (id = 1, then id = 2, :799-803); decay d takes its uniforms from block 5 + d of the slot map */
+  const int n_dec = !accepted ? 0 : p->proc_id == 51 ? 1 : p->proc_id == 111 ? 2 : 0;
+  for (int d = 0; d < n_dec; d++) {
+    const lv* part = &parts[d];
     double mDecay = 0.;
     double ePhot1 = lv_mag(part) / 2.;
     double pPhot1 = sqrt(ePhot1 * ePhot1 - mDecay * mDecay);
-    double phi1 = 2. * M_PI * u[10];
-    double cost1 = -1. + 2. * u[11];
+    double phi1 = 2. * M_PI * u[10 + 2 * d];
+    double cost1 = -1. + 2. * u[11 + 2 * d];
     double theta1 = acos(cost1);
     double vx = pPhot1 * sin(theta1) * cos(phi1), vy = pPhot1 * sin(theta1) * sin(phi1),
            vz = pPhot1 * cos(theta1);
@@ -1771,9 +1775,9 @@ int upco_generate_event_u(upco_ctx* c, const double* u, const double* cs_sum,
     v3_rotate_uz(&d1.x, &d1.y, &d1.z, ux, uy, uz);
     lv_boost(&d0, bx, by, bz);
     lv_boost(&d1, bx, by, bz);
-    parts[1] = d0; parts[2] = d1;
-    pdg[1] = pdg[2] = 22; status[1] = status[2] = 33; mother[1] = mother[2] = 1;
-    n = 3;
+    parts[n] = d0; parts[n + 1] = d1;
+    pdg[n] = pdg[n + 1] = 22; status[n] = status[n + 1] = 33; mother[n] = mother[n + 1] = d + 1;
+    n += 2;
   }
   if (!accepted) n = 0;
   *npart = n;
@@ -1791,7 +1795,7 @@ int upco_generate_event(upco_ctx* c, uint64_t seed, uint64_t cand, const double*
                         const double* z_sum, const double* z_sum_ps, const double* ratio, int* npart,
                         int* pdg, int* status, int* mother, double* p4, double* aux)
 {
-  double u[12];
-  for (uint32_t b = 0; b < 6; b++) upco_philox(seed, cand, b, &u[2 * b], &u[2 * b + 1]);
+  double u[14];
+  for (uint32_t b = 0; b < 7; b++) upco_philox(seed, cand, b, &u[2 * b], &u[2 * b + 1]);
   return upco_generate_event_u(c, u, cs_sum, z_sum, z_sum_ps, ratio, npart, pdg, status, mother, p4, aux);
 }

@@ -149,3 +149,68 @@ USE_HEPMC_OUTPUT 1
     assert [int(q[3]) for q in hep] == c["pdgCode"].tolist()
     for j, name in enumerate(("px", "py", "pz", "e")):
         assert np.allclose([float(q[4 + j]) for q in hep], c[name], rtol=2e-8, atol=1e-12)   # HepMC prints 9 digits
+
+
+def test_upcgen_cli_pi0_pairs_from_tabulated_cross_sections(tmp_path):
+    """PROC_ID 111 end to end through the C++ drop-in: UpcTwoPhotonDipion reads sigma(m) and dsigma/dz from ROOT files
+    (cross_sections/pi0pi0, src/UpcTwoPhotonDipion.cpp) -- here files of the same form written by this repository's
+    ROOT writer, because the reference's do not travel to the GPU box --, the generator forces its grid (:69-103),
+    and every event is a pi0 pair with both pi0 decayed uniformly into photons (:799-803): six particles, two decay
+    vertices.  The total cross section equals the fold of the same table through the C-ABI."""
+    from upcgen_b200 import capi
+    from upcgen_b200.config import UpcParams
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    xs = tmp_path / "xs" / "pi0pi0"
+    xs.mkdir(parents=True)
+    mc = 0.025 + 0.05 * np.arange(100)                  # bin centres of the reference's sigma(m) histogram: 100 bins on [0, 5]
+    sig_tab = np.where(mc > 0.27, 30.0 / (0.2 + mc) ** 2, 0.0)
+    capi.root_write_th1d(str(xs / "cross_section_m.root"), "hCrossSectionM", sig_tab, 0.0, 5.0)
+    zc = -0.99 + 0.02 * np.arange(100)
+    zm_tab = np.outer(1.0 + 0.5 * zc ** 2, sig_tab)    # [z bin][m bin]: x = z, y = m (UpcTwoPhotonTabulated::calcCrossSectionZM)
+    capi.root_write_th2d(str(xs / "cross_section_zm.root"), {"hCrossSectionZM": zm_tab}, 100, -1.0, 1.0, 100, 0.0, 5.0)
+    n = 4000
+    par = f"""NUCLEUS_Z 82
+NUCLEUS_A 208
+WS_R 6.68
+WS_A 0.447
+SQRTS 5020
+PROC_ID 111
+NEVENTS {n}
+YMIN -4
+YMAX 4
+BINS_Y 32
+FLUX_POINT 1
+BREAKUP_MODE 1
+NON_ZERO_GAM_PT 1
+SEED 5
+USE_ROOT_OUTPUT 0
+USE_HEPMC_OUTPUT 1
+"""
+    (tmp_path / "pi0.in").write_text(par)
+    r = subprocess.run([os.path.join(HOST, "upcgen"), "-parfile", "pi0.in"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=600, env={**os.environ, "UPCGEN_CROSS_SEC_DIR": str(tmp_path / "xs")})
+    assert r.returncode == 0, r.stderr[-3000:]
+    tot_cli = float([l for l in r.stdout.splitlines() if "total cross section" in l][0].split()[4])
+    # the same fold through the C-ABI: sigma(m) looked up as the plug-in does (TAxis::FindBin on the lower bin edges)
+    P = UpcParams.from_text(par).init()
+    assert (P.nm, P.mmin, P.mmax, P.nz) == (91, 0.275, 5.0, 100)
+    g = capi.UpcGpu(P, 0)
+    g.prepare_tables()
+    g.fill_lumi()
+    m = P.mmin + P.dm * np.arange(P.nm)
+    sig = sig_tab[np.minimum((100 * (m - 0.0) / (5.0 - 0.0)).astype(int), 99)]   # TAxis::FindBin: 1 + int(nbins (x - xmin) / (xmax - xmin))
+    _, _, tot = g.fold_sigma(sig_m=sig)
+    g.close()
+    assert tot_cli == pytest.approx(tot, rel=1e-5)        # six printed digits
+    lines = (tmp_path / "events.hepmc").read_text().splitlines()
+    ev = [l for l in lines if l.startswith("E ")]
+    assert len(ev) == n and all(l.split()[2:] == ["2", "6"] for l in ev)
+    parts = [l.split() for l in lines if l.startswith("P ")]
+    pdg = np.array([int(q[3]) for q in parts]).reshape(n, 6)
+    mo = np.array([int(q[2]) for q in parts]).reshape(n, 6)
+    st = np.array([int(q[9]) for q in parts]).reshape(n, 6)
+    p = np.array([[float(x) for x in q[4:8]] for q in parts]).reshape(n, 6, 4)
+    assert np.all(pdg == [111, 111, 22, 22, 22, 22]) and np.all(mo == [0, 0, 1, 1, 2, 2]) and np.all(st == [23, 23, 33, 33, 33, 33])
+    assert np.allclose(p[:, 2] + p[:, 3], p[:, 0], rtol=1e-6, atol=1e-7) and np.allclose(p[:, 4] + p[:, 5], p[:, 1], rtol=1e-6, atol=1e-7)
+    mass2 = lambda q: q[..., 3] ** 2 - (q[..., :3] ** 2).sum(-1)
+    assert np.allclose(np.sqrt(np.maximum(mass2(p[:, :2]), 0)), 0.1349770, atol=2e-4)    # nine printed digits of a boosted pi0

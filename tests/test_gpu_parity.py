@@ -500,6 +500,44 @@ def test_lbyl_unpolarised_fold_and_events(get_gpu, get_oracle):
     assert np.max(np.abs(mass2)) < 1e-9 * np.max(p4[..., 3] ** 2)      # massless photons
 
 
+def test_events_pi0_pairs_with_both_decays(get_gpu, get_oracle, capi):
+    """PROC_ID 111: a pi0 pair, each pi0 decaying uniformly into two photons (src/UpcGenerator.cpp:799-803,
+    twoPartDecayUniform with id 1 and 2): six particles per event, mothers 0 0 1 1 2 2.  Same Philox slots -> the
+    oracle's events to rounding; the photons are massless, each pair of them reconstructs its pi0.  (The elementary
+    cross sections are stand-ins: the reference's pi0 pi0 tables live in ROOT files that do not travel to the GPU box;
+    the event stage does not depend on their values.)"""
+    extra = "PROC_ID 111\nBINS_Y 24\nDO_PT_CUT 1\nPT_MIN 0.05\n"
+    P, g = get_gpu("cfg1", extra)
+    _, o = get_oracle("cfg1", extra)
+    assert (P.nm, P.nz, P.mmin, P.mmax) == (91, 100, 0.275, 5.0)     # the grid the generator forces (:69-103)
+    assert g.particles_per_event() == 6
+    lumi = g.fill_lumi()
+    m = P.mmin + P.dm * np.arange(P.nm)
+    sig = 40.0 / m ** 2
+    z = P.zmin + P.dz * np.arange(P.nz)
+    cszm = np.outer(1.0 / m, 1.0 + 0.6 * z * z)
+    cs, _, tot = g.fold_sigma(sig_m=sig)
+    g.sampler_build(cszm=cszm)
+    s2, sz, _ = g.sampler_cdf()
+    worst, nacc = _compare_events(P, g, o, 777, 400, s2, sz)
+    print("pi0 pi0 events: worst rel p4 diff", worst, "accepted", nacc)
+    assert worst < 1e-9 and 0 < nacc < 400
+    ev = g.generate_packed(777, 0, 20000)
+    acc = ev["npart"] == 6
+    assert acc.sum() == ev["n_accepted"] and np.all(ev["npart"][~acc] == 0)
+    assert np.all(ev["pdg"][acc] == [111, 111, 22, 22, 22, 22]) and np.all(ev["status"][acc] == [23, 23, 33, 33, 33, 33])
+    assert np.all(ev["mother"][acc] == [0, 0, 1, 1, 2, 2])
+    p4 = ev["p4"][acc]
+    mass2 = lambda q: q[..., 3] ** 2 - (q[..., :3] ** 2).sum(-1)
+    e2 = p4[..., 3].max() ** 2
+    assert np.max(np.abs(mass2(p4[:, 2:]))) < 1e-9 * e2                                  # massless photons
+    assert np.allclose(np.sqrt(mass2(p4[:, :2])), 0.1349770, rtol=0, atol=1e-7)           # pi0 on shell
+    assert np.allclose(p4[:, 2] + p4[:, 3], p4[:, 0], rtol=1e-9, atol=1e-9)               # gamma gamma = its pi0
+    assert np.allclose(p4[:, 4] + p4[:, 5], p4[:, 1], rtol=1e-9, atol=1e-9)
+    pair = p4[:, 0] + p4[:, 1]
+    assert np.allclose(np.sqrt(mass2(pair)), ev["aux"][acc, 1], rtol=1e-9)                 # pair mass = sampled m
+
+
 def test_events_distributions_independent_of_batching(get_gpu, get_oracle):
     P, g = get_gpu("cfg1")
     _, o = get_oracle("cfg1")
@@ -531,7 +569,7 @@ def test_packed_event_output_and_pipelined_chunks(get_gpu, get_oracle, capi):
     with pytest.raises(capi.UpcGpuError):
         g.generate_packed(7, 0, 100, part_stride=1)
     with pytest.raises(capi.UpcGpuError):
-        g.generate_packed(7, 0, 100, part_stride=5)
+        g.generate_packed(7, 0, 100, part_stride=capi.MAX_PART + 1)
     n = (1 << 21) + 70001
     whole = g.generate_packed(11, 1000, n, with_aux=False)
     h1 = g.generate_packed(11, 1000, 1 << 21, with_aux=False)

@@ -351,3 +351,26 @@ def test_tree_empty_and_small(tmp_path):
         t = read_tree(open(path, "rb").read(), "particles")
         assert t["entries"] == n
         assert np.array_equal(t["cols"]["e"][1], np.arange(n) * 0.5)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's cross_sections directory is not mounted")
+def test_th1d_bytes_equal_what_root_wrote(tmp_path):
+    """The TH1D the writer streams (upcgpu_root_write_th1d) is, byte for byte, the hCrossSectionM that ROOT 6.22/09 wrote
+    into the reference's cross_sections/lbyl/cross_section_m.root when given its name, axis and cells; and the reader gets
+    the cells back."""
+    from upcgen_b200 import capi
+    src = os.path.join(REF, "lbyl", "cross_section_m.root")
+    f = open(src, "rb").read()
+    _, keys = read_keys(f)
+    k = [k for k in keys if k["cls"] == "TH1D"][0]
+    real = key_data(f, k)
+    h = capi.root_hist_read(src, k["name"])
+    path = str(tmp_path / "copy.root")
+    capi.root_write_th1d(path, k["name"], None, h["xlo"], h["xhi"], cells=h["cells"].ravel())
+    g = open(path, "rb").read()
+    check_file_records(g)
+    _, keys2 = read_keys(g)
+    mine = key_data(g, [q for q in keys2 if q["cls"] == "TH1D"][0])
+    assert mine == real
+    back = capi.root_hist_read(path, k["name"])
+    assert back["dim"] == 1 and np.array_equal(back["cells"], h["cells"])

@@ -17,7 +17,7 @@ _LIB = None
 
 OK, EINVAL, ECUDA, ENODEV, EQAGS, ERANGE = 0, -1, -2, -3, -4, -5
 TABLE_GAA, TABLE_TA, TABLE_FORMFAC, TABLE_BREAKUP = 0, 1, 2, 3
-MAX_PART = 4
+MAX_PART = 6   # UPCGPU_MAX_PART (include/upcgpu.h)
 
 
 class UpcGpuError(RuntimeError):
@@ -69,7 +69,7 @@ SYMBOLS = [
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
     "upcgpu_create_multi", "upcgpu_group_size", "upcgpu_group_member", "upcgpu_group_set_exchange",
-    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_tree", "upcgpu_photon_flux",
+    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_th1d", "upcgpu_root_write_tree", "upcgpu_photon_flux",
     "upcgpu_lumi_ipc_export", "upcgpu_lumi_ipc_import", "upcgpu_fill_lumi_shard_peers",
 ]
 
@@ -152,6 +152,9 @@ def to_cparams(P: UpcParams) -> CParams:
     elif pid == 22:
         c.part_pdg, c.m_part, c.is_charged, c.is_pair, c.is_single = 22, 0.0, 0, 1, 0
         c.ignore_csz, c.decay_uniform_pdg = 0, 0
+    elif pid == 111:  # pi0 pi0, each decaying uniformly into two photons (src/UpcTwoPhotonDipion.cpp:37-39, UpcGenerator.cpp:799-803)
+        c.part_pdg, c.m_part, c.is_charged, c.is_pair, c.is_single = 111, 0.1349770, 0, 1, 0
+        c.ignore_csz, c.decay_uniform_pdg = 0, 22
     else:
         raise ValueError(f"PROC_ID {pid} is outside the GPU path (SURVEY.md section 2)")
     return c
@@ -511,6 +514,21 @@ def root_hist_read(path: str, name: str):
     out = dict(dim=dim.value, nx=nx.value, xlo=xlo.value, xhi=xhi.value, ny=ny.value, ylo=ylo.value, yhi=yhi.value)
     out["cells"] = cells.reshape(ny.value + 2, nx.value + 2) if dim.value == 2 else cells
     return out
+
+
+def root_write_th1d(path: str, name: str, values, xlo, xhi, cells=None, entries=None):
+    """Writes one TH1D (bin i + 1 = values[i]; or all nx + 2 cells) into a ROOT file, without ROOT."""
+    L = lib()
+    if cells is None:
+        v = _f64(values).ravel()
+        cells = np.concatenate([[0.0], v, [0.0]])
+    cells = _f64(cells).ravel()
+    nx = cells.size - 2
+    L.upcgpu_root_write_th1d.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_double]
+    rc = L.upcgpu_root_write_th1d(path.encode(), name.encode(), nx, float(xlo), float(xhi), _p(cells),
+                                  float(nx if entries is None else entries))
+    if rc != OK:
+        raise UpcGpuError(rc, "root_write_th1d failed")
 
 
 def root_write_th2d(path: str, hists: dict, nx, xlo, xhi, ny, ylo, yhi):

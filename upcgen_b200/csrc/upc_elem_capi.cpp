@@ -113,6 +113,20 @@ int upcgpu_root_write_th2d(const char* path, int n_hist, const char* const* name
   }
 }
 
+// ... a TH1D (the form of the reference's cross_sections/*/cross_section_m.root): cells = nx + 2 values, under-/overflow included
+int upcgpu_root_write_th1d(const char* path, const char* name, int nx, double xlo, double xhi, const double* cells, double entries)
+{
+  if (!path || !name || !cells || nx < 1) return UPCGPU_EINVAL;
+  try {
+    UpcRootFileWriter w;
+    w.AddTH1D(name, "", nx, xlo, xhi, std::vector<double>(cells, cells + nx + 2), entries);
+    std::string err;
+    return w.Write(path, err) ? UPCGPU_OK : UPCGPU_EINVAL;
+  } catch (...) {
+    return UPCGPU_EINVAL;
+  }
+}
+
 // ... and a TTree of flat branches (events.root: tree "particles", src/UpcGenerator.cpp:842-857): n_cols columns of
 // n_rows values each, types[i] = 'I' (Int_t) or 'D' (Double_t), integer columns passed as doubles
 int upcgpu_root_write_tree(const char* path, const char* tree, const char* title, int n_cols, const char* const* names,

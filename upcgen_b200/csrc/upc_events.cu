@@ -370,7 +370,7 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
   const double yPair = y[t], mPair = m[t], cz = cost[t];
   int np = 0;
   LV parts[UPCGPU_MAX_PART];
-  int ppdg[UPCGPU_MAX_PART] = {0, 0, 0, 0}, pst[UPCGPU_MAX_PART] = {0, 0, 0, 0}, pmo[UPCGPU_MAX_PART] = {0, 0, 0, 0};
+  int ppdg[UPCGPU_MAX_PART] = {}, pst[UPCGPU_MAX_PART] = {}, pmo[UPCGPU_MAX_PART] = {};
   double pt1 = 0, pt2 = 0;
   bool ok = !(mPair != mPair);
   if (ok) {
@@ -428,11 +428,13 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
         if (eta < P.eta_min || eta > P.eta_max) { ok = false; break; }
       }
     }
-    // twoPartDecayUniform(id = 1, mass 0) :526-561
-    if (ok && P.decay_pdg != 0 && np >= 1) {
+    // twoPartDecayUniform(id, mass 0) :526-561 of the single particle (ALP, :806-808) or of both particles of a pair
+    // (pi0 pi0, :799-803: id = 1, then id = 2); decay d takes its two uniforms from Philox block 5 + d
+    const int n_dec = (ok && P.decay_pdg != 0) ? (P.is_pair ? 2 : 1) : 0;
+    for (int dcy = 0; dcy < n_dec; ++dcy) {
       double u10, u11;
-      philox4x32_10(seed, cand, 5, u10, u11);
-      const LV part = parts[0];
+      philox4x32_10(seed, cand, 5 + dcy, u10, u11);
+      const LV part = parts[dcy];
       const double mm2 = part.t * part.t - (part.x * part.x + part.y * part.y + part.z * part.z);
       const double mag = mm2 < 0 ? -sqrt(-mm2) : sqrt(mm2);
       const double ePhot1 = mag / 2.;
@@ -456,7 +458,7 @@ __global__ void k_ev_kin(EvParams P, uint64_t seed, uint64_t first, size_t n, co
       parts[np] = d0; parts[np + 1] = d1;
       ppdg[np] = ppdg[np + 1] = P.decay_pdg;
       pst[np] = pst[np + 1] = 33;
-      pmo[np] = pmo[np + 1] = 1;
+      pmo[np] = pmo[np + 1] = dcy + 1;
       np += 2;
     }
   }
@@ -544,10 +546,12 @@ static EvParams make_evp(const upcgpu_ctx* c)
 }
 
 // particles an accepted event of this context's process has: the pair or the single particle, plus two decay products
+// of each when they decay (ALP: 3, pi0 pi0: 6)
 int particles_per_event(const upcgpu_ctx* c)
 {
   const EvParams P = make_evp(c);
-  return (P.is_pair ? 2 : 1) + (P.decay_pdg != 0 ? 2 : 0);
+  const int prim = P.is_pair ? 2 : 1;
+  return prim + (P.decay_pdg != 0 ? 2 * prim : 0);
 }
 
 // Candidates are processed in chunks.  Device-resident runs take chunks of kEvChunk (the photon-pT stage costs one table

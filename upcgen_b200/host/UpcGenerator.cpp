@@ -189,11 +189,6 @@ void UpcGenerator::init()
       usePolarizedCS = false;
       cs->usePolarizedCS = false;
     }
-    if (procID == 111) {
-      PLOG_FATAL << "pi0 pi0: the two pi0 -> gamma gamma decays of the event stage are not part of the GPU build; the cross "
-                 << "sections are available through UpcTwoPhotonDipion. Exiting...";
-      std::_Exit(-1);
-    }
   }
   if (procID == 51) {
     ignoreCSZ = true; // cos(theta) uniform for the ALP
@@ -225,7 +220,7 @@ void UpcGenerator::init()
   cs->evIsPair = isPairProduction;
   cs->evIsSingle = isSingleProduction;
   cs->evIgnoreCSZ = ignoreCSZ;
-  cs->evDecayUniformPDG = procID == 51 ? 22 : 0;
+  cs->evDecayUniformPDG = (procID == 51 || procID == 111) ? 22 : 0;  // :799-808: the ALP, or both pi0 of the pair
   cs->evDoPtCut = doPtCut; cs->evMinPt = minPt;
   cs->evDoEtaCut = doEtaCut; cs->evMinEta = minEta; cs->evMaxEta = maxEta;
 

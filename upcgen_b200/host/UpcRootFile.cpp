@@ -174,6 +174,23 @@ void UpcRootFileWriter::AddTH2D(const std::string& name, const std::string& titl
   records_.push_back(std::move(r));
 }
 
+// TH1D (version 3) = TH1 + TArrayD; the y and z axes of a one-dimensional histogram are ROOT's defaults (1 bin on [0, 1])
+void UpcRootFileWriter::AddTH1D(const std::string& name, const std::string& title, int nx, double xlo, double xhi,
+                                const std::vector<double>& cells, double entries)
+{
+  const size_t ncells = (size_t)nx + 2;
+  if (cells.size() != ncells) throw std::invalid_argument("AddTH1D: cells must hold nx + 2 values");
+  Out o;
+  const size_t p = o.begin(3);  // TH1D
+  th1(o, name, title, (int)ncells, nx, xlo, xhi, 1, 0., 1., entries);
+  o.i32((int32_t)ncells);  // TArrayD
+  for (double v : cells) o.f64(v);
+  o.end(p);
+  Record r;
+  r.cls = "TH1D"; r.name = name; r.title = title; r.data = std::move(o.b); r.listed = true;
+  records_.push_back(std::move(r));
+}
+
 void UpcRootFileWriter::AddTree(const std::string& name, const std::string& title, const std::vector<Column>& columns)
 {
   if (columns.empty()) throw std::invalid_argument("AddTree: no columns");

@@ -1,4 +1,5 @@
-// UpcRootFile.h -- a ROOT-less WRITER of the two kinds of .root files the reference produces on this path:
+// UpcRootFile.h -- a ROOT-less WRITER of the two kinds of .root files the reference produces on this path (and of TH1D
+// objects, the form of the elementary cross sections sigma(m) the reference reads from cross_sections/*/cross_section_m.root):
 //   * the two-photon-luminosity cache twoPhotonLumi[Pol].root with the TH2D hD2LDMDY[_s,_p]
 //     (src/UpcCrossSection.cpp:493-507, :564-585), so that a table filled on the GPU is picked up by the reference
 //     (and by this build) exactly like one the reference computed itself;
@@ -21,6 +22,10 @@ class UpcRootFileWriter
   // a TH2D with uniform axes; cells: (nx + 2) * (ny + 2) doubles, x fastest, under-/overflow cells included
   void AddTH2D(const std::string& name, const std::string& title, int nx, double xlo, double xhi, int ny, double ylo,
                double yhi, const std::vector<double>& cells, double entries);
+
+  // a TH1D with a uniform axis; cells: nx + 2 doubles, under-/overflow included
+  void AddTH1D(const std::string& name, const std::string& title, int nx, double xlo, double xhi,
+               const std::vector<double>& cells, double entries);
 
   // a TTree of flat branches, one leaf each: type 'I' (Int_t) or 'D' (Double_t); all columns the same length.
   // Integer columns are given as doubles holding integral values.
