@@ -75,6 +75,30 @@ class Reference:
         return cs, ratio, tot
 
 
+def put_hist(path, name, cells, xaxis, yaxis=None):
+    """Places a histogram into the shim's in-memory "ROOT file" `path` (what TFile(path)->Get(name) of the reference's
+    light-by-light / pi0 pi0 plug-ins will find): cells = all (nx + 2) [x (ny + 2)] bins, x fastest; axes (n, lo, hi)."""
+    L = C.CDLL(SO)
+    cells = np.ascontiguousarray(cells, dtype=np.float64).ravel()
+    d, i, p = C.c_double, C.c_int, C.c_void_p
+    if yaxis is None:
+        assert cells.size == xaxis[0] + 2
+        L.upcref_put_hist1.argtypes = [C.c_char_p, C.c_char_p, i, d, d, p]
+        L.upcref_put_hist1(path.encode(), name.encode(), int(xaxis[0]), float(xaxis[1]), float(xaxis[2]), cells.ctypes.data)
+    else:
+        assert cells.size == (xaxis[0] + 2) * (yaxis[0] + 2)
+        L.upcref_put_hist2.argtypes = [C.c_char_p, C.c_char_p, i, d, d, i, d, d, p]
+        L.upcref_put_hist2(path.encode(), name.encode(), int(xaxis[0]), float(xaxis[1]), float(xaxis[2]), int(yaxis[0]),
+                           float(yaxis[1]), float(yaxis[2]), cells.ctypes.data)
+
+
+def cross_sec_dir():
+    """CROSS_SEC_DIR the reference's sources were compiled with (the directory its plug-ins look into)."""
+    L = C.CDLL(SO)
+    L.upcref_cross_sec_dir.restype = C.c_char_p
+    return L.upcref_cross_sec_dir().decode()
+
+
 class RefGenerator:
     """The reference's own UpcGenerator, driven as main.cpp drives it (setParFile, configGeneratorFromFile, init,
     generateEvent), with the two-photon luminosity cache injected: the table is placed into the shim's in-memory
@@ -140,8 +164,8 @@ class RefGenerator:
 
     def generate(self, n):
         npart = np.zeros(n, np.int32)
-        pdg = np.zeros((n, 4), np.int32); st = np.zeros((n, 4), np.int32); mo = np.zeros((n, 4), np.int32)
-        p4 = np.zeros((n, 4, 4))
+        pdg = np.zeros((n, 6), np.int32); st = np.zeros((n, 6), np.int32); mo = np.zeros((n, 6), np.int32)
+        p4 = np.zeros((n, 6, 4))
         acc = self.L.upcrefgen_generate(n, npart.ctypes.data, pdg.ctypes.data, st.ctypes.data, mo.ctypes.data,
                                         p4.ctypes.data)
         return dict(npart=npart, pdg=pdg, status=st, mother=mo, p4=p4, n_accepted=acc)

@@ -105,7 +105,8 @@ void upcrefgen_cdfs(double* sum2d, double* sumz)
 }
 
 // n calls of UpcGenerator::generateEvent (src/UpcGenerator.cpp:715-832).  Per candidate: npart (0 = rejected by the
-// cuts), pdg/status/mother[4], p4[4][4] = (px, py, pz, E).  Returns the number of accepted events.
+// cuts), pdg/status/mother[6], p4[6][4] = (px, py, pz, E) (six slots: a pi0 pair and its four photons).  Returns the number
+// of accepted events.
 long upcrefgen_generate(long n, int* npart, int* pdg, int* status, int* mother, double* p4)
 {
   std::vector<int> pdgs, statuses, mothers;
@@ -115,12 +116,12 @@ long upcrefgen_generate(long n, int* npart, int* pdg, int* status, int* mother, 
     const long ok = g_gen->generateEvent(pdgs, statuses, mothers, particles);
     const int np = ok == 1 ? (int)particles.size() : 0;
     npart[i] = np;
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 6; j++) {
       const bool v = j < np;
-      pdg[i * 4 + j] = v ? pdgs[j] : 0;
-      status[i * 4 + j] = v ? statuses[j] : 0;
-      mother[i * 4 + j] = v ? mothers[j] : 0;
-      double* q = p4 + ((size_t)i * 4 + j) * 4;
+      pdg[i * 6 + j] = v ? pdgs[j] : 0;
+      status[i * 6 + j] = v ? statuses[j] : 0;
+      mother[i * 6 + j] = v ? mothers[j] : 0;
+      double* q = p4 + ((size_t)i * 6 + j) * 4;
       q[0] = v ? particles[j].Px() : 0; q[1] = v ? particles[j].Py() : 0;
       q[2] = v ? particles[j].Pz() : 0; q[3] = v ? particles[j].E() : 0;
     }

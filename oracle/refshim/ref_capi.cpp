@@ -10,15 +10,8 @@
 TRandom* gRandom = new TRandomMT64();
 TSystem* gSystem = new TSystem();
 
-// elementary processes that need ROOT histogram files: constructors exist only so that setElemProcess links; they are
-// never instantiated here (the vector-meson plug-in IS the reference's: src/UpcPhotoNuclearVM.cpp)
-UpcTwoPhotonLbyL::UpcTwoPhotonLbyL(bool, double, double) {}
-double UpcTwoPhotonLbyL::calcCrossSectionM(double) { return 0; }
-double UpcTwoPhotonLbyL::calcCrossSectionZM(double, double) { return 0; }
-UpcTwoPhotonDipion::UpcTwoPhotonDipion(bool, double, double) {}
-double UpcTwoPhotonDipion::calcCrossSectionM(double) { return 0; }
-double UpcTwoPhotonDipion::calcCrossSectionZM(double, double) { return 0; }
-
+// (every elementary process is the reference's own translation unit: dileptons, ALP, vector mesons, and the two that
+// read ROOT histogram files -- light-by-light, pi0 pi0 --, whose files the tests inject: upcref_put_hist1/2)
 extern gsl_spline* gslSplineGAA;
 extern gsl_spline* gslSplineFormFac;
 extern gsl_spline* gslSplineBreakP;
@@ -87,6 +80,24 @@ double upcref_sigma_m(double m) { return g_cs->elemProcess->calcCrossSectionM(m)
 double upcref_sigma_zm(double z, double m) { return g_cs->elemProcess->calcCrossSectionZM(z, m); }
 double upcref_sigma_m_pol(double m, int ps) { return ps ? g_cs->elemProcess->calcCrossSectionMPolPS(m) : g_cs->elemProcess->calcCrossSectionMPolS(m); }
 double upcref_sigma_zm_pol(double z, double m, int ps) { return ps ? g_cs->elemProcess->calcCrossSectionZMPolPS(z, m) : g_cs->elemProcess->calcCrossSectionZMPolS(z, m); }
+// Histograms of the "files" the light-by-light and pi0 pi0 plug-ins open (src/UpcTwoPhotonLbyL.cpp:40-47,
+// src/UpcTwoPhotonDipion.cpp:44-51): placed into the shim's in-memory TFile store under the path the plug-in will ask
+// for (CROSS_SEC_DIR/<process>/cross_section_[z]m.root).  cells: all (nx + 2) [x (ny + 2)] bins, x fastest.
+const char* upcref_cross_sec_dir() { return CROSS_SEC_DIR; }
+void upcref_put_hist1(const char* path, const char* name, int nx, double xlo, double xhi, const double* cells)
+{
+  auto* h = new TH1D(name, "", nx, xlo, xhi);
+  for (int i = 0; i < nx + 2; i++) h->SetBinContent(i, cells[i]);
+  TFile::store1()[path][name] = h;
+}
+void upcref_put_hist2(const char* path, const char* name, int nx, double xlo, double xhi, int ny, double ylo, double yhi,
+                      const double* cells)
+{
+  auto* h = new TH2D(name, "", nx, xlo, xhi, ny, ylo, yhi);
+  for (int iy = 0; iy < ny + 2; iy++)
+    for (int ix = 0; ix < nx + 2; ix++) h->SetBinContent(ix, iy, cells[(size_t)iy * (nx + 2) + ix]);
+  TFile::store()[path][name] = h;
+}
 // the reference's vector-meson plug-in (src/UpcPhotoNuclearVM.cpp, compiled unmodified): sigma(y) of
 // calcCrossSectionY for n rapidities; needs upcref_init (calcFormFac and the statics sqrts, mNucl, R, a, rho0).
 // getRgLtaVG keeps its table in function-local statics: one (PDG, SHADOWING 4) combination per process.

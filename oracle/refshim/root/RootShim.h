@@ -91,11 +91,29 @@ class TH1 : public TObject
   static void AddDirectory(bool) {}
 };
 
+// TAxis::FindBin on a uniform axis: 0 below, n + 1 at or above the upper edge, else 1 + int(n (x - lo) / (hi - lo))
+class TAxis
+{
+ public:
+  TAxis() = default;
+  TAxis(int n_, double lo_, double hi_) : n(n_), lo(lo_), hi(hi_) {}
+  int FindBin(double x) const
+  {
+    if (x < lo) return 0;
+    if (!(x < hi)) return n + 1;
+    return 1 + int(n * (x - lo) / (hi - lo));
+  }
+  int GetNbins() const { return n; }
+  int n{1};
+  double lo{0}, hi{1};
+};
+
 class TH1D : public TH1
 {
  public:
   TH1D() = default;
-  TH1D(const char* name, const char*, int nb, double lo, double hi) : name_(name), n(nb), xlo(lo), xhi(hi), c(nb + 2, 0.) {}
+  TH1D(const char* name, const char*, int nb, double lo, double hi) : name_(name), n(nb), xlo(lo), xhi(hi), c(nb + 2, 0.), xaxis_(nb, lo, hi) {}
+  const TAxis* GetXaxis() const { return &xaxis_; }
   void SetDirectory(void*) {}
   int Write() { return 0; }
   void SetBinContent(int bin, double v) { c[bin] = v; integral.clear(); }
@@ -123,13 +141,20 @@ class TH1D : public TH1
   int n{0};
   double xlo{0}, xhi{1};
   std::vector<double> c, integral;
+  TAxis xaxis_;
 };
 
 class TFile;
 class TH2D : public TObject
 {
  public:
-  TH2D(const char* name, const char*, int nx_, double, double, int ny_, double, double) : name_(name), nx(nx_), ny(ny_), c((size_t)(nx_ + 2) * (ny_ + 2), 0.) {}
+  TH2D(const char* name, const char*, int nx_, double xlo, double xhi, int ny_, double ylo, double yhi)
+      : name_(name), nx(nx_), ny(ny_), c((size_t)(nx_ + 2) * (ny_ + 2), 0.), xaxis_(nx_, xlo, xhi), yaxis_(ny_, ylo, yhi) {}
+  const TAxis* GetXaxis() const { return &xaxis_; }
+  const TAxis* GetYaxis() const { return &yaxis_; }
+  int GetNbinsX() const { return nx; }
+  int GetNbinsY() const { return ny; }
+  void SetDirectory(void*) {}
   TH2D(const char* name, const char*, int nx_, const double*, int ny_, const double*) : name_(name), nx(nx_), ny(ny_), c((size_t)(nx_ + 2) * (ny_ + 2), 0.) {}
   // debug-only projections of UpcGenerator::generateEvents (src/UpcGenerator.cpp:902-908)
   TH1D* ProjectionX() const
@@ -151,6 +176,7 @@ class TH2D : public TObject
   std::string name_;
   int nx, ny;
   std::vector<double> c;
+  TAxis xaxis_, yaxis_;
 };
 
 // files live in memory (plus an empty marker on disk so that gSystem->AccessPathName sees them)
@@ -165,6 +191,12 @@ class TFile
   static std::map<std::string, std::map<std::string, TH2D*>>& store()
   {
     static std::map<std::string, std::map<std::string, TH2D*>> s;
+    return s;
+  }
+  // one-dimensional histograms (the sigma(m) tables of the light-by-light and pi0 pi0 plug-ins: injected by the tests)
+  static std::map<std::string, std::map<std::string, TH1D*>>& store1()
+  {
+    static std::map<std::string, std::map<std::string, TH1D*>> s;
     return s;
   }
   static TFile*& current() { static TFile* c = nullptr; return c; }
@@ -183,7 +215,10 @@ inline TObject* TFile::Get(const char* name)
 {
   auto& m = store()[fname_];
   auto it = m.find(name);
-  return it == m.end() ? nullptr : new TH2D(*it->second);
+  if (it != m.end()) return new TH2D(*it->second);
+  auto& m1 = store1()[fname_];
+  auto it1 = m1.find(name);
+  return it1 == m1.end() ? nullptr : new TH1D(*it1->second);
 }
 inline int TH2D::Write()
 {

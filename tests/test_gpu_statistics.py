@@ -240,3 +240,62 @@ def test_two_sample_vs_reference_generate_event_alp(capi):
     # momentum conservation of the decay in both samples
     assert np.max(np.abs(ga[:, 1] + ga[:, 2] - ga[:, 0])) < 1e-9 * np.max(np.abs(ga[:, 0]))
     g.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libupcref.so")),
+                    reason="oracle/_ref not built")
+def test_two_sample_vs_reference_generate_event_pi0_pairs(capi):
+    """PROC_ID 111 (pi0 pairs, each decayed uniformly into two photons): GPU events against the reference's own
+    UpcGenerator + src/UpcTwoPhotonDipion.cpp, both fed the SAME sigma(m) and dsigma/dz histograms -- placed into the
+    shim's in-memory ROOT files for the reference, looked up with TAxis::FindBin arithmetic for the GPU side (the
+    reference's own pi0 pi0 files do not travel to the GPU box; the plug-in's look-ups on them are pinned bit for bit by
+    tests/test_reference_tabulated.py)."""
+    from oracle import pyref
+    from upcgen_b200.config import named_config, config_text
+    extra = "PROC_ID 111\nBINS_Y 40\nDO_PT_CUT 1\nPT_MIN 0.1\n"
+    P = named_config("cfg1", extra)
+    assert (P.nm, P.mmin, P.mmax, P.nz) == (91, 0.275, 5.0, 100)
+    # the two histograms of cross_sections/pi0pi0: sigma(m) on 100 bins of [0, 5], dsigma/dz on 100 x 100 bins of [-1, 1] x [0, 5]
+    mc = 0.025 + 0.05 * np.arange(100)
+    zc = -0.99 + 0.02 * np.arange(100)
+    h1 = np.concatenate([[0.0], np.where(mc > 0.27, 25.0 / (0.3 + mc) ** 3, 0.0), [0.0]])
+    h2 = np.zeros((102, 102))                                  # [m bin][z bin], z (x axis) fastest
+    h2[1:-1, 1:-1] = np.outer(h1[1:-1], 1.0 + 0.8 * zc ** 2)
+    d = pyref.cross_sec_dir()
+    pyref.put_hist(f"{d}/pi0pi0/cross_section_m.root", "hCrossSectionM", h1, (100, 0.0, 5.0))
+    pyref.put_hist(f"{d}/pi0pi0/cross_section_zm.root", "hCrossSectionZM", h2, (100, -1.0, 1.0), (100, 0.0, 5.0))
+    findbin = lambda x, n, lo, hi: 0 if x < lo else (n + 1 if not x < hi else 1 + int(n * (x - lo) / (hi - lo)))
+    m = P.mmin + P.dm * np.arange(P.nm)
+    z = P.zmin + P.dz * np.arange(P.nz)
+    sig = np.array([h1[findbin(x, 100, 0.0, 5.0)] for x in m])
+    hc = 0.1973269718
+    cszm = np.array([[h2[findbin(a, 100, 0.0, 5.0), findbin(b, 100, -1.0, 1.0)] * (hc * hc * 1e7) / P.dm for b in z] for a in m])
+    g = capi.UpcGpu(P, 0)
+    g.prepare_tables()
+    lumi = g.fill_lumi()
+    cs, _, tot = g.fold_sigma(sig_m=sig)
+    g.sampler_build(cszm=cszm)
+    n_gpu, n_ref = 600_000, 50_000
+    ev = _generate(g, n_gpu)
+    ref = pyref.RefGenerator(config_text("cfg1", extra + "BREAKUP_MODE 1\n"), tempfile.mkdtemp(), lumi=lumi,
+                             grid=(P.nm, P.ny, P.mmin, P.mmax, P.ymin, P.ymax))
+    assert ref.totcs() == pytest.approx(tot, rel=1e-12)       # the reference folded the same table with the same sigma(m)
+    ref.reseed_z(4242)
+    rv = ref.generate(n_ref)
+    a_gpu, a_ref = np.mean(ev["npart"] > 0), np.mean(rv["npart"] > 0)
+    sg = np.sqrt(a_ref * (1 - a_ref) * (1 / n_gpu + 1 / n_ref))
+    print(f"acceptance: GPU {a_gpu:.5f}, reference {a_ref:.5f}  ({abs(a_gpu - a_ref) / sg:.2f} sigma)")
+    assert abs(a_gpu - a_ref) < 4 * sg
+    ga, ra = ev["p4"][ev["npart"] > 0], rv["p4"][rv["npart"] > 0]
+    assert np.all(ev["npart"][ev["npart"] > 0] == 6) and np.all(rv["npart"][rv["npart"] > 0] == 6)
+    assert np.all(rv["pdg"][rv["npart"] > 0] == [111, 111, 22, 22, 22, 22]) and np.all(rv["mother"][rv["npart"] > 0] == [0, 0, 1, 1, 2, 2])
+    mass = lambda q: np.sqrt(np.maximum(q[:, 3] ** 2 - q[:, 0] ** 2 - q[:, 1] ** 2 - q[:, 2] ** 2, 0))
+    rap = lambda q: 0.5 * np.log((q[:, 3] + q[:, 2]) / (q[:, 3] - q[:, 2]))
+    _two_sample("pair mass", mass(ga[:, 0] + ga[:, 1]), mass(ra[:, 0] + ra[:, 1]))
+    _two_sample("pair rapidity", rap(ga[:, 0] + ga[:, 1]), rap(ra[:, 0] + ra[:, 1]))
+    _two_sample("pi0 pT", _pt(ga[:, 0]), _pt(ra[:, 0]))
+    _two_sample("pi0 eta", _eta(ga[:, 1]), _eta(ra[:, 1]))
+    _two_sample("photon pT (first decay)", _pt(ga[:, 2]), _pt(ra[:, 2]))
+    _two_sample("photon eta (second decay)", _eta(ga[:, 5]), _eta(ra[:, 5]))
+    _two_sample("photon energy (second decay)", ga[:, 4, 3], ra[:, 4, 3])
+    g.close()
