@@ -589,6 +589,12 @@ int generate(upcgpu_ctx* c, uint64_t seed, uint64_t first, size_t n, int part_st
   UPC_CUDA(c, cudaMemsetAsync(s->n_acc, 0, sizeof(unsigned long long), st));
   UPC_CUDA(c, cudaMemsetAsync(s->err, 0, sizeof(int), st));
   bool copies_in_flight = false;
+  // whichever way this function returns, no copy into the caller's buffers is left running
+  struct CopyGuard {
+    cudaStream_t s;
+    const bool& active;
+    ~CopyGuard() { if (active && s) cudaStreamSynchronize(s); }
+  } copy_guard{cs, copies_in_flight};
   for (size_t off = 0; off < n; off += chunk) {
     const size_t cn = std::min(chunk, n - off);
     const unsigned g = (unsigned)((cn + 127) / 128);
