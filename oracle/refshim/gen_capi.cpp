@@ -20,6 +20,7 @@
 #define private public         // ... so that only UpcGenerator's members open up: the tests read its tables and samplers
 #include "UpcGenerator.h"
 #undef private
+#include "param_dump.h"
 
 static UpcGenerator* g_gen = nullptr;
 
@@ -43,6 +44,21 @@ static void* gen_init_thread(void* vp)
 }
 
 extern "C" {
+
+// parameters.in through the REFERENCE's parser only (new UpcGenerator, setParFile, configGeneratorFromFile -- no init):
+// the resulting parameter block as "KEY value" lines.  Returns the text's length (truncated to cap - 1).
+long upcrefgen_parse(const char* parfile, char* out, long cap)
+{
+  auto* g = new UpcGenerator();
+  g->setDebugLevel(0);
+  g->setParFile(parfile);
+  g->configGeneratorFromFile();
+  const std::string s = upc_param_dump(*g);
+  const long n = (long)s.size() < cap - 1 ? (long)s.size() : cap - 1;
+  std::memcpy(out, s.data(), n);
+  out[n] = 0;
+  return n;   // (the generator is leaked on purpose: ~UpcGenerator deletes gRandom)
+}
 
 // Places a luminosity table into the shim's in-memory "ROOT file" <dir>/twoPhotonLumi[Pol].root as the TH2D(s) the
 // reference writes (src/UpcCrossSection.cpp:503-506, :564-571: bin (im + 1, iy + 1) = table[im][iy]), and the marker
