@@ -32,6 +32,14 @@ int main(int argc, char** argv)
     for (int i = 0; i < 8; i++) std::printf("%s%.17g", i ? ", " : "", vm.getRgLtaVG(xs[i]));
     std::printf("]");
   }
+  if (shad == 2 || shad == 3) {
+    // the FGS10 patch at the table's own nodes (first, an inner one, last in x; mu^2 of the plug-in) and between them
+    std::printf(", \"rg\": [");
+    const double xs[8] = {1e-6, 9.99999975e-6, 3e-5, 1.2e-4, 1.3e-3, 2e-2, 0.4, 0.99};
+    for (int i = 0; i < 8; i++) std::printf("%s%.17g", i ? ", " : "", vm.getRgLta(shad == 2 ? 0 : 1, xs[i]));
+    std::printf("]");
+    if (!vm.ok) std::printf(", \"error\": \"%s\"", vm.error.c_str());
+  }
   std::printf("}\n");
   return 0;
 }

@@ -133,6 +133,37 @@ def test_vm_plugin_lta_shadowing(get_oracle):
     assert np.max(np.abs(mine[sel] / ref[sel] - 1)) < 1e-8
 
 
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's cross_sections directory is not mounted")
+@pytest.mark.parametrize("shad,model", [(2, 2), (3, 1)])
+def test_vm_plugin_fgs10_nodes(shad, model, get_oracle):
+    """SHADOWING 2 / 3 for psi(2S) (mu^2 = 4 = the grid's first Q^2 row): a bicubic patch returns the table's glue
+    column at the table's own x nodes, clamps x to [9.99999975e-6, 0.95] (src/UpcPhotoNuclearVM.cpp:291-294) and is
+    smooth between nodes; J/psi (mu^2 = 3) keeps the impulse approximation (:366-374)."""
+    P, o = get_oracle("cfg1")
+    d = _vm_check(100443, shad, 13, P, o.rho0(), env={"UPCGEN_CROSS_SEC_DIR": REF})
+    assert "error" not in d, d
+    tok = open(os.path.join(REF, "vm", "lta", f"QCDEvolution_pb208proton_2009_model{model}.dat")).read().split()
+    assert float(tok[0]) == 4.0
+    rows = np.array(tok[1:1 + 90 * 9], dtype=float).reshape(90, 9)
+    xs_t, glue = rows[:, 0], rows[:, 7]
+    rg = np.array(d["rg"])
+    # vm_check's probes: below the grid (clamped to the first node), the first node, the node 3e-5 (9 printed digits:
+    # 2.99999992E-05, so the probe sits 8e-13 off it), between nodes, above 0.95 (clamped)
+    assert rg[0] == rg[1] == pytest.approx(glue[0], rel=1e-14)
+    assert rg[2] == pytest.approx(glue[4], rel=1e-6)
+    for x, v in zip((1.2e-4, 1.3e-3, 2e-2, 0.4), rg[3:7]):
+        k = np.searchsorted(xs_t, x)
+        lo, hi = sorted((glue[k - 1], glue[k]))
+        pad = 0.05 * (hi - lo) + 1e-3
+        assert lo - pad <= v <= hi + pad, (x, v, lo, hi)
+    k95 = np.searchsorted(xs_t, 0.95)
+    assert min(glue[k95 - 1:k95 + 1]) - 0.05 <= rg[7] <= max(glue[k95 - 1:k95 + 1]) + 0.05
+    # J/psi: the option leaves the impulse approximation in place
+    a = _vm_check(443, shad, 13, P, o.rho0(), env={"UPCGEN_CROSS_SEC_DIR": REF})
+    b = _vm_check(443, 0, 13, P, o.rho0())
+    assert a["sigma"] == b["sigma"]
+
+
 _VM_REF_CASE = r"""
 import json, sys
 sys.path.insert(0, {root!r})
@@ -151,11 +182,16 @@ print("RESULT " + json.dumps(out))
 
 
 @pytest.mark.skipif(not pyref.available(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("cases", [[(443, 4, 13), (553, 0, 11)], [(100443, 4, 13), (443, 0, 11)]])
+@pytest.mark.parametrize("cases", [[(443, 4, 13), (553, 0, 11)], [(100443, 4, 13), (443, 0, 11)],
+                                   [(100443, 2, 13), (443, 2, 13)], [(553, 2, 11)], [(553, 3, 11)], [(100443, 3, 13)]])
 def test_vm_plugin_equals_the_references_own(cases, get_oracle):
     """The host plug-in against the REFERENCE's src/UpcPhotoNuclearVM.cpp, compiled unmodified into oracle/_ref (TF1 /
     TGraph / TSpline3 behind it are shim restatements: QAGS at 1e-12, not-a-knot spline, linear TGraph::Eval): sigma(y)
-    on 25 rapidities for the impulse approximation and the LTA shadowing (SHADOWING 4), J/psi, psi(2S), Upsilon.  The
+    on 25 rapidities for the impulse approximation, the LTA shadowing (SHADOWING 4) and the FGS10 grids (SHADOWING 2 / 3:
+    gsl_spline2d's bicubic behind the reference is the shim's power-basis restatement of GSL's bicubic.c, the plug-in
+    evaluates the same patch in Hermite form; one FGS10 instance per case list -- the reference keeps "initialised" in a
+    function-level static but the spline in the instance, so a second instance of a process dereferences a null
+    spline), J/psi, psi(2S), Upsilon.  The
     two sides integrate the squared form factor with different adaptive rules: agreement is 3e-15, the bar 1e-12."""
     r = subprocess.run([sys.executable, "-c", _VM_REF_CASE.format(root=ROOT, cases=cases)], capture_output=True,
                        text=True, timeout=600)

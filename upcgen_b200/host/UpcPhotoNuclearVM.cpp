@@ -26,9 +26,10 @@ UpcPhotoNuclearVM::UpcPhotoNuclearVM(int partPDG_, int shadowingOpt, int dghtPDG
   else if (dghtPDG == 2212) mDght = phys_consts::mProt;
   else throw std::invalid_argument("Unsupported decay mode");
   fMmin = phys_consts::mProt + mPart;
-  if (fShadowing != 0 && fShadowing != 4) {
+  if (fShadowing != 0 && fShadowing != 2 && fShadowing != 3 && fShadowing != 4) {
     ok = false;
-    error = "SHADOWING " + std::to_string(fShadowing) + " is not available in this build (0: impulse approximation, 4: LTA tables)";
+    error = "SHADOWING " + std::to_string(fShadowing) +
+            " is not available in this build (0: impulse approximation, 2/3: FGS10 grids, 4: LTA tables)";
   }
 }
 
@@ -162,6 +163,115 @@ double UpcPhotoNuclearVM::getRgLtaVG(double x)
   return fY[up] + (x - fX[up]) * (fY[lo] - fY[up]) / (fX[lo] - fX[up]);
 }
 
+namespace
+{
+// first derivative of the natural cubic spline through (x_i, y_i) at its own knots (what GSL's bicubic initialisation
+// takes from gsl_spline_eval_deriv: interp2d/bicubic.c); second-derivative form, Thomas elimination
+std::vector<double> naturalSplineSlopes(const std::vector<double>& x, const std::vector<double>& y)
+{
+  const int n = (int)x.size();
+  std::vector<double> h(n - 1), s(n - 1), m(n, 0.), slope(n);
+  for (int i = 0; i < n - 1; ++i) { h[i] = x[i + 1] - x[i]; s[i] = (y[i + 1] - y[i]) / h[i]; }
+  if (n > 2) {
+    // h_{i-1} m_{i-1} + 2 (h_{i-1} + h_i) m_i + h_i m_{i+1} = 6 (s_i - s_{i-1}),  m_0 = m_{n-1} = 0
+    std::vector<double> diag(n), rhs(n);
+    for (int i = 1; i < n - 1; ++i) { diag[i] = 2 * (h[i - 1] + h[i]); rhs[i] = 6 * (s[i] - s[i - 1]); }
+    for (int i = 2; i < n - 1; ++i) {
+      const double f = h[i - 1] / diag[i - 1];
+      diag[i] -= f * h[i - 1];
+      rhs[i] -= f * rhs[i - 1];
+    }
+    for (int i = n - 2; i >= 1; --i) m[i] = (rhs[i] - (i + 1 < n - 1 ? h[i] * m[i + 1] : 0.)) / diag[i];
+  }
+  for (int i = 0; i < n - 1; ++i) slope[i] = s[i] - h[i] * (2 * m[i] + m[i + 1]) / 6;
+  slope[n - 1] = s[n - 2] + h[n - 2] * (m[n - 2] + 2 * m[n - 1]) / 6;
+  return slope;
+}
+} // namespace
+
+// :249-297: gluon shadowing of Frankfurt, Guzey and Strikman (Phys. Rept. 512 (2012) 255), models 2 (weak, type 0) and
+// 1 (strong, type 1): the glue column of QCDEvolution_pb<A>proton_2009_model<k>.dat on its 90 x 7 (x, Q^2) grid,
+// interpolated at (x, mu^2) as gsl_spline2d with gsl_interp2d_bicubic does -- a bicubic Hermite patch whose
+// derivatives z_x, z_y, z_xy at the grid points are those of natural cubic splines along the grid lines.
+double UpcPhotoNuclearVM::getRgLta(int type, double x)
+{
+  if (partPDG == 443) {
+    // :283-287 dereference graphs the reference never fills; unreachable there too (calcCrossSectionY asks for
+    // mu^2 >= 4) -- kept as an error instead of a crash
+    ok = false; error = "FGS10 shadowing is not available for J/psi"; return 1.;
+  }
+  if (fFgsType != type) {
+    const char* dir = std::getenv("UPCGEN_CROSS_SEC_DIR");
+#ifdef CROSS_SEC_DIR
+    if (!dir) dir = CROSS_SEC_DIR;
+#endif
+    if (!dir) { ok = false; error = "UPCGEN_CROSS_SEC_DIR is not set (vm/lta grids)"; return 1.; }
+    const std::string fname = std::string(dir) + "/vm/lta/QCDEvolution_pb" + std::to_string(UpcCrossSection::A) +
+                              "proton_2009_model" + std::to_string(type == 0 ? 2 : 1) + ".dat";
+    std::ifstream ifs(fname);
+    if (!ifs) { ok = false; error = "Missing file: " + fname; return 1.; }
+    const int nx = 90, nq = 7;
+    fGx.assign(nx, 0.); fGq.assign(nq, 0.);
+    fGz.assign((size_t)nx * nq, 0.);
+    double xx, dv, uv, ubar, dbar, sbar, cbar, glue, f2;
+    for (int i = 0; i < nq; ++i) {
+      ifs >> fGq[i];
+      for (int j = 0; j < nx; ++j) {
+        ifs >> xx >> dv >> uv >> ubar >> dbar >> sbar >> cbar >> glue >> f2;
+        fGx[j] = xx;
+        fGz[(size_t)i * nx + j] = glue;
+      }
+    }
+    if (!ifs) { ok = false; error = "Truncated file: " + fname; return 1.; }
+    fGzx.assign(fGz.size(), 0.); fGzy.assign(fGz.size(), 0.); fGzxy.assign(fGz.size(), 0.);
+    std::vector<double> line;
+    for (int i = 0; i < nq; ++i) {            // along x, one Q^2 row at a time
+      line.assign(fGz.begin() + (size_t)i * nx, fGz.begin() + (size_t)(i + 1) * nx);
+      const std::vector<double> d = naturalSplineSlopes(fGx, line);
+      for (int j = 0; j < nx; ++j) fGzx[(size_t)i * nx + j] = d[j];
+    }
+    for (int j = 0; j < nx; ++j) {            // along Q^2, one x column at a time
+      line.resize(nq);
+      for (int i = 0; i < nq; ++i) line[i] = fGz[(size_t)i * nx + j];
+      const std::vector<double> d = naturalSplineSlopes(fGq, line);
+      for (int i = 0; i < nq; ++i) fGzy[(size_t)i * nx + j] = d[i];
+    }
+    for (int i = 0; i < nq; ++i) {            // the cross derivative: along x of z_y (GSL's order)
+      line.assign(fGzy.begin() + (size_t)i * nx, fGzy.begin() + (size_t)(i + 1) * nx);
+      const std::vector<double> d = naturalSplineSlopes(fGx, line);
+      for (int j = 0; j < nx; ++j) fGzxy[(size_t)i * nx + j] = d[j];
+    }
+    fFgsType = type;
+  }
+  // grid limitations (:291-295)
+  if (x < 9.99999975e-6) x = 9.99999975e-6;
+  if (x > 0.95) x = 0.95;
+  const int nx = (int)fGx.size(), nq = (int)fGq.size();
+  const double q2 = fMu2;
+  if (x < fGx[0] || x > fGx[nx - 1] || q2 < fGq[0] || q2 > fGq[nq - 1]) {
+    ok = false; error = "FGS10 grid: (x, mu^2) outside the table (gsl: interpolation error)"; return 1.;
+  }
+  auto cell = [](const std::vector<double>& g, double v) {
+    int lo = 0, hi = (int)g.size() - 1;
+    while (hi - lo > 1) { const int mid = (lo + hi) / 2; if (g[mid] > v) hi = mid; else lo = mid; }
+    return lo;
+  };
+  const int ix = cell(fGx, x), iq = cell(fGq, q2);
+  const double dx = fGx[ix + 1] - fGx[ix], dq = fGq[iq + 1] - fGq[iq];
+  const double t = (x - fGx[ix]) / dx, u = (q2 - fGq[iq]) / dq;
+  // cubic Hermite basis on the unit interval: value at 0 / at 1, slope at 0 / at 1
+  const double ht[4] = {(2 * t - 3) * t * t + 1, (3 - 2 * t) * t * t, ((t - 2) * t + 1) * t, (t - 1) * t * t};
+  const double hu[4] = {(2 * u - 3) * u * u + 1, (3 - 2 * u) * u * u, ((u - 2) * u + 1) * u, (u - 1) * u * u};
+  double r = 0;
+  for (int b = 0; b < 2; ++b)
+    for (int a = 0; a < 2; ++a) {
+      const size_t k = (size_t)(iq + b) * nx + (ix + a);
+      r += fGz[k] * ht[a] * hu[b] + dx * fGzx[k] * ht[2 + a] * hu[b] + dq * fGzy[k] * ht[a] * hu[2 + b] +
+           dx * dq * fGzxy[k] * ht[2 + a] * hu[2 + b];
+    }
+  return r;
+}
+
 // :340-381
 double UpcPhotoNuclearVM::calcCrossSectionY(double y)
 {
@@ -177,6 +287,12 @@ double UpcPhotoNuclearVM::calcCrossSectionY(double y)
   const double PhiA = integrateFormFactorSq(tmin, tmax);
   double cAcP2 = 1.;
   double Rg = 1.;
+  // FGS10 parametrization works for psi(2s) and heavier (:366-374); for J/psi these two options leave the impulse
+  // approximation in place, as the reference does
+  if ((fShadowing == 2 || fShadowing == 3) && fMu2 > 4. - 1e-6) {
+    cAcP2 = 0.9 * 0.9;
+    Rg = getRgLta(fShadowing == 2 ? 0 : 1, x);
+  }
   if (fShadowing == 4) {
     cAcP2 = 0.9 * 0.9;
     Rg = getRgLtaVG(x);

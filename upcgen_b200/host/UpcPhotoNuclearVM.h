@@ -13,9 +13,10 @@
 //   (the reference uses TF1::Integral; here an adaptive Gauss-Kronrod rule to 1e-12);  Rg: gluon shadowing --
 //   SHADOWING 0 (impulse approximation, Rg = 1) and 4 (leading-twist approximation, Guzey-Zhalov tables
 //   cross_sections/vm/lta/LT2013_pb208_cteq6l1_m12_Q2_{3,4}.dat, read from $UPCGEN_CROSS_SEC_DIR; TSpline3 = a
-//   not-a-knot cubic spline through the 37 points).  SHADOWING 1 needs EPS09 grids the reference does not ship;
-//   2 / 3 use the FGS10 grids through gsl_spline2d (psi(2S), Upsilon) or graphs the reference never fills (J/psi):
-//   not provided here.
+//   not-a-knot cubic spline through the 37 points), 2 / 3 (FGS10 weak / strong shadowing for psi(2S) and Upsilon:
+//   cross_sections/vm/lta/QCDEvolution_pb208proton_2009_model{2,1}.dat through the bicubic interpolation of
+//   gsl_spline2d; for J/psi the reference's condition mu^2 >= 4 leaves the impulse approximation in place, and so
+//   does this).  SHADOWING 1 needs EPS09 grids the reference does not ship: not provided here.
 #pragma once
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ class UpcPhotoNuclearVM : public UpcElemProcess
   double dsdt(double Wgp) const;
   static double integrateFormFactorSq(double tmin, double tmax);
   double getRgLtaVG(double x);
+  double getRgLta(int type, double x);
 
  private:
   int fShadowing{0};
@@ -50,4 +52,7 @@ class UpcPhotoNuclearVM : public UpcElemProcess
   // the LTA table and its not-a-knot spline (TSpline3 of the reference)
   std::vector<double> fX, fY, fB, fC, fD;
   bool fLtaInit{false};
+  // the FGS10 glue ratio on its (x, Q^2) grid with the derivatives of the bicubic interpolation; row = Q^2 index
+  std::vector<double> fGx, fGq, fGz, fGzx, fGzy, fGzxy;
+  int fFgsType{-1};
 };
