@@ -58,7 +58,7 @@ int upcgpu_create(const upcgpu_params* params, int device, upcgpu_ctx** out)
   const upcgpu_params& p = *params;
   if (p.nm < 1 || p.ny < 1 || p.nz < 1 || p.nb1 < 2 || p.nb2 < 2 || p.A < 1 || p.Z < 1 || !(p.R > 0) || !(p.a > 0) ||
       !(p.g1 > 1) || !(p.g2 > 1) || p.breakup_mode < 1 || p.breakup_mode > 4 || !(p.mmax > p.mmin) ||
-      !(p.ymax > p.ymin) || !(p.mmin > 0)) {
+      !(p.ymax > p.ymin) || !(p.mmin > 0) || !(p.sqrts > 0) || !(p.gtot > 1) || !(p.zmax > p.zmin)) {
     g_create_err = "upcgpu_create: parameter block out of range";
     return UPCGPU_EINVAL;
   }
