@@ -244,6 +244,13 @@ int upcgpu_root_write_th2d(const char* path, int n_hist, const char* const* name
                            double ylo, double yhi, const double* const* cells);
 int upcgpu_root_write_tree(const char* path, const char* tree, const char* title, int n_cols, const char* const* names,
                            const char* types, const double* const* columns, size_t n_rows);
+/* upcgpu_root_write_sigma_hists: what the reference adds to events.root at debug level > 0
+ * (src/UpcGenerator.cpp:900-917) -- the nuclear cross section table as the TH2D "hNucCSYM" over the ny + 1 rapidity
+ * and nm + 1 mass bin edges (variable-bin axes, bin (iy + 1, im + 1) = cs[iy][im]) and its projections
+ * "hNucCSYM_py" (TH1D over m) and "hNucCSYM_px" (TH1D over y), with the entries and statistics TH2::ProjectionX/Y
+ * leave in them.  cs: [ny][nm], the table upcgpu_fold_sigma returns. */
+int upcgpu_root_write_sigma_hists(const char* path, int ny, const double* y_edges, int nm, const double* m_edges,
+                                  const double* cs);
 
 /* ---- samplers S1-S3 ------------------------------------------------------------------ */
 /* replaces the UpcSampler2D / UpcSampler1D constructors (include/UpcSampler.h:40-59, :81-109,

@@ -132,8 +132,8 @@ USE_HEPMC_OUTPUT 1
     lumi = o.fill_lumi()
     _, _, tot = o.fold(lumi)
     capi.root_write_th2d(str(tmp_path / "twoPhotonLumi.root"), {"hD2LDMDY": lumi}, P.nm, P.mmin, P.mmax, P.ny, P.ymin, P.ymax)
-    r = subprocess.run([os.path.join(HOST, "upcgen"), "-parfile", "my.in"], cwd=tmp_path, capture_output=True, text=True,
-                       timeout=300)
+    r = subprocess.run([os.path.join(HOST, "upcgen"), "-parfile", "my.in", "-debug", "1"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert "Found pre-calculated unpolarized 2D luminosity" in r.stderr
     line = [l for l in r.stdout.splitlines() if "total cross section" in l][0]
@@ -144,6 +144,19 @@ USE_HEPMC_OUTPUT 1
     c = {k: v[1] for k, v in t["cols"].items()}
     assert c["eventNumber"].tolist() == np.repeat(np.arange(2000), 2).tolist()
     assert c["particleID"].tolist() == [1, 2] * 2000 and set(c["statusID"]) == {23} and set(c["motherID"]) == {0}
+    # -debug 1: the cross section table and its projections next to the tree (src/UpcGenerator.cpp:900-917)
+    from test_root_file import read_keys, key_data, parse_hist
+    fb = (tmp_path / "events.root").read_bytes()
+    _, keys = read_keys(fb)
+    names = [(k["cls"], k["name"]) for k in keys if k["cls"] in ("TH1D", "TH2D", "TTree")]
+    assert names == [("TH1D", "hNucCSYM_py"), ("TH1D", "hNucCSYM_px"), ("TH2D", "hNucCSYM"), ("TTree", "particles")], names
+    h2 = parse_hist(key_data(fb, [k for k in keys if k["name"] == "hNucCSYM"][0]), "TH2D")
+    ocs, _, _ = o.fold(lumi)
+    assert np.array_equal(h2["cells"].reshape(P.nm + 2, P.ny + 2)[1:-1, 1:-1], ocs.T)
+    assert np.allclose(h2["axes"][0]["edges"], P.ymin + P.dy * np.arange(P.ny + 1), rtol=0, atol=1e-12)
+    assert np.allclose(h2["axes"][1]["edges"], P.mmin + P.dm * np.arange(P.nm + 1), rtol=0, atol=1e-12)
+    hm = parse_hist(key_data(fb, [k for k in keys if k["name"] == "hNucCSYM_py"][0]), "TH1D")
+    assert np.allclose(hm["cells"][1:-1], ocs.sum(axis=0), rtol=1e-13) and hm["cells"][0] == 0 and hm["cells"][-1] == 0
     hep = [l.split() for l in (tmp_path / "events.hepmc").read_text().splitlines() if l.startswith("P ")]
     assert len(hep) == 4000
     assert [int(q[3]) for q in hep] == c["pdgCode"].tolist()

@@ -374,3 +374,142 @@ def test_th1d_bytes_equal_what_root_wrote(tmp_path):
     assert mine == real
     back = capi.root_hist_read(path, k["name"])
     assert back["dim"] == 1 and np.array_equal(back["cells"], h["cells"])
+
+
+def parse_hist(data, cls):
+    """Independent parse of a streamed TH1D / TH2D (uniform or variable bins): name, the three axes with their fXbins,
+    entries, the four (seven) statistics sums, the cells.  Member order: TH1 v8 / TH2 v5 / TAxis v10 (ROOT 6.2x)."""
+    b = Buf(data)
+
+    def skip():
+        e, _ = b.obj()
+        b.p = e
+
+    def tnamed():
+        e, v = b.obj()
+        assert v == 1
+        assert b.rd("H") == 1            # TObject version
+        b.rd("I"); b.rd("I")             # fUniqueID, fBits
+        n, t = b.tstring(), b.tstring()
+        assert b.p == e
+        return n, t
+
+    def axis():
+        e, v = b.obj()
+        assert v == 10
+        name, _ = tnamed()
+        skip()                           # TAttAxis
+        nb, lo, hi = b.rd("i"), b.rd("d"), b.rd("d")
+        ne = b.rd("i")
+        edges = np.array([b.rd("d") for _ in range(ne)])
+        b.p = e
+        return dict(name=name, n=nb, lo=lo, hi=hi, edges=edges)
+
+    def th1():
+        e, v = b.obj()
+        assert v == 8
+        name, title = tnamed()
+        skip(); skip(); skip()           # TAttLine, TAttFill, TAttMarker
+        ncells = b.rd("i")
+        ax = [axis(), axis(), axis()]
+        b.rd("h"); b.rd("h")             # fBarOffset, fBarWidth
+        entries = b.rd("d")
+        stats = [b.rd("d") for _ in range(4)]
+        b.p = e
+        return dict(name=name, title=title, ncells=ncells, axes=ax, entries=entries, stats=stats)
+
+    e0, v0 = b.obj()
+    if cls == "TH2D":
+        assert v0 == 4
+        e2, v2 = b.obj()
+        assert v2 == 5
+        h = th1()
+        scale = b.rd("d")
+        assert scale == 1.0
+        h["stats"] += [b.rd("d") for _ in range(3)]
+        assert b.p == e2
+    else:
+        assert v0 == 3
+        h = th1()
+    n = b.rd("i")
+    assert n == h["ncells"]
+    h["cells"] = np.frombuffer(data, dtype=">f8", count=n, offset=b.p).astype(np.float64)
+    assert b.p + 8 * n == e0 == len(data)
+    return h
+
+
+def test_sigma_debug_histograms(tmp_path):
+    """What the reference adds to events.root at debug level > 0 (src/UpcGenerator.cpp:900-917): TH2D hNucCSYM over
+    the (y, m) bin edges (variable-bin axes), bin (iy + 1, im + 1) = cs[iy][im], entries ny * nm, no statistics; then
+    ProjectionY() -> hNucCSYM_py over m and ProjectionX() -> hNucCSYM_px over y, written first.  The projections are
+    checked against TH2::DoProjection's arithmetic restated here: cells = sequential sums over the integrated axis,
+    statistics recomputed from the cells at the bin centres (TH1::ResetStats), entries floor(total + 0.5)."""
+    from upcgen_b200 import capi
+    rng = np.random.default_rng(7)
+    ny, nm = 12, 29
+    ye = -6.0 + 1.0 * np.arange(ny + 1)
+    me = 3.56 + (50 - 3.56) / nm * np.arange(nm + 1)
+    cs = rng.random((ny, nm)) * 1e4
+    cs[3, :] = 0.0
+    path = str(tmp_path / "events.root")
+    capi.root_write_sigma_hists(path, ye, me, cs)
+    f = open(path, "rb").read()
+    hdr, keys, listed = check_file_records(f)
+    assert [(c, n) for _, c, n in listed] == [("TH1D", "hNucCSYM_py"), ("TH1D", "hNucCSYM_px"), ("TH2D", "hNucCSYM")]
+    by_name = {k["name"]: k for k in keys if k["cls"] in ("TH1D", "TH2D")}
+    h2 = parse_hist(key_data(f, by_name["hNucCSYM"]), "TH2D")
+    assert h2["title"] == "" and h2["entries"] == ny * nm and h2["stats"] == [0.0] * 7
+    ax, ay, az = h2["axes"]
+    assert (ax["name"], ax["n"], ax["lo"], ax["hi"]) == ("xaxis", ny, ye[0], ye[-1]) and np.array_equal(ax["edges"], ye)
+    assert (ay["name"], ay["n"], ay["lo"], ay["hi"]) == ("yaxis", nm, me[0], me[-1]) and np.array_equal(ay["edges"], me)
+    assert (az["n"], az["lo"], az["hi"], az["edges"].size) == (1, 0.0, 1.0, 0)
+    cells = h2["cells"].reshape(nm + 2, ny + 2)          # x (= y_pair) fastest
+    assert np.array_equal(cells[1:-1, 1:-1], cs.T)
+    assert np.all(cells[0] == 0) and np.all(cells[-1] == 0) and np.all(cells[:, 0] == 0) and np.all(cells[:, -1] == 0)
+
+    def projection(onx):
+        edges = ye if onx else me
+        nout = edges.size - 1
+        c = np.zeros(nout + 2)
+        tot = 0.0
+        for ob in range(nout + 2):
+            cont = 0.0
+            line = cells[:, ob] if onx else cells[ob, :]
+            for v in line:
+                cont += float(v)
+            c[ob] = cont
+            tot += cont
+        st = [0.0, 0.0, 0.0, 0.0]
+        for bn in range(1, nout + 1):
+            x = 0.5 * (edges[bn - 1] + edges[bn])
+            w = c[bn]
+            err = abs(np.sqrt(abs(w)))
+            st[0] += w; st[1] += err * err; st[2] += w * x; st[3] += w * x * x
+        return c, st, np.floor(tot + 0.5)
+
+    for name, onx, edges in (("hNucCSYM_py", False, me), ("hNucCSYM_px", True, ye)):
+        h = parse_hist(key_data(f, by_name[name]), "TH1D")
+        c, st, ent = projection(onx)
+        assert h["title"] == "" and np.array_equal(h["cells"], c) and h["stats"] == [float(s) for s in st] and h["entries"] == ent
+        a = h["axes"][0]
+        assert (a["n"], a["lo"], a["hi"]) == (edges.size - 1, edges[0], edges[-1]) and np.array_equal(a["edges"], edges)
+        assert (h["axes"][1]["n"], h["axes"][1]["edges"].size) == (1, 0)
+        # the product's reader (TAxis::FindBin on variable bins) finds the cells again
+        back = capi.root_hist_read(path, name)
+        assert back["dim"] == 1 and np.array_equal(back["cells"].ravel(), c)
+    assert h2["cells"].sum() == pytest.approx(cs.sum(), rel=1e-13)
+    back = capi.root_hist_read(path, "hNucCSYM")
+    assert back["dim"] == 2 and (back["nx"], back["ny"]) == (ny, nm) and np.array_equal(back["cells"], cells)
+
+
+def test_uniform_histograms_parse_with_the_same_parser(tmp_path):
+    """parse_hist on the writer's uniform-axis objects (the ones pinned byte for byte against ROOT's own): no fXbins."""
+    from upcgen_b200 import capi
+    path = str(tmp_path / "h.root")
+    t = np.arange(15.0).reshape(5, 3)
+    capi.root_write_th2d(path, {"hD2LDMDY": t}, 5, 1.0, 2.0, 3, -1.0, 1.0)
+    f = open(path, "rb").read()
+    _, keys = read_keys(f)
+    h = parse_hist(key_data(f, [k for k in keys if k["cls"] == "TH2D"][0]), "TH2D")
+    assert h["name"] == "hD2LDMDY" and h["axes"][0]["edges"].size == 0 and h["axes"][0]["n"] == 5 and h["entries"] == 15
+    assert np.array_equal(h["cells"].reshape(5, 7)[1:-1, 1:-1], t.T)

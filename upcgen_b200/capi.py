@@ -69,7 +69,7 @@ SYMBOLS = [
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
     "upcgpu_create_multi", "upcgpu_group_size", "upcgpu_group_member", "upcgpu_group_set_exchange",
-    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_th1d", "upcgpu_root_write_tree", "upcgpu_photon_flux",
+    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_th1d", "upcgpu_root_write_tree", "upcgpu_root_write_sigma_hists", "upcgpu_photon_flux",
     "upcgpu_lumi_ipc_export", "upcgpu_lumi_ipc_import", "upcgpu_fill_lumi_shard_peers",
 ]
 
@@ -566,6 +566,18 @@ def root_write_tree(path: str, tree: str, title: str, columns: dict):
                                   vals[0].size)
     if rc != OK:
         raise UpcGpuError(rc, f"root_write_tree: cannot write {path}")
+
+
+def root_write_sigma_hists(path: str, y_edges, m_edges, cs):
+    """hNucCSYM and its two projections as the reference writes them at debug level > 0 (src/UpcGenerator.cpp:900-917)."""
+    L = lib()
+    ye, me = _f64(y_edges), _f64(m_edges)
+    cs = _f64(cs)
+    assert cs.shape == (ye.size - 1, me.size - 1)
+    L.upcgpu_root_write_sigma_hists.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rc = L.upcgpu_root_write_sigma_hists(path.encode(), ye.size - 1, _p(ye), me.size - 1, _p(me), _p(cs))
+    if rc:
+        raise UpcGpuError(rc, f"root_write_sigma_hists: cannot write {path}")
 
 
 def philox(seed, ctr0, block, n):

@@ -150,4 +150,20 @@ int upcgpu_root_write_tree(const char* path, const char* tree, const char* title
   }
 }
 
+int upcgpu_root_write_sigma_hists(const char* path, int ny, const double* y_edges, int nm, const double* m_edges,
+                                  const double* cs)
+{
+  if (!path || ny < 1 || nm < 1 || !y_edges || !m_edges || !cs) return UPCGPU_EINVAL;
+  try {
+    UpcRootFileWriter w;
+    std::vector<std::vector<double>> table(ny);
+    for (int iy = 0; iy < ny; ++iy) table[iy].assign(cs + (size_t)iy * nm, cs + (size_t)(iy + 1) * nm);
+    UpcAddSigmaHists(w, std::vector<double>(y_edges, y_edges + ny + 1), std::vector<double>(m_edges, m_edges + nm + 1), table);
+    std::string err;
+    return w.Write(path, err) ? UPCGPU_OK : UPCGPU_EINVAL;
+  } catch (...) {
+    return UPCGPU_EINVAL;
+  }
+}
+
 } // extern "C"

@@ -501,6 +501,7 @@ void UpcGenerator::generateEvents()
   long int rejected = 0;
   long int evt = 0;
   while (evt < nEvents) {
+    if (debug > 1) PLOG_DEBUG << "Event number: " << evt + 1;  // :868-870
     if (debug <= 1 && ((evt + 1) % 100000 == 0)) PLOG_INFO << "Event number: " << evt + 1;
     if (generateEvent(pdgs, statuses, mothers, particles) == 1) {
       writeEvent(evt, pdgs, statuses, mothers, particles);
@@ -526,6 +527,7 @@ void UpcGenerator::generateEvents()
     }
     UpcRootFileWriter w;
     std::string err;
+    if (debug > 0) UpcAddSigmaHists(w, binEdgesY, binEdgesM, nucCSYM);  // :900-917: the cross section table and its projections
     w.AddTree("particles", "Generated particles", cols);
     if (!w.Write("events.root", err)) {
       PLOG_FATAL << "cannot write events.root: " << err;

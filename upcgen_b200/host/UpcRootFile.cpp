@@ -2,6 +2,7 @@
 // documented file format (TFile / TKey / TDirectory records, TBufferFile streaming).
 #include "UpcRootFile.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <ctime>
@@ -70,7 +71,8 @@ void tattline(Out& o) { const size_t p = o.begin(2); o.i16(602); o.i16(1); o.i16
 void tattfill(Out& o) { const size_t p = o.begin(2); o.i16(0); o.i16(1001); o.end(p); }
 void tattmarker(Out& o) { const size_t p = o.begin(2); o.i16(1); o.i16(1); o.f32(1.0f); o.end(p); }
 
-void taxis(Out& o, const std::string& name, int nbins, double lo, double hi, float title_offset)
+void taxis(Out& o, const std::string& name, int nbins, double lo, double hi, float title_offset,
+           const std::vector<double>* edges = nullptr)
 {
   const size_t p = o.begin(10);
   tnamed(o, name, "");
@@ -85,7 +87,12 @@ void taxis(Out& o, const std::string& name, int nbins, double lo, double hi, flo
   o.i32(nbins);
   o.f64(lo);
   o.f64(hi);
-  o.i32(0);             // fXbins: no variable edges
+  if (edges && !edges->empty()) {  // fXbins (TArrayD): the nbins + 1 edges of an axis with variable bins
+    o.i32((int32_t)edges->size());
+    for (double e : *edges) o.f64(e);
+  } else {
+    o.i32(0);           // no variable edges
+  }
   o.i32(0); o.i32(0);   // fFirst, fLast
   o.u16(0);             // fBits2
   o.u8(0);              // fTimeDisplay
@@ -106,7 +113,8 @@ void empty_tlist(Out& o, uint32_t bits)
 
 // TH1 (version 8) up to and including fStatOverflows
 void th1(Out& o, const std::string& name, const std::string& title, int ncells, int nx, double xlo, double xhi, int ny, double ylo,
-         double yhi, double entries)
+         double yhi, double entries, const std::vector<double>* xedges = nullptr, const std::vector<double>* yedges = nullptr,
+         const double* stats = nullptr)
 {
   const size_t p = o.begin(8);
   tnamed(o, name, title, 0x03000008u);
@@ -114,12 +122,13 @@ void th1(Out& o, const std::string& name, const std::string& title, int ncells, 
   tattfill(o);
   tattmarker(o);
   o.i32(ncells);
-  taxis(o, "xaxis", nx, xlo, xhi, 1.0f);
-  taxis(o, "yaxis", ny, ylo, yhi, 0.0f);
+  taxis(o, "xaxis", nx, xlo, xhi, 1.0f, xedges);
+  taxis(o, "yaxis", ny, ylo, yhi, 0.0f, yedges);
   taxis(o, "zaxis", 1, 0., 1., 1.0f);
   o.i16(0); o.i16(1000);  // fBarOffset, fBarWidth
   o.f64(entries);
-  o.f64(0); o.f64(0); o.f64(0); o.f64(0);  // fTsumw, fTsumw2, fTsumwx, fTsumwx2 (filled by SetBinContent: all zero)
+  // fTsumw, fTsumw2, fTsumwx, fTsumwx2 (a histogram filled by SetBinContent: all zero)
+  for (int i = 0; i < 4; i++) o.f64(stats ? stats[i] : 0.);
   o.f64(-1111.); o.f64(-1111.);            // fMaximum, fMinimum
   o.f64(0);                                // fNormFactor
   o.i32(0);                                // fContour
@@ -189,6 +198,106 @@ void UpcRootFileWriter::AddTH1D(const std::string& name, const std::string& titl
   Record r;
   r.cls = "TH1D"; r.name = name; r.title = title; r.data = std::move(o.b); r.listed = true;
   records_.push_back(std::move(r));
+}
+
+namespace {
+void check_edges(const std::vector<double>& e, const char* what)
+{
+  if (e.size() < 2) throw std::invalid_argument(std::string(what) + ": an axis needs at least two edges");
+  for (size_t i = 1; i < e.size(); ++i)
+    if (!(e[i] > e[i - 1])) throw std::invalid_argument(std::string(what) + ": edges must increase");
+}
+}  // namespace
+
+// TH2D(name, title, nx, xbins, ny, ybins): TAxis::Set(n, edges) keeps the edges in fXbins and takes fXmin / fXmax from them
+void UpcRootFileWriter::AddTH2D(const std::string& name, const std::string& title, const std::vector<double>& xedges,
+                                const std::vector<double>& yedges, const std::vector<double>& cells, double entries)
+{
+  check_edges(xedges, "AddTH2D"); check_edges(yedges, "AddTH2D");
+  const int nx = (int)xedges.size() - 1, ny = (int)yedges.size() - 1;
+  const size_t ncells = (size_t)(nx + 2) * (ny + 2);
+  if (cells.size() != ncells) throw std::invalid_argument("AddTH2D: cells must hold (nx + 2) * (ny + 2) values");
+  Out o;
+  const size_t p = o.begin(4);  // TH2D
+  {
+    const size_t q = o.begin(5);  // TH2
+    th1(o, name, title, (int)ncells, nx, xedges.front(), xedges.back(), ny, yedges.front(), yedges.back(), entries, &xedges, &yedges);
+    o.f64(1.0);                       // fScalefactor
+    o.f64(0); o.f64(0); o.f64(0);     // fTsumwy, fTsumwy2, fTsumwxy
+    o.end(q);
+  }
+  o.i32((int32_t)ncells);  // TArrayD
+  o.b.reserve(o.b.size() + 8 * ncells + 16);
+  for (double v : cells) o.f64(v);
+  o.end(p);
+  Record r;
+  r.cls = "TH2D"; r.name = name; r.title = title; r.data = std::move(o.b); r.listed = true;
+  records_.push_back(std::move(r));
+}
+
+void UpcRootFileWriter::AddTH1D(const std::string& name, const std::string& title, const std::vector<double>& xedges,
+                                const std::vector<double>& cells, double entries, const double* stats)
+{
+  check_edges(xedges, "AddTH1D");
+  const int nx = (int)xedges.size() - 1;
+  const size_t ncells = (size_t)nx + 2;
+  if (cells.size() != ncells) throw std::invalid_argument("AddTH1D: cells must hold nx + 2 values");
+  Out o;
+  const size_t p = o.begin(3);  // TH1D
+  th1(o, name, title, (int)ncells, nx, xedges.front(), xedges.back(), 1, 0., 1., entries, &xedges, nullptr, stats);
+  o.i32((int32_t)ncells);  // TArrayD
+  for (double v : cells) o.f64(v);
+  o.end(p);
+  Record r;
+  r.cls = "TH1D"; r.name = name; r.title = title; r.data = std::move(o.b); r.listed = true;
+  records_.push_back(std::move(r));
+}
+
+// src/UpcGenerator.cpp:900-917 (debug > 0, ROOT output): the nuclear cross section table as TH2D "hNucCSYM" over the
+// (y, m) bin edges, filled by SetBinContent(iy + 1, im + 1, cs[iy][im]) (entries = ny * nm, no statistics), and its two
+// projections, written in the reference's order: ProjectionY() -> "hNucCSYM_py" (over m), ProjectionX() ->
+// "hNucCSYM_px" (over y), then the table.  A projection is what TH2::DoProjection leaves behind: each cell the
+// sequential sum over the integrated axis (under- and overflow cells included: zero here); the statistics reset and
+// recomputed from the cells as TH1::ResetStats / TH1::GetStats do (bin centres, error^2 = (sqrt|w|)^2); the entries
+// floor(total + 0.5).
+void UpcAddSigmaHists(UpcRootFileWriter& w, const std::vector<double>& yEdges, const std::vector<double>& mEdges,
+                      const std::vector<std::vector<double>>& nucCSYM)
+{
+  const int ny = (int)yEdges.size() - 1, nm = (int)mEdges.size() - 1;
+  if (ny < 1 || nm < 1 || (int)nucCSYM.size() != ny) throw std::invalid_argument("UpcAddSigmaHists: table and edges disagree");
+  for (const auto& row : nucCSYM)
+    if ((int)row.size() != nm) throw std::invalid_argument("UpcAddSigmaHists: table and edges disagree");
+  std::vector<double> cells((size_t)(ny + 2) * (nm + 2), 0.);  // x = y_pair (fastest), y = m_pair
+  for (int iy = 0; iy < ny; ++iy)
+    for (int im = 0; im < nm; ++im) cells[(size_t)(im + 1) * (ny + 2) + (iy + 1)] = nucCSYM[iy][im];
+  auto projection = [&](bool onX, const std::vector<double>& edges, const char* name) {
+    const int nout = (int)edges.size() - 1, nin = onX ? nm : ny;
+    std::vector<double> c((size_t)nout + 2, 0.);
+    double totcont = 0;
+    for (int ob = 0; ob <= nout + 1; ++ob) {
+      double cont = 0;
+      for (int ib = 0; ib <= nin + 1; ++ib) {
+        const int bx = onX ? ob : ib, by = onX ? ib : ob;
+        cont += cells[(size_t)by * (ny + 2) + bx];
+      }
+      c[ob] = cont;
+      totcont += cont;
+    }
+    double st[4] = {0, 0, 0, 0};
+    for (int b = 1; b <= nout; ++b) {
+      const double x = 0.5 * (edges[b - 1] + edges[b]);
+      const double wgt = c[b];
+      const double err = std::fabs(std::sqrt(std::fabs(wgt)));
+      st[0] += wgt;
+      st[1] += err * err;
+      st[2] += wgt * x;
+      st[3] += wgt * x * x;
+    }
+    w.AddTH1D(name, "", edges, c, std::floor(totcont + 0.5), st);
+  };
+  projection(false, mEdges, "hNucCSYM_py");
+  projection(true, yEdges, "hNucCSYM_px");
+  w.AddTH2D("hNucCSYM", "", yEdges, mEdges, cells, (double)ny * nm);
 }
 
 void UpcRootFileWriter::AddTree(const std::string& name, const std::string& title, const std::vector<Column>& columns)

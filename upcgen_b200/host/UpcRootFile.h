@@ -27,6 +27,13 @@ class UpcRootFileWriter
   void AddTH1D(const std::string& name, const std::string& title, int nx, double xlo, double xhi,
                const std::vector<double>& cells, double entries);
 
+  // the same with variable bins: edges hold n + 1 increasing values per axis (TH2D(name, title, nx, xbins, ny, ybins));
+  // stats: fTsumw, fTsumw2, fTsumwx, fTsumwx2 of the TH1D (null: zero, a histogram filled by SetBinContent)
+  void AddTH2D(const std::string& name, const std::string& title, const std::vector<double>& xedges,
+               const std::vector<double>& yedges, const std::vector<double>& cells, double entries);
+  void AddTH1D(const std::string& name, const std::string& title, const std::vector<double>& xedges,
+               const std::vector<double>& cells, double entries, const double* stats = nullptr);
+
   // a TTree of flat branches, one leaf each: type 'I' (Int_t) or 'D' (Double_t); all columns the same length.
   // Integer columns are given as doubles holding integral values.
   struct Column {
@@ -55,3 +62,9 @@ class UpcRootFileWriter
   };
   std::vector<Tree> trees_;
 };
+
+// The three histograms the reference adds to events.root at debug level > 0 (src/UpcGenerator.cpp:900-917): the
+// nuclear cross section table "hNucCSYM" (TH2D over the y and m bin edges) and its projections "hNucCSYM_py" (over m)
+// and "hNucCSYM_px" (over y), in the reference's order of writing.  nucCSYM: [ny][nm].
+void UpcAddSigmaHists(UpcRootFileWriter& w, const std::vector<double>& yEdges, const std::vector<double>& mEdges,
+                      const std::vector<std::vector<double>>& nucCSYM);
