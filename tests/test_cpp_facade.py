@@ -227,3 +227,52 @@ USE_HEPMC_OUTPUT 1
     assert np.allclose(p[:, 2] + p[:, 3], p[:, 0], rtol=1e-6, atol=1e-7) and np.allclose(p[:, 4] + p[:, 5], p[:, 1], rtol=1e-6, atol=1e-7)
     mass2 = lambda q: q[..., 3] ** 2 - (q[..., :3] ** 2).sum(-1)
     assert np.allclose(np.sqrt(np.maximum(mass2(p[:, :2]), 0)), 0.1349770, atol=2e-4)    # nine printed digits of a boosted pi0
+
+
+def test_upcgen_cli_honours_the_lumi_lock_file(tmp_path):
+    """The lock protocol of prepareTwoPhotonLumi (src/UpcCrossSection.cpp:465-478, :587-591): while another generator's
+    .lumiIsCalculated exists in the luminosity directory the run waits (in one-second steps); once it is gone the run
+    takes the lock, fills and caches the table, and removes its own lock file."""
+    import time
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    par = """NUCLEUS_Z 82
+NUCLEUS_A 208
+SQRTS 5020
+PROC_ID 13
+NEVENTS 10
+MMIN 4
+MMAX 30
+BINS_M 6
+BINS_Y 4
+BINS_Z 10
+FLUX_POINT 1
+BREAKUP_MODE 1
+NON_ZERO_GAM_PT 0
+SEED 3
+USE_ROOT_OUTPUT 0
+USE_HEPMC_OUTPUT 1
+"""
+    (tmp_path / "my.in").write_text(par)
+    lock = tmp_path / ".lumiIsCalculated"
+    lock.write_text("")
+    err = open(tmp_path / "stderr.txt", "w")
+    p = subprocess.Popen([os.path.join(HOST, "upcgen"), "-parfile", "my.in"], cwd=tmp_path, stdout=subprocess.PIPE,
+                         stderr=err, text=True)
+    try:
+        deadline = time.time() + 120
+        while "waiting" not in (tmp_path / "stderr.txt").read_text():      # the tables are made first
+            assert p.poll() is None, (tmp_path / "stderr.txt").read_text()
+            assert time.time() < deadline
+            time.sleep(0.2)
+        time.sleep(1.5)
+        assert p.poll() is None and not (tmp_path / "twoPhotonLumi.root").exists() and lock.exists()
+        lock.unlink()
+        out, _ = p.communicate(timeout=120)
+    finally:
+        if p.poll() is None:
+            p.kill()
+        err.close()
+    assert p.returncode == 0, (tmp_path / "stderr.txt").read_text()
+    assert "total cross section" in out
+    assert (tmp_path / "twoPhotonLumi.root").exists() and not lock.exists()
+    assert len([l for l in (tmp_path / "events.hepmc").read_text().splitlines() if l.startswith("E ")]) == 10

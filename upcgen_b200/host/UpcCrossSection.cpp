@@ -6,8 +6,13 @@
 #include "UpcPhotoNuclearVM.h"
 #include "UpcTwoPhotonTabulated.h"
 
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <cerrno>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -237,9 +242,42 @@ void UpcCrossSection::fillCrossSectionZM(std::vector<std::vector<double>>& cross
   }
 }
 
+namespace
+{
+// The lock file of the reference (src/UpcCrossSection.cpp:465-478, :587-591): <dir>/.lumiIsCalculated[Pol], created with
+// O_CREAT | O_EXCL before the cache is looked for, removed after it is read or written; a generator that finds it waits
+// in one-second steps.  Kept so that this build and the reference -- or several jobs of either -- can share one cache
+// directory.  Two deviations: the descriptor is closed (the reference leaks it and treats descriptor 0 as a failure),
+// and an error other than "exists" (a read-only directory, say) is a warning and no lock, not an endless wait.
+struct LumiLock {
+  std::string path;
+  bool owned{false};
+  explicit LumiLock(const std::string& p) : path(p)
+  {
+    int waited = 0;
+    for (;;) {
+      const int fd = ::open(path.c_str(), O_CREAT | O_EXCL, 0644);
+      if (fd >= 0) { ::close(fd); owned = true; return; }
+      if (errno != EEXIST) {
+        PLOG_WARNING << "Cannot create the lock file " << path << " (" << std::strerror(errno) << "): continuing without it";
+        return;
+      }
+      if (waited % 30 == 0) PLOG_INFO << "Another generator holds " << path << ": waiting";
+      ::sleep(1);
+      ++waited;
+    }
+  }
+  ~LumiLock()
+  {
+    if (owned && std::remove(path.c_str()) != 0) PLOG_WARNING << "Lock file " << path << " was not properly removed!";
+  }
+};
+} // namespace
+
 void UpcCrossSection::prepareTwoPhotonLumi()
 {
   ensureTables();
+  LumiLock lock(std::string(lumiFileDirectory) + "/.lumiIsCalculated" + (usePolarizedCS ? "Pol" : ""));
   const size_t n = (size_t)nm * ny;
   // The cache file, as in the reference (src/UpcCrossSection.cpp:481-491, :578-585): twoPhotonLumi[Pol].root with the
   // TH2D hD2LDMDY (or hD2LDMDY_s / hD2LDMDY_p), bin (im + 1, iy + 1) = table[im][iy].  A file the REFERENCE wrote is
