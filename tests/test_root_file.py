@@ -78,6 +78,8 @@ def key_data(f, k):
     raw = f[k["pos"] + k["keylen"]:k["pos"] + k["nbytes"]]
     if len(raw) == k["objlen"]:
         return raw
+    if raw[:2] == b"L4":
+        return l4_unframe(raw, k["objlen"])
     out, q = b"", 0
     while len(out) < k["objlen"]:
         assert raw[q:q + 2] == b"ZL"
@@ -285,9 +287,9 @@ def read_tree(f, name):
         bseek = [b.rd("q") for _ in range(maxbaskets)]
         assert b.tstring() == ""
         assert b.p == e2 == end
-        assert entrynumber == bentries == entries and compress == 0
+        assert entrynumber == bentries == entries and compress == hdr["compress"]
         branches.append(dict(name=bname, title=btitle, leaf=lcls, lentype=lentype, nbaskets=writebasket, bytes=bbytes,
-                             entry=bentry, seek=bseek, tot=btot))
+                             entry=bentry, seek=bseek, tot=btot, zip=bzip))
     assert b.p == end_br
     end_lv, nlv = tobjarray()
     assert nlv == nbr
@@ -301,9 +303,10 @@ def read_tree(f, name):
     # baskets
     cols = {}
     by_pos = {k["pos"]: k for k in keys}
-    total = 0
+    total = total_unzipped = 0
     for br in branches:
         vals = []
+        br_tot = br_zip = 0
         for i in range(br["nbaskets"]):
             k = by_pos[br["seek"][i]]
             assert k["cls"] == "TBasket" and k["name"] == br["name"] and k["title"] == name and k["nbytes"] == br["bytes"][i]
@@ -314,13 +317,17 @@ def read_tree(f, name):
             nxt = br["entry"][i + 1]
             assert br["entry"][i] + nev == nxt
             dt = ">i4" if br["leaf"] == "TLeafI" else ">f8"
-            vals.append(np.frombuffer(f, dtype=dt, count=nev, offset=k["pos"] + k["keylen"]))
-            total += k["nbytes"]
-        assert br["entry"][br["nbaskets"]] == entries
+            vals.append(np.frombuffer(key_data(f, k), dtype=dt, count=nev))     # inflated if the basket is an L4 record
+            total += k["nbytes"]; br_zip += k["nbytes"]
+            total_unzipped += k["keylen"] + k["objlen"]; br_tot += k["keylen"] + k["objlen"]
+            assert k["nbytes"] <= k["keylen"] + k["objlen"]
+        assert br["entry"][br["nbaskets"]] == entries and (br["tot"], br["zip"]) == (br_tot, br_zip)
         cols[br["name"]] = (br["title"], np.concatenate(vals) if vals else np.zeros(0))
-    assert total == totbytes == zipbytes
+    assert total == zipbytes and total_unzipped == totbytes
+    if hdr["compress"] == 0:
+        assert totbytes == zipbytes
     assert all(k[1] != "TBasket" for k in listed)       # baskets are not in the directory's key list
-    return dict(name=tname, title=ttitle, entries=entries, autosave=autosave, cols=cols)
+    return dict(name=tname, title=ttitle, entries=entries, autosave=autosave, cols=cols, totbytes=totbytes, zipbytes=zipbytes)
 
 
 def test_tree_roundtrip(tmp_path):
@@ -513,3 +520,163 @@ def test_uniform_histograms_parse_with_the_same_parser(tmp_path):
     h = parse_hist(key_data(f, [k for k in keys if k["cls"] == "TH2D"][0]), "TH2D")
     assert h["name"] == "hD2LDMDY" and h["axes"][0]["edges"].size == 0 and h["axes"][0]["n"] == 5 and h["entries"] == 15
     assert np.array_equal(h["cells"].reshape(5, 7)[1:-1, 1:-1], t.T)
+
+
+# ---- LZ4 ("L4" records) ---------------------------------------------------------------------------------------
+def lz4_block_decode(src, out_n):
+    """Independent decoder of one LZ4 block (lz4_Block_format.md): token, literal run, offset, match."""
+    out = bytearray()
+    ip, n = 0, len(src)
+    while ip < n:
+        tok = src[ip]; ip += 1
+        lit = tok >> 4
+        if lit == 15:
+            while True:
+                b = src[ip]; ip += 1
+                lit += b
+                if b != 255:
+                    break
+        out += src[ip:ip + lit]
+        assert ip + lit <= n
+        ip += lit
+        if ip >= n:
+            break
+        off = src[ip] | src[ip + 1] << 8
+        ip += 2
+        assert 0 < off <= len(out)
+        ml = tok & 15
+        if ml == 15:
+            while True:
+                b = src[ip]; ip += 1
+                ml += b
+                if b != 255:
+                    break
+        ml += 4
+        if off >= ml:
+            out += out[len(out) - off:len(out) - off + ml]
+        else:
+            for _ in range(ml):
+                out.append(out[-off])
+    assert len(out) == out_n
+    return bytes(out)
+
+
+def l4_unframe(raw, objlen):
+    """ROOT's L4 framing: 9-byte header, 8-byte big-endian XXH64 of the LZ4 bytes, the LZ4 block; chained."""
+    import xxhash
+    out, q = b"", 0
+    while len(out) < objlen:
+        assert raw[q:q + 2] == b"L4" and raw[q + 2] == 1
+        csz = raw[q + 3] | raw[q + 4] << 8 | raw[q + 5] << 16
+        usz = raw[q + 6] | raw[q + 7] << 8 | raw[q + 8] << 16
+        payload = raw[q + 17:q + 9 + csz]
+        assert int.from_bytes(raw[q + 9:q + 17], "big") == xxhash.xxh64(payload, seed=0).intdigest()
+        out += lz4_block_decode(payload, usz)
+        q += 9 + csz
+    assert q == len(raw) and len(out) == objlen
+    return out
+
+
+@pytest.fixture(scope="module")
+def lz4_check(tmp_path_factory):
+    import subprocess
+    d = tmp_path_factory.mktemp("lz4")
+    exe = str(d / "lz4_check")
+    host = os.path.join(ROOT_DIR, "upcgen_b200", "host")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I", host, "-o", exe,
+                           os.path.join(ROOT_DIR, "tests", "cpp", "lz4_check.cpp"), os.path.join(host, "UpcLz4.cpp")])
+
+    def run(data: bytes):
+        import json
+        import subprocess as sp
+        (d / "in.bin").write_bytes(data)
+        r = sp.run([exe, str(d / "in.bin"), str(d / "out")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout), (d / "out.lz4").read_bytes(), (d / "out.l4").read_bytes()
+
+    return run
+
+
+def test_lz4_and_xxh64_against_independent_implementations(lz4_check):
+    """UpcLz4.cpp: XXH64 equals the xxhash module's on every length class (0, < 4, < 8, < 32, 32 k + r); the compressor's
+    blocks are decoded by the independent decoder above -- short inputs that must stay literal (the last 5 bytes, no
+    match in the last 12), literal runs and matches beyond the 15 / 270 thresholds of the length encoding, overlapping
+    matches (runs), incompressible bytes; the L4 framing carries the right sizes and checksum, chains blocks above
+    16 MB, and refuses data that does not shrink (ROOT stores those as they are)."""
+    import xxhash
+    rng = np.random.default_rng(11)
+    ints = np.repeat(np.arange(3000, dtype=">i4"), 3).tobytes()
+    cases = [b"", b"a", b"abc", b"abcdefg", b"0123456789a", b"0123456789ab", b"0123456789abc", b"x" * 12, b"x" * 13,
+             b"ab" * 40, b"x" * 5000, rng.bytes(3000), bytes(range(256)) * 3 + b"q" * 700 + bytes(range(256)) * 2,
+             ints, rng.bytes(300) + b"\0" * 100000 + rng.bytes(20), b"abcdefghij" * 31 + rng.bytes(31) + b"abcdefghij" * 7]
+    for data in cases:
+        res, blk, framed = lz4_check(data)
+        assert res["n"] == len(data)
+        assert int(res["xxh64"], 16) == xxhash.xxh64(data, seed=0).intdigest(), len(data)
+        assert res["block_roundtrip"] and res["frames_ok"]
+        assert lz4_block_decode(blk, len(data)) == data
+        if res["shrunk"]:
+            assert len(framed) < len(data) and l4_unframe(framed, len(data)) == data
+        else:
+            assert framed == b""
+    assert not lz4_check(rng.bytes(3000))[0]["shrunk"] and lz4_check(ints)[0]["shrunk"]
+    # more than one 0xffffff-byte chunk
+    big = np.repeat(np.arange(1_500_000, dtype=">i4"), 3).tobytes()        # 18 MB
+    res, blk, framed = lz4_check(big)
+    assert res["block_roundtrip"] and res["frames_ok"] and res["shrunk"]
+    assert framed[6] | framed[7] << 8 | framed[8] << 16 == 0xffffff
+    assert l4_unframe(framed, len(big)) == big
+
+
+def test_lz4_compressed_files_roundtrip(tmp_path):
+    """upcgpu_root_set_compression(409) -- the reference's setting for events.root (src/UpcGenerator.cpp:843): the tree's
+    baskets and the objects above 256 bytes become L4 records (sizes, XXH64 checksum and LZ4 stream checked by the
+    independent decoders above), fCompress is recorded in the file header and in every branch, fTotBytes / fZipBytes
+    account for both sizes, the columns and histograms come back bit for bit -- through the Python parser and through
+    the product's reader (UpcRootHist.cpp inflates L4 next to zlib).  Incompressible columns stay as they are."""
+    from upcgen_b200 import capi
+    rng = np.random.default_rng(5)
+    n = 1_200_001
+    cols = {"eventNumber": ("I", np.repeat(np.arange(n // 3 + 1), 3)[:n]), "pdgCode": ("I", rng.choice([13, -13, 22], n)),
+            "particleID": ("I", np.tile([1, 2, 3], n // 3 + 1)[:n]), "statusID": ("I", np.full(n, 23)),
+            "motherID": ("I", rng.integers(0, 3, n)), "px": ("D", rng.normal(size=n)), "e": ("D", np.round(rng.random(n) * 100, 1))}
+    assert capi.root_set_compression(409) == 0
+    try:
+        with pytest.raises(capi.UpcGpuError):
+            capi.root_set_compression(101)                # zlib is read, not written
+        path = str(tmp_path / "events.root")
+        capi.root_write_tree(path, "particles", "Generated particles", cols)
+        hpath = str(tmp_path / "twoPhotonLumi.root")
+        table = np.outer(np.linspace(1, 2, 300), np.ones(40))          # smooth: compresses well
+        capi.root_write_th2d(hpath, {"hD2LDMDY": table}, 300, 3.56, 50.0, 40, -6.0, 6.0)
+    finally:
+        assert capi.root_set_compression(0) == 409
+    f = open(path, "rb").read()
+    hdr, keys = read_keys(f)
+    assert hdr["compress"] == 409
+    t = read_tree(f, "particles")
+    assert t["entries"] == n and t["zipbytes"] < 0.62 * t["totbytes"]
+    for name, (typ, vals) in cols.items():
+        got = t["cols"][name][1]
+        assert np.array_equal(got, np.asarray(vals, dtype=got.dtype.newbyteorder("=")))
+    size = {name: sum(k["nbytes"] for k in keys if k["cls"] == "TBasket" and k["name"] == name) for name in cols}
+    raw = {name: sum(k["keylen"] + k["objlen"] for k in keys if k["cls"] == "TBasket" and k["name"] == name) for name in cols}
+    assert size["statusID"] < 0.01 * raw["statusID"] and size["eventNumber"] < 0.65 * raw["eventNumber"]
+    assert size["px"] == raw["px"]                       # random mantissas: stored as they are
+    tk = [k for k in keys if k["cls"] == "TTree"][0]
+    assert tk["nbytes"] < tk["keylen"] + tk["objlen"]    # the tree record itself is above 256 bytes and shrinks
+    g = open(hpath, "rb").read()
+    hh, hkeys = read_keys(g)
+    check_file_records(g)
+    hk = [k for k in hkeys if k["cls"] == "TH2D"][0]
+    assert hh["compress"] == 409 and hk["nbytes"] < 0.2 * (hk["keylen"] + hk["objlen"])
+    h = parse_hist(key_data(g, hk), "TH2D")
+    assert np.array_equal(h["cells"].reshape(42, 302)[1:-1, 1:-1], table.T)
+    back = capi.root_hist_read(hpath, "hD2LDMDY")
+    assert np.array_equal(back["cells"][1:-1, 1:-1].T, table)
+    # and with the default setting nothing is compressed
+    capi.root_write_th2d(hpath, {"hD2LDMDY": table}, 300, 3.56, 50.0, 40, -6.0, 6.0)
+    g = open(hpath, "rb").read()
+    hh, hkeys = read_keys(g)
+    hk = [k for k in hkeys if k["cls"] == "TH2D"][0]
+    assert hh["compress"] == 0 and hk["nbytes"] == hk["keylen"] + hk["objlen"]

@@ -29,7 +29,7 @@ def test_lookup_semantics_cpp(tmp_path):
     host = os.path.join(ROOT_DIR, "upcgen_b200", "host")
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", host, "-o", str(exe),
                            os.path.join(ROOT_DIR, "tests", "cpp", "roothist_check.cpp"),
-                           os.path.join(host, "UpcRootHist.cpp"), "-lz"])
+                           os.path.join(host, "UpcRootHist.cpp"), os.path.join(host, "UpcLz4.cpp"), "-lz"])
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "ROOTHIST_OK" in r.stdout, r.stdout + r.stderr
 

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libupcgpu.so")
 SOURCES = ["upc_capi.cu", "upc_tables.cu", "upc_lumi.cu", "upc_fold.cu", "upc_events.cu", "upc_group.cu", "upc_elem_capi.cpp",
            "../host/UpcTwoPhotonDilep.cpp", "../host/UpcTwoPhotonALP.cpp", "../host/UpcTwoPhotonTabulated.cpp",
-           "../host/UpcRootHist.cpp", "../host/UpcRootFile.cpp"]
+           "../host/UpcRootHist.cpp", "../host/UpcRootFile.cpp", "../host/UpcLz4.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v", "-ccbin", "/usr/bin/g++"]

@@ -69,7 +69,7 @@ SYMBOLS = [
     "upcgpu_stream_handle", "upcgpu_launch_count", "upcgpu_elem_sigma_m", "upcgpu_elem_fill_cs_zm",
     "upcgpu_hist_pdf_init", "upcgpu_hist_sample2d", "upcgpu_hist_sample1d", "upcgpu_root_hist_read",
     "upcgpu_create_multi", "upcgpu_group_size", "upcgpu_group_member", "upcgpu_group_set_exchange",
-    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_th1d", "upcgpu_root_write_tree", "upcgpu_root_write_sigma_hists", "upcgpu_photon_flux",
+    "upcgpu_group_describe", "upcgpu_root_write_th2d", "upcgpu_root_write_th1d", "upcgpu_root_write_tree", "upcgpu_root_write_sigma_hists", "upcgpu_root_set_compression", "upcgpu_photon_flux",
     "upcgpu_lumi_ipc_export", "upcgpu_lumi_ipc_import", "upcgpu_fill_lumi_shard_peers",
 ]
 
@@ -566,6 +566,17 @@ def root_write_tree(path: str, tree: str, title: str, columns: dict):
                                   vals[0].size)
     if rc != OK:
         raise UpcGpuError(rc, f"root_write_tree: cannot write {path}")
+
+
+def root_set_compression(setting: int) -> int:
+    """ROOT compression setting of the files written through this library (0: none, 4xx: LZ4); returns the previous one."""
+    L = lib()
+    prev = C.c_int()
+    L.upcgpu_root_set_compression.argtypes = [C.c_int, C.POINTER(C.c_int)]
+    rc = L.upcgpu_root_set_compression(int(setting), C.byref(prev))
+    if rc:
+        raise UpcGpuError(rc, f"root_set_compression: setting {setting} is not supported (0 or 4xx)")
+    return prev.value
 
 
 def root_write_sigma_hists(path: str, y_edges, m_edges, cs):

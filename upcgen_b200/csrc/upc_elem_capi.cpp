@@ -150,6 +150,14 @@ int upcgpu_root_write_tree(const char* path, const char* tree, const char* title
   }
 }
 
+int upcgpu_root_set_compression(int setting, int* previous)
+{
+  if (previous) *previous = UpcRootFileDefaultCompression();
+  if (setting != 0 && !(setting / 100 == 4 && setting % 100 > 0 && setting < 500)) return UPCGPU_EINVAL;
+  UpcRootFileDefaultCompression(setting);
+  return UPCGPU_OK;
+}
+
 int upcgpu_root_write_sigma_hists(const char* path, int ny, const double* y_edges, int nm, const double* m_edges,
                                   const double* cs)
 {

@@ -491,7 +491,7 @@ void UpcGenerator::generateEvents()
   std::vector<TLorentzVector> particles;
   if (useROOTOut) {
     // events.root, tree "particles" with the reference's nine branches (src/UpcGenerator.cpp:842-857), written without
-    // ROOT by UpcRootFile.cpp when the loop ends (uncompressed; the reference asks for LZ4 level 9)
+    // ROOT by UpcRootFile.cpp when the loop ends (uncompressed unless UPCGEN_ROOT_COMPRESSION=409 asks for the LZ4 records of the reference, :843)
     PLOG_WARNING << "Using ROOT tree for output!";
     PLOG_INFO << "Events will be written to events.root";
     treeCols.assign(9, std::vector<double>());

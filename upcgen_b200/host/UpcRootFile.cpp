@@ -1,9 +1,11 @@
 // UpcRootFile.cpp -- see UpcRootFile.h.  Nothing here links against or is copied from ROOT; the layout is ROOT's
 // documented file format (TFile / TKey / TDirectory records, TBufferFile streaming).
 #include "UpcRootFile.h"
+#include "UpcLz4.h"
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <stdexcept>
@@ -159,6 +161,19 @@ struct BasketInfo {
 };
 
 }  // namespace
+
+int UpcRootFileDefaultCompression(int setting)
+{
+  static int current = [] {
+    const char* e = std::getenv("UPCGEN_ROOT_COMPRESSION");
+    const int v = e ? std::atoi(e) : 0;
+    return (v / 100 == 4 && v % 100 > 0) ? v : 0;
+  }();
+  if (setting >= 0) current = setting;
+  return current;
+}
+
+UpcRootFileWriter::UpcRootFileWriter() : compression_(UpcRootFileDefaultCompression()) {}
 
 void UpcRootFileWriter::AddTH2D(const std::string& name, const std::string& title, int nx, double xlo, double xhi, int ny,
                                 double ylo, double yhi, const std::vector<double>& cells, double entries)
@@ -354,7 +369,18 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
     // trees: baskets first (their keys are not listed), then the TTree record, which needs the baskets' positions
     struct Placed { size_t idx; };
     std::vector<Record> out_recs;
+    const bool lz4 = compression_ / 100 == 4 && compression_ % 100 > 0;
+    if (compression_ != 0 && !lz4) throw std::invalid_argument("compression setting: only 0 and 4xx (LZ4) are written");
+    // TKey's rule: an object above 256 bytes is stored compressed if that makes it smaller.  `head` bytes at the front
+    // (the basket header, which belongs to the key) stay as they are.
+    auto finish = [&](Record& r, size_t head) {
+      r.objlen = (uint32_t)(r.data.size() - head);
+      if (!lz4 || r.objlen <= 256) return;
+      std::vector<unsigned char> z(r.data.begin(), r.data.begin() + head);
+      if (upc_lz4::root_zip(r.data.data() + head, r.objlen, z)) r.data.swap(z);
+    };
     auto place = [&](Record& r) {
+      finish(r, 0);
       r.seek = pos;
       const uint16_t kl = key_len(r.cls, r.name, r.title);
       pos += kl + (uint32_t)r.data.size();
@@ -367,7 +393,8 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
       const int64_t n = (int64_t)t.columns[0].values.size();
       const int nb = (int)t.columns.size();
       std::vector<std::vector<BasketInfo>> baskets(nb);
-      int64_t tot_bytes = 0;
+      int64_t tot_bytes = 0, zip_bytes = 0;
+      std::vector<int64_t> br_tot(nb, 0);
       for (int ib = 0; ib < nb; ++ib) {
         const Column& c = t.columns[ib];
         const int esz = c.type == 'I' ? 4 : 8;
@@ -392,10 +419,13 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
           Record r;
           r.cls = "TBasket"; r.name = c.name; r.title = t.name; r.data = std::move(o.b); r.listed = false;
           r.seek = pos;
-          BasketInfo bi{pos, (uint32_t)(kl + datalen), e0};
+          finish(r, 19);  // the 19 bytes of the basket header count as key, the buffer after them may be compressed
+          BasketInfo bi{pos, (uint32_t)(kl - 19 + r.data.size()), e0};
           baskets[ib].push_back(bi);
-          tot_bytes += bi.nbytes;
-          pos += bi.nbytes;  // = key header + basket header + data
+          tot_bytes += kl + datalen;
+          br_tot[ib] += kl + datalen;
+          zip_bytes += bi.nbytes;
+          pos += bi.nbytes;  // = key header + basket header + stored buffer
           out_recs.push_back(std::move(r));
         }
       }
@@ -410,7 +440,7 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
       tattmarker(o);
       o.i64(n);            // fEntries
       o.i64(tot_bytes);    // fTotBytes
-      o.i64(tot_bytes);    // fZipBytes (uncompressed)
+      o.i64(zip_bytes);    // fZipBytes (= fTotBytes when nothing is compressed)
       o.i64(0);            // fSavedBytes
       o.i64(0);            // fFlushedBytes
       o.f64(1.0);          // fWeight
@@ -456,7 +486,7 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
             const size_t bp = o.begin(13);  // TBranch
             tnamed(o, c.name, c.name + "/" + c.type);
             tattfill(o);
-            o.i32(0);           // fCompress
+            o.i32(compression_); // fCompress
             o.i32(32000);       // fBasketSize
             o.i32(0);           // fEntryOffsetLen
             o.i32(nbk);         // fWriteBasket
@@ -467,7 +497,7 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
             o.i32(0);           // fSplitLevel
             o.i64(n);           // fEntries
             o.i64(0);           // fFirstEntry
-            o.i64(br_bytes);    // fTotBytes
+            o.i64(br_tot[ib]);  // fTotBytes
             o.i64(br_bytes);    // fZipBytes
             {
               const size_t e = o.begin(3);  // fBranches: empty TObjArray
@@ -562,7 +592,7 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
       for (const Record& r : out_recs) {
         if (!r.listed) continue;
         const uint16_t kl = key_len(r.cls, r.name, r.title);
-        key_header(keys, kl + (uint32_t)r.data.size(), (uint32_t)r.data.size(), kl, r.seek, r.cls, r.name, r.title);
+        key_header(keys, kl + (uint32_t)r.data.size(), r.objlen, kl, r.seek, r.cls, r.name, r.title);
       }
     }
     const uint32_t nbytes_keys = dir_keylen + (uint32_t)keys.size();
@@ -591,7 +621,7 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
     f.i32(1);  // nfree
     f.i32((int32_t)(dir_keylen + dir_namelen));  // fNbytesName
     f.u8(4);   // fUnits
-    f.i32(0);  // fCompress
+    f.i32(compression_);  // fCompress
     f.i32((int32_t)seek_info);
     f.i32((int32_t)nbytes_info);
     f.b.insert(f.b.end(), uuid, uuid + 18);
@@ -620,14 +650,10 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
     for (const Record& r : out_recs) {
       if (f.size() != r.seek) throw std::runtime_error("internal: record offset mismatch");
       uint16_t kl = key_len(r.cls, r.name, r.title);
-      uint32_t objlen = (uint32_t)r.data.size();
-      uint32_t nbytes = kl + objlen;
-      if (r.cls == "TBasket") {
-        // the basket header (19 bytes) counts as part of the key: fKeylen includes it, fObjlen is the payload
-        kl = (uint16_t)(kl + 19);
-        objlen -= 19;
-      }
-      key_header(f, nbytes, objlen, kl, r.seek, r.cls, r.name, r.title);
+      const uint32_t nbytes = kl + (uint32_t)r.data.size();
+      // the basket header (19 bytes) counts as part of the key: fKeylen includes it, fObjlen is the payload
+      if (r.cls == "TBasket") kl = (uint16_t)(kl + 19);
+      key_header(f, nbytes, r.objlen, kl, r.seek, r.cls, r.name, r.title);
       f.raw(r.data);
     }
 

@@ -1,6 +1,7 @@
 // UpcRootHist.cpp -- see UpcRootHist.h.  The file layout is ROOT's documented one (TFile / TKey / TBuffer streaming);
 // nothing here links against or is copied from ROOT.
 #include "UpcRootHist.h"
+#include "UpcLz4.h"
 
 #include <zlib.h>
 
@@ -148,7 +149,16 @@ bool UpcRootHist::Read(const std::string& path, const std::string& objName, std:
       size_t q = 0, out = 0;
       while (out < buf.size()) {
         if (q + 9 > rawlen) throw std::runtime_error("truncated compressed object");
-        if (raw[q] != 'Z' || raw[q + 1] != 'L') throw std::runtime_error("compression other than zlib (ZL) is not supported");
+        if (raw[q] == 'L' && raw[q + 1] == '4') {  // LZ4 (ROOT 6.14-6.16 wrote it by default; the reference asks for it in events.root)
+          size_t used = 0, made = 0;
+          if (!upc_lz4::root_unzip_block(raw + q, rawlen - q, buf.data() + out, buf.size() - out, &used, &made))
+            throw std::runtime_error("LZ4 block: bad sizes, checksum or stream");
+          out += made;
+          q += used;
+          continue;
+        }
+        if (raw[q] != 'Z' || raw[q + 1] != 'L')
+          throw std::runtime_error(std::string("compression '") + (char)raw[q] + (char)raw[q + 1] + "' is not supported (zlib ZL and LZ4 L4 are)");
         const size_t csz = raw[q + 3] | raw[q + 4] << 8 | raw[q + 5] << 16;
         const size_t usz = raw[q + 6] | raw[q + 7] << 8 | raw[q + 8] << 16;
         if (q + 9 + csz > rawlen || out + usz > buf.size()) throw std::runtime_error("inconsistent compressed block");
