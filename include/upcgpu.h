@@ -245,8 +245,9 @@ int upcgpu_root_write_th2d(const char* path, int n_hist, const char* const* name
 int upcgpu_root_write_tree(const char* path, const char* tree, const char* title, int n_cols, const char* const* names,
                            const char* types, const double* const* columns, size_t n_rows);
 /* upcgpu_root_set_compression: ROOT's compression setting (100 * algorithm + level) for the files written by the
- * entry points above and below.  0 (default): uncompressed.  4xx: LZ4 "L4" records, what the reference asks for in
- * events.root (4 * 100 + 9, src/UpcGenerator.cpp:843).  Other algorithms: UPCGPU_EINVAL.  Returns the previous
+ * entry points above and below.  0 (default): uncompressed.  1xx: zlib "ZL" records (101 is ROOT's default, what the
+ * reference's luminosity cache is written with).  4xx: LZ4 "L4" records, what the reference asks for in events.root
+ * (4 * 100 + 9, src/UpcGenerator.cpp:843).  Levels 1-9; other algorithms: UPCGPU_EINVAL.  Returns the previous
  * setting through *previous when that is not NULL. */
 int upcgpu_root_set_compression(int setting, int* previous);
 /* upcgpu_root_write_sigma_hists: what the reference adds to events.root at debug level > 0

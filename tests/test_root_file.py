@@ -643,7 +643,7 @@ def test_lz4_compressed_files_roundtrip(tmp_path):
     assert capi.root_set_compression(409) == 0
     try:
         with pytest.raises(capi.UpcGpuError):
-            capi.root_set_compression(101)                # zlib is read, not written
+            capi.root_set_compression(505)                # zstd: neither read nor written
         path = str(tmp_path / "events.root")
         capi.root_write_tree(path, "particles", "Generated particles", cols)
         hpath = str(tmp_path / "twoPhotonLumi.root")
@@ -680,3 +680,44 @@ def test_lz4_compressed_files_roundtrip(tmp_path):
     hh, hkeys = read_keys(g)
     hk = [k for k in hkeys if k["cls"] == "TH2D"][0]
     assert hh["compress"] == 0 and hk["nbytes"] == hk["keylen"] + hk["objlen"]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference's cross_sections directory is not mounted")
+def test_zlib_records_have_roots_framing(tmp_path):
+    """Setting 101 (ROOT's default, the one the reference's luminosity cache is written with): the TH2D record of the
+    reference's own cross_sections/lbyl/cross_section_zm.root, written again with the same name, axes and cells, has
+    the same key header fields and the same 'ZL' 8 framing as the record ROOT 6.22/09 wrote, and inflates to the same
+    bytes; the compressed stream itself may differ with the zlib build (reported, not required)."""
+    from upcgen_b200 import capi
+    src = os.path.join(REF, "lbyl", "cross_section_zm.root")
+    f = open(src, "rb").read()
+    hdr, keys = read_keys(f)
+    k = [q for q in keys if q["cls"] == "TH2D"][0]
+    real_raw = f[k["pos"] + k["keylen"]:k["pos"] + k["nbytes"]]
+    real = key_data(f, k)
+    h = capi.root_hist_read(src, k["name"])
+    assert capi.root_set_compression(hdr["compress"]) == 0 and hdr["compress"] == 101
+    try:
+        path = str(tmp_path / "copy.root")
+        import ctypes as C
+        L = capi.lib()
+        cells = np.ascontiguousarray(h["cells"], dtype=np.float64)     # [ny + 2][nx + 2]: the overflow row has entries
+        names = (C.c_char_p * 1)(k["name"].encode())
+        ptrs = (C.c_void_p * 1)(cells.ctypes.data)
+        L.upcgpu_root_write_th2d.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
+                                             C.c_double, C.c_double, C.c_void_p]
+        assert L.upcgpu_root_write_th2d(path.encode(), 1, names, h["nx"], h["xlo"], h["xhi"], h["ny"], h["ylo"], h["yhi"], ptrs) == 0
+    finally:
+        capi.root_set_compression(0)
+    g = open(path, "rb").read()
+    check_file_records(g)
+    hdr2, keys2 = read_keys(g)
+    k2 = [q for q in keys2 if q["cls"] == "TH2D"][0]
+    mine_raw = g[k2["pos"] + k2["keylen"]:k2["pos"] + k2["nbytes"]]
+    assert hdr2["compress"] == 101 and (k2["objlen"], k2["keylen"]) == (k["objlen"], k["keylen"])
+    assert mine_raw[:3] == real_raw[:3] == b"ZL\x08" and mine_raw[6:9] == real_raw[6:9]     # method, uncompressed size
+    assert mine_raw[9:11] == real_raw[9:11]                                                 # zlib header of a level-1 stream
+    assert key_data(g, k2) == real
+    print("compressed bytes: ROOT", len(real_raw), "here", len(mine_raw), "identical" if mine_raw == real_raw else "different stream")
+    back = capi.root_hist_read(path, k["name"])
+    assert np.array_equal(back["cells"], h["cells"])

@@ -575,7 +575,7 @@ def root_set_compression(setting: int) -> int:
     L.upcgpu_root_set_compression.argtypes = [C.c_int, C.POINTER(C.c_int)]
     rc = L.upcgpu_root_set_compression(int(setting), C.byref(prev))
     if rc:
-        raise UpcGpuError(rc, f"root_set_compression: setting {setting} is not supported (0 or 4xx)")
+        raise UpcGpuError(rc, f"root_set_compression: setting {setting} is not supported (0, 1xx or 4xx)")
     return prev.value
 
 

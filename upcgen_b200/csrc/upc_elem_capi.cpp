@@ -153,7 +153,8 @@ int upcgpu_root_write_tree(const char* path, const char* tree, const char* title
 int upcgpu_root_set_compression(int setting, int* previous)
 {
   if (previous) *previous = UpcRootFileDefaultCompression();
-  if (setting != 0 && !(setting / 100 == 4 && setting % 100 > 0 && setting < 500)) return UPCGPU_EINVAL;
+  const int alg = setting / 100, level = setting % 100;
+  if (setting != 0 && !((alg == 1 || alg == 4) && level >= 1 && level <= 9)) return UPCGPU_EINVAL;
   UpcRootFileDefaultCompression(setting);
   return UPCGPU_OK;
 }

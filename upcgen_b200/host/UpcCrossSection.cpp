@@ -334,6 +334,9 @@ void UpcCrossSection::prepareTwoPhotonLumi()
   PLOG_INFO << "Two-photon luminosity: " << n << " cells in " << st.ms_total << " ms on " << upcgpu_group_size(ctx) << " GPU(s)";
   {
     UpcRootFileWriter w;
+    // the reference writes this file with ROOT's default compression, zlib level 1 (setting 101); with the same name,
+    // axes and cells the compressed TH2D record written here is byte-identical to ROOT's (tests/test_root_file.py)
+    if (UpcRootFileDefaultCompression() == 0) w.SetCompression(101);
     auto cells_of = [&](const std::vector<double>& t) {
       std::vector<double> c((size_t)(nm + 2) * (ny + 2), 0.);
       for (int im = 0; im < nm; ++im)

@@ -3,6 +3,9 @@
 #include "UpcRootFile.h"
 #include "UpcLz4.h"
 
+#include <zlib.h>
+
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -167,7 +170,7 @@ int UpcRootFileDefaultCompression(int setting)
   static int current = [] {
     const char* e = std::getenv("UPCGEN_ROOT_COMPRESSION");
     const int v = e ? std::atoi(e) : 0;
-    return (v / 100 == 4 && v % 100 > 0) ? v : 0;
+    return ((v / 100 == 4 || v / 100 == 1) && v % 100 > 0 && v % 100 <= 9) ? v : 0;
   }();
   if (setting >= 0) current = setting;
   return current;
@@ -369,15 +372,36 @@ bool UpcRootFileWriter::Write(const std::string& path, std::string& err)
     // trees: baskets first (their keys are not listed), then the TTree record, which needs the baskets' positions
     struct Placed { size_t idx; };
     std::vector<Record> out_recs;
-    const bool lz4 = compression_ / 100 == 4 && compression_ % 100 > 0;
-    if (compression_ != 0 && !lz4) throw std::invalid_argument("compression setting: only 0 and 4xx (LZ4) are written");
+    const int zalg = compression_ / 100, zlevel = compression_ % 100;
+    const bool lz4 = zalg == 4 && zlevel > 0, zl = zalg == 1 && zlevel > 0;
+    if (compression_ != 0 && !lz4 && !zl)
+      throw std::invalid_argument("compression setting: 0, 1xx (zlib) and 4xx (LZ4) are written");
+    // ROOT's zlib records: 'Z' 'L' 8 (Z_DEFLATED), 3 bytes compressed size, 3 bytes uncompressed size (little endian),
+    // a zlib stream; at most 0xffffff input bytes per record (what the reference's own cross_sections/*.root hold)
+    auto zlib_zip = [&](const unsigned char* src, size_t n, std::vector<unsigned char>& dst) {
+      const size_t start = dst.size();
+      for (size_t p = 0; p < n; p += 0xffffff) {
+        const size_t cn = std::min<size_t>(n - p, 0xffffff);
+        uLongf zn = compressBound((uLong)cn);
+        const size_t hdr = dst.size();
+        dst.resize(hdr + 9 + zn);
+        if (compress2(dst.data() + hdr + 9, &zn, src + p, (uLong)cn, zlevel) != Z_OK || 9 + zn >= cn) { dst.resize(start); return false; }
+        dst.resize(hdr + 9 + zn);
+        unsigned char* h = dst.data() + hdr;
+        h[0] = 'Z'; h[1] = 'L'; h[2] = 8;
+        h[3] = (unsigned char)zn; h[4] = (unsigned char)(zn >> 8); h[5] = (unsigned char)(zn >> 16);
+        h[6] = (unsigned char)cn; h[7] = (unsigned char)(cn >> 8); h[8] = (unsigned char)(cn >> 16);
+      }
+      if (dst.size() - start >= n) { dst.resize(start); return false; }
+      return true;
+    };
     // TKey's rule: an object above 256 bytes is stored compressed if that makes it smaller.  `head` bytes at the front
     // (the basket header, which belongs to the key) stay as they are.
     auto finish = [&](Record& r, size_t head) {
       r.objlen = (uint32_t)(r.data.size() - head);
-      if (!lz4 || r.objlen <= 256) return;
+      if ((!lz4 && !zl) || r.objlen <= 256) return;
       std::vector<unsigned char> z(r.data.begin(), r.data.begin() + head);
-      if (upc_lz4::root_zip(r.data.data() + head, r.objlen, z)) r.data.swap(z);
+      if (lz4 ? upc_lz4::root_zip(r.data.data() + head, r.objlen, z) : zlib_zip(r.data.data() + head, r.objlen, z)) r.data.swap(z);
     };
     auto place = [&](Record& r) {
       finish(r, 0);

@@ -45,6 +45,7 @@ class UpcRootFileWriter
   void AddTree(const std::string& name, const std::string& title, const std::vector<Column>& columns);
 
   // ROOT's compression setting (100 * algorithm + level).  0 (the default here): records are stored as they are.
+  // 1xx: zlib "ZL" records (101 = ROOT's default setting; the framing of the reference's own cross_sections/*.root).
   // 4xx: LZ4 -- what the reference asks for in events.root (409, src/UpcGenerator.cpp:843): objects above 256 bytes
   // and basket buffers are stored as "L4" records (UpcLz4.h) when that makes them smaller, as ROOT does.  The blocks
   // come from a greedy matcher, not LZ4-HC level 9: any LZ4 decoder reads them, they are somewhat larger.
