@@ -197,3 +197,48 @@ def test_c_abi_reader_equals_python_parse():
     assert h1["dim"] == 1 and h1["cells"].shape == (1002,)
     with pytest.raises(capi.UpcGpuError):
         capi.root_hist_read(f"{REF}/lbyl/cross_section_m.root", "noSuchObject")
+
+
+def test_reader_survives_corrupted_files(tmp_path):
+    """These files are external input (a luminosity cache left by another job, cross sections from
+    UPCGEN_CROSS_SEC_DIR): 600 truncated, byte-flipped and word-overwritten copies of an uncompressed, a zlib and an LZ4
+    file go through the reader built with AddressSanitizer and UBSan -- every one must end in a value or an error
+    message, never in a memory fault."""
+    import subprocess
+    from upcgen_b200 import capi
+    host = os.path.join(ROOT_DIR, "upcgen_b200", "host")
+    exe = str(tmp_path / "roothist_fuzz")
+    r = subprocess.run(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                        "-I", host, "-o", exe, os.path.join(ROOT_DIR, "tests", "cpp", "roothist_fuzz.cpp"),
+                        os.path.join(host, "UpcRootHist.cpp"), os.path.join(host, "UpcLz4.cpp"), "-lz"], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no sanitizer runtime in this toolchain: " + r.stderr[-200:])
+    rng = np.random.default_rng(99)
+    table = np.outer(np.linspace(1, 2, 60), np.ones(20))
+    files = []
+    try:
+        for comp in (0, 101, 409):
+            capi.root_set_compression(comp)
+            p = str(tmp_path / f"h{comp}.root")
+            capi.root_write_th2d(p, {"hD2LDMDY": table}, 60, 3.56, 50.0, 20, -6.0, 6.0)
+            files.append(open(p, "rb").read())
+    finally:
+        capi.root_set_compression(0)
+    names = [str(tmp_path / f"h{c}.root") for c in (0, 101, 409)]
+    for it in range(600):
+        f = bytearray(files[it % 3])
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            for _ in range(rng.integers(1, 6)):
+                f[rng.integers(0, len(f))] = rng.integers(0, 256)
+        elif mode == 1:
+            f = f[:rng.integers(0, len(f))]
+        else:
+            i = rng.integers(0, len(f) - 4)
+            f[i:i + 4] = bytes(rng.integers(0, 256, 4).astype(np.uint8))
+        names.append(str(tmp_path / f"x{it}.root"))
+        open(names[-1], "wb").write(bytes(f))
+    r = subprocess.run([exe] + names, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ok, bad = [int(x) for x in r.stdout.split("ok")[1].replace("bad", "").split()]
+    assert ok >= 3 and bad > 100 and ok + bad == 603
