@@ -24,7 +24,8 @@ def _newest_src():
     t = 0.0
     for root in (CSRC, os.path.join(HERE, "host"), os.path.join(os.path.dirname(HERE), "include")):
         for f in os.listdir(root):
-            t = max(t, os.path.getmtime(os.path.join(root, f)))
+            if f.endswith((".cu", ".cuh", ".cpp", ".h")):   # sources only: host/ also holds libupcgen_host.so and upcgen
+                t = max(t, os.path.getmtime(os.path.join(root, f)))
     return t
 
 
